@@ -1,0 +1,75 @@
+// Internal GEMM interface: D[M,N] = epilogue( A[M,K] * B[N,K]^T ).
+// Two implementations share it: the tcgen05/TMA TF32 kernel (product path) and an exact-fp32 SIMT
+// kernel used to verify it on device (tests only, selected with eegb200_set_gemm_backend).
+#pragma once
+#include "common.cuh"
+
+namespace eegb200 {
+
+struct GemmOperand {
+  const float* ptr;
+  int ld;         // leading dimension in floats (multiple of 4, TMA needs 16-byte strides)
+  int mn_major;   // 0: K-major, element (i,k) at ptr[i*ld + k];  1: MN-major, element (i,k) at ptr[k*ld + i]
+};
+
+enum { EPI_ACT_NONE = 0, EPI_ACT_GELU = 1 };
+enum { EPI_STORE = 0, EPI_ADD = 1, EPI_ATOMIC = 2 };
+
+// order: v = alpha*acc; +bias; aux_out=v; act; dropout; *gelu'(mul_in); +resid; tf32 round; store
+struct Epilogue {
+  float* C = nullptr;
+  int ldc = 0;
+  float alpha = 1.f;
+  const float* bias = nullptr;   // per column, or table [bias_period][ld_bias] indexed by (row % bias_period)
+  int bias_period = 0;           // 0 -> per-column vector
+  int ld_bias = 0;
+  float* aux_out = nullptr;      // pre-activation copy
+  int ld_aux = 0;
+  int act = EPI_ACT_NONE;
+  DropoutCfg drop = {0, 0, 0.f, 1.f, 0};
+  int drop_ld = 0;               // mask element index = row*drop_ld + col
+  const float* mul_in = nullptr; // v *= gelu'(mul_in[row,col])
+  int ld_mul = 0;
+  const float* resid = nullptr;
+  int ld_res = 0;
+  int round_tf32 = 0;
+  int store_mode = EPI_STORE;
+};
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  GemmOperand A{nullptr, 0, 0}, B{nullptr, 0, 0};
+  Epilogue epi;
+  int split_k = 1;   // >1 requires epi.store_mode == EPI_ATOMIC and a pre-zeroed C
+};
+
+enum { GEMM_BACKEND_TCGEN05 = 0, GEMM_BACKEND_SIMT_FP32 = 1 };
+void gemm_set_backend(int backend);
+int gemm_get_backend();
+int gemm_launch(const GemmArgs& g, cudaStream_t stream);           // dispatches on the backend switch
+int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream);
+int gemm_launch_simt(const GemmArgs& g, cudaStream_t stream);
+long long gemm_launch_count();                                      // kernels launched so far (bench bookkeeping)
+void count_launch(int n = 1);
+long long total_launch_count();
+
+// ---- epilogue math shared by both kernels ----
+__device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, float acc) {
+  float v = e.alpha * acc;
+  if (e.bias) v += e.bias_period ? e.bias[(size_t)(row % e.bias_period) * e.ld_bias + col] : e.bias[col];
+  if (e.aux_out) e.aux_out[(size_t)row * e.ld_aux + col] = v;
+  if (e.act == EPI_ACT_GELU) v = gelu_exact(v);
+  if (e.drop.p > 0.f) v = dropout_keep(e.drop, (uint64_t)row * e.drop_ld + col) ? v * e.drop.scale : 0.f;
+  if (e.mul_in) v *= gelu_grad(e.mul_in[(size_t)row * e.ld_mul + col]);
+  if (e.resid) v += e.resid[(size_t)row * e.ld_res + col];
+  if (e.round_tf32) v = tf32_rn(v);
+  return v;
+}
+__device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, float v) {
+  float* p = e.C + (size_t)row * e.ldc + col;
+  if (e.store_mode == EPI_STORE) *p = v;
+  else if (e.store_mode == EPI_ADD) *p += v;
+  else atomicAdd(p, v);
+}
+
+}  // namespace eegb200

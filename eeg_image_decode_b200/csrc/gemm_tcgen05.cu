@@ -1,0 +1,276 @@
+// TF32 GEMM on the 5th-gen tensor cores:  D[M,N] = epilogue(A[M,K] * B[N,K]^T), fp32 in HBM.
+//
+//   warp 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier complete_tx)
+//   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, fp32 accumulators in TMEM)
+//   warps 2..5 : epilogue    (tcgen05.ld 32x32b -> registers -> fused bias/GELU/dropout/residual -> global)
+//
+// Tile 128 x BN x 32(K, = one 128-byte swizzle row of fp32).  K-major operands use the SWIZZLE_128B
+// canonical layout; MN-major operands (needed by the weight-gradient GEMMs, whose reduction runs over
+// the token dimension) use the 32-bit-only SWIZZLE_128B_ATOM_32B layout (UMMA layout type 1).
+// Out-of-range rows / columns / K are zero-filled by TMA, the epilogue masks the stores.
+#include "gemm.h"
+#include <mutex>
+
+namespace eegb200 {
+
+static constexpr int BM = 128;
+static constexpr int BK = 32;   // floats per k-block (128 B)
+static constexpr int UMMA_K = 8;
+static constexpr int GEMM_THREADS = 192;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int k_blocks_per_split;   // k-blocks handled by one blockIdx.z
+  int stages;
+  Epilogue epi;
+};
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 4;
+  constexpr uint32_t B_BYTES = BN * BK * 4;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int MAX_STAGES = 8;
+
+  // 1024-byte aligned tile area (swizzle atoms), then barriers
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
+  const int kb_end = min(total_kb, kb_begin + p.k_blocks_per_split);
+  const int num_kb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && num_kb > 0) {
+      // ================= TMA producer =================
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * BK;
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], sa + j * (BK * 128), tile_m * BM + j * 32, k0);
+        } else {
+          tma_load_2d(&tmA, &full_bar[s], sa, k0, tile_m * BM);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], sb + j * (BK * 128), tile_n * BN + j * 32, k0);
+        } else {
+          tma_load_2d(&tmB, &full_bar[s], sb, k0, tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num_kb > 0) {
+      // ================= MMA issuer (one thread) =================
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          // K-major : 8 rows x 128 B swizzle atoms, SBO = 1024 B, advance 32 B (8 floats) per MMA inside the atom
+          // MN-major: [k][32 mn] slabs of BK*128 B (LBO), 4-k-row atoms of 512 B (SBO), advance 8 k-rows = 1024 B
+          const uint64_t adesc = A_MN ? umma_smem_desc(sa + kk * 1024, BK * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                                      : umma_smem_desc(sa + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+          const uint64_t bdesc = B_MN ? umma_smem_desc(sb + kk * 1024, BK * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                                      : umma_smem_desc(sb + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+          tc_mma_tf32(tmem_base, adesc, bdesc, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);   // frees this smem stage once the MMAs above have read it
+      }
+      tc_commit(tmem_full_bar);     // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    const int q = warp & 3;
+    const int row = tile_m * BM + q * 32 + lane;
+    const Epilogue& e = p.epi;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const bool vec_ok = e.store_mode == EPI_STORE && (e.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = tile_n * BN + c * 32;
+      if (col0 >= p.N) break;                       // warp-uniform
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (row < p.M) {
+        if (col0 + 32 <= p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = epi_value(e, row, col0 + j, v[j]);
+          if (vec_ok) {
+            float4* dst = reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) epi_store(e, row, col0 + j, v[j]);
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) epi_store(e, row, col0 + j, epi_value(e, row, col0 + j, v[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static int resolve_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (!g_encode) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return 3;
+  }
+  return 0;
+}
+
+// operand viewed as logical [rows, K]
+static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int box_rows) {
+  EEG_REQUIRE(op.ptr != nullptr, "gemm: null operand");
+  EEG_REQUIRE((op.ld & 3) == 0, "gemm: leading dimension %d is not a multiple of 4 floats (TMA needs 16-byte strides)", op.ld);
+  EEG_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "gemm: operand pointer not 16-byte aligned");
+  cuuint64_t dims[2];
+  cuuint64_t strides[1] = {(cuuint64_t)op.ld * 4};
+  cuuint32_t box[2];
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw;
+  if (op.mn_major) {
+    EEG_REQUIRE(op.ld >= rows, "gemm: MN-major operand ld %d < rows %d", op.ld, rows);
+    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+    box[0] = 32; box[1] = BK;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  } else {
+    EEG_REQUIRE(op.ld >= K, "gemm: K-major operand ld %d < K %d", op.ld, K);
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
+    box[0] = BK; box[1] = (cuuint32_t)box_rows;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  }
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows %d K %d ld %d mn %d)", (int)r, rows, K, op.ld,
+              op.mn_major);
+  return 0;
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  const int total_kb = cdiv(g.K, BK);
+  int split = g.split_k < 1 ? 1 : g.split_k;
+  if (split > total_kb) split = total_kb > 0 ? total_kb : 1;
+  GemmKernelParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.k_blocks_per_split = cdiv(total_kb, split);
+  split = p.k_blocks_per_split > 0 ? cdiv(total_kb, p.k_blocks_per_split) : 1;
+  const int stage_bytes = (BM + BN) * BK * 4;
+  // short K: shallow pipeline so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop);
+  // long K: deep pipeline, one CTA per SM.
+  const int budget = p.k_blocks_per_split >= 16 ? 196608 : 98304;
+  int stages = budget / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > p.k_blocks_per_split) stages = p.k_blocks_per_split;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  p.epi = g.epi;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  static size_t configured = 0;   // per template instantiation
+  if (smem > configured) {
+    EEG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), split);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const GemmArgs& g, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  EEG_TRY(make_operand_map(&ta, g.A, g.M, g.K, BM));
+  EEG_TRY(make_operand_map(&tb, g.B, g.N, g.K, BN));
+  if (!g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 0, 0>(g, ta, tb, stream);
+  if (!g.A.mn_major && g.B.mn_major) return launch_cfg<BN, 0, 1>(g, ta, tb, stream);
+  if (g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 1, 0>(g, ta, tb, stream);
+  return launch_cfg<BN, 1, 1>(g, ta, tb, stream);
+}
+
+int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream) {
+  EEG_REQUIRE(g.M > 0 && g.N > 0 && g.K >= 0, "gemm: bad shape %d x %d x %d", g.M, g.N, g.K);
+  EEG_REQUIRE(g.epi.C != nullptr, "gemm: null output");
+  EEG_REQUIRE(g.split_k <= 1 || g.epi.store_mode == EPI_ATOMIC, "gemm: split-K needs the atomic store mode");
+  EEG_TRY(resolve_encode());
+  if (g.N <= 64) return launch_bn<64>(g, stream);
+  if (g.N <= 128) return launch_bn<128>(g, stream);
+  return launch_bn<256>(g, stream);
+}
+
+}  // namespace eegb200

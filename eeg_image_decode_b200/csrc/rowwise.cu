@@ -1,0 +1,380 @@
+// Row-wise / elementwise kernels around the GEMMs: input padding, subject token, LayerNorm fwd/bwd,
+// column sums (bias gradients), dropout-mask dump, TF32 rounding copies.
+#include "kernels.h"
+
+namespace eegb200 {
+
+// ------------------------------------------------------------------------------------------------
+// x (B,63,250) -> token matrix Xp [B*64, 256]: row b*64+0 = 0 (subject-token slot), rows 1..63 = channels,
+// columns 250..255 = 0; values rounded to TF32 (they only feed the value-embedding GEMM, Embed.py:146).
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_input_kernel(const float* __restrict__ x, float* __restrict__ xp, int B) {
+  const long long total = (long long)B * 64 * 64;   // float4 slots
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 63);
+    const long long row = i >> 6;
+    const int t = (int)(row & 63);
+    const long long b = row >> 6;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) {
+      const float* src = x + (b * 63 + (t - 1)) * 250;
+      const int c = c4 * 4;
+      if (c < 250) v.x = tf32_rn(src[c]);
+      if (c + 1 < 250) v.y = tf32_rn(src[c + 1]);
+      if (c + 2 < 250) v.z = tf32_rn(src[c + 2]);
+      if (c + 3 < 250) v.w = tf32_rn(src[c + 3]);
+    }
+    reinterpret_cast<float4*>(xp)[i] = v;
+  }
+}
+int pad_input(const float* x, float* xp, int B, cudaStream_t s) {
+  const long long total = (long long)B * 64 * 64;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  pad_input_kernel<<<blocks, 256, 0, s>>>(x, xp, B);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// flag[0] = 1 if any subject id >= n_subj or < 0 (SubjectEmbedding.forward, Embed.py:117: the WHOLE batch then
+// uses the shared token)
+__global__ void subject_flag_kernel(const long long* __restrict__ ids, int B, int n_subj, int* __restrict__ flag) {
+  __shared__ int any;
+  if (threadIdx.x == 0) any = 0;
+  __syncthreads();
+  int a = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) a |= (ids[i] >= n_subj || ids[i] < 0) ? 1 : 0;
+  if (a) atomicOr(&any, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) flag[0] = any;
+}
+// H0[b*64 + 0, :] = dropout(subject row)   (Embed.py:158-162)
+__global__ void subject_token_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
+                                     const float* __restrict__ shared_tok, const int* __restrict__ flag,
+                                     float* __restrict__ h0, int B, DropoutCfg drop, int round_tf) {
+  const int b = blockIdx.x;
+  const int c = threadIdx.x;   // 256 threads
+  const float* src = flag[0] ? shared_tok : table + ids[b] * 250;
+  float v = c < 250 ? src[c] : 0.f;
+  const size_t row = (size_t)b * 64;
+  if (drop.p > 0.f) v = dropout_keep(drop, row * 256 + c) ? v * drop.scale : 0.f;
+  h0[row * 256 + c] = round_tf ? tf32_rn(v) : v;
+}
+int subject_token(const long long* ids, const float* table, const float* shared_tok, int n_subj, int* flag, float* h0,
+                  int B, DropoutCfg drop, int round_tf, cudaStream_t s) {
+  subject_flag_kernel<<<1, 256, 0, s>>>(ids, B, n_subj, flag);
+  subject_token_kernel<<<B, 256, 0, s>>>(ids, table, shared_tok, flag, h0, B, drop, round_tf);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+// backward of the subject token: g[b*64+0, :] (after the embed dropout mask) is scattered into the table
+// (dense grad, unused rows stay 0) or summed into the shared token.
+__global__ void subject_token_bwd_kernel(const long long* __restrict__ ids, const int* __restrict__ flag,
+                                         const float* __restrict__ dh0, float* __restrict__ dtable,
+                                         float* __restrict__ dshared, int B, DropoutCfg drop) {
+  const int b = blockIdx.x;
+  const int c = threadIdx.x;
+  if (c >= 250) return;
+  const size_t row = (size_t)b * 64;
+  float g = dh0[row * 256 + c];
+  if (drop.p > 0.f) g = dropout_keep(drop, row * 256 + c) ? g * drop.scale : 0.f;
+  if (flag[0]) atomicAdd(&dshared[c], g);
+  else atomicAdd(&dtable[ids[b] * 250 + c], g);
+}
+int subject_token_bwd(const long long* ids, const int* flag, const float* dh0, float* dtable, float* dshared, int B,
+                      DropoutCfg drop, cudaStream_t s) {
+  subject_token_bwd_kernel<<<B, 256, 0, s>>>(ids, flag, dh0, dtable, dshared, B, drop);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim D (valid columns), row stride ld; one warp per row.
+// stats[row] = (mean, rstd).  Columns D..ld_out-1 of the output are written as 0.
+// `second`: optional chained LayerNorm (EncoderLayer.norm2 followed by Encoder.norm,
+// Transformer_EncDec.py:51,77-78) applied to the first one's output.
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>   // MAXV = ceil(D/32) values per lane held in registers
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ld, int rows, int D, const float* __restrict__ g1,
+                                     const float* __restrict__ b1, float* __restrict__ stats1,
+                                     const float* __restrict__ g2, const float* __restrict__ b2,
+                                     float* __restrict__ stats2, float* __restrict__ y, int ld_out, int round_tf,
+                                     float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * ld;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < D ? xr[c] : 0.f;
+    s += v[i];
+  }
+  float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    const float d = c < D ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  float rstd = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) { stats1[2 * warp] = mean; stats1[2 * warp + 1] = rstd; }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < D ? (v[i] - mean) * rstd * g1[c] + b1[c] : 0.f;
+  }
+  if (g2 != nullptr) {
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) s += v[i];
+    mean = warp_sum(s) / D;
+    q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      const float d = c < D ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    rstd = rsqrtf(warp_sum(q) / D + eps);
+    if (lane == 0) { stats2[2 * warp] = mean; stats2[2 * warp + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < D ? (v[i] - mean) * rstd * g2[c] + b2[c] : 0.f;
+    }
+  }
+  float* yr = y + (size_t)warp * ld_out;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < ld_out) yr[c] = round_tf ? tf32_rn(v[i]) : v[i];
+  }
+}
+
+int layernorm_fwd(const float* x, int ld, int rows, int D, const float* g1, const float* b1, float* stats1,
+                  const float* g2, const float* b2, float* stats2, float* y, int ld_out, int round_tf, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = cdiv(rows * 32, threads);
+  if (D <= 256 && ld_out <= 256)
+    layernorm_fwd_kernel<8><<<blocks, threads, 0, s>>>(x, ld, rows, D, g1, b1, stats1, g2, b2, stats2, y, ld_out, round_tf, 1e-5f);
+  else if (D <= 1024 && ld_out <= 1024)
+    layernorm_fwd_kernel<32><<<blocks, threads, 0, s>>>(x, ld, rows, D, g1, b1, stats1, g2, b2, stats2, y, ld_out, round_tf, 1e-5f);
+  else {
+    set_error("layernorm_fwd: D=%d unsupported", D);
+    return 2;
+  }
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// LayerNorm backward (optionally through the chained pair).  dy: gradient wrt the final output.
+// x: input of the first LN.  Writes dx; accumulates dgamma/dbeta (atomics on per-block partials).
+template <int MAXV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, int ld,
+                                     int rows, int D, const float* __restrict__ g1, const float* __restrict__ b1,
+                                     const float* __restrict__ stats1, const float* __restrict__ g2,
+                                     const float* __restrict__ stats2, float* __restrict__ dx, int ld_dx,
+                                     float* __restrict__ dg1, float* __restrict__ db1, float* __restrict__ dg2,
+                                     float* __restrict__ db2, int round_tf) {
+  // per-block partial sums of the affine gradients live in shared memory: [4][MAXV*32]
+  extern __shared__ float sh[];
+  const int W = MAXV * 32;
+  for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float acc_g1[MAXV], acc_b1[MAXV], acc_g2[MAXV], acc_b2[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) acc_g1[i] = acc_b1[i] = acc_g2[i] = acc_b2[i] = 0.f;
+
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const float* xr = x + (size_t)row * ld;
+    const float* dyr = dy + (size_t)row * ld_dy;
+    const float m1 = stats1[2 * row], r1 = stats1[2 * row + 1];
+    float xh1[MAXV], g[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      xh1[i] = c < D ? (xr[c] - m1) * r1 : 0.f;
+      g[i] = c < D ? dyr[c] : 0.f;
+    }
+    if (g2 != nullptr) {
+      // second LN: its input is u = xh1*g1 + b1
+      const float m2 = stats2[2 * row], r2 = stats2[2 * row + 1];
+      float s1 = 0.f, s2 = 0.f;
+      float xh2[MAXV];
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        const float u = c < D ? xh1[i] * g1[c] + b1[c] : 0.f;
+        xh2[i] = c < D ? (u - m2) * r2 : 0.f;
+        acc_g2[i] += g[i] * xh2[i];
+        acc_b2[i] += g[i];
+        const float dxh = c < D ? g[i] * g2[c] : 0.f;
+        g[i] = dxh;
+        s1 += dxh;
+        s2 += dxh * xh2[i];
+      }
+      s1 = warp_sum(s1) / D;
+      s2 = warp_sum(s2) / D;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        g[i] = c < D ? r2 * (g[i] - s1 - xh2[i] * s2) : 0.f;
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      acc_g1[i] += g[i] * xh1[i];
+      acc_b1[i] += g[i];
+      const float dxh = c < D ? g[i] * g1[c] : 0.f;
+      g[i] = dxh;
+      s1 += dxh;
+      s2 += dxh * xh1[i];
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+    float* dxr = dx + (size_t)row * ld_dx;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < ld_dx) {
+        const float v = c < D ? r1 * (g[i] - s1 - xh1[i] * s2) : 0.f;
+        dxr[c] = round_tf ? tf32_rn(v) : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + 32 * i;
+    atomicAdd(&sh[c], acc_g1[i]);
+    atomicAdd(&sh[W + c], acc_b1[i]);
+    if (g2 != nullptr) {
+      atomicAdd(&sh[2 * W + c], acc_g2[i]);
+      atomicAdd(&sh[3 * W + c], acc_b2[i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(&dg1[c], sh[c]);
+    atomicAdd(&db1[c], sh[W + c]);
+    if (g2 != nullptr) {
+      atomicAdd(&dg2[c], sh[2 * W + c]);
+      atomicAdd(&db2[c], sh[3 * W + c]);
+    }
+  }
+}
+
+int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, int D, const float* g1, const float* b1,
+                  const float* stats1, const float* g2, const float* stats2, float* dx, int ld_dx, float* dg1,
+                  float* db1, float* dg2, float* db2, int round_tf, cudaStream_t s) {
+  const int threads = 256;
+  int blocks = cdiv(rows, threads / 32);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (D <= 256 && ld_dx <= 256)
+    layernorm_bwd_kernel<8><<<blocks, threads, 4 * 256 * sizeof(float), s>>>(dy, ld_dy, x, ld, rows, D, g1, b1, stats1, g2,
+                                                                            stats2, dx, ld_dx, dg1, db1, dg2, db2, round_tf);
+  else if (D <= 1024 && ld_dx <= 1024)
+    layernorm_bwd_kernel<32><<<blocks, threads, 4 * 1024 * sizeof(float), s>>>(dy, ld_dy, x, ld, rows, D, g1, b1, stats1,
+                                                                              g2, stats2, dx, ld_dx, dg1, db1, dg2, db2,
+                                                                              round_tf);
+  else {
+    set_error("layernorm_bwd: D=%d unsupported", D);
+    return 2;
+  }
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c] += sum_r x[r*ld + c] (c < cols); optional dropout mask on the fly (bias grads of layers whose
+// output passes through a dropout before the residual).
+// ------------------------------------------------------------------------------------------------
+__global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, float* __restrict__ out,
+                              int row_mod, int row_skip) {
+  // block handles a slab of rows; thread = column (blockDim.x >= cols rounded to 32), blockDim.y row lanes
+  __shared__ float part[8][257];
+  const int c = threadIdx.x;
+  float s = 0.f;
+  for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += gridDim.x * blockDim.y) {
+    if (row_mod > 0 && (r % row_mod) == row_skip) continue;
+    if (c < cols) s += x[(size_t)r * ld + c];
+  }
+  part[threadIdx.y][c] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+    for (int i = 0; i < blockDim.y; ++i) t += part[i][c];
+    atomicAdd(&out[c], t);
+  }
+}
+// cols <= 256 per launch slab; wider matrices are handled in column slabs
+int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s) {
+  for (int c0 = 0; c0 < cols; c0 += 256) {
+    const int w = cols - c0 < 256 ? cols - c0 : 256;
+    const int tx = (w + 31) / 32 * 32;
+    const int ty = 1024 / tx > 8 ? 8 : 1024 / tx;
+    int blocks = cdiv(rows, ty * 8);
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    colsum_kernel<<<blocks, dim3(tx, ty), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
+    count_launch();
+  }
+  EEG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_mask_kernel(DropoutCfg cfg, int rows, int cols, int ld, float* __restrict__ out) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    out[i] = (cfg.p <= 0.f || dropout_keep(cfg, (uint64_t)r * ld + c)) ? 1.f : 0.f;
+  }
+}
+int dropout_mask(DropoutCfg cfg, int rows, int cols, int ld, float* out, cudaStream_t s) {
+  const long long total = (long long)rows * cols;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dropout_mask_kernel<<<blocks, 256, 0, s>>>(cfg, rows, cols, ld, out);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// dst[r*ld_dst + c] = (r < rows && c < cols) ? tf32(src[r*ld_src + c]) : 0     for r < rows_dst, c < ld_dst
+__global__ void pad_copy_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ dst,
+                                int ld_dst, int rows_dst, int round_tf, float scale) {
+  const long long total = (long long)rows_dst * ld_dst;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld_dst;
+    const int c = (int)(i % ld_dst);
+    float v = (r < rows && c < cols) ? src[r * ld_src + c] * scale : 0.f;
+    dst[i] = round_tf ? tf32_rn(v) : v;
+  }
+}
+int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, int rows_dst, int round_tf,
+             float scale, cudaStream_t s) {
+  const long long total = (long long)rows_dst * ld_dst;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pad_copy_kernel<<<blocks, 256, 0, s>>>(src, ld_src, rows, cols, dst, ld_dst, rows_dst, round_tf, scale);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace eegb200
