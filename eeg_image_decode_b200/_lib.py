@@ -89,3 +89,192 @@ def gemm(A, B, C, M, N, K, *, lda=None, ldb=None, ldc=None, a_mn=False, b_mn=Fal
     d.resid, d.ld_res = ptr(resid), ld_res
     d.round_tf32, d.store_mode, d.split_k = int(round_tf32), store_mode, split_k
     check(lib().eegb200_gemm(ctypes.byref(d), stream_ptr()), "gemm")
+
+
+# ------------------------------------------------------------------------------------------------
+# ATM-S / InfoNCE / retrieval / AdamW bindings
+# ------------------------------------------------------------------------------------------------
+P_NAMES = [  # order == enum eegb200_param; values == reference state_dict keys
+    "encoder.enc_embedding.value_embedding.weight",
+    "encoder.enc_embedding.value_embedding.bias",
+    "encoder.enc_embedding.subject_embedding.subject_embedding.weight",
+    "encoder.enc_embedding.subject_embedding.shared_embedding",
+    "encoder.encoder.attn_layers.0.attention.query_projection.weight",
+    "encoder.encoder.attn_layers.0.attention.query_projection.bias",
+    "encoder.encoder.attn_layers.0.attention.key_projection.weight",
+    "encoder.encoder.attn_layers.0.attention.key_projection.bias",
+    "encoder.encoder.attn_layers.0.attention.value_projection.weight",
+    "encoder.encoder.attn_layers.0.attention.value_projection.bias",
+    "encoder.encoder.attn_layers.0.attention.out_projection.weight",
+    "encoder.encoder.attn_layers.0.attention.out_projection.bias",
+    "encoder.encoder.attn_layers.0.conv1.weight",
+    "encoder.encoder.attn_layers.0.conv1.bias",
+    "encoder.encoder.attn_layers.0.conv2.weight",
+    "encoder.encoder.attn_layers.0.conv2.bias",
+    "encoder.encoder.attn_layers.0.norm1.weight",
+    "encoder.encoder.attn_layers.0.norm1.bias",
+    "encoder.encoder.attn_layers.0.norm2.weight",
+    "encoder.encoder.attn_layers.0.norm2.bias",
+    "encoder.encoder.norm.weight",
+    "encoder.encoder.norm.bias",
+    "enc_eeg.0.tsconv.0.weight",
+    "enc_eeg.0.tsconv.0.bias",
+    "enc_eeg.0.tsconv.2.weight",
+    "enc_eeg.0.tsconv.2.bias",
+    "enc_eeg.0.tsconv.4.weight",
+    "enc_eeg.0.tsconv.4.bias",
+    "enc_eeg.0.tsconv.5.weight",
+    "enc_eeg.0.tsconv.5.bias",
+    "enc_eeg.0.projection.0.weight",
+    "enc_eeg.0.projection.0.bias",
+    "proj_eeg.0.weight",
+    "proj_eeg.0.bias",
+    "proj_eeg.1.fn.1.weight",
+    "proj_eeg.1.fn.1.bias",
+    "proj_eeg.2.weight",
+    "proj_eeg.2.bias",
+]
+P_SUBJ_TABLE, P_SUBJ_SHARED = 2, 3
+BUF_NAMES = [  # order == enum eegb200_buffer
+    "encoder.enc_embedding.position_embedding.pe",
+    "enc_eeg.0.tsconv.2.running_mean",
+    "enc_eeg.0.tsconv.2.running_var",
+    "enc_eeg.0.tsconv.5.running_mean",
+    "enc_eeg.0.tsconv.5.running_var",
+]
+SITE_COUNT = 8
+PHASE_A, PHASE_B, PHASE_C, PHASE_ALL = 1, 2, 4, 7
+REF_DROPOUT_P = (0.0, 0.25, 0.25, 0.25, 0.25, 0.25, 0.5, 0.5)
+
+PtrArrayP = ctypes.c_void_p * len(P_NAMES)
+PtrArrayB = ctypes.c_void_p * len(BUF_NAMES)
+FloatArrayS = ctypes.c_float * SITE_COUNT
+
+
+class AtmsIO(ctypes.Structure):
+    _fields_ = [
+        ("params", ctypes.POINTER(ctypes.c_void_p)),
+        ("buffers", ctypes.POINTER(ctypes.c_void_p)),
+        ("x", ctypes.c_void_p),
+        ("subject_ids", ctypes.c_void_p),
+        ("B", ctypes.c_int),
+        ("n_subjects", ctypes.c_int),
+        ("train", ctypes.c_int),
+        ("update_running_stats", ctypes.c_int),
+        ("seed", ctypes.c_uint64),
+        ("dropout_p", ctypes.POINTER(ctypes.c_float)),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+        ("out", ctypes.c_void_p),
+    ]
+
+
+class InfoNceIO(ctypes.Structure):
+    _fields_ = [
+        ("eeg", ctypes.c_void_p), ("tgt_img", ctypes.c_void_p), ("tgt_txt", ctypes.c_void_p),
+        ("B", ctypes.c_int), ("N", ctypes.c_int), ("D", ctypes.c_int), ("row_offset", ctypes.c_int),
+        ("logit_scale", ctypes.c_void_p),
+        ("w_img", ctypes.c_float), ("w_txt", ctypes.c_float), ("grad_out", ctypes.c_float),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("col_stats", ctypes.c_void_p), ("col_parts", ctypes.c_void_p), ("n_parts", ctypes.c_int),
+        ("loss", ctypes.c_void_p), ("d_eeg", ctypes.c_void_p), ("d_logit_scale", ctypes.c_void_p),
+    ]
+
+
+def _sig():
+    L = lib()
+    if getattr(L, "_eeg_sig_done", False):
+        return L
+    L.eegb200_atms_workspace_bytes.restype = ctypes.c_size_t
+    L.eegb200_atms_workspace_bytes.argtypes = [ctypes.c_int]
+    L.eegb200_infonce_workspace_bytes.restype = ctypes.c_size_t
+    L.eegb200_infonce_workspace_bytes.argtypes = [ctypes.c_int] * 4
+    L.eegb200_atms_forward.argtypes = [ctypes.POINTER(AtmsIO), ctypes.c_int, ctypes.c_void_p]
+    L.eegb200_atms_backward.argtypes = [ctypes.POINTER(AtmsIO), ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                         ctypes.c_int, ctypes.c_void_p]
+    L.eegb200_atms_ws_tensor.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_int)]
+    L.eegb200_infonce.argtypes = [ctypes.POINTER(InfoNceIO), ctypes.c_int, ctypes.c_void_p]
+    L.eegb200_retrieval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+    L.eegb200_adamw_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                      ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    L.eegb200_dropout_mask.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    L._eeg_sig_done = True
+    return L
+
+
+def atms_workspace_bytes(B: int) -> int:
+    return int(_sig().eegb200_atms_workspace_bytes(int(B)))
+
+
+def infonce_workspace_bytes(B: int, N: int, D: int, nt: int) -> int:
+    return int(_sig().eegb200_infonce_workspace_bytes(int(B), int(N), int(D), int(nt)))
+
+
+def atms_forward(io: AtmsIO, phases: int = PHASE_ALL) -> None:
+    check(_sig().eegb200_atms_forward(ctypes.byref(io), phases, stream_ptr()), "atms_forward")
+
+
+def atms_backward(io: AtmsIO, d_out, grads_array, phases: int = PHASE_ALL) -> None:
+    check(_sig().eegb200_atms_backward(ctypes.byref(io), ptr(d_out), grads_array, phases, stream_ptr()), "atms_backward")
+
+
+def ws_tensor(workspace, B: int, name: str):
+    """view of a named intermediate inside an ATM-S workspace (float32, or float64 for the *_sums entries)"""
+    import torch
+    p, r, c, ld = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(_sig().eegb200_atms_ws_tensor(ptr(workspace), B, name.encode(), ctypes.byref(p), ctypes.byref(r),
+                                        ctypes.byref(c), ctypes.byref(ld)), "ws_tensor")
+    off = p.value - workspace.data_ptr()
+    if name.endswith("_sums"):
+        return workspace[off:off + 80 * 8].view(torch.float64)
+    n = r.value * ld.value
+    return workspace[off:off + n * 4].view(torch.float32).view(r.value, ld.value)[:, :c.value]
+
+
+def infonce(io: InfoNceIO, phases: int) -> None:
+    check(_sig().eegb200_infonce(ctypes.byref(io), phases, stream_ptr()), "infonce")
+
+
+def adamw_step(p, g, m, v, n, lr, b1, b2, eps, wd, step) -> None:
+    check(_sig().eegb200_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, int(step), stream_ptr()),
+          "adamw_step")
+
+
+def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int):
+    import torch
+    out = torch.empty(rows, cols, device="cuda", dtype=torch.float32)
+    check(_sig().eegb200_dropout_mask(seed, site, p, rows, cols, ld, ptr(out), stream_ptr()), "dropout_mask")
+    return out
+
+
+def retrieval(eeg, gallery, logit_scale, sel=None, labels=None, want_top5=True):
+    """scores = logit_scale * eeg @ gallery.T on device; returns dict(top1, top5, correct, logits)."""
+    import torch
+    Q, D = eeg.shape
+    G = gallery.shape[0]
+    ld = (G + 3) // 4 * 4
+    dev = eeg.device
+    logits = torch.empty(Q, ld, device=dev, dtype=torch.float32)
+    round_ws = torch.empty(2 * (Q + G) * D, device=dev, dtype=torch.float32)
+    top1 = torch.empty(Q, device=dev, dtype=torch.int64)
+    top5 = torch.empty(Q, 5, device=dev, dtype=torch.int32) if want_top5 else None
+    correct = torch.zeros(1, device=dev, dtype=torch.int32)
+    k = 0
+    sel_ws = None
+    if sel is not None:
+        sel = sel.to(device=dev, dtype=torch.int32).contiguous()
+        k = sel.shape[1]
+        sel_ws = torch.empty(Q, k, device=dev, dtype=torch.float32)
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int64).contiguous()
+    check(_sig().eegb200_retrieval(ptr(eeg.contiguous()), ptr(gallery.contiguous()), Q, G, D, ptr(logit_scale), ptr(logits),
+                                   ld, ptr(round_ws), ptr(sel), k, ptr(sel_ws), ptr(labels), ptr(correct), ptr(top1),
+                                   ptr(top5), stream_ptr()), "retrieval")
+    return {"top1": top1, "top5": top5, "correct": correct, "logits": logits[:, :G]}

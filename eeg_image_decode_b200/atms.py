@@ -1,0 +1,309 @@
+"""ATM-S encoder behind the reference's Python surface.
+
+Drop-in for ``ATMS`` of Retrieval/ATMS_retrieval.py:171-191: same constructor, ``forward(x, subject_ids)``,
+``.logit_scale``, ``.loss_func`` and a ``state_dict`` with the reference's keys/shapes, so a
+reference ``.pth`` loads with ``strict=True`` and vice versa.  The sub-modules below are parameter
+containers only: all arithmetic happens in libeegdecode_b200.so (hand-written sm_100a kernels); there is no
+PyTorch-eager or CPU path -- calling the model on CPU tensors raises.
+
+Parameters are views into one flat fp32 arena (``ATMS.flat_params``) so that the fused AdamW kernel and the
+data-parallel gradient all-reduce work on a single buffer.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .loss import ClipLoss
+
+N_SUBJECT_ROWS = 10   # iTransformer(num_subjects=10) default (ATMS_retrieval.py:62)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names and nesting give the reference state_dict keys)
+# ------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("this sub-module only holds parameters; call ATMS.forward (CUDA kernels) instead")
+
+
+class _PositionalEmbedding(_Holder):          # Embed.py:8-26
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model).float()
+        position = torch.arange(0, max_len).float().unsqueeze(1)
+        div_term = (torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model)).exp()
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+
+class _TimeFeatureEmbedding(_Holder):         # Embed.py:96-106 (instantiated, never used: x_mark is None)
+    def __init__(self, d_model):
+        super().__init__()
+        self.embed = nn.Linear(4, d_model, bias=False)
+
+
+class _SubjectEmbedding(_Holder):             # Embed.py:109-121
+    def __init__(self, num_subjects, d_model):
+        super().__init__()
+        self.subject_embedding = nn.Embedding(num_subjects, d_model)
+        self.shared_embedding = nn.Parameter(torch.randn(1, d_model))
+        self.mask_embedding = nn.Parameter(torch.randn(1, d_model))
+
+
+class _DataEmbedding(_Holder):                # Embed.py:124-139
+    def __init__(self, c_in, d_model, num_subjects):
+        super().__init__()
+        self.value_embedding = nn.Linear(c_in, d_model)
+        self.position_embedding = _PositionalEmbedding(d_model)
+        self.temporal_embedding = _TimeFeatureEmbedding(d_model)
+        self.subject_embedding = _SubjectEmbedding(num_subjects, d_model)
+        self.mask_token = nn.Parameter(torch.randn(1, d_model))
+
+
+class _AttentionLayer(_Holder):               # SelfAttention_Family.py:179-192
+    def __init__(self, d_model, n_heads):
+        super().__init__()
+        dk = d_model // n_heads
+        self.query_projection = nn.Linear(d_model, dk * n_heads)
+        self.key_projection = nn.Linear(d_model, dk * n_heads)
+        self.value_projection = nn.Linear(d_model, dk * n_heads)
+        self.out_projection = nn.Linear(dk * n_heads, d_model)
+
+
+class _EncoderLayer(_Holder):                 # Transformer_EncDec.py:27-37
+    def __init__(self, d_model, n_heads, d_ff):
+        super().__init__()
+        self.attention = _AttentionLayer(d_model, n_heads)
+        self.conv1 = nn.Conv1d(d_model, d_ff, 1)
+        self.conv2 = nn.Conv1d(d_ff, d_model, 1)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class _Encoder(_Holder):                      # Transformer_EncDec.py:54-59
+    def __init__(self, d_model, n_heads, d_ff):
+        super().__init__()
+        self.attn_layers = nn.ModuleList([_EncoderLayer(d_model, n_heads, d_ff)])
+        self.norm = nn.LayerNorm(d_model)
+
+
+class _ITransformer(_Holder):                 # ATMS_retrieval.py:61-85
+    def __init__(self, seq_len=250, d_model=250, n_heads=4, d_ff=256, num_subjects=N_SUBJECT_ROWS):
+        super().__init__()
+        self.enc_embedding = _DataEmbedding(seq_len, d_model, num_subjects)
+        self.encoder = _Encoder(d_model, n_heads, d_ff)
+
+
+class _PatchEmbedding(_Holder):               # ATMS_retrieval.py:97-116
+    def __init__(self, emb_size=40):
+        super().__init__()
+        self.tsconv = nn.Sequential(
+            nn.Conv2d(1, 40, (1, 25), stride=(1, 1)), nn.Identity(), nn.BatchNorm2d(40), nn.Identity(),
+            nn.Conv2d(40, 40, (63, 1), stride=(1, 1)), nn.BatchNorm2d(40), nn.Identity(), nn.Identity())
+        self.projection = nn.Sequential(nn.Conv2d(40, emb_size, (1, 1), stride=(1, 1)), nn.Identity())
+
+
+class _Fn(_Holder):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+# ------------------------------------------------------------------------------------------------
+class ATMS(nn.Module):
+    """``ATMS(num_channels=63, sequence_length=250, num_subjects=2, num_features=64, num_latents=1024, num_blocks=1)``"""
+
+    def __init__(self, num_channels=63, sequence_length=250, num_subjects=2, num_features=64, num_latents=1024,
+                 num_blocks=1):
+        super().__init__()
+        if num_channels != 63 or sequence_length != 250 or num_latents != 1024:
+            raise ValueError("the sm_100a kernels are specialised for the reference geometry: 63 channels x 250 samples -> 1024")
+        self.encoder = _ITransformer()
+        self.subject_wise_linear = nn.ModuleList([nn.Linear(250, sequence_length) for _ in range(num_subjects)])
+        self.enc_eeg = nn.Sequential(_PatchEmbedding(), nn.Identity())
+        self.proj_eeg = nn.Sequential(
+            nn.Linear(1440, 1024),
+            _Fn(nn.Sequential(nn.Identity(), nn.Linear(1024, 1024), nn.Identity())),
+            nn.LayerNorm(1024))
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
+        self.loss_func = ClipLoss()
+        # runtime state (not part of the state_dict)
+        self.dropout_p = list(_lib.REF_DROPOUT_P)   # index = eegb200_dropout_site
+        self._seed_gen = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
+        self._ws: Dict[int, torch.Tensor] = {}
+        self._last = None
+        self._flatten()
+
+    # ---------------------------------------------------------------- flat arena
+    def _hot_order(self) -> List[str]:
+        names = [n for i, n in enumerate(_lib.P_NAMES) if i not in (_lib.P_SUBJ_TABLE, _lib.P_SUBJ_SHARED)]
+        return names + ["logit_scale", _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]]
+
+    def _flatten(self) -> None:
+        """(re)build the flat arenas and point every parameter at its slice"""
+        named = dict(self.named_parameters())
+        hot = self._hot_order()
+        cold = [n for n in named if n not in hot]
+        dev = named["logit_scale"].device
+        offs, off = {}, 0
+        for n in hot + cold:
+            offs[n] = off
+            off += (named[n].numel() + 63) // 64 * 64
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for n in hot + cold:
+            p = named[n]
+            sl = flat[offs[n]:offs[n] + p.numel()].view(p.shape)
+            sl.copy_(p.data)
+            p.data = sl
+        self.flat_params = flat
+        self._offs = offs
+        self._n_main = offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]            # always-trained prefix (incl. logit_scale)
+        self._n_hot = offs[cold[0]] if cold else off
+        self.flat_grads = torch.zeros(self._n_hot, dtype=torch.float32, device=dev)
+        self._adam_m = None
+        self._adam_v = None
+        self._adam_steps = {"main": 0, "table": 0, "shared": 0}
+        self._ptr_cache = None
+        self._ws = {}
+
+    def _apply(self, fn, recurse=True):
+        r = super()._apply(fn, recurse)
+        self._flatten()
+        return r
+
+    def grad_view(self, name: str) -> torch.Tensor:
+        p = dict(self.named_parameters())[name]
+        o = self._offs[name]
+        return self.flat_grads[o:o + p.numel()].view(p.shape)
+
+    def _pointers(self):
+        if self._ptr_cache is None:
+            named = dict(self.named_parameters())
+            bufs = dict(self.named_buffers())
+            for n in _lib.P_NAMES:
+                if not named[n].is_cuda:
+                    raise RuntimeError("ATMS lives on %s: this implementation is CUDA-only (sm_100a kernels, no CPU "
+                                       "fallback); call .to('cuda') first" % named[n].device)
+            P = _lib.PtrArrayP(*[named[n].data_ptr() for n in _lib.P_NAMES])
+            G = _lib.PtrArrayP(*[self.flat_grads.data_ptr() + 4 * self._offs[n] for n in _lib.P_NAMES])
+            Bf = _lib.PtrArrayB(*[bufs[n].data_ptr() for n in _lib.BUF_NAMES])
+            self._ptr_cache = (P, G, Bf)
+        return self._ptr_cache
+
+    def workspace(self, B: int) -> torch.Tensor:
+        ws = self._ws.get(B)
+        if ws is None:
+            ws = torch.empty(_lib.atms_workspace_bytes(B), dtype=torch.uint8, device=self.flat_params.device)
+            self._ws = {B: ws}          # keep only the latest batch size resident
+        return ws
+
+    # ---------------------------------------------------------------- engine-level API (no autograd)
+    def _make_io(self, x, subject_ids, train: bool, seed: int, out):
+        P, G, Bf = self._pointers()
+        B = x.shape[0]
+        ws = self.workspace(B)
+        io = _lib.AtmsIO()
+        io.params = ctypes.cast(P, ctypes.POINTER(ctypes.c_void_p))
+        io.buffers = ctypes.cast(Bf, ctypes.POINTER(ctypes.c_void_p))
+        io.x = x.data_ptr()
+        io.subject_ids = subject_ids.data_ptr()
+        io.B = B
+        io.n_subjects = N_SUBJECT_ROWS
+        io.train = int(train)
+        io.update_running_stats = int(train)
+        io.seed = seed
+        self._p_arr = _lib.FloatArrayS(*self.dropout_p)
+        io.dropout_p = ctypes.cast(self._p_arr, ctypes.POINTER(ctypes.c_float))
+        io.workspace = ws.data_ptr()
+        io.workspace_bytes = ws.numel()
+        io.out = out.data_ptr()
+        return io
+
+    def _check_inputs(self, x, subject_ids):
+        if not (torch.is_tensor(x) and x.is_cuda):
+            raise RuntimeError("ATMS.forward expects a CUDA tensor (no CPU fallback on this path)")
+        if x.dim() != 3 or x.shape[1] != 63 or x.shape[2] != 250:
+            raise RuntimeError(f"expected EEG of shape [B,63,250], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        subject_ids = subject_ids.to(device=x.device, dtype=torch.int64).contiguous()
+        if subject_ids.numel() != x.shape[0]:
+            raise RuntimeError("subject_ids must have one entry per trial")
+        return x, subject_ids
+
+    def next_seed(self) -> int:
+        return int(torch.randint(0, 2 ** 62, (1,), generator=self._seed_gen).item())
+
+    def encode(self, x, subject_ids, train: Optional[bool] = None, seed: Optional[int] = None,
+               phases: int = _lib.PHASE_ALL, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """forward through the CUDA kernels; keeps what the backward needs in the workspace"""
+        x, subject_ids = self._check_inputs(x, subject_ids)
+        train = self.training if train is None else train
+        if seed is None:
+            seed = self.next_seed() if train else 0
+        if out is None:
+            out = torch.empty(x.shape[0], 1024, device=x.device, dtype=torch.float32)
+        io = self._make_io(x, subject_ids, train, seed, out)
+        _lib.atms_forward(io, phases)
+        if train and (phases & _lib.PHASE_C):
+            for bn in (self.enc_eeg[0].tsconv[2], self.enc_eeg[0].tsconv[5]):
+                bn.num_batches_tracked.add_(1)
+        self._last = (io, x, subject_ids, out)
+        return out
+
+    def backprop(self, d_out: torch.Tensor, phases: int = _lib.PHASE_ALL) -> None:
+        """accumulates d loss / d params into ``flat_grads`` (views: ``grad_view(name)``)"""
+        if self._last is None:
+            raise RuntimeError("backprop() needs a preceding train-mode encode()")
+        io = self._last[0]
+        _, G, _ = self._pointers()
+        _lib.atms_backward(io, d_out.contiguous() if d_out is not None else None,
+                           ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)), phases)
+
+    def zero_flat_grads(self) -> None:
+        self.flat_grads.zero_()
+
+    def ws_tensor(self, name: str) -> torch.Tensor:
+        io = self._last[0]
+        return _lib.ws_tensor(self.workspace(io.B), io.B, name)
+
+    # ---------------------------------------------------------------- drop-in forward (autograd)
+    def forward(self, x, subject_ids):
+        if torch.is_grad_enabled() and self.training:
+            named = dict(self.named_parameters())
+            plist = [named[n] for n in _lib.P_NAMES]
+            return _ATMSFunction.apply(self, x, subject_ids, *plist)
+        return self.encode(x, subject_ids, train=self.training)
+
+
+class _ATMSFunction(torch.autograd.Function):
+    """autograd bridge: lets reference-style code do ``loss.backward()`` through the CUDA backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, subject_ids, *params):
+        out = model.encode(x, subject_ids, train=True)
+        ctx.model = model
+        ctx.use_shared = bool((subject_ids >= N_SUBJECT_ROWS).any().item()) or bool((subject_ids < 0).any().item())
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        model = ctx.model
+        model.flat_grads.zero_()
+        model.backprop(d_out.contiguous())
+        grads = []
+        for i, n in enumerate(_lib.P_NAMES):
+            if i == _lib.P_SUBJ_TABLE and ctx.use_shared:
+                grads.append(None)
+            elif i == _lib.P_SUBJ_SHARED and not ctx.use_shared:
+                grads.append(None)
+            else:
+                grads.append(model.grad_view(n).clone())
+        return (None, None, None, *grads)

@@ -41,3 +41,150 @@ int eegb200_gemm(const eegb200_gemm_desc* d, void* stream) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+#include "kernels.h"
+
+namespace {
+struct InfoWs {
+  float *E_r, *T_r, *logits, *row_lse, *diag, *part_max, *part_sum, *col_lse;
+  int ld, ncol, chunks;
+};
+size_t info_carve(void* base, int B, int N, int D, int nt, InfoWs* out) {
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    off = align_up(off, 256);
+    float* p = b ? reinterpret_cast<float*>(b + off) : nullptr;
+    off += n * sizeof(float);
+    return p;
+  };
+  InfoWs w;
+  w.ncol = nt * N;
+  w.ld = (w.ncol + 3) / 4 * 4;
+  w.chunks = infonce_col_chunks(B);
+  w.E_r = take((size_t)B * D);
+  w.T_r = take((size_t)w.ncol * D);
+  w.logits = take((size_t)B * w.ld);
+  w.row_lse = take((size_t)nt * B);
+  w.diag = take((size_t)nt * B);
+  w.part_max = take((size_t)w.chunks * w.ncol);
+  w.part_sum = take((size_t)w.chunks * w.ncol);
+  w.col_lse = take((size_t)w.ncol);
+  if (out) *out = w;
+  return align_up(off, 256);
+}
+}  // namespace
+
+extern "C" {
+
+int eegb200_dropout_mask(uint64_t seed, uint32_t site, float p, int rows, int cols, int ld, float* out, void* stream) {
+  EEG_REQUIRE(out && rows > 0 && cols > 0 && ld >= cols, "dropout_mask: bad arguments");
+  return dropout_mask(make_dropout(seed, site, p, true), rows, cols, ld, out, (cudaStream_t)stream);
+}
+
+size_t eegb200_infonce_workspace_bytes(int B, int N, int D, int n_targets) {
+  if (B <= 0 || N <= 0 || D <= 0 || n_targets < 1 || n_targets > 2) return 0;
+  return info_carve(nullptr, B, N, D, n_targets, nullptr);
+}
+
+int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream) {
+  EEG_REQUIRE(io && io->eeg && io->tgt_img && io->logit_scale && io->workspace && io->col_stats, "infonce: null pointer");
+  EEG_REQUIRE(io->B > 0 && io->N >= io->B && io->D > 0 && (io->D & 3) == 0, "infonce: bad shape B=%d N=%d D=%d", io->B,
+              io->N, io->D);
+  EEG_REQUIRE(io->row_offset >= 0 && io->row_offset + io->B <= io->N, "infonce: row block [%d,%d) outside N=%d",
+              io->row_offset, io->row_offset + io->B, io->N);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nt = io->tgt_txt ? 2 : 1;
+  InfoWs w;
+  const size_t need = info_carve(nullptr, io->B, io->N, io->D, nt, nullptr);
+  EEG_REQUIRE(io->workspace_bytes >= need, "infonce: workspace too small: %zu < %zu", io->workspace_bytes, need);
+  info_carve(io->workspace, io->B, io->N, io->D, nt, &w);
+  InfoNceArgs a{w.logits, w.ld, io->B, io->N, io->row_offset, nt};
+  const float w_img = io->w_img, w_txt = nt == 2 ? io->w_txt : 0.f;
+
+  if (phase_mask & EEGB200_PHASE_A) {
+    EEG_TRY(pad_copy(io->eeg, io->D, io->B, io->D, w.E_r, io->D, io->B, 1, 1.f, s));
+    EEG_TRY(pad_copy(io->tgt_img, io->D, io->N, io->D, w.T_r, io->D, io->N, 1, 1.f, s));
+    if (nt == 2) EEG_TRY(pad_copy(io->tgt_txt, io->D, io->N, io->D, w.T_r + (size_t)io->N * io->D, io->D, io->N, 1, 1.f, s));
+    GemmArgs g;
+    g.M = io->B; g.N = w.ncol; g.K = io->D;
+    g.A = {w.E_r, io->D, 0};
+    g.B = {w.T_r, io->D, 0};
+    g.epi.C = w.logits; g.epi.ldc = w.ld;
+    g.epi.alpha_dev = io->logit_scale;
+    EEG_TRY(gemm_launch(g, s));
+    EEG_TRY(infonce_row_lse(a, w.row_lse, w.diag, s));
+    EEG_TRY(infonce_col_partial(a, w.part_max, w.part_sum, s));
+    EEG_TRY(infonce_col_reduce(w.part_max, w.part_sum, w.chunks, (size_t)w.ncol, w.ncol, io->col_stats,
+                               io->col_stats + w.ncol, nullptr, s));
+  }
+  if (phase_mask & EEGB200_PHASE_B) {
+    EEG_REQUIRE(io->loss != nullptr, "infonce: null loss output");
+    const float* parts = io->col_parts ? io->col_parts : io->col_stats;
+    const int n_parts = io->col_parts ? io->n_parts : 1;
+    EEG_REQUIRE(n_parts >= 1, "infonce: n_parts must be >= 1");
+    EEG_TRY(infonce_col_reduce(parts, parts + w.ncol, n_parts, (size_t)2 * w.ncol, w.ncol, nullptr, nullptr, w.col_lse, s));
+    EEG_TRY(infonce_loss(a, w.row_lse, w.diag, w.col_lse, w_img, w_txt, io->loss, s));
+    if (io->d_eeg) {
+      float* ds = io->d_logit_scale;
+      EEG_REQUIRE(ds != nullptr, "infonce: d_logit_scale must be provided together with d_eeg");
+      EEG_TRY(infonce_grad(a, w.logits, w.row_lse, w.col_lse, w_img, w_txt, io->logit_scale, ds, io->grad_out, s));
+      GemmArgs g;                                  // dE = s * G . Tcat
+      g.M = io->B; g.N = io->D; g.K = w.ncol;
+      g.A = {w.logits, w.ld, 0};
+      g.B = {w.T_r, io->D, 1};
+      g.epi.C = io->d_eeg; g.epi.ldc = io->D;
+      g.epi.alpha_dev = io->logit_scale;
+      EEG_TRY(gemm_launch(g, s));
+    }
+  }
+  return 0;
+}
+
+int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int D, const float* logit_scale,
+                      float* logits_ws, int ld, void* round_ws, const int32_t* sel, int k, float* sel_ws,
+                      const int64_t* labels, int* correct, int64_t* top1, int32_t* top5, void* stream) {
+  EEG_REQUIRE(eeg && gallery && logit_scale && logits_ws && round_ws, "retrieval: null pointer");
+  EEG_REQUIRE(Q > 0 && G > 0 && D > 0 && (D & 3) == 0 && ld >= G && (ld & 3) == 0, "retrieval: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  // 3xTF32: near-fp32 scores so that retrieval ranks match the fp32 reference except for exact ties
+  float* e_hi = reinterpret_cast<float*>(round_ws);
+  float* e_lo = e_hi + (size_t)Q * D;
+  float* g_hi = e_lo + (size_t)Q * D;
+  float* g_lo = g_hi + (size_t)G * D;
+  EEG_TRY(split_tf32(eeg, e_hi, e_lo, (long long)Q * D, s));
+  EEG_TRY(split_tf32(gallery, g_hi, g_lo, (long long)G * D, s));
+  const float* As[3] = {e_lo, e_hi, e_hi};
+  const float* Bs[3] = {g_hi, g_lo, g_hi};
+  for (int i = 0; i < 3; ++i) {                    // small terms first
+    GemmArgs g;
+    g.M = Q; g.N = G; g.K = D;
+    g.A = {As[i], D, 0};
+    g.B = {Bs[i], D, 0};
+    g.epi.C = logits_ws; g.epi.ldc = ld;
+    g.epi.alpha_dev = logit_scale;
+    g.epi.store_mode = i == 0 ? EPI_STORE : EPI_ADD;
+    EEG_TRY(gemm_launch(g, s));
+  }
+  const float* scores = logits_ws;
+  int cols = G, sld = ld;
+  if (sel) {
+    EEG_REQUIRE(k > 0 && sel_ws, "retrieval: candidate lists need k > 0 and sel_ws");
+    EEG_TRY(gather_cols(logits_ws, ld, sel, Q, k, sel_ws, s));
+    scores = sel_ws; cols = k; sld = k;
+  }
+  if (top1 || (labels && correct))
+    EEG_TRY(argmax_count(scores, sld, Q, cols, reinterpret_cast<const long long*>(labels), correct,
+                         reinterpret_cast<long long*>(top1), s));
+  if (top5) EEG_TRY(topk5(scores, sld, Q, cols, top5, s));
+  return 0;
+}
+
+int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, void* stream) {
+  EEG_REQUIRE(p && g && m && v && n > 0, "adamw: bad arguments");
+  return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
+}
+
+}  // extern "C"

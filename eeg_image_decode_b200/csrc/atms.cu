@@ -1,0 +1,538 @@
+// ATM-S encoder forward / backward orchestration behind the C ABI (include/eegdecode_b200.h).
+// Every Linear / 1x1-conv / spatial-conv contraction runs through gemm_launch (tcgen05 TF32); the glue
+// between them are the fused row-wise, attention and conv kernels.  Reference: ATMS.forward,
+// Retrieval/ATMS_retrieval.py:182-191 and the modules it composes.
+#include "../../include/eegdecode_b200.h"
+#include "kernels.h"
+#include <string.h>
+
+namespace eegb200 {
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving
+// ------------------------------------------------------------------------------------------------
+struct Ws {
+  // packed / TF32-rounded weights
+  float *Wv_p, *tokbias, *Wqkv_p, *bqkv_p, *Wo_p, *bo_p, *W1_p, *b1_p, *W2_p, *b2_p, *Ws_p, *Wp1_r, *Wp2_r;
+  // forward activations (kept for the backward)
+  float *Xp, *H0, *QKV, *O, *R1, *X1, *U, *Hf, *R2, *X3, *st1, *st2, *stf;
+  float *Y1, *A1, *Y2, *feat, *Z1, *G, *Z2, *stp;
+  double *bn1_sums, *bn2_sums, *bn1_bsums, *bn2_bsums;
+  float *bn1_mr, *bn2_mr;
+  int* flag;
+  // backward temporaries
+  float *dZ2, *dZ2d, *dZ1, *dfeat, *dz2, *dY2, *dA1, *dX3, *dR2, *T1, *dU, *dX1, *dR1, *T2, *dO, *dQKV, *dH0, *T3;
+  float *dWqkv_p, *dbqkv_p, *dWo_p, *dWs_p;
+};
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static size_t carve(void* base, int B, Ws* w) {
+  Carver c{reinterpret_cast<uint8_t*>(base)};
+  const size_t M = (size_t)B * N_TOK;          // token rows
+  const size_t R = (size_t)B * N_POOL;         // (b, j) rows of the conv stack
+  Ws t;
+  t.Wv_p = c.take<float>(256 * 256);
+  t.tokbias = c.take<float>(64 * 256);
+  t.Wqkv_p = c.take<float>(768 * 256);
+  t.bqkv_p = c.take<float>(768);
+  t.Wo_p = c.take<float>(256 * 256);
+  t.bo_p = c.take<float>(256);
+  t.W1_p = c.take<float>(256 * 256);
+  t.b1_p = c.take<float>(256);
+  t.W2_p = c.take<float>(256 * 256);
+  t.b2_p = c.take<float>(256);
+  t.Ws_p = c.take<float>((size_t)N_FILT * K_SPAT);
+  t.Wp1_r = c.take<float>((size_t)D_OUT * D_FEAT);
+  t.Wp2_r = c.take<float>((size_t)D_OUT * D_OUT);
+  t.Xp = c.take<float>(M * 256);
+  t.H0 = c.take<float>(M * 256);
+  t.QKV = c.take<float>(M * 768);
+  t.O = c.take<float>(M * 256);
+  t.R1 = c.take<float>(M * 256);
+  t.X1 = c.take<float>(M * 256);
+  t.U = c.take<float>(M * 256);
+  t.Hf = c.take<float>(M * 256);
+  t.R2 = c.take<float>(M * 256);
+  t.X3 = c.take<float>(M * 256);
+  t.st1 = c.take<float>(M * 2);
+  t.st2 = c.take<float>(M * 2);
+  t.stf = c.take<float>(M * 2);
+  t.Y1 = c.take<float>(R * K_SPAT);
+  t.A1 = c.take<float>(R * K_SPAT);
+  t.Y2 = c.take<float>(R * N_FILT);
+  t.feat = c.take<float>((size_t)B * D_FEAT);
+  t.Z1 = c.take<float>((size_t)B * D_OUT);
+  t.G = c.take<float>((size_t)B * D_OUT);
+  t.Z2 = c.take<float>((size_t)B * D_OUT);
+  t.stp = c.take<float>((size_t)B * 2);
+  t.bn1_sums = c.take<double>(2 * N_FILT);
+  t.bn2_sums = c.take<double>(2 * N_FILT);
+  t.bn1_bsums = c.take<double>(2 * N_FILT);
+  t.bn2_bsums = c.take<double>(2 * N_FILT);
+  t.bn1_mr = c.take<float>(2 * N_FILT);
+  t.bn2_mr = c.take<float>(2 * N_FILT);
+  t.flag = c.take<int>(4);
+  t.dZ2 = c.take<float>((size_t)B * D_OUT);
+  t.dZ2d = c.take<float>((size_t)B * D_OUT);
+  t.dZ1 = c.take<float>((size_t)B * D_OUT);
+  t.dfeat = c.take<float>((size_t)B * D_FEAT);
+  t.dz2 = c.take<float>(R * N_FILT);
+  t.dY2 = c.take<float>(R * N_FILT);
+  t.dA1 = c.take<float>(R * K_SPAT);
+  t.dX3 = c.take<float>(M * 256);
+  t.dR2 = c.take<float>(M * 256);
+  t.T1 = c.take<float>(M * 256);
+  t.dU = c.take<float>(M * 256);
+  t.dX1 = c.take<float>(M * 256);
+  t.dR1 = c.take<float>(M * 256);
+  t.T2 = c.take<float>(M * 256);
+  t.dO = c.take<float>(M * 256);
+  t.dQKV = c.take<float>(M * 768);
+  t.dH0 = c.take<float>(M * 256);
+  t.T3 = c.take<float>(M * 256);
+  t.dWqkv_p = c.take<float>(768 * 256);
+  t.dbqkv_p = c.take<float>(768);
+  t.dWo_p = c.take<float>(256 * 256);
+  t.dWs_p = c.take<float>((size_t)N_FILT * K_SPAT);
+  if (w) *w = t;
+  return align_up(c.off, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (TF32-rounded, zero-padded GEMM operands) and gradient unpacking
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_qkv_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
+                                float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 768 * 256) return;
+  const int row = idx >> 8, c = idx & 255;
+  const int which = row >> 8, hh = (row & 255) >> 6, e = row & 63;
+  const float* w = which == 0 ? wq : (which == 1 ? wk : wv);
+  out[idx] = (e < D_HEAD && c < N_T) ? tf32_rn(w[(hh * D_HEAD + e) * N_T + c]) : 0.f;
+}
+__global__ void pack_wo_kernel(const float* __restrict__ wo, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 256 * 256) return;
+  const int o = idx >> 8, c = idx & 255;
+  const int hh = c >> 6, e = c & 63;
+  out[idx] = (o < N_T && e < D_HEAD) ? tf32_rn(wo[o * (N_HEAD * D_HEAD) + hh * D_HEAD + e]) : 0.f;
+}
+// tsconv.4.weight [k2][k1][r] -> [k2][r*40 + k1]
+__global__ void pack_ws_kernel(const float* __restrict__ ws, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N_FILT * K_SPAT) return;
+  const int k2 = idx / K_SPAT, kk = idx % K_SPAT;
+  const int r = kk / N_FILT, k1 = kk % N_FILT;
+  out[idx] = tf32_rn(ws[(k2 * N_FILT + k1) * N_CH + r]);
+}
+__global__ void pack_small_kernel(const float* __restrict__ bv, const float* __restrict__ pe, const float* __restrict__ bq,
+                                  const float* __restrict__ bk, const float* __restrict__ bvv,
+                                  const float* __restrict__ bo, const float* __restrict__ b1,
+                                  const float* __restrict__ b2, float* __restrict__ tokbias,
+                                  float* __restrict__ bqkv_p, float* __restrict__ bo_p, float* __restrict__ b1_p,
+                                  float* __restrict__ b2_p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 64 * 256) {
+    const int t = idx >> 8, c = idx & 255;
+    // value-embedding bias + positional table row of the channel token (Embed.py:146-149); token 0 is the subject slot
+    tokbias[idx] = (t > 0 && c < N_T) ? bv[c] + pe[(t - 1) * N_T + c] : 0.f;
+  }
+  if (idx < 768) {
+    const int which = idx >> 8, hh = (idx & 255) >> 6, e = idx & 63;
+    const float* b = which == 0 ? bq : (which == 1 ? bk : bvv);
+    bqkv_p[idx] = e < D_HEAD ? b[hh * D_HEAD + e] : 0.f;
+  }
+  if (idx < 256) {
+    bo_p[idx] = idx < N_T ? bo[idx] : 0.f;
+    b1_p[idx] = b1[idx];
+    b2_p[idx] = idx < N_T ? b2[idx] : 0.f;
+  }
+}
+__global__ void unpack_qkv_grad_kernel(const float* __restrict__ dw_p, const float* __restrict__ db_p, float* dwq,
+                                       float* dwk, float* dwv, float* dbq, float* dbk, float* dbv) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 768 * 256) return;
+  const int row = idx >> 8, c = idx & 255;
+  const int which = row >> 8, hh = (row & 255) >> 6, e = row & 63;
+  if (e >= D_HEAD) return;
+  float* dw = which == 0 ? dwq : (which == 1 ? dwk : dwv);
+  float* db = which == 0 ? dbq : (which == 1 ? dbk : dbv);
+  if (c < N_T) dw[(hh * D_HEAD + e) * N_T + c] += dw_p[idx];
+  if (c == 0) db[hh * D_HEAD + e] += db_p[row];
+}
+__global__ void unpack_wo_grad_kernel(const float* __restrict__ dw_p, float* dwo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 256 * 256) return;
+  const int o = idx >> 8, c = idx & 255;
+  const int hh = c >> 6, e = c & 63;
+  if (o < N_T && e < D_HEAD) dwo[o * (N_HEAD * D_HEAD) + hh * D_HEAD + e] += dw_p[idx];
+}
+__global__ void unpack_ws_grad_kernel(const float* __restrict__ dw_p, float* dws) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N_FILT * K_SPAT) return;
+  const int k2 = idx / K_SPAT, kk = idx % K_SPAT;
+  const int r = kk / N_FILT, k1 = kk % N_FILT;
+  dws[(k2 * N_FILT + k1) * N_CH + r] += dw_p[idx];
+}
+
+static int pack_weights(const float* const* P, float* const* BUF, const Ws& w, cudaStream_t s) {
+  EEG_TRY(pad_copy(P[EEGB200_P_VALUE_W], N_T, N_T, N_T, w.Wv_p, 256, 256, 1, 1.f, s));
+  pack_qkv_kernel<<<768, 256, 0, s>>>(P[EEGB200_P_WQ], P[EEGB200_P_WK], P[EEGB200_P_WV], w.Wqkv_p);
+  pack_wo_kernel<<<256, 256, 0, s>>>(P[EEGB200_P_WO], w.Wo_p);
+  EEG_TRY(pad_copy(P[EEGB200_P_W1], N_T, D_FF, N_T, w.W1_p, 256, 256, 1, 1.f, s));
+  EEG_TRY(pad_copy(P[EEGB200_P_W2], D_FF, N_T, D_FF, w.W2_p, 256, 256, 1, 1.f, s));
+  pack_ws_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(P[EEGB200_P_WS], w.Ws_p);
+  EEG_TRY(pad_copy(P[EEGB200_P_WP1], D_FEAT, D_OUT, D_FEAT, w.Wp1_r, D_FEAT, D_OUT, 1, 1.f, s));
+  EEG_TRY(pad_copy(P[EEGB200_P_WP2], D_OUT, D_OUT, D_OUT, w.Wp2_r, D_OUT, D_OUT, 1, 1.f, s));
+  pack_small_kernel<<<64, 256, 0, s>>>(P[EEGB200_P_VALUE_B], BUF[EEGB200_BUF_PE], P[EEGB200_P_BQ], P[EEGB200_P_BK],
+                                        P[EEGB200_P_BV], P[EEGB200_P_BO], P[EEGB200_P_B1], P[EEGB200_P_B2], w.tokbias,
+                                        w.bqkv_p, w.bo_p, w.b1_p, w.b2_p);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch(4);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int run_gemm(int M, int N, int K, const float* A, int lda, int amn, const float* B, int ldb, int bmn,
+                    const Epilogue& e, int split, cudaStream_t s) {
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = {A, lda, amn};
+  g.B = {B, ldb, bmn};
+  g.epi = e;
+  g.split_k = split;
+  return gemm_launch(g, s);
+}
+// split-K factor for the weight-gradient GEMMs (tiny outputs, reduction over all tokens)
+static int pick_split(int M, int N, int K) {
+  const int tiles = cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  const int kb = cdiv(K, 32);
+  int split = cdiv(296, tiles);
+  if (split > kb / 4) split = kb / 4;
+  if (split < 1) split = 1;
+  return split;
+}
+static Epilogue epi_out(float* C, int ldc) {
+  Epilogue e;
+  e.C = C; e.ldc = ldc;
+  return e;
+}
+static Epilogue epi_wgrad(float* C, int ldc) {   // accumulate into a (pre-zeroed or running) gradient
+  Epilogue e;
+  e.C = C; e.ldc = ldc;
+  e.store_mode = EPI_ATOMIC;
+  return e;
+}
+
+struct Cfg {
+  DropoutCfg d[EEGB200_SITE_COUNT];
+};
+static Cfg make_cfg(const eegb200_atms_io* io) {
+  static const float ref_p[EEGB200_SITE_COUNT] = {0.f, 0.25f, 0.25f, 0.25f, 0.25f, 0.25f, 0.5f, 0.5f};
+  Cfg c;
+  for (int i = 0; i < EEGB200_SITE_COUNT; ++i) {
+    const float p = io->dropout_p ? io->dropout_p[i] : ref_p[i];
+    c.d[i] = make_dropout(io->seed, (uint32_t)i, p, io->train != 0);
+  }
+  return c;
+}
+
+static int check_io(const eegb200_atms_io* io, Ws* w) {
+  EEG_REQUIRE(io != nullptr, "null io");
+  EEG_REQUIRE(io->B > 0, "batch must be positive (got %d)", io->B);
+  EEG_REQUIRE(io->params && io->buffers && io->x && io->subject_ids && io->workspace, "null pointer in atms io");
+  for (int i = 0; i < EEGB200_P_COUNT; ++i) EEG_REQUIRE(io->params[i] != nullptr, "params[%d] is null", i);
+  for (int i = 0; i < EEGB200_BUF_COUNT; ++i) EEG_REQUIRE(io->buffers[i] != nullptr, "buffers[%d] is null", i);
+  const size_t need = carve(nullptr, io->B, nullptr);
+  EEG_REQUIRE(io->workspace_bytes >= need, "workspace too small: %zu < %zu", io->workspace_bytes, need);
+  EEG_REQUIRE((reinterpret_cast<uintptr_t>(io->workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  carve(io->workspace, io->B, w);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
+  Ws w;
+  EEG_TRY(check_io(io, &w));
+  EEG_REQUIRE(io->out != nullptr || !(phases & EEGB200_PHASE_C), "null output");
+  const float* const* P = io->params;
+  float* const* BUF = io->buffers;
+  const int B = io->B;
+  const int M = B * N_TOK;
+  const int R = B * N_POOL;
+  const Cfg cfg = make_cfg(io);
+  const int train = io->train != 0;
+  const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;   // SyncBN: statistics cover wmul*B samples
+
+  if (phases & EEGB200_PHASE_A) {
+    EEG_TRY(pack_weights(P, BUF, w, s));
+    // ---- DataEmbedding (Embed.py:141-162) ----
+    EEG_TRY(pad_input(io->x, w.Xp, B, s));
+    {
+      Epilogue e = epi_out(w.H0, 256);
+      e.bias = w.tokbias; e.bias_period = 64; e.ld_bias = 256;
+      e.drop = cfg.d[EEGB200_SITE_EMBED]; e.drop_ld = 256;
+      e.round_tf32 = 1;
+      EEG_TRY(run_gemm(M, 256, 256, w.Xp, 256, 0, w.Wv_p, 256, 0, e, 1, s));
+    }
+    EEG_TRY(subject_token(reinterpret_cast<const long long*>(io->subject_ids), P[EEGB200_P_SUBJ_TABLE],
+                          P[EEGB200_P_SUBJ_SHARED], io->n_subjects, w.flag, w.H0, B, cfg.d[EEGB200_SITE_EMBED], 1, s));
+    // ---- AttentionLayer (SelfAttention_Family.py:194-213) ----
+    {
+      Epilogue e = epi_out(w.QKV, 768);
+      e.bias = w.bqkv_p;
+      EEG_TRY(run_gemm(M, 768, 256, w.H0, 256, 0, w.Wqkv_p, 256, 0, e, 1, s));
+    }
+    EEG_TRY(attention_fwd(w.QKV, w.O, B, cfg.d[EEGB200_SITE_ATTN], s));
+    {
+      Epilogue e = epi_out(w.R1, 256);          // x + dropout(out_projection(attn))   (Transformer_EncDec.py:45)
+      e.bias = w.bo_p;
+      e.drop = cfg.d[EEGB200_SITE_RES1]; e.drop_ld = 256;
+      e.resid = w.H0; e.ld_res = 256;
+      EEG_TRY(run_gemm(M, 256, 256, w.O, 256, 0, w.Wo_p, 256, 0, e, 1, s));
+    }
+    EEG_TRY(layernorm_fwd(w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr, nullptr,
+                          w.X1, 256, 1, s));
+    // ---- position-wise FFN (Transformer_EncDec.py:48-51) ----
+    {
+      Epilogue e = epi_out(w.Hf, 256);
+      e.bias = w.b1_p;
+      e.aux_out = w.U; e.ld_aux = 256;
+      e.act = EPI_ACT_GELU;
+      e.drop = cfg.d[EEGB200_SITE_FFN1]; e.drop_ld = 256;
+      e.round_tf32 = 1;
+      EEG_TRY(run_gemm(M, 256, 256, w.X1, 256, 0, w.W1_p, 256, 0, e, 1, s));
+    }
+    {
+      Epilogue e = epi_out(w.R2, 256);
+      e.bias = w.b2_p;
+      e.drop = cfg.d[EEGB200_SITE_FFN2]; e.drop_ld = 256;
+      e.resid = w.X1; e.ld_res = 256;
+      EEG_TRY(run_gemm(M, 256, 256, w.Hf, 256, 0, w.W2_p, 256, 0, e, 1, s));
+    }
+    // norm2 then the encoder's final norm (Transformer_EncDec.py:51, 77-78)
+    EEG_TRY(layernorm_fwd(w.R2, 256, M, N_T, P[EEGB200_P_LN2_G], P[EEGB200_P_LN2_B], w.st2, P[EEGB200_P_LNF_G],
+                          P[EEGB200_P_LNF_B], w.stf, w.X3, 256, 0, s));
+    // ---- PatchEmbedding temporal conv + pool (ATMS_retrieval.py:102-103) on tokens 0..62 ----
+    if (train) EEG_CUDA_OK(cudaMemsetAsync(w.bn1_sums, 0, 2 * N_FILT * sizeof(double), s));
+    EEG_TRY(conv_temporal_fwd(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.Y1, train ? w.bn1_sums : nullptr, B, s));
+  }
+  if (phases & EEGB200_PHASE_B) {
+    BnState bn1{w.bn1_sums, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], BUF[EEGB200_BUF_BN1_RM], BUF[EEGB200_BUF_BN1_RV]};
+    EEG_TRY(bn_finalize(bn1, wmul * B * N_CH * N_POOL, train, train && io->update_running_stats, s));
+    EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, 1, s));
+    {
+      Epilogue e = epi_out(w.Y2, N_FILT);        // spatial conv (63,1) == GEMM over (r,k1)  (ATMS_retrieval.py:106)
+      e.bias = P[EEGB200_P_BS];
+      EEG_TRY(run_gemm(R, N_FILT, K_SPAT, w.A1, K_SPAT, 0, w.Ws_p, K_SPAT, 0, e, 1, s));
+    }
+    if (train) {
+      EEG_CUDA_OK(cudaMemsetAsync(w.bn2_sums, 0, 2 * N_FILT * sizeof(double), s));
+      EEG_TRY(colstats(w.Y2, N_FILT, R, N_FILT, w.bn2_sums, s));
+    }
+  }
+  if (phases & EEGB200_PHASE_C) {
+    BnState bn2{w.bn2_sums, w.bn2_mr, P[EEGB200_P_BN2_G], P[EEGB200_P_BN2_B], BUF[EEGB200_BUF_BN2_RM], BUF[EEGB200_BUF_BN2_RV]};
+    EEG_TRY(bn_finalize(bn2, wmul * R, train, train && io->update_running_stats, s));
+    EEG_TRY(conv_head_fwd(w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], P[EEGB200_P_BN2_B], P[EEGB200_P_WC], P[EEGB200_P_BC], w.feat,
+                          B, cfg.d[EEGB200_SITE_CONV], s));
+    // ---- Proj_eeg (ATMS_retrieval.py:157-167) ----
+    {
+      Epilogue e = epi_out(w.G, D_OUT);
+      e.bias = P[EEGB200_P_BP1];
+      e.aux_out = w.Z1; e.ld_aux = D_OUT;
+      e.act = EPI_ACT_GELU;
+      e.round_tf32 = 1;
+      EEG_TRY(run_gemm(B, D_OUT, D_FEAT, w.feat, D_FEAT, 0, w.Wp1_r, D_FEAT, 0, e, 1, s));
+    }
+    {
+      Epilogue e = epi_out(w.Z2, D_OUT);
+      e.bias = P[EEGB200_P_BP2];
+      e.drop = cfg.d[EEGB200_SITE_PROJ]; e.drop_ld = D_OUT;
+      e.resid = w.Z1; e.ld_res = D_OUT;
+      EEG_TRY(run_gemm(B, D_OUT, D_OUT, w.G, D_OUT, 0, w.Wp2_r, D_OUT, 0, e, 1, s));
+    }
+    EEG_TRY(layernorm_fwd(w.Z2, D_OUT, B, D_OUT, P[EEGB200_P_LNP_G], P[EEGB200_P_LNP_B], w.stp, nullptr, nullptr, nullptr,
+                          io->out, D_OUT, 0, s));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+static int backward(const eegb200_atms_io* io, const float* d_out, float* const* GR, int phases, cudaStream_t s) {
+  Ws w;
+  EEG_TRY(check_io(io, &w));
+  EEG_REQUIRE(io->train != 0, "backward needs the workspace of a train-mode forward");
+  EEG_REQUIRE(GR != nullptr, "null grads");
+  for (int i = 0; i < EEGB200_P_COUNT; ++i)
+    EEG_REQUIRE(GR[i] != nullptr || i == EEGB200_P_SUBJ_TABLE || i == EEGB200_P_SUBJ_SHARED, "grads[%d] is null", i);
+  const float* const* P = io->params;
+  const int B = io->B;
+  const int M = B * N_TOK;
+  const int R = B * N_POOL;
+  const Cfg cfg = make_cfg(io);
+  const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;
+
+  if (phases & EEGB200_PHASE_A) {
+    EEG_REQUIRE(d_out != nullptr, "null d_out");
+    // ---- Proj_eeg backward ----
+    EEG_TRY(layernorm_bwd(d_out, D_OUT, w.Z2, D_OUT, B, D_OUT, P[EEGB200_P_LNP_G], P[EEGB200_P_LNP_B], w.stp, nullptr,
+                          nullptr, w.dZ2, D_OUT, GR[EEGB200_P_LNP_G], GR[EEGB200_P_LNP_B], nullptr, nullptr, 0, s));
+    EEG_TRY(dropout_apply(w.dZ2, w.dZ2d, B, D_OUT, cfg.d[EEGB200_SITE_PROJ], 1, s));
+    EEG_TRY(colsum(w.dZ2d, D_OUT, B, D_OUT, GR[EEGB200_P_BP2], 0, 0, s));
+    EEG_TRY(run_gemm(D_OUT, D_OUT, B, w.dZ2d, D_OUT, 1, w.G, D_OUT, 1, epi_wgrad(GR[EEGB200_P_WP2], D_OUT),
+                     pick_split(D_OUT, D_OUT, B), s));
+    {
+      Epilogue e = epi_out(w.dZ1, D_OUT);        // dZ1 = dZ2 + (dZ2d . Wp2) * GELU'(Z1)
+      e.mul_in = w.Z1; e.ld_mul = D_OUT;
+      e.resid = w.dZ2; e.ld_res = D_OUT;
+      e.round_tf32 = 1;
+      EEG_TRY(run_gemm(B, D_OUT, D_OUT, w.dZ2d, D_OUT, 0, w.Wp2_r, D_OUT, 1, e, 1, s));
+    }
+    EEG_TRY(colsum(w.dZ1, D_OUT, B, D_OUT, GR[EEGB200_P_BP1], 0, 0, s));
+    EEG_TRY(run_gemm(D_OUT, D_FEAT, B, w.dZ1, D_OUT, 1, w.feat, D_FEAT, 1, epi_wgrad(GR[EEGB200_P_WP1], D_FEAT),
+                     pick_split(D_OUT, D_FEAT, B), s));
+    EEG_TRY(run_gemm(B, D_FEAT, D_OUT, w.dZ1, D_OUT, 0, w.Wp1_r, D_FEAT, 1, epi_out(w.dfeat, D_FEAT), 1, s));
+    // ---- conv head backward down to d(BN2 out) + BN2 reductions ----
+    EEG_CUDA_OK(cudaMemsetAsync(w.bn2_bsums, 0, 2 * N_FILT * sizeof(double), s));
+    EEG_TRY(conv_head_bwd(w.dfeat, w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], P[EEGB200_P_BN2_B], P[EEGB200_P_WC], w.dz2,
+                          GR[EEGB200_P_WC], GR[EEGB200_P_BC], w.bn2_bsums, B, cfg.d[EEGB200_SITE_CONV], s));
+  }
+  if (phases & EEGB200_PHASE_B) {
+    EEG_TRY(bn_bwd_apply(w.dz2, w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], w.bn2_bsums, wmul * R, w.dY2, GR[EEGB200_P_BN2_G],
+                         GR[EEGB200_P_BN2_B], (long long)R * N_FILT, 1, 1.f / (float)wmul, s));
+    EEG_TRY(colsum(w.dY2, N_FILT, R, N_FILT, GR[EEGB200_P_BS], 0, 0, s));
+    // dWs[k2][(r,k1)] = sum_{(b,j)} dY2[(b,j)][k2] * A1[(b,j)][(r,k1)]
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), s));
+    EEG_TRY(run_gemm(N_FILT, K_SPAT, R, w.dY2, N_FILT, 1, w.A1, K_SPAT, 1, epi_wgrad(w.dWs_p, K_SPAT),
+                     pick_split(N_FILT, K_SPAT, R), s));
+    unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(w.dWs_p, GR[EEGB200_P_WS]);
+    count_launch();
+    // dA1 = dY2 . Ws
+    EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, epi_out(w.dA1, K_SPAT), 1, s));
+    EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
+    EEG_TRY(bn1_bwd_reduce(w.dA1, w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.bn1_bsums,
+                           (long long)R * K_SPAT, s));
+  }
+  if (phases & EEGB200_PHASE_C) {
+    EEG_TRY(conv_temporal_bwd(w.dA1, w.Y1, w.X3, P[EEGB200_P_WT], w.bn1_mr, P[EEGB200_P_BN1_G], w.bn1_bsums,
+                              wmul * B * N_CH * N_POOL, w.dX3, GR[EEGB200_P_WT], GR[EEGB200_P_BT],
+                              GR[EEGB200_P_BN1_G], GR[EEGB200_P_BN1_B], B, 1.f / (float)wmul, s));
+    // ---- final norm + norm2 ----
+    EEG_TRY(layernorm_bwd(w.dX3, 256, w.R2, 256, M, N_T, P[EEGB200_P_LN2_G], P[EEGB200_P_LN2_B], w.st2,
+                          P[EEGB200_P_LNF_G], w.stf, w.dR2, 256, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B],
+                          GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
+    // ---- FFN ----
+    EEG_TRY(dropout_apply(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], 1, s));
+    EEG_TRY(colsum(w.T1, 256, M, N_T, GR[EEGB200_P_B2], 0, 0, s));
+    EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), s));
+    {
+      Epilogue e = epi_out(w.dU, 256);           // dU = dropout_ffn1(T1 . W2) * GELU'(U)
+      e.drop = cfg.d[EEGB200_SITE_FFN1]; e.drop_ld = 256;
+      e.mul_in = w.U; e.ld_mul = 256;
+      e.round_tf32 = 1;
+      EEG_TRY(run_gemm(M, 256, 256, w.T1, 256, 0, w.W2_p, 256, 1, e, 1, s));
+    }
+    EEG_TRY(colsum(w.dU, 256, M, D_FF, GR[EEGB200_P_B1], 0, 0, s));
+    EEG_TRY(run_gemm(D_FF, N_T, M, w.dU, 256, 1, w.X1, 256, 1, epi_wgrad(GR[EEGB200_P_W1], N_T), pick_split(D_FF, N_T, M), s));
+    {
+      Epilogue e = epi_out(w.dX1, 256);          // dX1 = dR2 + dU . W1
+      e.resid = w.dR2; e.ld_res = 256;
+      EEG_TRY(run_gemm(M, 256, 256, w.dU, 256, 0, w.W1_p, 256, 1, e, 1, s));
+    }
+    // ---- norm1 ----
+    EEG_TRY(layernorm_bwd(w.dX1, 256, w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr,
+                          w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
+    // ---- attention ----
+    EEG_TRY(dropout_apply(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], 1, s));
+    EEG_TRY(colsum(w.T2, 256, M, N_T, GR[EEGB200_P_BO], 0, 0, s));
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), s));
+    EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), s));
+    unpack_wo_grad_kernel<<<256, 256, 0, s>>>(w.dWo_p, GR[EEGB200_P_WO]);
+    count_launch();
+    EEG_TRY(run_gemm(M, 256, 256, w.T2, 256, 0, w.Wo_p, 256, 1, epi_out(w.dO, 256), 1, s));
+    EEG_TRY(attention_bwd(w.QKV, w.dO, w.dQKV, B, cfg.d[EEGB200_SITE_ATTN], s));
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWqkv_p, 0, 768 * 256 * sizeof(float), s));
+    EEG_CUDA_OK(cudaMemsetAsync(w.dbqkv_p, 0, 768 * sizeof(float), s));
+    EEG_TRY(colsum(w.dQKV, 768, M, 768, w.dbqkv_p, 0, 0, s));
+    EEG_TRY(run_gemm(768, 256, M, w.dQKV, 768, 1, w.H0, 256, 1, epi_wgrad(w.dWqkv_p, 256), pick_split(768, 256, M), s));
+    unpack_qkv_grad_kernel<<<768, 256, 0, s>>>(w.dWqkv_p, w.dbqkv_p, GR[EEGB200_P_WQ], GR[EEGB200_P_WK], GR[EEGB200_P_WV],
+                                               GR[EEGB200_P_BQ], GR[EEGB200_P_BK], GR[EEGB200_P_BV]);
+    count_launch();
+    {
+      Epilogue e = epi_out(w.dH0, 256);          // dH0 = dR1 + dQKV . Wqkv
+      e.resid = w.dR1; e.ld_res = 256;
+      EEG_TRY(run_gemm(M, 256, 768, w.dQKV, 768, 0, w.Wqkv_p, 256, 1, e, 1, s));
+    }
+    // ---- DataEmbedding ----
+    EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], 1, s));
+    EEG_TRY(colsum(w.T3, 256, M, N_T, GR[EEGB200_P_VALUE_B], N_TOK, 0, s));   // token-0 rows carry no value embedding
+    EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), s));
+    EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,
+                "subject-token gradients need both the table and the shared-token grad buffers");
+    EEG_TRY(subject_token_bwd(reinterpret_cast<const long long*>(io->subject_ids), w.flag, w.dH0, GR[EEGB200_P_SUBJ_TABLE],
+                              GR[EEGB200_P_SUBJ_SHARED], B, cfg.d[EEGB200_SITE_EMBED], s));
+    EEG_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+struct NamedTensor { const char* name; void* ptr; int rows, cols, ld; };
+
+}  // namespace eegb200
+
+using namespace eegb200;
+
+extern "C" {
+
+size_t eegb200_atms_workspace_bytes(int B) { return B > 0 ? carve(nullptr, B, nullptr) : 0; }
+
+int eegb200_atms_forward(const eegb200_atms_io* io, int phase_mask, void* stream) {
+  return forward(io, phase_mask, (cudaStream_t)stream);
+}
+int eegb200_atms_backward(const eegb200_atms_io* io, const float* d_out, float* const* grads, int phase_mask, void* stream) {
+  return backward(io, d_out, grads, phase_mask, (cudaStream_t)stream);
+}
+
+int eegb200_atms_ws_tensor(void* workspace, int B, const char* name, void** ptr, int* rows, int* cols, int* ld) {
+  EEG_REQUIRE(workspace && name && ptr && rows && cols && ld && B > 0, "ws_tensor: bad arguments");
+  Ws w;
+  carve(workspace, B, &w);
+  const int M = B * N_TOK, R = B * N_POOL;
+  const NamedTensor t[] = {
+      {"xp", w.Xp, M, 256, 256},      {"h0", w.H0, M, 256, 256},       {"qkv", w.QKV, M, 768, 768},
+      {"attn_o", w.O, M, 256, 256},   {"r1", w.R1, M, 256, 256},       {"x1", w.X1, M, 256, 256},
+      {"ffn_u", w.U, M, 256, 256},    {"ffn_h", w.Hf, M, 256, 256},    {"r2", w.R2, M, 256, 256},
+      {"x3", w.X3, M, 256, 256},      {"y1", w.Y1, R, K_SPAT, K_SPAT}, {"a1", w.A1, R, K_SPAT, K_SPAT},
+      {"y2", w.Y2, R, N_FILT, N_FILT}, {"feat", w.feat, B, D_FEAT, D_FEAT}, {"z1", w.Z1, B, D_OUT, D_OUT},
+      {"z2", w.Z2, B, D_OUT, D_OUT},  {"bn1_sums", w.bn1_sums, 1, 80, 80}, {"bn2_sums", w.bn2_sums, 1, 80, 80},
+      {"bn1_bwd_sums", w.bn1_bsums, 1, 80, 80}, {"bn2_bwd_sums", w.bn2_bsums, 1, 80, 80},
+      {"dx3", w.dX3, M, 256, 256},    {"dh0", w.dH0, M, 256, 256},     {"dfeat", w.dfeat, B, D_FEAT, D_FEAT},
+      {"dqkv", w.dQKV, M, 768, 768},  {"dr1", w.dR1, M, 256, 256},     {"dr2", w.dR2, M, 256, 256},
+      {"da1", w.dA1, R, K_SPAT, K_SPAT}, {"dy2", w.dY2, R, N_FILT, N_FILT},
+  };
+  for (const NamedTensor& e : t)
+    if (strcmp(e.name, name) == 0) {
+      *ptr = e.ptr; *rows = e.rows; *cols = e.cols; *ld = e.ld;
+      return 0;
+    }
+  set_error("ws_tensor: unknown name '%s'", name);
+  return 2;
+}
+
+}  // extern "C"

@@ -267,7 +267,8 @@ int conv_head_bwd(const float* dfeat, const float* y2, const float* mean_rstd, c
 __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dz, const float4* __restrict__ y,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                     const double* __restrict__ bwd_sums, long long count, float4* __restrict__ dy,
-                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long n4, int round_tf) {
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long n4, int round_tf,
+                                    float gscale) {
   __shared__ float mu[N_FILT], rs[N_FILT], gr[N_FILT], m1[N_FILT], m2[N_FILT];
   if (threadIdx.x < N_FILT) {
     const int k = threadIdx.x;
@@ -277,8 +278,8 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dz, const float4*
     m1[k] = (float)(bwd_sums[k] / (double)count);
     m2[k] = (float)(bwd_sums[N_FILT + k] / (double)count);
     if (blockIdx.x == 0) {
-      dgamma[k] += (float)bwd_sums[N_FILT + k];
-      dbeta[k] += (float)bwd_sums[k];
+      dgamma[k] += gscale * (float)bwd_sums[N_FILT + k];
+      dbeta[k] += gscale * (float)bwd_sums[k];
     }
   }
   __syncthreads();
@@ -296,14 +297,15 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dz, const float4*
   }
 }
 int bn_bwd_apply(const float* dz, const float* y, const float* mean_rstd, const float* gamma, const double* bwd_sums,
-                 long long count, float* dy, float* dgamma, float* dbeta, long long n, int round_tf, cudaStream_t s) {
+                 long long count, float* dy, float* dgamma, float* dbeta, long long n, int round_tf, float gscale,
+                 cudaStream_t s) {
   const long long n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   bn_bwd_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dz), reinterpret_cast<const float4*>(y),
                                              mean_rstd, gamma, bwd_sums, count, reinterpret_cast<float4*>(dy), dgamma,
-                                             dbeta, n4, round_tf);
+                                             dbeta, n4, round_tf, gscale);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_bwd_kernel(
     const float* __restrict__ dz1, const float* __restrict__ y1, const float* __restrict__ x3,
     const float* __restrict__ wt, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
     const double* __restrict__ bwd_sums, long long count, float* __restrict__ dx3, float* __restrict__ dwt,
-    float* __restrict__ dbt, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float* __restrict__ dbt, float* __restrict__ dgamma, float* __restrict__ dbeta, float gscale) {
   __shared__ float xs[256 + 64];
   __shared__ float ps[N_PSUM];
   __shared__ float dys[N_POOL * N_FILT];
@@ -384,8 +386,8 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_bwd_kernel(
   const float m1 = (float)(bwd_sums[k] / (double)count);
   const float m2 = (float)(bwd_sums[N_FILT + k] / (double)count);
   if (b == 0 && threadIdx.x < N_FILT) {
-    dgamma[k] += (float)bwd_sums[N_FILT + k];
-    dbeta[k] += (float)bwd_sums[k];
+    dgamma[k] += gscale * (float)bwd_sums[N_FILT + k];
+    dbeta[k] += gscale * (float)bwd_sums[k];
   }
   float accw[7];
 #pragma unroll
@@ -457,9 +459,9 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_bwd_kernel(
 }
 int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
-                      float* dgamma, float* dbeta, int B, cudaStream_t s) {
+                      float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s) {
   conv_temporal_bwd_kernel<<<B, CT_THREADS, 0, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt,
-                                                    dgamma, dbeta);
+                                                    dgamma, dbeta, gscale);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

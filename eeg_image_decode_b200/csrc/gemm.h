@@ -20,6 +20,7 @@ struct Epilogue {
   float* C = nullptr;
   int ldc = 0;
   float alpha = 1.f;
+  const float* alpha_dev = nullptr;   // optional device scalar multiplied into alpha (e.g. the logit_scale parameter)
   const float* bias = nullptr;   // per column, or table [bias_period][ld_bias] indexed by (row % bias_period)
   int bias_period = 0;           // 0 -> per-column vector
   int ld_bias = 0;
@@ -56,6 +57,7 @@ long long total_launch_count();
 // ---- epilogue math shared by both kernels ----
 __device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, float acc) {
   float v = e.alpha * acc;
+  if (e.alpha_dev) v *= __ldg(e.alpha_dev);
   if (e.bias) v += e.bias_period ? e.bias[(size_t)(row % e.bias_period) * e.ld_bias + col] : e.bias[col];
   if (e.aux_out) e.aux_out[(size_t)row * e.ld_aux + col] = v;
   if (e.act == EPI_ACT_GELU) v = gelu_exact(v);

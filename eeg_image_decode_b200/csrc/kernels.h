@@ -50,6 +50,8 @@ int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, 
                   float* db1, float* dg2, float* db2, int round_tf, cudaStream_t s);
 int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s);
 int dropout_mask(DropoutCfg cfg, int rows, int cols, int ld, float* out, cudaStream_t s);
+// dst[r*ld+c] = tf32?(keep(r*ld+c) ? src*scale : 0) over [rows, ld]
+int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, cudaStream_t s);
 int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, int rows_dst, int round_tf,
              float scale, cudaStream_t s);
 
@@ -76,13 +78,14 @@ int conv_head_bwd(const float* dfeat, const float* y2, const float* mean_rstd, c
                   cudaStream_t s);
 // dy = gamma*rstd*(dz - mean(dz) - yhat*mean(dz*yhat)) elementwise over [rows, 40]; also dgamma/dbeta
 int bn_bwd_apply(const float* dz, const float* y, const float* mean_rstd, const float* gamma, const double* bwd_sums,
-                 long long count, float* dy, float* dgamma, float* dbeta, long long n, int round_tf, cudaStream_t s);
+                 long long count, float* dy, float* dgamma, float* dbeta, long long n, int round_tf, float gscale,
+                 cudaStream_t s);
 // dz1 = da1 * ELU'(bn1(y1)) in place + reduction sums for the BN1 backward
 int bn1_bwd_reduce(float* da1, const float* y1, const float* mean_rstd, const float* gamma, const float* beta,
                    double* bwd_sums, long long n, cudaStream_t s);
 int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
-                      float* dgamma, float* dbeta, int B, cudaStream_t s);
+                      float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s);
 
 // ---- loss.cu ----
 struct InfoNceArgs {
@@ -91,16 +94,21 @@ struct InfoNceArgs {
   int B;                 // local rows
   int N;                 // global batch (columns per target)
   int row_offset;        // rank * B : global index of local row 0
+  int nt;                // number of targets concatenated along the columns (1 or 2)
 };
 int infonce_row_lse(const InfoNceArgs& a, float* row_lse /*[2][B]*/, float* diag /*[2][B]*/, cudaStream_t s);
-int infonce_col_partial(const InfoNceArgs& a, float* col_max /*[2N]*/, float* col_sum /*[2N]*/, cudaStream_t s);
-int infonce_col_finalize(const float* col_max, const float* col_sum, float* col_lse, int n, cudaStream_t s);
+int infonce_col_chunks(int B);   // number of row chunks (= partial sets) infonce_col_partial writes
+int infonce_col_partial(const InfoNceArgs& a, float* part_max /*[chunks][2N]*/, float* part_sum, cudaStream_t s);
+int infonce_col_reduce(const float* part_max, const float* part_sum, int n_parts, size_t stride, int n, float* out_max,
+                       float* out_sum, float* out_lse, cudaStream_t s);
+int gather_cols(const float* logits, int ld, const int* sel, int Q, int k, float* out, cudaStream_t s);
+int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s);
 // loss_partial[0] += alpha*..., per rank partial of the global loss (sum over ranks = loss)
 int infonce_loss(const InfoNceArgs& a, const float* row_lse, const float* diag, const float* col_lse, float w_img,
                  float w_txt, float* loss_out, cudaStream_t s);
 // G (in place over logits) and d(logit_scale) partial
 int infonce_grad(const InfoNceArgs& a, float* logits_inout, const float* row_lse, const float* col_lse, float w_img,
-                 float w_txt, float logit_scale, float* dscale, float grad_out_scale, cudaStream_t s);
+                 float w_txt, const float* logit_scale_dev, float* dscale, float grad_out_scale, cudaStream_t s);
 int argmax_count(const float* logits, int ld, int rows, int cols, const long long* labels, int* correct,
                  long long* pred_out, cudaStream_t s);
 int topk5(const float* logits, int ld, int rows, int cols, int* top5_out /*[rows][5]*/, cudaStream_t s);

@@ -378,3 +378,33 @@ int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int l
 }
 
 }  // namespace eegb200
+
+namespace eegb200 {
+__global__ void dropout_apply_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4, DropoutCfg cfg,
+                                     int round_tf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = src[i];
+    if (cfg.p > 0.f) {
+      const uint32_t m = dropout_keep4(cfg, (uint64_t)i * 4);
+      v.x = (m & 1u) ? v.x * cfg.scale : 0.f;
+      v.y = (m & 2u) ? v.y * cfg.scale : 0.f;
+      v.z = (m & 4u) ? v.z * cfg.scale : 0.f;
+      v.w = (m & 8u) ? v.w * cfg.scale : 0.f;
+    }
+    if (round_tf) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+    dst[i] = v;
+  }
+}
+int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, cudaStream_t s) {
+  EEG_REQUIRE((ld & 3) == 0, "dropout_apply: ld %d not a multiple of 4", ld);
+  const long long n4 = (long long)rows * ld / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dropout_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), n4, cfg,
+                                              round_tf);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+}  // namespace eegb200

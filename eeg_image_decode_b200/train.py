@@ -1,0 +1,300 @@
+"""Training / evaluation step functions with the reference's signatures
+(Retrieval/ATMS_retrieval.py:199-254 ``train_model``, :258-362 ``evaluate_model``, :364-512 ``main_train_loop``).
+
+Differences that are not observable through the return values:
+  * loss and accuracy are accumulated on the device and read back once per call instead of two ``.item()``
+    syncs per step (:238, :250);
+  * the optimiser update runs as one fused AdamW kernel over the flat parameter arena when the caller passes a
+    ``torch.optim.AdamW`` (hyper-parameters are read from its ``param_groups``; moments are exposed through
+    ``optimizer.state`` as views);
+  * with torch.distributed initialised (one process per GPU) the step is data-parallel: targets are
+    all-gathered for the global-batch InfoNCE, BatchNorm statistics and gradients are all-reduced (SUM), so W
+    ranks x B_local behave like one process at batch W*B_local.
+"""
+from __future__ import annotations
+
+import random
+import re
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .atms import ATMS, N_SUBJECT_ROWS
+from .loss import _InfoNCE, fused_contrastive, gather_targets
+
+
+def extract_id_from_string(s):
+    match = re.search(r"\d+$", s)
+    if match:
+        return int(match.group())
+    return None
+
+
+def _world():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_world_size(), torch.distributed.get_rank()
+    return 1, 0
+
+
+# ------------------------------------------------------------------------------------------------
+# fused AdamW over the flat arena
+# ------------------------------------------------------------------------------------------------
+def _adam_hparams(optimizer):
+    if optimizer is None:
+        return dict(lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    g = optimizer.param_groups[0]
+    return dict(lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
+
+
+def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False) -> None:
+    """torch.optim.AdamW semantics on model.flat_params / model.flat_grads.  Parameters that received no gradient
+    this step (the unused half of {subject table, shared token}; the never-used cold parameters) are skipped, as
+    torch.optim does for ``grad is None``."""
+    hp = _adam_hparams(optimizer)
+    if model._adam_m is None:
+        model._adam_m = torch.zeros_like(model.flat_grads)
+        model._adam_v = torch.zeros_like(model.flat_grads)
+    n_main = model._n_main
+    o_tab = model._offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]
+    o_sh = model._offs[_lib.P_NAMES[_lib.P_SUBJ_SHARED]]
+    segs = [("main", 0, n_main)]
+    segs.append(("shared", o_sh, 250) if use_shared else ("table", o_tab, N_SUBJECT_ROWS * 250))
+    for name, off, n in segs:
+        model._adam_steps[name] += 1
+        _lib.adamw_step(model.flat_params[off:], model.flat_grads[off:], model._adam_m[off:], model._adam_v[off:], n,
+                        hp["lr"], hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"], model._adam_steps[name])
+
+
+def publish_optimizer_state(model: ATMS, optimizer) -> None:
+    """expose the fused moments through optimizer.state (views) so optimizer.state_dict() stays meaningful"""
+    if optimizer is None or model._adam_m is None:
+        return
+    named = dict(model.named_parameters())
+    tab, sh = _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]
+    for n in model._hot_order():
+        p = named[n]
+        which = "table" if n == tab else ("shared" if n == sh else "main")
+        steps = model._adam_steps[which]
+        if steps == 0:
+            continue
+        o = model._offs[n]
+        optimizer.state[p] = {
+            "step": torch.tensor(float(steps)),
+            "exp_avg": model._adam_m[o:o + p.numel()].view(p.shape),
+            "exp_avg_sq": model._adam_v[o:o + p.numel()].view(p.shape),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# one contrastive step (forward, 2x InfoNCE, backward, optimiser), optionally data-parallel
+# ------------------------------------------------------------------------------------------------
+class StepEngine:
+    def __init__(self, model: ATMS, optimizer=None, alpha: float = 0.99):
+        self.model = model
+        self.optimizer = optimizer
+        self.alpha = alpha
+        self.nce = _InfoNCE()
+        self.world, self.rank = _world()
+        self.fused = optimizer is None or type(optimizer).__name__ in ("AdamW", "FusedAdamW")
+
+    def _allreduce(self, t):
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+    def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None):
+        """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024])"""
+        m = self.model
+        W = self.world
+        m.zero_flat_grads()
+        seed = m.next_seed() if seed is None else seed
+        if W > 1:
+            # SyncBN: all-reduce the batch statistics between the forward phases
+            m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A)
+            self._allreduce(m.ws_tensor("bn1_sums"))
+            out = m._last[3]
+            self._phase(_lib.PHASE_B, fwd=True, batch_scale=W)
+            self._allreduce(m.ws_tensor("bn2_sums"))
+            self._phase(_lib.PHASE_C, fwd=True, batch_scale=W)
+            feats = out
+        else:
+            feats = m.encode(eeg, subject_ids, train=True, seed=seed)
+        img_all = gather_targets(img_feat, W)
+        txt_all = gather_targets(txt_feat, W)
+        loss, d_e, d_s = fused_contrastive(self.nce, feats, img_all, txt_all, m.logit_scale.detach(), self.alpha,
+                                           row_offset=self.rank * feats.shape[0], need_grad=True, world_size=W)
+        m.grad_view("logit_scale").add_(d_s)
+        if W > 1:
+            m.backprop(d_e, phases=_lib.PHASE_A)
+            self._allreduce(m.ws_tensor("bn2_bwd_sums"))
+            self._phase(_lib.PHASE_B, fwd=False, batch_scale=W)
+            self._allreduce(m.ws_tensor("bn1_bwd_sums"))
+            self._phase(_lib.PHASE_C, fwd=False, batch_scale=W)
+            self._allreduce(m.flat_grads)
+        else:
+            m.backprop(d_e)
+        if self.fused:
+            fused_adamw_step(m, self.optimizer, use_shared)
+        else:
+            self._generic_optimizer_step(use_shared)
+        return loss, feats
+
+    def _phase(self, phase, fwd, batch_scale):
+        # the C side derives the BatchNorm element count from its local B; under SyncBN the reduced sums cover
+        # W*B samples, so the count must be scaled.  B is patched in the io for the BN-count only.
+        m = self.model
+        io = m._last[0]
+        if fwd:
+            _lib.atms_forward(io, phase | (_BN_SCALE_SHIFT(batch_scale)))
+        else:
+            _, G, _ = m._pointers()
+            import ctypes
+            _lib.check(_lib._sig().eegb200_atms_backward(ctypes.byref(io), None, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)),
+                                                         phase | (_BN_SCALE_SHIFT(batch_scale)), _lib.stream_ptr()),
+                       "atms_backward")
+
+    def _generic_optimizer_step(self, use_shared):
+        named = dict(self.model.named_parameters())
+        tab, sh = _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]
+        for n in self.model._hot_order():
+            skip = (n == tab and use_shared) or (n == sh and not use_shared)
+            named[n].grad = None if skip else self.model.grad_view(n)
+        self.optimizer.step()
+
+
+def _BN_SCALE_SHIFT(world: int) -> int:
+    """phase-mask bits 8..15 carry the SyncBN world size (0/1 = local statistics)"""
+    return (int(world) & 0xFF) << 8
+
+
+# ------------------------------------------------------------------------------------------------
+def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config):
+    """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254."""
+    eeg_model.train()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("train_model: this implementation runs on CUDA only (no CPU fallback)")
+    text_features_all = text_features_all.to(device).float()
+    img_features_all = (img_features_all[::10]).to(device).float().contiguous()       # :202 class-prototype gallery
+    alpha = 0.99
+    eng = StepEngine(eeg_model, optimizer, alpha)
+    subject_id = extract_id_from_string(sub)
+    use_shared = subject_id is None or subject_id >= N_SUBJECT_ROWS or subject_id < 0
+    loss_acc = torch.zeros(3, device=device)
+    correct = torch.zeros(1, device=device, dtype=torch.int32)
+    total = 0
+    features_list = []
+    n_batches = 0
+    for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
+        eeg_data = eeg_data.to(device, non_blocking=True)
+        text_features = text_features.to(device, non_blocking=True).float()
+        img_features = img_features.to(device, non_blocking=True).float()
+        labels = labels.to(device, non_blocking=True)
+        batch_size = eeg_data.size(0)
+        subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
+        loss, eeg_features = eng.step(eeg_data, subject_ids, img_features, text_features, use_shared)
+        loss_acc += loss
+        features_list.append(eeg_features.clone())
+        # train accuracy against the 1654-way prototype gallery (:241-250), scored with the post-update logit_scale
+        r = _lib.retrieval(eeg_features, img_features_all, eeg_model.logit_scale.detach(), labels=labels, want_top5=False)
+        correct += r["correct"]
+        total += batch_size
+        n_batches += 1
+    if n_batches == 0:
+        raise RuntimeError("train_model: empty dataloader")
+    if eng.world > 1:
+        torch.distributed.all_reduce(loss_acc)
+    publish_optimizer_state(eeg_model, optimizer if eng.fused else None)
+    average_loss = float(loss_acc[0].item()) / n_batches
+    accuracy = int(correct.item()) / total
+    return average_loss, accuracy, torch.cat(features_list, dim=0)
+
+
+def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, config):
+    """k-way zero-shot retrieval.  Returns (average_loss, accuracy, top5_acc) like ATMS_retrieval.py:258-362.
+    The candidate sets are drawn with the same ``random.sample`` calls, in the same order, as the reference."""
+    eeg_model.eval()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("evaluate_model: this implementation runs on CUDA only (no CPU fallback)")
+    if k not in (2, 4, 10, 50, 100, 200):
+        print("Error.")
+    text_features_all = text_features_all.to(device).float()
+    img_features_all = img_features_all.to(device).float().contiguous()
+    n_cls = text_features_all.size(0)
+    all_labels = set(range(n_cls))
+    alpha = 0.99
+    nce = _InfoNCE()
+    total_loss = torch.zeros(3, device=device)
+    correct = 0
+    top5_correct_count = 0
+    total = 0
+    n_batches = 0
+    subject_id = extract_id_from_string(sub)
+    pend = []
+    with torch.no_grad():
+        for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
+            eeg_data = eeg_data.to(device)
+            text_features = text_features.to(device).float()
+            img_features = img_features.to(device).float()
+            batch_size = eeg_data.size(0)
+            subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
+            eeg_features = eeg_model.encode(eeg_data, subject_ids, train=False)
+            loss, _, _ = fused_contrastive(nce, eeg_features, img_features.contiguous(), text_features.contiguous(),
+                                           eeg_model.logit_scale.detach(), alpha, need_grad=False)
+            total_loss += loss
+            n_batches += 1
+            # host side: the reference's per-sample candidate draw (:297-300; for k in {50,100} it draws twice, :323-325)
+            label_list = labels.tolist()
+            sel_rows = []
+            for label in label_list:
+                possible_classes = list(all_labels - {label})
+                selected_classes = random.sample(possible_classes, k - 1) + [label]
+                if k == 50 or k == 100:
+                    random.sample(possible_classes, k - 1)   # second draw only consumes RNG: the features were already gathered
+                sel_rows.append(selected_classes)
+            pend.append((eeg_features, torch.tensor(sel_rows, dtype=torch.int32), label_list))
+        for eeg_features, sel, label_list in pend:
+            r = _lib.retrieval(eeg_features, img_features_all, eeg_model.logit_scale.detach(), sel=sel,
+                               want_top5=(k >= 50))
+            top1 = r["top1"].tolist()
+            top5 = r["top5"].tolist() if k >= 50 else None
+            sel_l = sel.tolist()
+            for i, label in enumerate(label_list):
+                if sel_l[i][top1[i]] == label:
+                    correct += 1
+                if top5 is not None and label in [sel_l[i][j] for j in top5[i] if j >= 0]:
+                    top5_correct_count += 1
+                total += 1
+    average_loss = float(total_loss[0].item()) / max(n_batches, 1)
+    accuracy = correct / total
+    top5_acc = top5_correct_count / total
+    return average_loss, accuracy, top5_acc
+
+
+def main_train_loop(sub, current_time, eeg_model, train_dataloader, test_dataloader, optimizer, device,
+                    text_features_train_all, text_features_test_all, img_features_train_all, img_features_test_all,
+                    config, logger=None):
+    """epoch loop of ATMS_retrieval.py:364-512 without the plotting / wandb side effects (``logger`` is any object
+    with ``log(dict)``; checkpoints are the caller's business: ``eeg_model.state_dict()`` is reference-compatible)."""
+    results = []
+    for epoch in range(config.epochs):
+        train_loss, train_accuracy, _ = train_model(sub, eeg_model, train_dataloader, optimizer, device,
+                                                    text_features_train_all, img_features_train_all, config=config)
+        ev = {}
+        for k in (200, 2, 4, 10, 50, 100):
+            ev[k] = evaluate_model(sub, eeg_model, test_dataloader, device, text_features_test_all,
+                                   img_features_test_all, k=k, config=config)
+        test_loss, test_accuracy, top5_acc = ev[200]
+        epoch_results = {
+            "epoch": epoch + 1, "test_loss": test_loss, "test_accuracy": test_accuracy, "v2_acc": ev[2][1],
+            "v4_acc": ev[4][1], "v10_acc": ev[10][1], "top5_acc": top5_acc, "v50_acc": ev[50][1],
+            "v100_acc": ev[100][1], "v50_top5_acc": ev[50][2], "v100_top5_acc": ev[100][2],
+        }
+        results.append(epoch_results)
+        if logger is not None and hasattr(logger, "log"):
+            logger.log({"Train Loss": train_loss, "Train Accuracy": train_accuracy, "Test Loss": test_loss,
+                        "Test Accuracy": test_accuracy, "v2 Accuracy": ev[2][1], "v4 Accuracy": ev[4][1],
+                        "v10 Accuracy": ev[10][1], "Epoch": epoch})
+        print(f"Epoch {epoch + 1}/{config.epochs} - Train Loss: {train_loss:.4f}, Train Accuracy: {train_accuracy:.4f}, "
+              f"Test Loss: {test_loss:.4f}, Test Accuracy: {test_accuracy:.4f}, Top5 Accuracy: {top5_acc:.4f}")
+    return results

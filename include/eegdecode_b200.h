@@ -58,6 +58,122 @@ int eegb200_gemm(const eegb200_gemm_desc* d, void* stream);
  * out[r*cols + c].  Lets the tests feed the library's own masks to the oracle. */
 int eegb200_dropout_mask(uint64_t seed, uint32_t site, float p, int rows, int cols, int ld, float* out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * ATM-S encoder  (replaces ATMS.forward, Retrieval/ATMS_retrieval.py:182-191, and its autograd graph)
+ * ------------------------------------------------------------------------------------------------ */
+/* trainable tensors, in the reference state_dict layouts */
+enum eegb200_param {
+  EEGB200_P_VALUE_W = 0,  /* encoder.enc_embedding.value_embedding.weight            [250,250] */
+  EEGB200_P_VALUE_B,      /* ...value_embedding.bias                                  [250]     */
+  EEGB200_P_SUBJ_TABLE,   /* ...subject_embedding.subject_embedding.weight            [n_subj,250] */
+  EEGB200_P_SUBJ_SHARED,  /* ...subject_embedding.shared_embedding                    [1,250]   */
+  EEGB200_P_WQ, EEGB200_P_BQ,   /* attention.query_projection  [248,250],[248] */
+  EEGB200_P_WK, EEGB200_P_BK,   /* attention.key_projection */
+  EEGB200_P_WV, EEGB200_P_BV,   /* attention.value_projection */
+  EEGB200_P_WO, EEGB200_P_BO,   /* attention.out_projection    [250,248],[250] */
+  EEGB200_P_W1, EEGB200_P_B1,   /* attn_layers.0.conv1         [256,250,1],[256] */
+  EEGB200_P_W2, EEGB200_P_B2,   /* attn_layers.0.conv2         [250,256,1],[250] */
+  EEGB200_P_LN1_G, EEGB200_P_LN1_B,   /* attn_layers.0.norm1 */
+  EEGB200_P_LN2_G, EEGB200_P_LN2_B,   /* attn_layers.0.norm2 */
+  EEGB200_P_LNF_G, EEGB200_P_LNF_B,   /* encoder.encoder.norm */
+  EEGB200_P_WT, EEGB200_P_BT,         /* enc_eeg.0.tsconv.0  [40,1,1,25],[40] */
+  EEGB200_P_BN1_G, EEGB200_P_BN1_B,   /* enc_eeg.0.tsconv.2 */
+  EEGB200_P_WS, EEGB200_P_BS,         /* enc_eeg.0.tsconv.4  [40,40,63,1],[40] */
+  EEGB200_P_BN2_G, EEGB200_P_BN2_B,   /* enc_eeg.0.tsconv.5 */
+  EEGB200_P_WC, EEGB200_P_BC,         /* enc_eeg.0.projection.0 [40,40,1,1],[40] */
+  EEGB200_P_WP1, EEGB200_P_BP1,       /* proj_eeg.0          [1024,1440],[1024] */
+  EEGB200_P_WP2, EEGB200_P_BP2,       /* proj_eeg.1.fn.1     [1024,1024],[1024] */
+  EEGB200_P_LNP_G, EEGB200_P_LNP_B,   /* proj_eeg.2 */
+  EEGB200_P_COUNT
+};
+/* non-trainable buffers */
+enum eegb200_buffer {
+  EEGB200_BUF_PE = 0,     /* position_embedding.pe [1,5000,250] (rows 0..62 used) */
+  EEGB200_BUF_BN1_RM, EEGB200_BUF_BN1_RV,   /* tsconv.2.running_mean / running_var [40] */
+  EEGB200_BUF_BN2_RM, EEGB200_BUF_BN2_RV,   /* tsconv.5.* */
+  EEGB200_BUF_COUNT
+};
+/* dropout sites; dropout_p[site] overrides the reference probabilities (0.25 x5, 0.5, 0.5) */
+enum eegb200_dropout_site {
+  EEGB200_SITE_EMBED = 1, EEGB200_SITE_ATTN = 2, EEGB200_SITE_RES1 = 3, EEGB200_SITE_FFN1 = 4,
+  EEGB200_SITE_FFN2 = 5, EEGB200_SITE_CONV = 6, EEGB200_SITE_PROJ = 7, EEGB200_SITE_COUNT = 8
+};
+/* phases: the forward (backward) is cut where train-mode BatchNorm needs batch statistics, so that a
+ * data-parallel caller can all-reduce the 80 doubles between phases (SyncBN); single GPU: mask 7. */
+#define EEGB200_PHASE_A 1
+#define EEGB200_PHASE_B 2
+#define EEGB200_PHASE_C 4
+#define EEGB200_PHASE_ALL 7
+/* bits 8..15 of the phase mask: number of ranks whose BatchNorm sums were all-reduced into the workspace
+ * (0/1 = local statistics).  The element count used for mean/var becomes world*B*... */
+#define EEGB200_SYNCBN_WORLD(w) (((w) & 0xFF) << 8)
+
+typedef struct eegb200_atms_io {
+  const float* const* params;    /* [EEGB200_P_COUNT] device pointers */
+  float* const* buffers;         /* [EEGB200_BUF_COUNT] */
+  const float* x;                /* [B,63,250] */
+  const int64_t* subject_ids;    /* [B] */
+  int B;
+  int n_subjects;                /* rows of the subject table (10) */
+  int train;                     /* nn.Module.train(): batch-stat BatchNorm + dropout */
+  int update_running_stats;
+  uint64_t seed;                 /* dropout seed of this step (the backward must get the same value) */
+  const float* dropout_p;        /* host float[EEGB200_SITE_COUNT] or NULL for the reference values */
+  void* workspace;               /* >= eegb200_atms_workspace_bytes(B); holds the saved activations */
+  size_t workspace_bytes;
+  float* out;                    /* [B,1024] */
+} eegb200_atms_io;
+
+size_t eegb200_atms_workspace_bytes(int B);
+int eegb200_atms_forward(const eegb200_atms_io* io, int phase_mask, void* stream);
+/* grads[i] += d loss / d params[i] (caller zeroes; NULL entries are skipped where legal).
+ * Needs the workspace of the matching forward (train mode). */
+int eegb200_atms_backward(const eegb200_atms_io* io, const float* d_out, float* const* grads, int phase_mask, void* stream);
+/* intermediates inside the workspace, for stage-level parity tests and SyncBN exchange.
+ * name: "h0","qkv","attn_o","x1","ffn_u","x3","y1","a1","y2","feat","z1","z2",
+ *       "bn1_sums","bn2_sums","bn1_bwd_sums","bn2_bwd_sums" (the last four are double[80]). */
+int eegb200_atms_ws_tensor(void* workspace, int B, const char* name, void** ptr, int* rows, int* cols, int* ld);
+
+/* ------------------------------------------------------------------------------------------------
+ * Contrastive loss (replaces ClipLoss.forward, models/loss.py:100-141, called twice per step at
+ * ATMS_retrieval.py:229-230 and mixed 0.99/0.01 at :234).  Row block of this rank against the
+ * global target matrix; never builds the N x N problem more than B x N per rank.
+ * Phase A: logits + row/column statistics.  Between the phases a multi-GPU caller all-gathers
+ * `col_stats` ([2][n_targets*N]: running max, sum) from every rank.  Phase B: loss share + grads.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct eegb200_infonce_io {
+  const float* eeg;            /* [B,D] local embeddings (first ClipLoss argument) */
+  const float* tgt_img;        /* [N,D] global targets */
+  const float* tgt_txt;        /* [N,D] or NULL (single ClipLoss) */
+  int B, N, D, row_offset;     /* row_offset = rank*B */
+  const float* logit_scale;    /* device scalar, used RAW like the reference (no exp) */
+  float w_img, w_txt;          /* 0.99 / 0.01 */
+  float grad_out;              /* upstream d(total)/d(loss) */
+  void* workspace; size_t workspace_bytes;   /* >= eegb200_infonce_workspace_bytes */
+  float* col_stats;            /* out (phase A): [2][nt*N] local (max,sum) per column */
+  const float* col_parts;      /* in (phase B): [n_parts][2][nt*N]; NULL -> use col_stats, n_parts=1 */
+  int n_parts;
+  float* loss;                 /* out (phase B): [3] = mix, img, txt shares of this rank (sum over ranks = loss) */
+  float* d_eeg;                /* out (phase B): [B,D], may be NULL */
+  float* d_logit_scale;        /* += (phase B), device scalar, may be NULL */
+} eegb200_infonce_io;
+size_t eegb200_infonce_workspace_bytes(int B, int N, int D, int n_targets);
+int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
+
+/* scores = logit_scale * eeg @ gallery^T into logits_ws [Q, ld >= G rounded up to 4]; optional argmax
+ * count against labels (train accuracy, ATMS_retrieval.py:241-250), top-1 / top-5 indices
+ * (evaluate_model, :306-320).  `sel` (int32 [Q,k] or NULL) restricts each query to its own candidate
+ * list: results are positions into that list. */
+int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int D, const float* logit_scale,
+                      float* logits_ws, int ld, void* round_ws /* (Q+G)*D floats */,
+                      const int32_t* sel, int k, float* sel_ws /* [Q,k] */,
+                      const int64_t* labels, int* correct, int64_t* top1, int32_t* top5, void* stream);
+
+/* torch.optim.AdamW semantics on a flat arena (ATMS_retrieval.py:548, :237) */
+int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
