@@ -278,3 +278,14 @@ def retrieval(eeg, gallery, logit_scale, sel=None, labels=None, want_top5=True):
                                    ld, ptr(round_ws), ptr(sel), k, ptr(sel_ws), ptr(labels), ptr(correct), ptr(top1),
                                    ptr(top5), stream_ptr()), "retrieval")
     return {"top1": top1, "top5": top5, "correct": correct, "logits": logits[:, :G]}
+
+
+def prof_enable(on: bool) -> None:
+    lib().eegb200_prof_enable(int(on))
+
+
+def prof_report() -> dict:
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().eegb200_prof_report(buf, ctypes.c_size_t(len(buf))), "prof_report")
+    return json.loads(buf.value.decode())

@@ -18,6 +18,13 @@ int eegb200_set_gemm_backend(int backend) {
   return 0;
 }
 int eegb200_get_gemm_backend(void) { return gemm_get_backend(); }
+int eegb200_prof_enable(int on) { prof_enable(on); return 0; }
+int eegb200_prof_report(char* buf, size_t cap) {
+  EEG_REQUIRE(buf && cap > 2, "prof_report: bad buffer");
+  int rc = prof_report(buf, cap);
+  EEG_REQUIRE(rc == 0, "prof_report: buffer too small");
+  return 0;
+}
 
 int eegb200_gemm(const eegb200_gemm_desc* d, void* stream) {
   EEG_REQUIRE(d != nullptr, "null gemm desc");
@@ -104,9 +111,9 @@ int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream) 
   const float w_img = io->w_img, w_txt = nt == 2 ? io->w_txt : 0.f;
 
   if (phase_mask & EEGB200_PHASE_A) {
-    EEG_TRY(pad_copy(io->eeg, io->D, io->B, io->D, w.E_r, io->D, io->B, 1, 1.f, s));
-    EEG_TRY(pad_copy(io->tgt_img, io->D, io->N, io->D, w.T_r, io->D, io->N, 1, 1.f, s));
-    if (nt == 2) EEG_TRY(pad_copy(io->tgt_txt, io->D, io->N, io->D, w.T_r + (size_t)io->N * io->D, io->D, io->N, 1, 1.f, s));
+    EEG_TRY(pad_copy(io->eeg, io->D, io->B, io->D, w.E_r, io->D, io->B, tf32_rounding(), 1.f, s));
+    EEG_TRY(pad_copy(io->tgt_img, io->D, io->N, io->D, w.T_r, io->D, io->N, tf32_rounding(), 1.f, s));
+    if (nt == 2) EEG_TRY(pad_copy(io->tgt_txt, io->D, io->N, io->D, w.T_r + (size_t)io->N * io->D, io->D, io->N, tf32_rounding(), 1.f, s));
     GemmArgs g;
     g.M = io->B; g.N = w.ncol; g.K = io->D;
     g.A = {w.E_r, io->D, 0};

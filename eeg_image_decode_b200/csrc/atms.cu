@@ -113,28 +113,28 @@ static size_t carve(void* base, int B, Ws* w) {
 // weight packing (TF32-rounded, zero-padded GEMM operands) and gradient unpacking
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_qkv_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
-                                float* __restrict__ out) {
+                                float* __restrict__ out, int rt) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 768 * 256) return;
   const int row = idx >> 8, c = idx & 255;
   const int which = row >> 8, hh = (row & 255) >> 6, e = row & 63;
   const float* w = which == 0 ? wq : (which == 1 ? wk : wv);
-  out[idx] = (e < D_HEAD && c < N_T) ? tf32_rn(w[(hh * D_HEAD + e) * N_T + c]) : 0.f;
+  out[idx] = (e < D_HEAD && c < N_T) ? tf32_if(w[(hh * D_HEAD + e) * N_T + c], rt) : 0.f;
 }
-__global__ void pack_wo_kernel(const float* __restrict__ wo, float* __restrict__ out) {
+__global__ void pack_wo_kernel(const float* __restrict__ wo, float* __restrict__ out, int rt) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 256 * 256) return;
   const int o = idx >> 8, c = idx & 255;
   const int hh = c >> 6, e = c & 63;
-  out[idx] = (o < N_T && e < D_HEAD) ? tf32_rn(wo[o * (N_HEAD * D_HEAD) + hh * D_HEAD + e]) : 0.f;
+  out[idx] = (o < N_T && e < D_HEAD) ? tf32_if(wo[o * (N_HEAD * D_HEAD) + hh * D_HEAD + e], rt) : 0.f;
 }
 // tsconv.4.weight [k2][k1][r] -> [k2][r*40 + k1]
-__global__ void pack_ws_kernel(const float* __restrict__ ws, float* __restrict__ out) {
+__global__ void pack_ws_kernel(const float* __restrict__ ws, float* __restrict__ out, int rt) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N_FILT * K_SPAT) return;
   const int k2 = idx / K_SPAT, kk = idx % K_SPAT;
   const int r = kk / N_FILT, k1 = kk % N_FILT;
-  out[idx] = tf32_rn(ws[(k2 * N_FILT + k1) * N_CH + r]);
+  out[idx] = tf32_if(ws[(k2 * N_FILT + k1) * N_CH + r], rt);
 }
 __global__ void pack_small_kernel(const float* __restrict__ bv, const float* __restrict__ pe, const float* __restrict__ bq,
                                   const float* __restrict__ bk, const float* __restrict__ bvv,
@@ -187,14 +187,16 @@ __global__ void unpack_ws_grad_kernel(const float* __restrict__ dw_p, float* dws
 }
 
 static int pack_weights(const float* const* P, float* const* BUF, const Ws& w, cudaStream_t s) {
-  EEG_TRY(pad_copy(P[EEGB200_P_VALUE_W], N_T, N_T, N_T, w.Wv_p, 256, 256, 1, 1.f, s));
-  pack_qkv_kernel<<<768, 256, 0, s>>>(P[EEGB200_P_WQ], P[EEGB200_P_WK], P[EEGB200_P_WV], w.Wqkv_p);
-  pack_wo_kernel<<<256, 256, 0, s>>>(P[EEGB200_P_WO], w.Wo_p);
-  EEG_TRY(pad_copy(P[EEGB200_P_W1], N_T, D_FF, N_T, w.W1_p, 256, 256, 1, 1.f, s));
-  EEG_TRY(pad_copy(P[EEGB200_P_W2], D_FF, N_T, D_FF, w.W2_p, 256, 256, 1, 1.f, s));
-  pack_ws_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(P[EEGB200_P_WS], w.Ws_p);
-  EEG_TRY(pad_copy(P[EEGB200_P_WP1], D_FEAT, D_OUT, D_FEAT, w.Wp1_r, D_FEAT, D_OUT, 1, 1.f, s));
-  EEG_TRY(pad_copy(P[EEGB200_P_WP2], D_OUT, D_OUT, D_OUT, w.Wp2_r, D_OUT, D_OUT, 1, 1.f, s));
+  const int RT = tf32_rounding();
+  ProfScope _ps("pack_weights", s, 0.0, 3.2e6 * 8.0);
+  EEG_TRY(pad_copy(P[EEGB200_P_VALUE_W], N_T, N_T, N_T, w.Wv_p, 256, 256, RT, 1.f, s));
+  pack_qkv_kernel<<<768, 256, 0, s>>>(P[EEGB200_P_WQ], P[EEGB200_P_WK], P[EEGB200_P_WV], w.Wqkv_p, RT);
+  pack_wo_kernel<<<256, 256, 0, s>>>(P[EEGB200_P_WO], w.Wo_p, RT);
+  EEG_TRY(pad_copy(P[EEGB200_P_W1], N_T, D_FF, N_T, w.W1_p, 256, 256, RT, 1.f, s));
+  EEG_TRY(pad_copy(P[EEGB200_P_W2], D_FF, N_T, D_FF, w.W2_p, 256, 256, RT, 1.f, s));
+  pack_ws_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(P[EEGB200_P_WS], w.Ws_p, RT);
+  EEG_TRY(pad_copy(P[EEGB200_P_WP1], D_FEAT, D_OUT, D_FEAT, w.Wp1_r, D_FEAT, D_OUT, RT, 1.f, s));
+  EEG_TRY(pad_copy(P[EEGB200_P_WP2], D_OUT, D_OUT, D_OUT, w.Wp2_r, D_OUT, D_OUT, RT, 1.f, s));
   pack_small_kernel<<<64, 256, 0, s>>>(P[EEGB200_P_VALUE_B], BUF[EEGB200_BUF_PE], P[EEGB200_P_BQ], P[EEGB200_P_BK],
                                         P[EEGB200_P_BV], P[EEGB200_P_BO], P[EEGB200_P_B1], P[EEGB200_P_B2], w.tokbias,
                                         w.bqkv_p, w.bo_p, w.b1_p, w.b2_p);
@@ -274,6 +276,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
   const int M = B * N_TOK;
   const int R = B * N_POOL;
   const Cfg cfg = make_cfg(io);
+  const int RT = tf32_rounding();
   const int train = io->train != 0;
   const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;   // SyncBN: statistics cover wmul*B samples
 
@@ -285,11 +288,11 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
       Epilogue e = epi_out(w.H0, 256);
       e.bias = w.tokbias; e.bias_period = 64; e.ld_bias = 256;
       e.drop = cfg.d[EEGB200_SITE_EMBED]; e.drop_ld = 256;
-      e.round_tf32 = 1;
+      e.round_tf32 = RT;
       EEG_TRY(run_gemm(M, 256, 256, w.Xp, 256, 0, w.Wv_p, 256, 0, e, 1, s));
     }
     EEG_TRY(subject_token(reinterpret_cast<const long long*>(io->subject_ids), P[EEGB200_P_SUBJ_TABLE],
-                          P[EEGB200_P_SUBJ_SHARED], io->n_subjects, w.flag, w.H0, B, cfg.d[EEGB200_SITE_EMBED], 1, s));
+                          P[EEGB200_P_SUBJ_SHARED], io->n_subjects, w.flag, w.H0, B, cfg.d[EEGB200_SITE_EMBED], RT, s));
     // ---- AttentionLayer (SelfAttention_Family.py:194-213) ----
     {
       Epilogue e = epi_out(w.QKV, 768);
@@ -305,7 +308,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
       EEG_TRY(run_gemm(M, 256, 256, w.O, 256, 0, w.Wo_p, 256, 0, e, 1, s));
     }
     EEG_TRY(layernorm_fwd(w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr, nullptr,
-                          w.X1, 256, 1, s));
+                          w.X1, 256, RT, s));
     // ---- position-wise FFN (Transformer_EncDec.py:48-51) ----
     {
       Epilogue e = epi_out(w.Hf, 256);
@@ -313,7 +316,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
       e.aux_out = w.U; e.ld_aux = 256;
       e.act = EPI_ACT_GELU;
       e.drop = cfg.d[EEGB200_SITE_FFN1]; e.drop_ld = 256;
-      e.round_tf32 = 1;
+      e.round_tf32 = RT;
       EEG_TRY(run_gemm(M, 256, 256, w.X1, 256, 0, w.W1_p, 256, 0, e, 1, s));
     }
     {
@@ -333,7 +336,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
   if (phases & EEGB200_PHASE_B) {
     BnState bn1{w.bn1_sums, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], BUF[EEGB200_BUF_BN1_RM], BUF[EEGB200_BUF_BN1_RV]};
     EEG_TRY(bn_finalize(bn1, wmul * B * N_CH * N_POOL, train, train && io->update_running_stats, s));
-    EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, 1, s));
+    EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
     {
       Epilogue e = epi_out(w.Y2, N_FILT);        // spatial conv (63,1) == GEMM over (r,k1)  (ATMS_retrieval.py:106)
       e.bias = P[EEGB200_P_BS];
@@ -355,7 +358,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
       e.bias = P[EEGB200_P_BP1];
       e.aux_out = w.Z1; e.ld_aux = D_OUT;
       e.act = EPI_ACT_GELU;
-      e.round_tf32 = 1;
+      e.round_tf32 = RT;
       EEG_TRY(run_gemm(B, D_OUT, D_FEAT, w.feat, D_FEAT, 0, w.Wp1_r, D_FEAT, 0, e, 1, s));
     }
     {
@@ -386,6 +389,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
   const int M = B * N_TOK;
   const int R = B * N_POOL;
   const Cfg cfg = make_cfg(io);
+  const int RT = tf32_rounding();
   const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;
 
   if (phases & EEGB200_PHASE_A) {
@@ -393,7 +397,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     // ---- Proj_eeg backward ----
     EEG_TRY(layernorm_bwd(d_out, D_OUT, w.Z2, D_OUT, B, D_OUT, P[EEGB200_P_LNP_G], P[EEGB200_P_LNP_B], w.stp, nullptr,
                           nullptr, w.dZ2, D_OUT, GR[EEGB200_P_LNP_G], GR[EEGB200_P_LNP_B], nullptr, nullptr, 0, s));
-    EEG_TRY(dropout_apply(w.dZ2, w.dZ2d, B, D_OUT, cfg.d[EEGB200_SITE_PROJ], 1, s));
+    EEG_TRY(dropout_apply(w.dZ2, w.dZ2d, B, D_OUT, cfg.d[EEGB200_SITE_PROJ], RT, s));
     EEG_TRY(colsum(w.dZ2d, D_OUT, B, D_OUT, GR[EEGB200_P_BP2], 0, 0, s));
     EEG_TRY(run_gemm(D_OUT, D_OUT, B, w.dZ2d, D_OUT, 1, w.G, D_OUT, 1, epi_wgrad(GR[EEGB200_P_WP2], D_OUT),
                      pick_split(D_OUT, D_OUT, B), s));
@@ -401,7 +405,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       Epilogue e = epi_out(w.dZ1, D_OUT);        // dZ1 = dZ2 + (dZ2d . Wp2) * GELU'(Z1)
       e.mul_in = w.Z1; e.ld_mul = D_OUT;
       e.resid = w.dZ2; e.ld_res = D_OUT;
-      e.round_tf32 = 1;
+      e.round_tf32 = RT;
       EEG_TRY(run_gemm(B, D_OUT, D_OUT, w.dZ2d, D_OUT, 0, w.Wp2_r, D_OUT, 1, e, 1, s));
     }
     EEG_TRY(colsum(w.dZ1, D_OUT, B, D_OUT, GR[EEGB200_P_BP1], 0, 0, s));
@@ -415,7 +419,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
   }
   if (phases & EEGB200_PHASE_B) {
     EEG_TRY(bn_bwd_apply(w.dz2, w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], w.bn2_bsums, wmul * R, w.dY2, GR[EEGB200_P_BN2_G],
-                         GR[EEGB200_P_BN2_B], (long long)R * N_FILT, 1, 1.f / (float)wmul, s));
+                         GR[EEGB200_P_BN2_B], (long long)R * N_FILT, RT, 1.f / (float)wmul, s));
     EEG_TRY(colsum(w.dY2, N_FILT, R, N_FILT, GR[EEGB200_P_BS], 0, 0, s));
     // dWs[k2][(r,k1)] = sum_{(b,j)} dY2[(b,j)][k2] * A1[(b,j)][(r,k1)]
     EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), s));
@@ -438,14 +442,14 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                           P[EEGB200_P_LNF_G], w.stf, w.dR2, 256, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B],
                           GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
     // ---- FFN ----
-    EEG_TRY(dropout_apply(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], 1, s));
+    EEG_TRY(dropout_apply(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, s));
     EEG_TRY(colsum(w.T1, 256, M, N_T, GR[EEGB200_P_B2], 0, 0, s));
     EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), s));
     {
       Epilogue e = epi_out(w.dU, 256);           // dU = dropout_ffn1(T1 . W2) * GELU'(U)
       e.drop = cfg.d[EEGB200_SITE_FFN1]; e.drop_ld = 256;
       e.mul_in = w.U; e.ld_mul = 256;
-      e.round_tf32 = 1;
+      e.round_tf32 = RT;
       EEG_TRY(run_gemm(M, 256, 256, w.T1, 256, 0, w.W2_p, 256, 1, e, 1, s));
     }
     EEG_TRY(colsum(w.dU, 256, M, D_FF, GR[EEGB200_P_B1], 0, 0, s));
@@ -459,7 +463,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     EEG_TRY(layernorm_bwd(w.dX1, 256, w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr,
                           w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
     // ---- attention ----
-    EEG_TRY(dropout_apply(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], 1, s));
+    EEG_TRY(dropout_apply(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, s));
     EEG_TRY(colsum(w.T2, 256, M, N_T, GR[EEGB200_P_BO], 0, 0, s));
     EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), s));
     EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), s));
@@ -480,7 +484,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       EEG_TRY(run_gemm(M, 256, 768, w.dQKV, 768, 0, w.Wqkv_p, 256, 1, e, 1, s));
     }
     // ---- DataEmbedding ----
-    EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], 1, s));
+    EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
     EEG_TRY(colsum(w.T3, 256, M, N_T, GR[EEGB200_P_VALUE_B], N_TOK, 0, s));   // token-0 rows carry no value embedding
     EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), s));
     EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,

@@ -49,7 +49,7 @@ __device__ __forceinline__ void softmax_row(const float* __restrict__ Q, const f
 }
 
 __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ o,
-                                                                    DropoutCfg drop) {
+                                                                    DropoutCfg drop, int rt) {
   extern __shared__ float sm[];
   float* Q = sm;
   float* K = Q + 64 * LDS;
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const float*
 #pragma unroll
   for (int ee = 0; ee < 16; ++ee) {
     const int e = ee * 4 + g;
-    orow[e] = e < D_HEAD ? tf32_rn(acc[ee]) : 0.f;
+    orow[e] = e < D_HEAD ? tf32_if(acc[ee], rt) : 0.f;
   }
 }
 
 __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const float* __restrict__ qkv,
                                                                     const float* __restrict__ d_o,
-                                                                    float* __restrict__ dqkv, DropoutCfg drop) {
+                                                                    float* __restrict__ dqkv, DropoutCfg drop, int rt) {
   extern __shared__ float sm[];
   float* Q = sm;
   float* K = Q + 64 * LDS;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const float*
 #pragma unroll
     for (int ee = 0; ee < 16; ++ee) {
       const int e = ee * 4 + g;
-      out[e] = e < D_HEAD ? tf32_rn(acc[ee]) : 0.f;
+      out[e] = e < D_HEAD ? tf32_if(acc[ee], rt) : 0.f;
     }
   }
   __syncthreads();
@@ -174,33 +174,35 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const float*
 #pragma unroll
     for (int ee = 0; ee < 16; ++ee) {
       const int e = ee * 4 + g;
-      oq[e] = e < D_HEAD ? tf32_rn(aq[ee]) : 0.f;
-      ok[e] = e < D_HEAD ? tf32_rn(ak[ee]) : 0.f;
+      oq[e] = e < D_HEAD ? tf32_if(aq[ee], rt) : 0.f;
+      ok[e] = e < D_HEAD ? tf32_if(ak[ee], rt) : 0.f;
     }
   }
 }
 
 int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("attention_fwd", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
   const size_t smem = 4 * 64 * LDS * sizeof(float);
   static bool configured = false;
   if (!configured) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attention_fwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, o, drop);
+  attention_fwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, o, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
 int attention_bwd(const float* qkv, const float* d_o, float* dqkv, int B, DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("attention_bwd", s, (double)B * 4 * 12.0 * 64 * 64 * 62, (double)B * 64 * 1792 * 4.0);
   const size_t smem = 5 * 64 * LDS * sizeof(float);
   static bool configured = false;
   if (!configured) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  attention_bwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, d_o, dqkv, drop);
+  attention_bwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, d_o, dqkv, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

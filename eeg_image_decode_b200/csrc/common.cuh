@@ -51,6 +51,7 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+__device__ __forceinline__ float tf32_if(float x, int on) { return on ? tf32_rn(x) : x; }
 __device__ __forceinline__ float gelu_exact(float x) {   // F.gelu default (erf form)
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

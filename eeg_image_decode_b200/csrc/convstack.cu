@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_fwd_kernel(const flo
   }
 }
 int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s) {
+  ProfScope _ps("conv_temporal_fwd", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * (63 * 1000.0 + 36 * 2520 * 4.0));
   conv_temporal_fwd_kernel<<<B, CT_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -93,6 +94,7 @@ __global__ void bn_finalize_kernel(BnState bn, long long count, int train, int u
   }
 }
 int bn_finalize(BnState bn, long long count, int train, int update_running, cudaStream_t s) {
+  ProfScope _ps("bn_finalize", s);
   bn_finalize_kernel<<<1, 64, 0, s>>>(bn, count, train, update_running);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -123,6 +125,7 @@ __global__ void bn_elu_apply_kernel(const float4* __restrict__ y, const float* _
 }
 int bn_elu_apply(const float* y, const float* mean_rstd, const float* gamma, const float* beta, float* a, long long n,
                  int round_tf, cudaStream_t s) {
+  ProfScope _ps("bn_elu_apply", s, 0.0, (double)n * 8.0);
   const long long n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -154,6 +157,7 @@ __global__ void colstats_kernel(const float* __restrict__ y, int ld, int rows, i
   }
 }
 int colstats(const float* y, int ld, int rows, int cols, double* sums, cudaStream_t s) {
+  ProfScope _ps("colstats", s, 0.0, (double)rows * cols * 4.0);
   EEG_REQUIRE(cols <= 64, "colstats: cols %d > 64", cols);
   int blocks = cdiv(rows, 4 * 16);
   if (blocks > 148 * 2) blocks = 148 * 2;
@@ -168,7 +172,7 @@ int colstats(const float* y, int ld, int rows, int cols, double* sums, cudaStrea
 __global__ void conv_head_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ mean_rstd,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ feat,
-                                     int rows, DropoutCfg drop) {
+                                     int rows, DropoutCfg drop, int rt) {
   __shared__ float a2[N_FILT];
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int k = threadIdx.x;
@@ -183,16 +187,17 @@ __global__ void conv_head_fwd_kernel(const float* __restrict__ y2, const float* 
       float acc = bc[k];
 #pragma unroll 8
       for (int c = 0; c < N_FILT; ++c) acc = fmaf(wc[k * N_FILT + c], a2[c], acc);
-      feat[(size_t)row * N_FILT + k] = tf32_rn(acc);
+      feat[(size_t)row * N_FILT + k] = tf32_if(acc, rt);
     }
     __syncthreads();
   }
 }
 int conv_head_fwd(const float* y2, const float* mean_rstd, const float* gamma, const float* beta, const float* wc,
                   const float* bc, float* feat, int B, DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("conv_head_fwd", s, (double)B * 36 * 3200.0, (double)B * 36 * 320.0);
   const int rows = B * N_POOL;
   int blocks = rows < 148 * 32 ? rows : 148 * 32;
-  conv_head_fwd_kernel<<<blocks, 64, 0, s>>>(y2, mean_rstd, gamma, beta, wc, bc, feat, rows, drop);
+  conv_head_fwd_kernel<<<blocks, 64, 0, s>>>(y2, mean_rstd, gamma, beta, wc, bc, feat, rows, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -255,6 +260,7 @@ __global__ void __launch_bounds__(256) conv_head_bwd_kernel(const float* __restr
 int conv_head_bwd(const float* dfeat, const float* y2, const float* mean_rstd, const float* gamma, const float* beta,
                   const float* wc, float* dz2, float* dwc, float* dbc, double* bwd_sums, int B, DropoutCfg drop,
                   cudaStream_t s) {
+  ProfScope _ps("conv_head_bwd", s, (double)B * 36 * 6400.0, (double)B * 36 * 480.0);
   const int rows = B * N_POOL;
   int blocks = rows < 148 * 2 ? rows : 148 * 2;
   conv_head_bwd_kernel<<<blocks, 256, 0, s>>>(dfeat, y2, mean_rstd, gamma, beta, wc, dz2, dwc, dbc, bwd_sums, rows, drop);
@@ -299,6 +305,7 @@ __global__ void bn_bwd_apply_kernel(const float4* __restrict__ dz, const float4*
 int bn_bwd_apply(const float* dz, const float* y, const float* mean_rstd, const float* gamma, const double* bwd_sums,
                  long long count, float* dy, float* dgamma, float* dbeta, long long n, int round_tf, float gscale,
                  cudaStream_t s) {
+  ProfScope _ps("bn_bwd_apply", s, 0.0, (double)n * 12.0);
   const long long n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -355,6 +362,7 @@ __global__ void __launch_bounds__(320) bn1_bwd_reduce_kernel(float4* __restrict_
 }
 int bn1_bwd_reduce(float* da1, const float* y1, const float* mean_rstd, const float* gamma, const float* beta,
                    double* bwd_sums, long long n, cudaStream_t s) {
+  ProfScope _ps("bn1_bwd_reduce", s, 0.0, (double)n * 12.0);
   const long long n4 = n / 4;
   // grid stride must keep the channel quad fixed: gridDim*320*4 % 40 == 0 holds for every gridDim
   int blocks = (int)((n4 + 319) / 320);
@@ -460,6 +468,7 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_bwd_kernel(
 int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
                       float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s) {
+  ProfScope _ps("conv_temporal_bwd", s, (double)B * 63 * 36 * 40 * 100.0, (double)B * (36 * 2520 * 8.0 + 63 * 2000.0));
   conv_temporal_bwd_kernel<<<B, CT_THREADS, 0, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt,
                                                     dgamma, dbeta, gscale);
   EEG_CUDA_OK(cudaGetLastError());

@@ -45,6 +45,8 @@ struct GemmArgs {
 };
 
 enum { GEMM_BACKEND_TCGEN05 = 0, GEMM_BACKEND_SIMT_FP32 = 1 };
+// 1 when GEMM operands should be pre-rounded to TF32 (tensor-core backend), 0 for the exact-fp32 verification backend
+int tf32_rounding();
 void gemm_set_backend(int backend);
 int gemm_get_backend();
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);           // dispatches on the backend switch
@@ -53,6 +55,20 @@ int gemm_launch_simt(const GemmArgs& g, cudaStream_t stream);
 long long gemm_launch_count();                                      // kernels launched so far (bench bookkeeping)
 void count_launch(int n = 1);
 long long total_launch_count();
+
+// ---- optional per-launch event profiler (bench.py's roofline leg; off by default) ----
+// ProfScope brackets the launches issued in its lifetime with CUDA events on `stream` when profiling is on.
+void prof_enable(int on);
+int prof_enabled();
+int prof_report(char* buf, size_t cap);   // JSON {"name": {"ms":..,"n":..,"flops":..,"bytes":..}, ...}; clears records
+struct ProfScope {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  ProfScope(const char* name, cudaStream_t stream, double flops = 0.0, double bytes = 0.0);
+  ~ProfScope();
+  const char* name_;
+  double flops_, bytes_;
+};
 
 // ---- epilogue math shared by both kernels ----
 __device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, float acc) {

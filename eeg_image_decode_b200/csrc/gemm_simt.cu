@@ -6,6 +6,11 @@
 #include <atomic>
 #include <stdarg.h>
 #include <string.h>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
 
 namespace eegb200 {
 
@@ -26,8 +31,72 @@ long long total_launch_count() { return g_launches.load(); }
 static std::atomic<int> g_backend{GEMM_BACKEND_TCGEN05};
 void gemm_set_backend(int b) { g_backend = b; }
 int gemm_get_backend() { return g_backend.load(); }
+int tf32_rounding() { return g_backend.load() == GEMM_BACKEND_TCGEN05 ? 1 : 0; }
+static const char* intern_name(const std::string& n);
 int gemm_launch(const GemmArgs& g, cudaStream_t stream) {
+  const char* nm = "gemm";
+  if (prof_enabled()) {
+    char tmp[128];
+    snprintf(tmp, sizeof(tmp), "gemm_tf32 M=%d N=%d K=%d %c%c%s", g.M, g.N, g.K, g.A.mn_major ? 'm' : 'k',
+             g.B.mn_major ? 'n' : 'k', g.split_k > 1 ? " splitK" : "");
+    nm = intern_name(tmp);
+  }
+  ProfScope _ps(nm, stream, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N));
   return g_backend.load() == GEMM_BACKEND_SIMT_FP32 ? gemm_launch_simt(g, stream) : gemm_launch_tcgen05(g, stream);
+}
+
+// ---------------- event profiler ----------------
+struct ProfRec { std::string name; cudaEvent_t a, b; double flops, bytes; };
+static std::atomic<int> g_prof{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+void prof_enable(int on) { g_prof = on; }
+int prof_enabled() { return g_prof.load(); }
+ProfScope::ProfScope(const char* name, cudaStream_t stream, double flops, double bytes)
+    : s(stream), name_(name), flops_(flops), bytes_(bytes) {
+  if (!g_prof.load()) return;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, s);
+}
+ProfScope::~ProfScope() {
+  if (!a) return;
+  cudaEventRecord(b, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_recs.push_back({name_, a, b, flops_, bytes_});
+}
+static const char* intern_name(const std::string& n) {
+  static std::set<std::string> names;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return names.insert(n).first->c_str();
+}
+int prof_report(char* buf, size_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_prof_recs) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg& g = agg[r.name];
+    g.ms += ms; g.n += 1; g.flops += r.flops; g.bytes += r.bytes;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof_recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char tmp[512];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"n\": %ld, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.ms, kv.second.n, kv.second.flops, kv.second.bytes);
+    out += tmp;
+    first = false;
+  }
+  out += "}";
+  if (out.size() + 1 > cap) return 4;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
 }
 
 // ---------------- kernel ----------------

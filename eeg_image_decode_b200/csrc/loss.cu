@@ -28,6 +28,7 @@ __global__ void infonce_row_lse_kernel(InfoNceArgs a, float* __restrict__ row_ls
   }
 }
 int infonce_row_lse(const InfoNceArgs& a, float* row_lse, float* diag, cudaStream_t s) {
+  ProfScope _ps("infonce_row_lse", s, 0.0, (double)a.B * a.nt * a.N * 4.0);
   const int warps = a.nt * a.B;
   infonce_row_lse_kernel<<<cdiv(warps * 32, 256), 256, 0, s>>>(a, row_lse, diag);
   EEG_CUDA_OK(cudaGetLastError());
@@ -73,6 +74,7 @@ int infonce_col_chunks(int B) {
   return chunks;
 }
 int infonce_col_partial(const InfoNceArgs& a, float* part_max, float* part_sum, cudaStream_t s) {
+  ProfScope _ps("infonce_col_partial", s, 0.0, (double)a.B * a.nt * a.N * 4.0);
   const int chunks = infonce_col_chunks(a.B);
   const int rpc = cdiv(a.B, chunks);
   dim3 grid(cdiv(a.nt * a.N, 32), chunks);
@@ -101,6 +103,7 @@ __global__ void infonce_col_reduce_kernel(const float* __restrict__ part_max, co
 }
 int infonce_col_reduce(const float* part_max, const float* part_sum, int n_parts, size_t stride, int n, float* out_max,
                        float* out_sum, float* out_lse, cudaStream_t s) {
+  ProfScope _ps("infonce_col_reduce", s);
   infonce_col_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part_max, part_sum, n_parts, stride, n, out_max, out_sum, out_lse);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -135,6 +138,7 @@ __global__ void infonce_loss_kernel(InfoNceArgs a, const float* __restrict__ row
 }
 int infonce_loss(const InfoNceArgs& a, const float* row_lse, const float* diag, const float* col_lse, float w_img,
                  float w_txt, float* loss_out, cudaStream_t s) {
+  ProfScope _ps("infonce_loss", s);
   infonce_loss_kernel<<<1, 1024, 0, s>>>(a, row_lse, diag, col_lse, w_img, w_txt, loss_out);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -143,7 +147,7 @@ int infonce_loss(const InfoNceArgs& a, const float* row_lse, const float* diag, 
 
 __global__ void infonce_grad_kernel(InfoNceArgs a, float* __restrict__ L, const float* __restrict__ row_lse,
                                     const float* __restrict__ col_lse, float w_img, float w_txt,
-                                    const float* __restrict__ scale_dev, float* __restrict__ dscale, float gout) {
+                                    const float* __restrict__ scale_dev, float* __restrict__ dscale, float gout, int rt) {
   __shared__ float red[32];
   const int ncol = a.nt * a.N;
   const long long total = (long long)a.B * ncol;
@@ -159,7 +163,7 @@ __global__ void infonce_grad_kernel(InfoNceArgs a, float* __restrict__ L, const 
     if (j == a.row_offset + i) g -= 2.f;
     g *= w;
     ds = fmaf(g, l, ds);
-    L[(size_t)i * a.ld + c] = tf32_rn(g);
+    L[(size_t)i * a.ld + c] = tf32_if(g, rt);
   }
   ds = warp_sum(ds);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
@@ -172,11 +176,12 @@ __global__ void infonce_grad_kernel(InfoNceArgs a, float* __restrict__ L, const 
 }
 int infonce_grad(const InfoNceArgs& a, float* logits_inout, const float* row_lse, const float* col_lse, float w_img,
                  float w_txt, const float* logit_scale_dev, float* dscale, float grad_out_scale, cudaStream_t s) {
+  ProfScope _ps("infonce_grad", s, 0.0, (double)a.B * a.nt * a.N * 8.0);
   const long long total = (long long)a.B * a.nt * a.N;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   infonce_grad_kernel<<<blocks, 256, 0, s>>>(a, logits_inout, row_lse, col_lse, w_img, w_txt, logit_scale_dev, dscale,
-                                             grad_out_scale);
+                                             grad_out_scale, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -210,6 +215,7 @@ __global__ void argmax_count_kernel(const float* __restrict__ logits, int ld, in
 }
 int argmax_count(const float* logits, int ld, int rows, int cols, const long long* labels, int* correct,
                  long long* pred_out, cudaStream_t s) {
+  ProfScope _ps("argmax_count", s, 0.0, (double)rows * cols * 4.0);
   argmax_count_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(logits, ld, rows, cols, labels, correct, pred_out);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -244,6 +250,7 @@ __global__ void topk5_kernel(const float* __restrict__ logits, int ld, int rows,
   }
 }
 int topk5(const float* logits, int ld, int rows, int cols, int* top5_out, cudaStream_t s) {
+  ProfScope _ps("topk5", s, 0.0, (double)rows * cols * 20.0);
   topk5_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(logits, ld, rows, cols, top5_out);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -260,6 +267,7 @@ __global__ void gather_cols_kernel(const float* __restrict__ logits, int ld, con
   }
 }
 int gather_cols(const float* logits, int ld, const int* sel, int Q, int k, float* out, cudaStream_t s) {
+  ProfScope _ps("gather_cols", s);
   const long long total = (long long)Q * k;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -271,19 +279,21 @@ int gather_cols(const float* logits, int ld, const int* sel, int Q, int k, float
 }
 
 // x = hi + lo with both parts exactly representable in TF32 (3xTF32 split: a.b ~ hi.hi + hi.lo + lo.hi)
-__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n,
+                                  int rt) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
-    const float h = tf32_rn(v);
+    const float h = tf32_if(v, rt);
     hi[i] = h;
-    lo[i] = tf32_rn(v - h);
+    lo[i] = tf32_if(v - h, rt);
   }
 }
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s) {
+  ProfScope _ps("split_tf32", s, 0.0, (double)n * 12.0);
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  split_tf32_kernel<<<blocks, 256, 0, s>>>(x, hi, lo, n);
+  split_tf32_kernel<<<blocks, 256, 0, s>>>(x, hi, lo, n, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -36,6 +36,7 @@ __global__ void adamw_tail_kernel(float* p, const float* g, float* m, float* v, 
 
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                float wd, int step, cudaStream_t s) {
+  ProfScope _ps("adamw", s, 0.0, (double)n * 28.0);
   EEG_REQUIRE(step >= 1, "adamw: step must start at 1");
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);

@@ -8,7 +8,7 @@ namespace eegb200 {
 // x (B,63,250) -> token matrix Xp [B*64, 256]: row b*64+0 = 0 (subject-token slot), rows 1..63 = channels,
 // columns 250..255 = 0; values rounded to TF32 (they only feed the value-embedding GEMM, Embed.py:146).
 // ------------------------------------------------------------------------------------------------
-__global__ void pad_input_kernel(const float* __restrict__ x, float* __restrict__ xp, int B) {
+__global__ void pad_input_kernel(const float* __restrict__ x, float* __restrict__ xp, int B, int rt) {
   const long long total = (long long)B * 64 * 64;   // float4 slots
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i & 63);
@@ -19,18 +19,19 @@ __global__ void pad_input_kernel(const float* __restrict__ x, float* __restrict_
     if (t > 0) {
       const float* src = x + (b * 63 + (t - 1)) * 250;
       const int c = c4 * 4;
-      if (c < 250) v.x = tf32_rn(src[c]);
-      if (c + 1 < 250) v.y = tf32_rn(src[c + 1]);
-      if (c + 2 < 250) v.z = tf32_rn(src[c + 2]);
-      if (c + 3 < 250) v.w = tf32_rn(src[c + 3]);
+      if (c < 250) v.x = tf32_if(src[c], rt);
+      if (c + 1 < 250) v.y = tf32_if(src[c + 1], rt);
+      if (c + 2 < 250) v.z = tf32_if(src[c + 2], rt);
+      if (c + 3 < 250) v.w = tf32_if(src[c + 3], rt);
     }
     reinterpret_cast<float4*>(xp)[i] = v;
   }
 }
 int pad_input(const float* x, float* xp, int B, cudaStream_t s) {
+  ProfScope _ps("pad_input", s, 0.0, (double)B * (63000.0 + 65536.0));
   const long long total = (long long)B * 64 * 64;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-  pad_input_kernel<<<blocks, 256, 0, s>>>(x, xp, B);
+  pad_input_kernel<<<blocks, 256, 0, s>>>(x, xp, B, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -62,6 +63,7 @@ __global__ void subject_token_kernel(const long long* __restrict__ ids, const fl
 }
 int subject_token(const long long* ids, const float* table, const float* shared_tok, int n_subj, int* flag, float* h0,
                   int B, DropoutCfg drop, int round_tf, cudaStream_t s) {
+  ProfScope _ps("subject_token", s, 0.0, (double)B * 2000.0);
   subject_flag_kernel<<<1, 256, 0, s>>>(ids, B, n_subj, flag);
   subject_token_kernel<<<B, 256, 0, s>>>(ids, table, shared_tok, flag, h0, B, drop, round_tf);
   EEG_CUDA_OK(cudaGetLastError());
@@ -84,6 +86,7 @@ __global__ void subject_token_bwd_kernel(const long long* __restrict__ ids, cons
 }
 int subject_token_bwd(const long long* ids, const int* flag, const float* dh0, float* dtable, float* dshared, int B,
                       DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("subject_token_bwd", s, 0.0, (double)B * 2000.0);
   subject_token_bwd_kernel<<<B, 256, 0, s>>>(ids, flag, dh0, dtable, dshared, B, drop);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -159,6 +162,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ld, int ro
 
 int layernorm_fwd(const float* x, int ld, int rows, int D, const float* g1, const float* b1, float* stats1,
                   const float* g2, const float* b2, float* stats2, float* y, int ld_out, int round_tf, cudaStream_t s) {
+  ProfScope _ps(D > 256 ? "layernorm_fwd_1024" : (g2 ? "layernorm2x_fwd" : "layernorm_fwd"), s, 0.0, (double)rows * (ld + ld_out) * 4.0);
   const int threads = 256;
   const int blocks = cdiv(rows * 32, threads);
   if (D <= 256 && ld_out <= 256)
@@ -277,6 +281,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, int ld_dy, co
 int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, int D, const float* g1, const float* b1,
                   const float* stats1, const float* g2, const float* stats2, float* dx, int ld_dx, float* dg1,
                   float* db1, float* dg2, float* db2, int round_tf, cudaStream_t s) {
+  ProfScope _ps(D > 256 ? "layernorm_bwd_1024" : (g2 ? "layernorm2x_bwd" : "layernorm_bwd"), s, 0.0, (double)rows * (ld_dy + ld + ld_dx) * 4.0);
   const int threads = 256;
   int blocks = cdiv(rows, threads / 32);
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -320,6 +325,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int
 }
 // cols <= 256 per launch slab; wider matrices are handled in column slabs
 int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s) {
+  ProfScope _ps("colsum", s, 0.0, (double)rows * cols * 4.0);
   for (int c0 = 0; c0 < cols; c0 += 256) {
     const int w = cols - c0 < 256 ? cols - c0 : 256;
     const int tx = (w + 31) / 32 * 32;
@@ -367,6 +373,7 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, int ld_src, int r
 }
 int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, int rows_dst, int round_tf,
              float scale, cudaStream_t s) {
+  ProfScope _ps("pad_copy", s, 0.0, (double)rows_dst * ld_dst * 8.0);
   const long long total = (long long)rows_dst * ld_dst;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -396,6 +403,7 @@ __global__ void dropout_apply_kernel(const float4* __restrict__ src, float4* __r
   }
 }
 int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, cudaStream_t s) {
+  ProfScope _ps("dropout_apply", s, 0.0, (double)rows * ld * 8.0);
   EEG_REQUIRE((ld & 3) == 0, "dropout_apply: ld %d not a multiple of 4", ld);
   const long long n4 = (long long)rows * ld / 4;
   int blocks = (int)((n4 + 255) / 256);

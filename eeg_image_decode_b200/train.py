@@ -167,8 +167,11 @@ def _BN_SCALE_SHIFT(world: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
-def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config):
-    """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254."""
+def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
+                step_callback=None):
+    """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254.
+    ``step_callback(step_index, loss_tensor[3])`` (optional, keyword only) is invoked after every step, e.g. to read
+    the loss back to the host like the reference does (:238)."""
     eeg_model.train()
     device = torch.device(device)
     if device.type != "cuda":
@@ -199,6 +202,8 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
         correct += r["correct"]
         total += batch_size
         n_batches += 1
+        if step_callback is not None:
+            step_callback(batch_idx, loss)
     if n_batches == 0:
         raise RuntimeError("train_model: empty dataloader")
     if eng.world > 1:

@@ -31,6 +31,10 @@ long long eegb200_launch_count(void);
 /* 0 = tcgen05 TF32 tensor-core GEMMs (product path), 1 = exact-fp32 SIMT verification GEMM (tests only) */
 int eegb200_set_gemm_backend(int backend);
 int eegb200_get_gemm_backend(void);
+/* per-kernel CUDA-event profiler (bench.py roofline leg): enable, run steps, then fetch a JSON report
+ * {"kernel name": {"ms": total, "n": launches, "flops": algorithmic, "bytes": algorithmic}} */
+int eegb200_prof_enable(int on);
+int eegb200_prof_report(char* buf, size_t cap);
 
 /* ---- generic fused GEMM: C[M,N] = epilogue(A[M,K] * B[N,K]^T).  Building block of every Linear /
  * 1x1-conv / spatial-conv / logits product on the path (nn.Linear & F.linear call sites:
