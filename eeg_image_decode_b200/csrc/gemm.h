@@ -90,4 +90,61 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, f
   else atomicAdd(p, v);
 }
 
+// 4 consecutive columns of one row (col % 4 == 0, col + 4 <= N, every used pointer 16-byte aligned with ld % 4 == 0)
+__device__ __forceinline__ void epi_apply4(const Epilogue& e, int row, int col, float4 acc) {
+  float v[4] = {acc.x, acc.y, acc.z, acc.w};
+  float a = e.alpha;
+  if (e.alpha_dev) a *= __ldg(e.alpha_dev);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] *= a;
+  if (e.bias) {
+    const float4 b = *reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col);
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (e.aux_out) *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
+  if (e.act == EPI_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = gelu_exact(v[i]);
+  }
+  if (e.drop.p > 0.f) {
+    const uint32_t m = dropout_keep4(e.drop, (uint64_t)row * e.drop_ld + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (m >> i) & 1u ? v[i] * e.drop.scale : 0.f;
+  }
+  if (e.mul_in) {
+    const float4 u = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
+    v[0] *= gelu_grad(u.x); v[1] *= gelu_grad(u.y); v[2] *= gelu_grad(u.z); v[3] *= gelu_grad(u.w);
+  }
+  if (e.resid) {
+    const float4 r = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+  if (e.round_tf32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = tf32_rn(v[i]);
+  }
+  float* p = e.C + (size_t)row * e.ldc + col;
+  if (e.store_mode == EPI_STORE) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (e.store_mode == EPI_ADD) {
+    float4 o = *reinterpret_cast<float4*>(p);
+    o.x += v[0]; o.y += v[1]; o.z += v[2]; o.w += v[3];
+    *reinterpret_cast<float4*>(p) = o;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(p + i, v[i]);
+  }
+}
+// host-side: can the vector path be used for this epilogue?
+static inline bool epi_vec_ok(const Epilogue& e) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool ok = al(e.C) && (e.ldc & 3) == 0;
+  if (e.bias) ok = ok && al(e.bias) && (e.bias_period == 0 || (e.ld_bias & 3) == 0);
+  if (e.aux_out) ok = ok && al(e.aux_out) && (e.ld_aux & 3) == 0;
+  if (e.mul_in) ok = ok && al(e.mul_in) && (e.ld_mul & 3) == 0;
+  if (e.resid) ok = ok && al(e.resid) && (e.ld_res & 3) == 0;
+  if (e.drop.p > 0.f) ok = ok && (e.drop_ld & 3) == 0;
+  return ok;
+}
+
 }  // namespace eegb200

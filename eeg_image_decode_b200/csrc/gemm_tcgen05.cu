@@ -22,6 +22,7 @@ struct GemmKernelParams {
   int M, N, K;
   int k_blocks_per_split;   // k-blocks handled by one blockIdx.z
   int stages;
+  int vec_ok;
   Epilogue epi;
 };
 
@@ -123,14 +124,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    // TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns: every global access of the
+    // fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row segment.
     const int q = warp & 3;
-    const int row = tile_m * BM + q * 32 + lane;
     const Epilogue& e = p.epi;
     if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+      mbar_wait(tmem_full_bar, 0);    // all MMAs done => every smem stage has been consumed: the tile area is free
       tc_fence_after();
     }
-    const bool vec_ok = e.store_mode == EPI_STORE && (e.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+    constexpr int SLD = 36;           // staging row stride in floats (16-byte aligned, conflict-free float4 phases)
+    float* stage = reinterpret_cast<float*>(tiles) + (size_t)q * 32 * SLD;
+    const int r_sub = lane >> 3;      // 4 rows per pass
+    const int cq = (lane & 7) * 4;    // 4 consecutive columns per lane
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = tile_n * BN + c * 32;
@@ -142,22 +147,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      if (row < p.M) {
-        if (col0 + 32 <= p.N) {
+      float4* srow = reinterpret_cast<float4*>(stage + lane * SLD);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = epi_value(e, row, col0 + j, v[j]);
-          if (vec_ok) {
-            float4* dst = reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + r_sub;
+        const int row = tile_m * BM + q * 32 + rl;
+        const int col = col0 + cq;
+        if (row < p.M && col < p.N) {
+          const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
+          if (p.vec_ok && col + 4 <= p.N) {
+            epi_apply4(e, row, col, a4);
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) epi_store(e, row, col0 + j, v[j]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
           }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) epi_store(e, row, col0 + j, epi_value(e, row, col0 + j, v[j]));
         }
       }
+      __syncwarp();
     }
   }
 
@@ -238,6 +247,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   if (stages < 1) stages = 1;
   p.stages = stages;
   p.epi = g.epi;
+  p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static size_t configured = 0;   // per template instantiation

@@ -238,8 +238,9 @@ def test_train_step_gradients_and_update(lib, backend):
         if gr is None or k in noise:
             continue
         d = (new[k].cpu() - sd_new[k]).abs()
-        frac_bad = (d > 1e-5).float().mean().item()
-        assert frac_bad < (1e-3 if backend == 1 else 2e-2), f"{k}: {frac_bad} of the entries moved differently"
+        n_bad = int((d > 1e-5).sum().item())
+        allowed = max(2, int((1e-3 if backend == 1 else 2e-2) * d.numel()))
+        assert n_bad <= allowed, f"{k}: {n_bad} of {d.numel()} entries moved differently"
     # unused parameters untouched
     ref0 = recipe.make_state_dict()
     for k in ("encoder.enc_embedding.mask_token", "subject_wise_linear.0.weight",
