@@ -285,7 +285,7 @@ def bench_ours(args):
         tot = sum(v["ms"] for v in prof.values())
         ranked = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
         top = [{"kernel": k, "share": v["ms"] / tot, "ms_per_launch": v["ms"] / v["n"], "launches_per_step": v["n"] / n_prof}
-               for k, v in ranked[:8]]
+               for k, v in ranked[:40]]
         name, v = ranked[0]
         per_launch_ms = v["ms"] / v["n"]
         if name.startswith("gemm_tf32"):

@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const float*
   }
 }
 
-int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s) {
-  ProfScope _ps("attention_fwd", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
+int attention_fwd_simt(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("attention_fwd_simt", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
   const size_t smem = 4 * 64 * LDS * sizeof(float);
   static bool configured = false;
   if (!configured) {
@@ -194,8 +194,8 @@ int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream
   return 0;
 }
 
-int attention_bwd(const float* qkv, const float* d_o, float* dqkv, int B, DropoutCfg drop, cudaStream_t s) {
-  ProfScope _ps("attention_bwd", s, (double)B * 4 * 12.0 * 64 * 64 * 62, (double)B * 64 * 1792 * 4.0);
+int attention_bwd_simt(const float* qkv, const float* d_o, float* dqkv, int B, DropoutCfg drop, cudaStream_t s) {
+  ProfScope _ps("attention_bwd_simt", s, (double)B * 4 * 12.0 * 64 * 64 * 62, (double)B * 64 * 1792 * 4.0);
   const size_t smem = 5 * 64 * LDS * sizeof(float);
   static bool configured = false;
   if (!configured) {

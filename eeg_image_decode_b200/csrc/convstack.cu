@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_fwd_kernel(const flo
     }
   }
 }
-int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s) {
-  ProfScope _ps("conv_temporal_fwd", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * (63 * 1000.0 + 36 * 2520 * 4.0));
+int conv_temporal_fwd_simt(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s) {
+  ProfScope _ps("conv_temporal_fwd_simt", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * (63 * 1000.0 + 36 * 2520 * 4.0));
   conv_temporal_fwd_kernel<<<B, CT_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -465,10 +465,10 @@ __global__ void __launch_bounds__(CT_THREADS) conv_temporal_bwd_kernel(
   // accb holds this thread's partial over its (jq) quarter; reduce the 4 quarters through atomics
   atomicAdd(&dbt[k], accb);
 }
-int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
+int conv_temporal_bwd_simt(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
                       float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s) {
-  ProfScope _ps("conv_temporal_bwd", s, (double)B * 63 * 36 * 40 * 100.0, (double)B * (36 * 2520 * 8.0 + 63 * 2000.0));
+  ProfScope _ps("conv_temporal_bwd_simt", s, (double)B * 63 * 36 * 40 * 100.0, (double)B * (36 * 2520 * 8.0 + 63 * 2000.0));
   conv_temporal_bwd_kernel<<<B, CT_THREADS, 0, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt,
                                                     dgamma, dbeta, gscale);
   EEG_CUDA_OK(cudaGetLastError());

@@ -90,17 +90,20 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, f
   else atomicAdd(p, v);
 }
 
-// 4 consecutive columns of one row (col % 4 == 0, col + 4 <= N, every used pointer 16-byte aligned with ld % 4 == 0)
-__device__ __forceinline__ void epi_apply4(const Epilogue& e, int row, int col, float4 acc) {
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  float a = e.alpha;
-  if (e.alpha_dev) a *= __ldg(e.alpha_dev);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] *= a;
-  if (e.bias) {
-    const float4 b = *reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col);
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
+// 4 consecutive columns of one row (col % 4 == 0, col + 4 <= N, every used pointer 16-byte aligned with ld % 4 == 0).
+// Split in two so the caller can issue the global loads of several rows before consuming any (latency hiding).
+struct EpiLoads { float4 bias, mul, resid; };
+__device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int col) {
+  EpiLoads L;
+  L.bias = L.mul = L.resid = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
+  if (e.mul_in) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
+  if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
+  return L;
+}
+__device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a) {
+  float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
+  if (e.bias) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
   if (e.aux_out) *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
   if (e.act == EPI_ACT_GELU) {
 #pragma unroll
@@ -112,13 +115,9 @@ __device__ __forceinline__ void epi_apply4(const Epilogue& e, int row, int col, 
     for (int i = 0; i < 4; ++i) v[i] = (m >> i) & 1u ? v[i] * e.drop.scale : 0.f;
   }
   if (e.mul_in) {
-    const float4 u = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
-    v[0] *= gelu_grad(u.x); v[1] *= gelu_grad(u.y); v[2] *= gelu_grad(u.z); v[3] *= gelu_grad(u.w);
+    v[0] *= gelu_grad(L.mul.x); v[1] *= gelu_grad(L.mul.y); v[2] *= gelu_grad(L.mul.z); v[3] *= gelu_grad(L.mul.w);
   }
-  if (e.resid) {
-    const float4 r = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
-    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
-  }
+  if (e.resid) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
   if (e.round_tf32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = tf32_rn(v[i]);

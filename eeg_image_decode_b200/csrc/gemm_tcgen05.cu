@@ -2,7 +2,7 @@
 //
 //   warp 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier complete_tx)
 //   warp 1 : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, fp32 accumulators in TMEM)
-//   warps 2..5 : epilogue    (tcgen05.ld 32x32b -> registers -> fused bias/GELU/dropout/residual -> global)
+//   warps 2..9 : epilogue    (tcgen05.ld 32x32b -> registers -> smem transpose -> fused, coalesced float4 I/O)
 //
 // Tile 128 x BN x 32(K, = one 128-byte swizzle row of fp32).  K-major operands use the SWIZZLE_128B
 // canonical layout; MN-major operands (needed by the weight-gradient GEMMs, whose reduction runs over
@@ -16,18 +16,19 @@ namespace eegb200 {
 static constexpr int BM = 128;
 static constexpr int BK = 32;   // floats per k-block (128 B)
 static constexpr int UMMA_K = 8;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 struct GemmKernelParams {
   int M, N, K;
   int k_blocks_per_split;   // k-blocks handled by one blockIdx.z
   int stages;
+  int tile_bytes;           // smem bytes reserved for the pipeline stages / epilogue staging (barriers follow)
   int vec_ok;
   Epilogue epi;
 };
 
 template <int BN, int A_MN, int B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -40,7 +41,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // 1024-byte aligned tile area (swizzle atoms), then barriers
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + (size_t)p.tile_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -123,21 +124,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_commit(tmem_full_bar);     // accumulator complete
     }
   } else {
-    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    // ================= epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps share a quarter) =========
     // TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns: every global access of the
-    // fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row segment.
+    // fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row segment, and the
+    // loads of 4 row groups are in flight before the first is consumed.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const Epilogue& e = p.epi;
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);    // all MMAs done => every smem stage has been consumed: the tile area is free
       tc_fence_after();
     }
     constexpr int SLD = 36;           // staging row stride in floats (16-byte aligned, conflict-free float4 phases)
-    float* stage = reinterpret_cast<float*>(tiles) + (size_t)q * 32 * SLD;
+    float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * SLD;
     const int r_sub = lane >> 3;      // 4 rows per pass
     const int cq = (lane & 7) * 4;    // 4 consecutive columns per lane
+    float alpha = e.alpha;
+    if (e.alpha_dev) alpha *= __ldg(e.alpha_dev);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half; c < BN / 32; c += 2) {
       const int col0 = tile_n * BN + c * 32;
       if (col0 >= p.N) break;                       // warp-uniform
       float v[32];
@@ -151,16 +156,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + r_sub;
-        const int row = tile_m * BM + q * 32 + rl;
-        const int col = col0 + cq;
-        if (row < p.M && col < p.N) {
-          const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
-          if (p.vec_ok && col + 4 <= p.N) {
-            epi_apply4(e, row, col, a4);
-          } else {
+      const int col = col0 + cq;
+      const int row0 = tile_m * BM + q * 32 + r_sub;
+      if (p.vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+        for (int g4 = 0; g4 < 2; ++g4) {
+          EpiLoads L[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = row0 + (g4 * 4 + u) * 4;
+            if (row < p.M) L[u] = epi_load4(e, row, col);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rl = (g4 * 4 + u) * 4 + r_sub;
+            const int row = row0 + (g4 * 4 + u) * 4;
+            if (row < p.M) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha);
+          }
+        }
+      } else {
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + r_sub;
+          const int row = row0 + it * 4;
+          if (row < p.M && col < p.N) {
+            const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
             const float av[4] = {a4.x, a4.y, a4.z, a4.w};
             for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
           }
@@ -248,7 +267,10 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   p.stages = stages;
   p.epi = g.epi;
   p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  size_t tile_bytes = (size_t)stages * stage_bytes;
+  if (tile_bytes < 36864) tile_bytes = 36864;      // epilogue staging (8 warps x 32 x 36 floats) reuses the tile area
+  const size_t smem = tile_bytes + 1024 + 256;
+  p.tile_bytes = (int)tile_bytes;
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static size_t configured = 0;   // per template instantiation
   if (smem > configured) {

@@ -439,3 +439,33 @@ def test_state_dict_roundtrip_and_keys(lib):
     # parameters are views of one arena
     p = dict(m.named_parameters())["proj_eeg.0.weight"]
     assert p.data_ptr() >= m.flat_params.data_ptr() and p.data_ptr() < m.flat_params.data_ptr() + 4 * m.flat_params.numel()
+
+
+def test_dropout_tensorcore_path_matches_fp32_path(lib):
+    """same dropout seed through the product kernels (tcgen05 GEMMs, mma.sync attention/conv) and through the
+    exact-fp32 verification kernels: identical masks, TF32-level differences only"""
+    from eeg_image_decode_b200.train import StepEngine
+    B = 16
+    x = recipe.make_eeg(B, seed=61).cuda()
+    sid = torch.full((B,), 3).cuda()
+    img = recipe.make_targets(B, seed=61, tag="img").cuda()
+    txt = recipe.make_targets(B, seed=61, tag="txt").cuda()
+    res = {}
+    for backend in (1, 0):
+        lib.set_gemm_backend(backend)
+        try:
+            m = make_model().train()
+            loss, feats = StepEngine(m, None).step(x, sid, img, txt, use_shared=False, seed=987654321)
+            res[backend] = (loss.clone(), feats.clone(), {k: m.grad_view(k).clone() for k in
+                            ("proj_eeg.0.weight", "enc_eeg.0.tsconv.0.weight", "enc_eeg.0.tsconv.4.weight",
+                             "encoder.encoder.attn_layers.0.attention.query_projection.weight",
+                             "encoder.encoder.attn_layers.0.attention.value_projection.weight",
+                             "encoder.encoder.attn_layers.0.attention.key_projection.weight",
+                             "encoder.encoder.attn_layers.0.conv1.weight",
+                             "encoder.enc_embedding.value_embedding.weight", "enc_eeg.0.tsconv.2.weight")})
+        finally:
+            lib.set_gemm_backend(0)
+    assert rows_rel(res[0][1], res[1][1]) < 1.5e-3
+    assert abs(res[0][0][0].item() - res[1][0][0].item()) < 3e-3 * abs(res[1][0][0].item())
+    for k in res[0][2]:
+        assert rel_l2(res[0][2][k], res[1][2][k]) < 3e-2, k
