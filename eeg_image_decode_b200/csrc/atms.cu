@@ -186,22 +186,75 @@ __global__ void unpack_ws_grad_kernel(const float* __restrict__ dw_p, float* dws
   dws[(k2 * N_FILT + k1) * N_CH + r] += dw_p[idx];
 }
 
+// one launch for every packed operand: segment table in kernel arguments
+struct PackArgs {
+  const float *value_w, *wq, *wk, *wv, *wo, *w1, *w2, *ws, *wp1, *wp2;
+  float *Wv_p, *Wqkv_p, *Wo_p, *W1_p, *W2_p, *Ws_p, *Wp1_r, *Wp2_r;
+};
+__global__ void pack_all_kernel(PackArgs a, int rt) {
+  constexpr long long N0 = 256 * 256, N1 = 768 * 256, N2 = 256 * 256, N3 = 256 * 256, N4 = 256 * 256,
+                      N5 = (long long)N_FILT * K_SPAT, N6 = (long long)D_OUT * D_FEAT, N7 = (long long)D_OUT * D_OUT;
+  constexpr long long TOTAL = N0 + N1 + N2 + N3 + N4 + N5 + N6 + N7;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < TOTAL; i += (long long)gridDim.x * blockDim.x) {
+    long long j = i;
+    if (j < N0) {                                    // value embedding [250,250] -> [256,256]
+      const int r = (int)(j >> 8), c = (int)(j & 255);
+      a.Wv_p[j] = (r < N_T && c < N_T) ? tf32_if(a.value_w[r * N_T + c], rt) : 0.f;
+      continue;
+    }
+    j -= N0;
+    if (j < N1) {                                    // q|k|v [248,250] x3 -> [768,256], heads padded 62 -> 64
+      const int row = (int)(j >> 8), c = (int)(j & 255);
+      const int which = row >> 8, hh = (row & 255) >> 6, e = row & 63;
+      const float* w = which == 0 ? a.wq : (which == 1 ? a.wk : a.wv);
+      a.Wqkv_p[j] = (e < D_HEAD && c < N_T) ? tf32_if(w[(hh * D_HEAD + e) * N_T + c], rt) : 0.f;
+      continue;
+    }
+    j -= N1;
+    if (j < N2) {                                    // out projection [250,248] -> [256,256]
+      const int o = (int)(j >> 8), c = (int)(j & 255);
+      const int hh = c >> 6, e = c & 63;
+      a.Wo_p[j] = (o < N_T && e < D_HEAD) ? tf32_if(a.wo[o * (N_HEAD * D_HEAD) + hh * D_HEAD + e], rt) : 0.f;
+      continue;
+    }
+    j -= N2;
+    if (j < N3) {                                    // conv1 [256,250] -> [256,256]
+      const int r = (int)(j >> 8), c = (int)(j & 255);
+      a.W1_p[j] = c < N_T ? tf32_if(a.w1[r * N_T + c], rt) : 0.f;
+      continue;
+    }
+    j -= N3;
+    if (j < N4) {                                    // conv2 [250,256] -> [256,256]
+      const int r = (int)(j >> 8);
+      a.W2_p[j] = r < N_T ? tf32_if(a.w2[j], rt) : 0.f;
+      continue;
+    }
+    j -= N4;
+    if (j < N5) {                                    // tsconv.4.weight [k2][k1][r] -> [k2][r*40 + k1]
+      const int k2 = (int)(j / K_SPAT), kk = (int)(j % K_SPAT);
+      const int r = kk / N_FILT, k1 = kk % N_FILT;
+      a.Ws_p[j] = tf32_if(a.ws[(k2 * N_FILT + k1) * N_CH + r], rt);
+      continue;
+    }
+    j -= N5;
+    if (j < N6) { a.Wp1_r[j] = tf32_if(a.wp1[j], rt); continue; }
+    j -= N6;
+    a.Wp2_r[j] = tf32_if(a.wp2[j], rt);
+  }
+}
+
 static int pack_weights(const float* const* P, float* const* BUF, const Ws& w, cudaStream_t s) {
   const int RT = tf32_rounding();
   ProfScope _ps("pack_weights", s, 0.0, 3.2e6 * 8.0);
-  EEG_TRY(pad_copy(P[EEGB200_P_VALUE_W], N_T, N_T, N_T, w.Wv_p, 256, 256, RT, 1.f, s));
-  pack_qkv_kernel<<<768, 256, 0, s>>>(P[EEGB200_P_WQ], P[EEGB200_P_WK], P[EEGB200_P_WV], w.Wqkv_p, RT);
-  pack_wo_kernel<<<256, 256, 0, s>>>(P[EEGB200_P_WO], w.Wo_p, RT);
-  EEG_TRY(pad_copy(P[EEGB200_P_W1], N_T, D_FF, N_T, w.W1_p, 256, 256, RT, 1.f, s));
-  EEG_TRY(pad_copy(P[EEGB200_P_W2], D_FF, N_T, D_FF, w.W2_p, 256, 256, RT, 1.f, s));
-  pack_ws_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(P[EEGB200_P_WS], w.Ws_p, RT);
-  EEG_TRY(pad_copy(P[EEGB200_P_WP1], D_FEAT, D_OUT, D_FEAT, w.Wp1_r, D_FEAT, D_OUT, RT, 1.f, s));
-  EEG_TRY(pad_copy(P[EEGB200_P_WP2], D_OUT, D_OUT, D_OUT, w.Wp2_r, D_OUT, D_OUT, RT, 1.f, s));
+  PackArgs a{P[EEGB200_P_VALUE_W], P[EEGB200_P_WQ], P[EEGB200_P_WK], P[EEGB200_P_WV], P[EEGB200_P_WO], P[EEGB200_P_W1],
+             P[EEGB200_P_W2], P[EEGB200_P_WS], P[EEGB200_P_WP1], P[EEGB200_P_WP2],
+             w.Wv_p, w.Wqkv_p, w.Wo_p, w.W1_p, w.W2_p, w.Ws_p, w.Wp1_r, w.Wp2_r};
+  pack_all_kernel<<<148 * 8, 256, 0, s>>>(a, RT);
   pack_small_kernel<<<64, 256, 0, s>>>(P[EEGB200_P_VALUE_B], BUF[EEGB200_BUF_PE], P[EEGB200_P_BQ], P[EEGB200_P_BK],
                                         P[EEGB200_P_BV], P[EEGB200_P_BO], P[EEGB200_P_B1], P[EEGB200_P_B2], w.tokbias,
                                         w.bqkv_p, w.bo_p, w.b1_p, w.b2_p);
   EEG_CUDA_OK(cudaGetLastError());
-  count_launch(4);
+  count_launch(2);
   return 0;
 }
 

@@ -168,36 +168,46 @@ int colstats(const float* y, int ld, int rows, int cols, double* sums, cudaStrea
   return 0;
 }
 
-// BN2 -> ELU -> Dropout(0.5) -> 1x1 conv, one (b,j) row per 64-thread block
-__global__ void conv_head_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ mean_rstd,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ feat,
-                                     int rows, DropoutCfg drop, int rt) {
-  __shared__ float a2[N_FILT];
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int k = threadIdx.x;
-    if (k < N_FILT) {
-      const float z = (y2[(size_t)row * N_FILT + k] - mean_rstd[k]) * mean_rstd[N_FILT + k] * gamma[k] + beta[k];
-      float a = elu1(z);
+// BN2 -> ELU -> Dropout(0.5) -> 1x1 conv; 16 (b,j) rows per 256-thread block
+static constexpr int HB = 16;
+__global__ void __launch_bounds__(256) conv_head_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ mean_rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ wc, const float* __restrict__ bc,
+                                                            float* __restrict__ feat, int rows, DropoutCfg drop, int rt) {
+  __shared__ float a2[HB][N_FILT + 1], swc[N_FILT * N_FILT + N_FILT], sc[N_FILT], sh[N_FILT];
+  for (int i = threadIdx.x; i < N_FILT * N_FILT; i += 256) swc[i + i / N_FILT] = wc[i];   // row stride 41: conflict-free
+  if (threadIdx.x < N_FILT) {
+    const float r = mean_rstd[N_FILT + threadIdx.x] * gamma[threadIdx.x];
+    sc[threadIdx.x] = r;
+    sh[threadIdx.x] = beta[threadIdx.x] - mean_rstd[threadIdx.x] * r;
+  }
+  __syncthreads();
+  const int row0 = blockIdx.x * HB;
+  for (int idx = threadIdx.x; idx < HB * N_FILT; idx += 256) {
+    const int r = idx / N_FILT, k = idx % N_FILT, row = row0 + r;
+    float a = 0.f;
+    if (row < rows) {
+      a = elu1(fmaf(y2[(size_t)row * N_FILT + k], sc[k], sh[k]));
       if (drop.p > 0.f) a = dropout_keep(drop, (uint64_t)row * N_FILT + k) ? a * drop.scale : 0.f;
-      a2[k] = a;
     }
-    __syncthreads();
-    if (k < N_FILT) {
-      float acc = bc[k];
+    a2[r][k] = a;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < HB * N_FILT; idx += 256) {
+    const int r = idx / N_FILT, e = idx % N_FILT, row = row0 + r;
+    if (row < rows) {
+      float acc = bc[e];
 #pragma unroll 8
-      for (int c = 0; c < N_FILT; ++c) acc = fmaf(wc[k * N_FILT + c], a2[c], acc);
-      feat[(size_t)row * N_FILT + k] = tf32_if(acc, rt);
+      for (int c = 0; c < N_FILT; ++c) acc = fmaf(swc[e * (N_FILT + 1) + c], a2[r][c], acc);
+      feat[(size_t)row * N_FILT + e] = tf32_if(acc, rt);
     }
-    __syncthreads();
   }
 }
 int conv_head_fwd(const float* y2, const float* mean_rstd, const float* gamma, const float* beta, const float* wc,
                   const float* bc, float* feat, int B, DropoutCfg drop, cudaStream_t s) {
   ProfScope _ps("conv_head_fwd", s, (double)B * 36 * 3200.0, (double)B * 36 * 320.0);
   const int rows = B * N_POOL;
-  int blocks = rows < 148 * 32 ? rows : 148 * 32;
-  conv_head_fwd_kernel<<<blocks, 64, 0, s>>>(y2, mean_rstd, gamma, beta, wc, bc, feat, rows, drop, tf32_rounding());
+  conv_head_fwd_kernel<<<cdiv(rows, HB), 256, 0, s>>>(y2, mean_rstd, gamma, beta, wc, bc, feat, rows, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -211,38 +221,53 @@ __global__ void __launch_bounds__(256) conv_head_bwd_kernel(const float* __restr
                                                             float* __restrict__ dz2, float* __restrict__ dwc,
                                                             float* __restrict__ dbc, double* __restrict__ bwd_sums,
                                                             int rows, DropoutCfg drop) {
-  __shared__ float df[N_FILT], a2[N_FILT], swc[N_FILT * N_FILT];
-  for (int i = threadIdx.x; i < N_FILT * N_FILT; i += blockDim.x) swc[i] = wc[i];
+  __shared__ float df[HB][N_FILT + 1], a2[HB][N_FILT + 1], zk[HB][N_FILT + 1], yhs[HB][N_FILT + 1];
+  __shared__ float swc[N_FILT * N_FILT], sred[3][N_FILT];
+  for (int i = threadIdx.x; i < N_FILT * N_FILT; i += 256) swc[i] = wc[i];
+  if (threadIdx.x < 3 * N_FILT) (&sred[0][0])[threadIdx.x] = 0.f;
   float accw[7];
 #pragma unroll
   for (int q = 0; q < 7; ++q) accw[q] = 0.f;
-  float accb = 0.f, s1 = 0.f, s2 = 0.f;
-  const int k = threadIdx.x;
   __syncthreads();
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    float z = 0.f, yh = 0.f, keep = 1.f;
-    if (k < N_FILT) {
-      df[k] = dfeat[(size_t)row * N_FILT + k];
-      yh = (y2[(size_t)row * N_FILT + k] - mean_rstd[k]) * mean_rstd[N_FILT + k];
-      z = yh * gamma[k] + beta[k];
-      if (drop.p > 0.f) keep = dropout_keep(drop, (uint64_t)row * N_FILT + k) ? drop.scale : 0.f;
-      a2[k] = elu1(z) * keep;
+  for (int row0 = blockIdx.x * HB; row0 < rows; row0 += gridDim.x * HB) {
+    for (int idx = threadIdx.x; idx < HB * N_FILT; idx += 256) {
+      const int r = idx / N_FILT, k = idx % N_FILT, row = row0 + r;
+      float d = 0.f, a = 0.f, zz = 0.f, yh = 0.f;
+      if (row < rows) {
+        d = dfeat[(size_t)row * N_FILT + k];
+        yh = (y2[(size_t)row * N_FILT + k] - mean_rstd[k]) * mean_rstd[N_FILT + k];
+        const float z = yh * gamma[k] + beta[k];
+        float keep = 1.f;
+        if (drop.p > 0.f) keep = dropout_keep(drop, (uint64_t)row * N_FILT + k) ? drop.scale : 0.f;
+        a = elu1(z) * keep;
+        zz = keep * elu1_grad(z);
+      }
+      df[r][k] = d; a2[r][k] = a; zk[r][k] = zz; yhs[r][k] = yh;
     }
     __syncthreads();
-    if (k < N_FILT) {
-      float da = 0.f;
+    for (int idx = threadIdx.x; idx < HB * N_FILT; idx += 256) {
+      const int r = idx / N_FILT, k = idx % N_FILT, row = row0 + r;
+      if (row < rows) {
+        float da = 0.f;
 #pragma unroll 8
-      for (int e = 0; e < N_FILT; ++e) da = fmaf(swc[e * N_FILT + k], df[e], da);
-      const float dz = da * keep * elu1_grad(z);
-      dz2[(size_t)row * N_FILT + k] = dz;
-      s1 += dz;
-      s2 = fmaf(dz, yh, s2);
-      accb += df[k];
+        for (int e = 0; e < N_FILT; ++e) da = fmaf(swc[e * N_FILT + k], df[r][e], da);
+        const float dz = da * zk[r][k];
+        dz2[(size_t)row * N_FILT + k] = dz;
+        atomicAdd(&sred[0][k], dz);
+        atomicAdd(&sred[1][k], dz * yhs[r][k]);
+        atomicAdd(&sred[2][k], df[r][k]);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
       const int idx = threadIdx.x + 256 * q;
-      if (idx < N_FILT * N_FILT) accw[q] = fmaf(df[idx / N_FILT], a2[idx % N_FILT], accw[q]);
+      if (idx < N_FILT * N_FILT) {
+        const int e = idx / N_FILT, k = idx % N_FILT;
+        float a = accw[q];
+#pragma unroll
+        for (int r = 0; r < HB; ++r) a = fmaf(df[r][e], a2[r][k], a);
+        accw[q] = a;
+      }
     }
     __syncthreads();
   }
@@ -251,10 +276,11 @@ __global__ void __launch_bounds__(256) conv_head_bwd_kernel(const float* __restr
     const int idx = threadIdx.x + 256 * q;
     if (idx < N_FILT * N_FILT) atomicAdd(&dwc[idx], accw[q]);
   }
-  if (k < N_FILT) {
-    atomicAdd(&dbc[k], accb);
-    atomicAdd(&bwd_sums[k], (double)s1);
-    atomicAdd(&bwd_sums[N_FILT + k], (double)s2);
+  if (threadIdx.x < N_FILT) {
+    const int k = threadIdx.x;
+    atomicAdd(&dbc[k], sred[2][k]);
+    atomicAdd(&bwd_sums[k], (double)sred[0][k]);
+    atomicAdd(&bwd_sums[N_FILT + k], (double)sred[1][k]);
   }
 }
 int conv_head_bwd(const float* dfeat, const float* y2, const float* mean_rstd, const float* gamma, const float* beta,
@@ -262,7 +288,8 @@ int conv_head_bwd(const float* dfeat, const float* y2, const float* mean_rstd, c
                   cudaStream_t s) {
   ProfScope _ps("conv_head_bwd", s, (double)B * 36 * 6400.0, (double)B * 36 * 480.0);
   const int rows = B * N_POOL;
-  int blocks = rows < 148 * 2 ? rows : 148 * 2;
+  int blocks = cdiv(rows, HB);
+  if (blocks > 148 * 4) blocks = 148 * 4;
   conv_head_bwd_kernel<<<blocks, 256, 0, s>>>(dfeat, y2, mean_rstd, gamma, beta, wc, dz2, dwc, dbc, bwd_sums, rows, drop);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -24,6 +24,7 @@ struct GemmKernelParams {
   int stages;
   int tile_bytes;           // smem bytes reserved for the pipeline stages / epilogue staging (barriers follow)
   int vec_ok;
+  int a_3d, b_3d;           // MN-major operand loaded with one 3-D TMA box per stage (else one 2-D box per 32-wide slab)
   Epilogue epi;
 };
 
@@ -85,14 +86,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sb = sa + A_BYTES;
         const int k0 = (kb_begin + i) * BK;
         if (A_MN) {
+          if (p.a_3d) {
+            tma_load_3d(&tmA, &full_bar[s], sa, 0, k0, tile_m * (BM / 32));     // lands as [slab][k][32 mn]
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], sa + j * (BK * 128), tile_m * BM + j * 32, k0);
+            for (int j = 0; j < BM / 32; ++j) tma_load_2d(&tmA, &full_bar[s], sa + j * (BK * 128), tile_m * BM + j * 32, k0);
+          }
         } else {
           tma_load_2d(&tmA, &full_bar[s], sa, k0, tile_m * BM);
         }
         if (B_MN) {
+          if (p.b_3d) {
+            tma_load_3d(&tmB, &full_bar[s], sb, 0, k0, tile_n * (BN / 32));
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], sb + j * (BK * 128), tile_n * BN + j * 32, k0);
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(&tmB, &full_bar[s], sb + j * (BK * 128), tile_n * BN + j * 32, k0);
+          }
         } else {
           tma_load_2d(&tmB, &full_bar[s], sb, k0, tile_n * BN);
         }
@@ -219,27 +228,40 @@ static int resolve_encode() {
 }
 
 // operand viewed as logical [rows, K]
-static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int box_rows) {
+static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int box_rows, int* is_3d) {
+  *is_3d = 0;
   EEG_REQUIRE(op.ptr != nullptr, "gemm: null operand");
   EEG_REQUIRE((op.ld & 3) == 0, "gemm: leading dimension %d is not a multiple of 4 floats (TMA needs 16-byte strides)", op.ld);
   EEG_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0, "gemm: operand pointer not 16-byte aligned");
-  cuuint64_t dims[2];
-  cuuint64_t strides[1] = {(cuuint64_t)op.ld * 4};
-  cuuint32_t box[2];
-  cuuint32_t estr[2] = {1, 1};
+  cuuint64_t dims[3];
+  cuuint64_t strides[2] = {(cuuint64_t)op.ld * 4, 128};
+  cuuint32_t box[3];
+  cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapSwizzle sw;
+  int rank = 2;
   if (op.mn_major) {
+    // stored [K][rows]; viewed as (32 mn, K, rows/32 slabs) so that one box lands as [slab][k][32 mn] in smem,
+    // the canonical MN-major SWIZZLE_128B_ATOM_32B layout (slab stride = LBO, 4-k-row atoms = SBO)
     EEG_REQUIRE(op.ld >= rows, "gemm: MN-major operand ld %d < rows %d", op.ld, rows);
-    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
-    box[0] = 32; box[1] = BK;
     sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const int slabs = (rows + 31) / 32;
+    if (slabs * 32 <= op.ld) {
+      // the last slab reaches past `rows` but stays inside the row pitch (pad columns): one 3-D box per stage
+      rank = 3;
+      *is_3d = 1;
+      dims[0] = 32; dims[1] = (cuuint64_t)K; dims[2] = (cuuint64_t)slabs;
+      box[0] = 32; box[1] = BK; box[2] = (cuuint32_t)(box_rows / 32);
+    } else {
+      dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+      box[0] = 32; box[1] = BK;
+    }
   } else {
     EEG_REQUIRE(op.ld >= K, "gemm: K-major operand ld %d < K %d", op.ld, K);
     dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
     box[0] = BK; box[1] = (cuuint32_t)box_rows;
     sw = CU_TENSOR_MAP_SWIZZLE_128B;
   }
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(op.ptr), dims, strides, box, estr,
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(op.ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   EEG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows %d K %d ld %d mn %d)", (int)r, rows, K, op.ld,
@@ -248,7 +270,7 @@ static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, in
 }
 
 template <int BN, int A_MN, int B_MN>
-static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, int a3, int b3, cudaStream_t stream) {
   const int total_kb = cdiv(g.K, BK);
   int split = g.split_k < 1 ? 1 : g.split_k;
   if (split > total_kb) split = total_kb > 0 ? total_kb : 1;
@@ -267,6 +289,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   p.stages = stages;
   p.epi = g.epi;
   p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
+  p.a_3d = a3; p.b_3d = b3;
   size_t tile_bytes = (size_t)stages * stage_bytes;
   if (tile_bytes < 36864) tile_bytes = 36864;      // epilogue staging (8 warps x 32 x 36 floats) reuses the tile area
   const size_t smem = tile_bytes + 1024 + 256;
@@ -287,12 +310,13 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
 template <int BN>
 static int launch_bn(const GemmArgs& g, cudaStream_t stream) {
   CUtensorMap ta, tb;
-  EEG_TRY(make_operand_map(&ta, g.A, g.M, g.K, BM));
-  EEG_TRY(make_operand_map(&tb, g.B, g.N, g.K, BN));
-  if (!g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 0, 0>(g, ta, tb, stream);
-  if (!g.A.mn_major && g.B.mn_major) return launch_cfg<BN, 0, 1>(g, ta, tb, stream);
-  if (g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 1, 0>(g, ta, tb, stream);
-  return launch_cfg<BN, 1, 1>(g, ta, tb, stream);
+  int a3 = 0, b3 = 0;
+  EEG_TRY(make_operand_map(&ta, g.A, g.M, g.K, BM, &a3));
+  EEG_TRY(make_operand_map(&tb, g.B, g.N, g.K, BN, &b3));
+  if (!g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 0, 0>(g, ta, tb, a3, b3, stream);
+  if (!g.A.mn_major && g.B.mn_major) return launch_cfg<BN, 0, 1>(g, ta, tb, a3, b3, stream);
+  if (g.A.mn_major && !g.B.mn_major) return launch_cfg<BN, 1, 0>(g, ta, tb, a3, b3, stream);
+  return launch_cfg<BN, 1, 1>(g, ta, tb, a3, b3, stream);
 }
 
 int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream) {
@@ -300,9 +324,14 @@ int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   EEG_REQUIRE(g.epi.C != nullptr, "gemm: null output");
   EEG_REQUIRE(g.split_k <= 1 || g.epi.store_mode == EPI_ATOMIC, "gemm: split-K needs the atomic store mode");
   EEG_TRY(resolve_encode());
-  if (g.N <= 64) return launch_bn<64>(g, stream);
-  if (g.N <= 128) return launch_bn<128>(g, stream);
-  return launch_bn<256>(g, stream);
+  // widest tile that still yields >= ~one wave of CTAs (small-M problems: projector, logits, retrieval)
+  const int mt = cdiv(g.M, BM);
+  const int split = g.split_k > 1 ? g.split_k : 1;
+  auto ctas = [&](int bn) { return mt * cdiv(g.N, bn) * split; };
+  if (g.N > 128 && ctas(256) >= 120) return launch_bn<256>(g, stream);
+  if (g.N > 64 && (ctas(128) >= 120 || g.N <= 128)) return launch_bn<128>(g, stream);
+  if (g.N <= 64 || ctas(128) < 120) return launch_bn<64>(g, stream);
+  return launch_bn<128>(g, stream);
 }
 
 }  // namespace eegb200

@@ -305,9 +305,44 @@ int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, 
 // out[c] += sum_r x[r*ld + c] (c < cols); optional dropout mask on the fly (bias grads of layers whose
 // output passes through a dropout before the residual).
 // ------------------------------------------------------------------------------------------------
+// float4 columns x 16 row lanes per block; rows strided over the grid, 4 rows in flight per thread
+__global__ void __launch_bounds__(1024) colsum_vec_kernel(const float* __restrict__ x, int ld, int rows, int cols,
+                                                          float* __restrict__ out, int row_mod, int row_skip) {
+  __shared__ float4 part[16][64];
+  const int c4 = threadIdx.x;            // 64 float4 columns = 256 floats
+  const int ry = threadIdx.y;            // 16 row lanes
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 * 4 < cols) {
+    const int stride = gridDim.x * 16;
+    int r = blockIdx.x * 16 + ry;
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(x + (size_t)(r + u * stride) * ld + c4 * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (row_mod > 0 && ((r + u * stride) % row_mod) == row_skip) continue;
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+    for (; r < rows; r += stride) {
+      if (row_mod > 0 && (r % row_mod) == row_skip) continue;
+      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c4 * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[ry][c4] = acc;
+  __syncthreads();
+  if (ry == 0 && c4 * 4 < cols) {
+    float4 t = part[0][c4];
+    for (int i = 1; i < 16; ++i) { t.x += part[i][c4].x; t.y += part[i][c4].y; t.z += part[i][c4].z; t.w += part[i][c4].w; }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    for (int q = 0; q < 4; ++q)
+      if (c4 * 4 + q < cols) atomicAdd(&out[c4 * 4 + q], tv[q]);
+  }
+}
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, float* __restrict__ out,
                               int row_mod, int row_skip) {
-  // block handles a slab of rows; thread = column (blockDim.x >= cols rounded to 32), blockDim.y row lanes
   __shared__ float part[8][257];
   const int c = threadIdx.x;
   float s = 0.f;
@@ -323,17 +358,26 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int
     atomicAdd(&out[c], t);
   }
 }
-// cols <= 256 per launch slab; wider matrices are handled in column slabs
+// out[c] += sum_r x[r*ld + c]; rows with r % row_mod == row_skip are left out (row_mod 0: none).
+// Reads up to the next multiple of 4 columns of each row: callers pass padded rows (ld >= cols rounded up to 4).
 int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s) {
   ProfScope _ps("colsum", s, 0.0, (double)rows * cols * 4.0);
+  const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld >= (cols + 3) / 4 * 4;
   for (int c0 = 0; c0 < cols; c0 += 256) {
     const int w = cols - c0 < 256 ? cols - c0 : 256;
-    const int tx = (w + 31) / 32 * 32;
-    const int ty = 1024 / tx > 8 ? 8 : 1024 / tx;
-    int blocks = cdiv(rows, ty * 8);
-    if (blocks > 148 * 2) blocks = 148 * 2;
-    if (blocks < 1) blocks = 1;
-    colsum_kernel<<<blocks, dim3(tx, ty), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
+    if (vec) {
+      int blocks = cdiv(rows, 16 * 4);
+      if (blocks > 148 * 2) blocks = 148 * 2;
+      if (blocks < 1) blocks = 1;
+      colsum_vec_kernel<<<blocks, dim3(64, 16), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
+    } else {
+      const int tx = (w + 31) / 32 * 32;
+      const int ty = 1024 / tx > 8 ? 8 : 1024 / tx;
+      int blocks = cdiv(rows, ty * 8);
+      if (blocks > 148 * 2) blocks = 148 * 2;
+      if (blocks < 1) blocks = 1;
+      colsum_kernel<<<blocks, dim3(tx, ty), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
+    }
     count_launch();
   }
   EEG_CUDA_OK(cudaGetLastError());
