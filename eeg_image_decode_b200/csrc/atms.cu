@@ -273,7 +273,7 @@ static int run_gemm(int M, int N, int K, const float* A, int lda, int amn, const
 static int pick_split(int M, int N, int K) {
   const int tiles = cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256));
   const int kb = cdiv(K, 32);
-  int split = cdiv(296, tiles);
+  int split = cdiv(148, tiles);          // ~one deep-pipelined CTA per SM: halves the L2 atomic traffic of the reduction
   if (split > kb / 4) split = kb / 4;
   if (split < 1) split = 1;
   return split;

@@ -3,8 +3,9 @@
 // 16 query rows.  The whole 64x64 score tile of a head lives in registers; the probability tile is fed back as the
 // A operand of P.V by choosing the reduction-slot order of the MMA (slot t <-> key 2t, slot t+4 <-> key 2t+1), which is
 // exactly the accumulator ownership, so no shuffles or shared-memory round trip are needed.
-// Forward: 3xTF32 split on both products (the forward parity budget is 1e-3 end to end).  Backward: plain TF32, P and
-// dS are exchanged through shared memory for the two products that reduce over the query index.
+// Plain TF32 (RN) products; a 3xTF32 variant is kept as a template parameter (the legacy mma.sync pipe is the issue
+// limit of this kernel, see conv_mma.cu).  Backward: P and dS are exchanged through shared memory for the two
+// products that reduce over the query index.
 #include "kernels.h"
 
 namespace eegb200 {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const flo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
   float s[8][4];
-  qk_scores<3>(Q, K, row0, g, t, s);
+  qk_scores<1>(Q, K, row0, g, t, s);
   softmax_rows(s);
   if (drop.p > 0.f) {
     float kf[8][4];
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const flo
       for (int q = 0; q < 4; ++q) s[nt][q] *= kf[nt][q];
   }
   float acc[8][4];
-  pv_product<3>(s, V, g, t, acc);
+  pv_product<1>(s, V, g, t, acc);
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     float* orow = o + ((size_t)b * 64 + row0 + g + 8 * hrow) * 256 + h * 64;

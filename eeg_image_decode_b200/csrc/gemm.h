@@ -130,8 +130,7 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
     o.x += v[0]; o.y += v[1]; o.z += v[2]; o.w += v[3];
     *reinterpret_cast<float4*>(p) = o;
   } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(p + i, v[i]);
+    red_add_v4(p, v[0], v[1], v[2], v[3]);
   }
 }
 // host-side: can the vector path be used for this epilogue?

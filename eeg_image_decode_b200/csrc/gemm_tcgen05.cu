@@ -24,6 +24,7 @@ struct GemmKernelParams {
   int stages;
   int tile_bytes;           // smem bytes reserved for the pipeline stages / epilogue staging (barriers follow)
   int vec_ok;
+  int pair_atomic;          // store_mode ATOMIC with nothing else fused and even ldc: red.v2 pairs
   int a_3d, b_3d;           // MN-major operand loaded with one 3-D TMA box per stage (else one 2-D box per 32-wide slab)
   Epilogue epi;
 };
@@ -190,7 +191,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (row < p.M && col < p.N) {
             const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
             const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
+            if (p.pair_atomic && col + 4 <= p.N) {      // plain split-K accumulation into an 8-byte aligned row
+              float* dst = e.C + (size_t)row * e.ldc + col;
+              red_add_v2(dst, alpha * av[0], alpha * av[1]);
+              red_add_v2(dst + 2, alpha * av[2], alpha * av[3]);
+            } else {
+              for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
+            }
           }
         }
       }
@@ -281,7 +288,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   const int stage_bytes = (BM + BN) * BK * 4;
   // short K: shallow pipeline so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop);
   // long K: deep pipeline, one CTA per SM.
-  const int budget = p.k_blocks_per_split >= 16 ? 196608 : 98304;
+  const int budget = (p.k_blocks_per_split >= 16 || split > 1) ? 196608 : 98304;
   int stages = budget / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.k_blocks_per_split) stages = p.k_blocks_per_split;
@@ -290,6 +297,11 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   p.epi = g.epi;
   p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
   p.a_3d = a3; p.b_3d = b3;
+  {
+    const Epilogue& e = g.epi;
+    p.pair_atomic = (e.store_mode == EPI_ATOMIC && !e.bias && !e.aux_out && !e.mul_in && !e.resid && e.act == EPI_ACT_NONE &&
+                     e.drop.p <= 0.f && !e.round_tf32 && (e.ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 7) == 0) ? 1 : 0;
+  }
   size_t tile_bytes = (size_t)stages * stage_bytes;
   if (tile_bytes < 36864) tile_bytes = 36864;      // epilogue staging (8 warps x 32 x 36 floats) reuses the tile area
   const size_t smem = tile_bytes + 1024 + 256;
