@@ -10,6 +10,7 @@
 // Out-of-range rows / columns / K are zero-filled by TMA, the epilogue masks the stores.
 #include "gemm.h"
 #include <mutex>
+#include <stdlib.h>
 
 namespace eegb200 {
 
@@ -28,6 +29,240 @@ struct GemmKernelParams {
   int a_3d, b_3d;           // MN-major operand loaded with one 3-D TMA box per stage (else one 2-D box per 32-wide slab)
   Epilogue epi;
 };
+
+static constexpr int EPI_SLD = 36;   // staging row stride in floats (16-byte aligned, conflict-free float4 phases)
+
+// Epilogue of one 128 x BN accumulator tile by warps 2..9 (TMEM lane quarter = warp % 4, two warps share a quarter and
+// split the 32-column chunks).  TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns:
+// every global access of the fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row
+// segment, and the loads of 4 row groups are in flight before the first is consumed.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t tmem_acc, float* stage, int tile_m,
+                                              int tile_n, int warp, int lane, bool has_acc) {
+  const int q = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const Epilogue& e = p.epi;
+  constexpr int SLD = EPI_SLD;
+  const int r_sub = lane >> 3;      // 4 rows per pass
+  const int cq = (lane & 7) * 4;    // 4 consecutive columns per lane
+  float alpha = e.alpha;
+  if (e.alpha_dev) alpha *= __ldg(e.alpha_dev);
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += 2) {
+    const int col0 = tile_n * BN + c * 32;
+    if (col0 >= p.N) break;                       // warp-uniform
+    float v[32];
+    if (has_acc) {
+      tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    float4* srow = reinterpret_cast<float4*>(stage + lane * SLD);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int col = col0 + cq;
+    const int row0 = tile_m * BM + q * 32 + r_sub;
+    if (p.vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+      for (int g4 = 0; g4 < 2; ++g4) {
+        EpiLoads L[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int row = row0 + (g4 * 4 + u) * 4;
+          if (row < p.M) L[u] = epi_load4(e, row, col);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rl = (g4 * 4 + u) * 4 + r_sub;
+          const int row = row0 + (g4 * 4 + u) * 4;
+          if (row < p.M) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha);
+        }
+      }
+    } else {
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + r_sub;
+        const int row = row0 + it * 4;
+        if (row < p.M && col < p.N) {
+          const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+          if (p.pair_atomic && col + 4 <= p.N) {      // plain split-K accumulation into an 8-byte aligned row
+            float* dst = e.C + (size_t)row * e.ldc + col;
+            red_add_v2(dst, alpha * av[0], alpha * av[1]);
+            red_add_v2(dst + 2, alpha * av[2], alpha * av[3]);
+          } else {
+            for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// producer / MMA helpers shared by the two kernels
+template <int BN, int A_MN, int B_MN>
+__device__ __forceinline__ void issue_stage_loads(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmKernelParams& p,
+                                                  uint64_t* bar, uint8_t* sa, uint8_t* sb, int tile_m, int tile_n, int k0) {
+  if (A_MN) {
+    if (p.a_3d) {
+      tma_load_3d(tmA, bar, sa, 0, k0, tile_m * (BM / 32));     // lands as [slab][k][32 mn]
+    } else {
+#pragma unroll
+      for (int j = 0; j < BM / 32; ++j) tma_load_2d(tmA, bar, sa + j * (BK * 128), tile_m * BM + j * 32, k0);
+    }
+  } else {
+    tma_load_2d(tmA, bar, sa, k0, tile_m * BM);
+  }
+  if (B_MN) {
+    if (p.b_3d) {
+      tma_load_3d(tmB, bar, sb, 0, k0, tile_n * (BN / 32));
+    } else {
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) tma_load_2d(tmB, bar, sb + j * (BK * 128), tile_n * BN + j * 32, k0);
+    }
+  } else {
+    tma_load_2d(tmB, bar, sb, k0, tile_n * BN);
+  }
+}
+template <int BN, int A_MN, int B_MN>
+__device__ __forceinline__ void issue_stage_mmas(uint32_t sa, uint32_t sb, uint32_t tmem_acc, bool first) {
+  constexpr uint32_t idesc = umma_idesc_tf32(BM, BN, A_MN, B_MN);
+#pragma unroll
+  for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+    // K-major : 8 rows x 128 B swizzle atoms, SBO = 1024 B, advance 32 B (8 floats) per MMA inside the atom
+    // MN-major: [k][32 mn] slabs of BK*128 B (LBO), 4-k-row atoms of 512 B (SBO), advance 8 k-rows = 1024 B
+    const uint64_t adesc = A_MN ? umma_smem_desc(sa + kk * 1024, BK * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                                : umma_smem_desc(sa + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+    const uint64_t bdesc = B_MN ? umma_smem_desc(sb + kk * 1024, BK * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                                : umma_smem_desc(sb + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+    tc_mma_tf32(tmem_acc, adesc, bdesc, idesc, (!first || kk > 0) ? 1u : 0u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM loops over (m-tile, n-tile, k-split) work items.  Two TMEM accumulators
+// (2 x BN columns) let the epilogue of item i overlap the TMA/MMA main loop of item i+1; the smem ring keeps
+// streaming across items.  Epilogue staging has its own smem (the ring is never idle).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const GemmKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 4;
+  constexpr uint32_t B_BYTES = BN * BK * 4;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int MAX_STAGES = 8;
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* tiles = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  float* staging = reinterpret_cast<float*>(tiles + (size_t)p.tile_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * 32 * EPI_SLD);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int splits = (total_kb + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  const int items = tiles_m * tiles_n * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 8);        // one arrival per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (split, m, n): n fastest so that CTAs running at the same time share the A rows in L2
+  auto decode = [&](int item, int& tm, int& tn, int& kb0, int& nkb) {
+    tn = item % tiles_n;
+    const int rest = item / tiles_n;
+    tm = rest % tiles_m;
+    const int sp = rest / tiles_m;
+    kb0 = sp * p.k_blocks_per_split;
+    nkb = min(total_kb, kb0 + p.k_blocks_per_split) - kb0;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int tm, tn, kb0, nkb;
+        decode(item, tm, tn, kb0, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+          issue_stage_loads<BN, A_MN, B_MN>(&tmA, &tmB, p, &full_bar[s], sa, sa + A_BYTES, tm, tn, (kb0 + i) * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, j = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
+        int tm, tn, kb0, nkb;
+        decode(item, tm, tn, kb0, nkb);
+        const int acc = j & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((uint32_t)(j >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * BN);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+          issue_stage_mmas<BN, A_MN, B_MN>(sa, sa + A_BYTES, tacc, i == 0);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    float* stage = staging + (size_t)(warp - 2) * 32 * EPI_SLD;
+    int j = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++j) {
+      int tm, tn, kb0, nkb;
+      decode(item, tm, tn, kb0, nkb);
+      const int acc = j & 1;
+      mbar_wait(&tmem_full_bar[acc], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
 
 template <int BN, int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -135,74 +370,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ================= epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps share a quarter) =========
-    // TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns: every global access of the
-    // fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row segment, and the
-    // loads of 4 row groups are in flight before the first is consumed.
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const Epilogue& e = p.epi;
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);    // all MMAs done => every smem stage has been consumed: the tile area is free
       tc_fence_after();
     }
-    constexpr int SLD = 36;           // staging row stride in floats (16-byte aligned, conflict-free float4 phases)
-    float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * SLD;
-    const int r_sub = lane >> 3;      // 4 rows per pass
-    const int cq = (lane & 7) * 4;    // 4 consecutive columns per lane
-    float alpha = e.alpha;
-    if (e.alpha_dev) alpha *= __ldg(e.alpha_dev);
-#pragma unroll 1
-    for (int c = half; c < BN / 32; c += 2) {
-      const int col0 = tile_n * BN + c * 32;
-      if (col0 >= p.N) break;                       // warp-uniform
-      float v[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      float4* srow = reinterpret_cast<float4*>(stage + lane * SLD);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      const int col = col0 + cq;
-      const int row0 = tile_m * BM + q * 32 + r_sub;
-      if (p.vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-        for (int g4 = 0; g4 < 2; ++g4) {
-          EpiLoads L[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int row = row0 + (g4 * 4 + u) * 4;
-            if (row < p.M) L[u] = epi_load4(e, row, col);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int rl = (g4 * 4 + u) * 4 + r_sub;
-            const int row = row0 + (g4 * 4 + u) * 4;
-            if (row < p.M) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha);
-          }
-        }
-      } else {
-        for (int it = 0; it < 8; ++it) {
-          const int rl = it * 4 + r_sub;
-          const int row = row0 + it * 4;
-          if (row < p.M && col < p.N) {
-            const float4 a4 = *reinterpret_cast<const float4*>(stage + rl * SLD + cq);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            if (p.pair_atomic && col + 4 <= p.N) {      // plain split-K accumulation into an 8-byte aligned row
-              float* dst = e.C + (size_t)row * e.ldc + col;
-              red_add_v2(dst, alpha * av[0], alpha * av[1]);
-              red_add_v2(dst + 2, alpha * av[2], alpha * av[3]);
-            } else {
-              for (int i = 0; i < 4 && col + i < p.N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
+    float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_SLD;
+    epilogue_tile<BN>(p, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0);
   }
 
   tc_fence_before();
@@ -304,6 +477,44 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   }
   size_t tile_bytes = (size_t)stages * stage_bytes;
   if (tile_bytes < 36864) tile_bytes = 36864;      // epilogue staging (8 warps x 32 x 36 floats) reuses the tile area
+  p.epi = g.epi;
+  p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
+  p.a_3d = a3; p.b_3d = b3;
+  {
+    const Epilogue& e = g.epi;
+    p.pair_atomic = (e.store_mode == EPI_ATOMIC && !e.bias && !e.aux_out && !e.mul_in && !e.resid && e.act == EPI_ACT_NONE &&
+                     e.drop.p <= 0.f && !e.round_tf32 && (e.ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 7) == 0) ? 1 : 0;
+  }
+  static int persistent = -1, num_sms = 148;
+  if (persistent < 0) {
+    const char* env = getenv("EEGB200_GEMM_PERSISTENT");
+    persistent = (env && env[0] == '0') ? 0 : 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (persistent && total_kb > 0) {
+    // one CTA per SM: stages fill what is left of the 227 KB after the dedicated epilogue staging
+    int pst = (227 * 1024 - 1024 - 8 * 32 * EPI_SLD * 4 - 512) / stage_bytes;
+    if (pst > 8) pst = 8;
+    if (pst > 2 * p.k_blocks_per_split) pst = 2 * p.k_blocks_per_split;    // ring streams across items
+    if (pst < 2) pst = 2;
+    p.stages = pst;
+    p.tile_bytes = pst * stage_bytes;
+    const size_t psmem = (size_t)p.tile_bytes + 8 * 32 * EPI_SLD * 4 + 1024 + 512;
+    auto pk = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
+    static bool pconf = false;
+    if (!pconf) {
+      EEG_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      pconf = true;
+    }
+    const int items = cdiv(g.N, BN) * cdiv(g.M, BM) * split;
+    const int grid_p = items < num_sms ? items : num_sms;
+    pk<<<grid_p, GEMM_THREADS, psmem, stream>>>(ta, tb, p);
+    EEG_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const size_t smem = tile_bytes + 1024 + 256;
   p.tile_bytes = (int)tile_bytes;
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;

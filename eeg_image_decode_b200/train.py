@@ -187,11 +187,32 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
     total = 0
     features_list = []
     n_batches = 0
-    for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
-        eeg_data = eeg_data.to(device, non_blocking=True)
-        text_features = text_features.to(device, non_blocking=True).float()
-        img_features = img_features.to(device, non_blocking=True).float()
-        labels = labels.to(device, non_blocking=True)
+    # host->device copies of batch i+1 run on a side stream while batch i computes (the reference copies synchronously
+    # at the top of every step, :210-213)
+    copy_stream = torch.cuda.Stream(device=device)
+    main_stream = torch.cuda.current_stream(device)
+
+    def stage(batch):
+        eeg_data, labels, text, text_features, img, img_features = batch
+        with torch.cuda.stream(copy_stream):
+            t = (eeg_data.to(device, non_blocking=True), labels.to(device, non_blocking=True),
+                 text_features.to(device, non_blocking=True).float(), img_features.to(device, non_blocking=True).float())
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return t, ev
+
+    it = iter(dataloader)
+    nxt = next(it, None)
+    staged = stage(nxt) if nxt is not None else None
+    batch_idx = -1
+    while staged is not None:
+        batch_idx += 1
+        (eeg_data, labels, text_features, img_features), ev = staged
+        nxt = next(it, None)
+        staged = stage(nxt) if nxt is not None else None
+        main_stream.wait_event(ev)
+        for t_ in (eeg_data, labels, text_features, img_features):
+            t_.record_stream(main_stream)
         batch_size = eeg_data.size(0)
         subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
         loss, eeg_features = eng.step(eeg_data, subject_ids, img_features, text_features, use_shared)
