@@ -495,8 +495,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                           P[EEGB200_P_LNF_G], w.stf, w.dR2, 256, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B],
                           GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
     // ---- FFN ----
-    EEG_TRY(dropout_apply(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, s));
-    EEG_TRY(colsum(w.T1, 256, M, N_T, GR[EEGB200_P_B2], 0, 0, s));
+    EEG_TRY(dropout_apply_colsum(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, GR[EEGB200_P_B2], N_T, 0, 0, s));
     EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), s));
     {
       Epilogue e = epi_out(w.dU, 256);           // dU = dropout_ffn1(T1 . W2) * GELU'(U)
@@ -516,8 +515,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     EEG_TRY(layernorm_bwd(w.dX1, 256, w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr,
                           w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
     // ---- attention ----
-    EEG_TRY(dropout_apply(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, s));
-    EEG_TRY(colsum(w.T2, 256, M, N_T, GR[EEGB200_P_BO], 0, 0, s));
+    EEG_TRY(dropout_apply_colsum(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, GR[EEGB200_P_BO], N_T, 0, 0, s));
     EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), s));
     EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), s));
     unpack_wo_grad_kernel<<<256, 256, 0, s>>>(w.dWo_p, GR[EEGB200_P_WO]);
@@ -537,8 +535,8 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       EEG_TRY(run_gemm(M, 256, 768, w.dQKV, 768, 0, w.Wqkv_p, 256, 1, e, 1, s));
     }
     // ---- DataEmbedding ----
-    EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
-    EEG_TRY(colsum(w.T3, 256, M, N_T, GR[EEGB200_P_VALUE_B], N_TOK, 0, s));   // token-0 rows carry no value embedding
+    // token-0 rows carry no value embedding -> excluded from the bias gradient
+    EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
     EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), s));
     EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,
                 "subject-token gradients need both the table and the shared-token grad buffers");

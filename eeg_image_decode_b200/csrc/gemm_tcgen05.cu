@@ -493,7 +493,9 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (persistent && total_kb > 0) {
+  // persistent (1 CTA/SM, overlapped epilogue) pays off when the main loop is long; the short-K token GEMMs are bound by
+  // epilogue memory latency and run faster as two co-resident CTAs per SM (16 epilogue warps) -- measured on B200
+  if (persistent && total_kb > 0 && p.k_blocks_per_split >= 16) {
     // one CTA per SM: stages fill what is left of the 227 KB after the dedicated epilogue staging
     int pst = (227 * 1024 - 1024 - 8 * 32 * EPI_SLD * 4 - 512) / stage_bytes;
     if (pst > 8) pst = 8;

@@ -52,6 +52,8 @@ int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, 
 int dropout_mask(DropoutCfg cfg, int rows, int cols, int ld, float* out, cudaStream_t s);
 // dst[r*ld+c] = tf32?(keep(r*ld+c) ? src*scale : 0) over [rows, ld]
 int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, cudaStream_t s);
+int dropout_apply_colsum(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, float* colsum_out,
+                         int cs_cols, int row_mod, int row_skip, cudaStream_t s);
 int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, int rows_dst, int round_tf,
              float scale, cudaStream_t s);
 

@@ -431,6 +431,56 @@ int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int l
 }  // namespace eegb200
 
 namespace eegb200 {
+// dst = tf32?(dropout(src)) over [rows, ld]; optionally colsum[c] += sum_r dst[r][c] for c < cs_cols (bias gradient
+// of the layer whose output fed this dropout), rows with r % row_mod == row_skip excluded.  Block = 64 float4
+// columns x 4 row lanes (ld <= 256) so that each thread stays on one column quad.
+__global__ void __launch_bounds__(256) dropout_apply_colsum_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                   int rows, int ld, DropoutCfg cfg, int round_tf,
+                                                                   float* __restrict__ colsum, int cs_cols, int row_mod,
+                                                                   int row_skip) {
+  __shared__ float4 part[4][64];
+  const int c4 = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int ld4 = ld >> 2;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < ld4) {
+    for (int r = blockIdx.x * 4 + ry; r < rows; r += gridDim.x * 4) {
+      const size_t i = (size_t)r * ld4 + c4;
+      float4 v = reinterpret_cast<const float4*>(src)[i];
+      if (cfg.p > 0.f) {
+        const uint32_t m = dropout_keep4(cfg, (uint64_t)i * 4);
+        v.x = (m & 1u) ? v.x * cfg.scale : 0.f;
+        v.y = (m & 2u) ? v.y * cfg.scale : 0.f;
+        v.z = (m & 4u) ? v.z * cfg.scale : 0.f;
+        v.w = (m & 8u) ? v.w * cfg.scale : 0.f;
+      }
+      if (round_tf) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
+      reinterpret_cast<float4*>(dst)[i] = v;
+      if (!(row_mod > 0 && (r % row_mod) == row_skip)) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+    }
+  }
+  part[ry][c4] = acc;
+  __syncthreads();
+  if (ry == 0 && c4 < ld4) {
+    float4 t = part[0][c4];
+    for (int i = 1; i < 4; ++i) { t.x += part[i][c4].x; t.y += part[i][c4].y; t.z += part[i][c4].z; t.w += part[i][c4].w; }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+    for (int q = 0; q < 4; ++q)
+      if (c4 * 4 + q < cs_cols) atomicAdd(&colsum[c4 * 4 + q], tv[q]);
+  }
+}
+int dropout_apply_colsum(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, float* colsum_out,
+                         int cs_cols, int row_mod, int row_skip, cudaStream_t s) {
+  ProfScope _ps("dropout_apply_colsum", s, 0.0, (double)rows * ld * 8.0);
+  EEG_REQUIRE((ld & 3) == 0 && ld <= 256, "dropout_apply_colsum: ld %d must be a multiple of 4 and <= 256", ld);
+  int blocks = cdiv(rows, 4 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dropout_apply_colsum_kernel<<<blocks, 256, 0, s>>>(src, dst, rows, ld, cfg, round_tf, colsum_out, cs_cols, row_mod, row_skip);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 __global__ void dropout_apply_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long n4, DropoutCfg cfg,
                                      int round_tf) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

@@ -108,6 +108,7 @@ class StepEngine:
         m.zero_flat_grads()
         seed = m.next_seed() if seed is None else seed
         if W > 1:
+            seed ^= (self.rank + 1) * 0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF     # decorrelate the ranks' dropout masks
             # SyncBN: all-reduce the batch statistics between the forward phases
             m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A)
             self._allreduce(m.ws_tensor("bn1_sums"))
@@ -115,6 +116,8 @@ class StepEngine:
             self._phase(_lib.PHASE_B, fwd=True, batch_scale=W)
             self._allreduce(m.ws_tensor("bn2_sums"))
             self._phase(_lib.PHASE_C, fwd=True, batch_scale=W)
+            for bn in (m.enc_eeg[0].tsconv[2], m.enc_eeg[0].tsconv[5]):
+                bn.num_batches_tracked.add_(1)
             feats = out
         else:
             feats = m.encode(eeg, subject_ids, train=True, seed=seed)

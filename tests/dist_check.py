@@ -1,0 +1,100 @@
+"""Data-parallel equivalence check (run under torchrun, one process per GPU):
+W ranks x B_local  ==  one process at batch W*B_local  (loss, embeddings, every gradient, BN running stats, updated
+parameters).  Both sides run the exact-fp32 verification backend so the comparison is tight (1e-4), then the product
+(TF32) backend is checked against the same reference with TF32 tolerances."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import recipe  # noqa: E402
+from eeg_image_decode_b200 import _lib  # noqa: E402
+from eeg_image_decode_b200.atms import ATMS  # noqa: E402
+from eeg_image_decode_b200.train import StepEngine  # noqa: E402
+
+
+def make_model(p_drop):
+    m = ATMS()
+    m.load_state_dict(recipe.make_state_dict())
+    m = m.cuda().train()
+    m.dropout_p = [p_drop] * 8
+    return m
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    Bl = 8
+    N = Bl * world
+    x = recipe.make_eeg(N, seed=71).cuda()
+    sid = torch.full((N,), 8).cuda()
+    img = recipe.make_targets(N, seed=71, tag="img").cuda()
+    txt = recipe.make_targets(N, seed=71, tag="txt").cuda()
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    ok = True
+    for backend, tol_f, tol_g in ((1, 5e-5, 2e-3), (0, 1.5e-3, 4e-2)):
+        _lib.set_gemm_backend(backend)
+        # --- data parallel
+        m = make_model(0.0)
+        eng = StepEngine(m, None)
+        assert eng.world == world
+        loss, feats = eng.step(x[sl], sid[sl], img[sl], txt[sl], use_shared=False)
+        total = loss.clone()
+        dist.all_reduce(total)
+        # --- single process at the global batch (same library, no collectives)
+        ref = make_model(0.0)
+        e1 = StepEngine(ref, None)
+        e1.world, e1.rank = 1, 0
+        rloss, rfeats = e1.step(x, sid, img, txt, use_shared=False)
+        torch.cuda.synchronize()
+
+        def rel(a, b):
+            return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+        errs = {"loss": abs(total[0].item() - rloss[0].item()) / abs(rloss[0].item()), "feats": rel(feats, rfeats[sl])}
+        worst_g = 0.0
+        for k in ("proj_eeg.0.weight", "proj_eeg.2.weight", "enc_eeg.0.tsconv.0.weight", "enc_eeg.0.tsconv.2.weight",
+                  "enc_eeg.0.tsconv.4.weight", "enc_eeg.0.tsconv.5.bias", "enc_eeg.0.projection.0.weight",
+                  "encoder.encoder.attn_layers.0.attention.query_projection.weight",
+                  "encoder.encoder.attn_layers.0.conv1.weight", "encoder.encoder.attn_layers.0.norm1.weight",
+                  "encoder.enc_embedding.value_embedding.weight",
+                  "encoder.enc_embedding.subject_embedding.subject_embedding.weight", "logit_scale"):
+            worst_g = max(worst_g, rel(m.grad_view(k), ref.grad_view(k)))
+        errs["grads"] = worst_g
+        bn = max(rel(m.state_dict()[k], ref.state_dict()[k]) for k in
+                 ("enc_eeg.0.tsconv.2.running_mean", "enc_eeg.0.tsconv.2.running_var", "enc_eeg.0.tsconv.5.running_var"))
+        errs["bn_running"] = bn
+        good = errs["loss"] < tol_f * 10 and errs["feats"] < tol_f and errs["grads"] < tol_g and bn < tol_f * 10
+        # ranks stay in sync after the update
+        w = m.state_dict()["proj_eeg.0.weight"].clone()
+        w0 = w.clone()
+        dist.broadcast(w0, 0)
+        sync = torch.equal(w, w0)
+        if rank == 0:
+            print(f"backend={backend} world={world} errs={errs} ranks_in_sync={sync} -> {'PASS' if good and sync else 'FAIL'}", flush=True)
+        ok = ok and good and sync
+    _lib.set_gemm_backend(0)
+    # dropout on: just has to run and stay finite / in sync
+    m = make_model(0.25)
+    eng = StepEngine(m, None)
+    loss, feats = eng.step(x[sl], sid[sl], img[sl], txt[sl], use_shared=False)
+    fin = bool(torch.isfinite(loss).all().item()) and bool(torch.isfinite(m.flat_params).all().item())
+    if rank == 0:
+        print(f"dropout step finite={fin}", flush=True)
+    ok = ok and fin
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("DIST_CHECK " + ("PASS" if ok else "FAIL"), flush=True)
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
