@@ -166,6 +166,7 @@ class AtmsIO(ctypes.Structure):
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
         ("out", ctypes.c_void_p),
+        ("seed_offset_dev", ctypes.c_void_p),
     ]
 
 
@@ -203,6 +204,9 @@ def _sig():
     L.eegb200_adamw_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    L.eegb200_adamw_step_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
     L.eegb200_dropout_mask.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L._eeg_sig_done = True
@@ -245,6 +249,11 @@ def infonce(io: InfoNceIO, phases: int) -> None:
 def adamw_step(p, g, m, v, n, lr, b1, b2, eps, wd, step) -> None:
     check(_sig().eegb200_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, int(step), stream_ptr()),
           "adamw_step")
+
+
+def adamw_step_dev(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev) -> None:
+    check(_sig().eegb200_adamw_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, ptr(step_dev),
+                                        stream_ptr()), "adamw_step_dev")
 
 
 def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int):

@@ -173,6 +173,8 @@ class ATMS(nn.Module):
         self._adam_steps = {"main": 0, "table": 0, "shared": 0}
         self._ptr_cache = None
         self._ws = {}
+        # device counter mixed into the dropout seed by the kernels (0 unless a captured CUDA graph advances it)
+        self._seed_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def _apply(self, fn, recurse=True):
         r = super()._apply(fn, recurse)
@@ -225,6 +227,7 @@ class ATMS(nn.Module):
         io.workspace = ws.data_ptr()
         io.workspace_bytes = ws.numel()
         io.out = out.data_ptr()
+        io.seed_offset_dev = self._seed_ctr.data_ptr() if self._seed_ctr.is_cuda else None
         return io
 
     def _check_inputs(self, x, subject_ids):

@@ -194,4 +194,10 @@ int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n
   return adamw_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
 }
 
+int eegb200_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, const long long* step_dev, void* stream) {
+  EEG_REQUIRE(p && g && m && v && n > 0 && step_dev, "adamw_dev: bad arguments");
+  return adamw_step_dev(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, (cudaStream_t)stream);
+}
+
 }  // extern "C"

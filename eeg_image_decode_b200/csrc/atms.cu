@@ -298,7 +298,8 @@ static Cfg make_cfg(const eegb200_atms_io* io) {
   Cfg c;
   for (int i = 0; i < EEGB200_SITE_COUNT; ++i) {
     const float p = io->dropout_p ? io->dropout_p[i] : ref_p[i];
-    c.d[i] = make_dropout(io->seed, (uint32_t)i, p, io->train != 0);
+    c.d[i] = make_dropout(io->seed, (uint32_t)i, p, io->train != 0,
+                           reinterpret_cast<const unsigned long long*>(io->seed_offset_dev));
   }
   return c;
 }

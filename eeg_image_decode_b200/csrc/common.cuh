@@ -97,14 +97,18 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
 }
 
 struct DropoutCfg {
+  const unsigned long long* seed_dev;   // optional device counter added to `seed` at run time (lets a captured CUDA graph
+                                        // draw fresh masks on every replay); nullptr -> `seed` alone
   uint64_t seed;
   uint32_t site;     // which dropout layer
   float p;           // drop probability; p <= 0 disables
   float scale;       // 1/(1-p)
   uint32_t thresh;   // keep iff rnd >= thresh
 };
-static inline DropoutCfg make_dropout(uint64_t seed, uint32_t site, float p, bool train) {
+static inline DropoutCfg make_dropout(uint64_t seed, uint32_t site, float p, bool train,
+                                      const unsigned long long* seed_dev = nullptr) {
   DropoutCfg d;
+  d.seed_dev = seed_dev;
   d.seed = seed; d.site = site;
   d.p = (train && p > 0.f) ? p : 0.f;
   d.scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
@@ -113,19 +117,22 @@ static inline DropoutCfg make_dropout(uint64_t seed, uint32_t site, float p, boo
   return d;
 }
 // keep-mask for element `idx` of site `cfg.site`: 4 consecutive elements share one Philox call.
+__device__ __forceinline__ uint64_t dropout_seed(const DropoutCfg& cfg) {
+  return cfg.seed_dev ? cfg.seed + __ldg(cfg.seed_dev) * 0x9E3779B97F4A7C15ull : cfg.seed;
+}
 __device__ __forceinline__ bool dropout_keep(const DropoutCfg& cfg, uint64_t idx) {
   uint32_t r[4];
   const uint64_t blk = idx >> 2;
-  philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), cfg.site, 0x5EEDu,
-                (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), r);
+  const uint64_t sd = dropout_seed(cfg);
+  philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), cfg.site, 0x5EEDu, (uint32_t)sd, (uint32_t)(sd >> 32), r);
   return r[idx & 3] >= cfg.thresh;
 }
 // keep-masks for the 4 consecutive elements starting at idx (idx % 4 == 0); bit i = keep element i
 __device__ __forceinline__ uint32_t dropout_keep4(const DropoutCfg& cfg, uint64_t idx) {
   uint32_t r[4];
   const uint64_t blk = idx >> 2;
-  philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), cfg.site, 0x5EEDu,
-                (uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32), r);
+  const uint64_t sd = dropout_seed(cfg);
+  philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), cfg.site, 0x5EEDu, (uint32_t)sd, (uint32_t)(sd >> 32), r);
   return (r[0] >= cfg.thresh ? 1u : 0u) | (r[1] >= cfg.thresh ? 2u : 0u) |
          (r[2] >= cfg.thresh ? 4u : 0u) | (r[3] >= cfg.thresh ? 8u : 0u);
 }

@@ -27,7 +27,7 @@ struct Epilogue {
   float* aux_out = nullptr;      // pre-activation copy
   int ld_aux = 0;
   int act = EPI_ACT_NONE;
-  DropoutCfg drop = {0, 0, 0.f, 1.f, 0};
+  DropoutCfg drop = {nullptr, 0, 0, 0.f, 1.f, 0};
   int drop_ld = 0;               // mask element index = row*drop_ld + col
   const float* mul_in = nullptr; // v *= gelu'(mul_in[row,col])
   int ld_mul = 0;

@@ -116,6 +116,8 @@ int argmax_count(const float* logits, int ld, int rows, int cols, const long lon
 int topk5(const float* logits, int ld, int rows, int cols, int* top5_out /*[rows][5]*/, cudaStream_t s);
 
 // ---- optim.cu ----
+int adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                   float wd, const long long* step_dev, cudaStream_t s);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                float wd, int step, cudaStream_t s);
 

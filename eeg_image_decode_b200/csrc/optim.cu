@@ -34,6 +34,38 @@ __global__ void adamw_tail_kernel(float* p, const float* g, float* m, float* v, 
   p[i] = P; m[i] = M; v[i] = V;
 }
 
+// bias corrections computed on the device from a step counter in global memory
+__global__ void adamw_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                                 const long long* __restrict__ step_dev) {
+  __shared__ float s_step, s_isq;
+  if (threadIdx.x == 0) {
+    const double st = (double)step_dev[0];
+    s_step = (float)((double)lr / (1.0 - pow((double)b1, st)));
+    s_isq = (float)(1.0 / sqrt(1.0 - pow((double)b2, st)));
+  }
+  __syncthreads();
+  const float step_size = s_step, inv_sqrt_bc2 = s_isq, decay = 1.f - lr * wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float P = p[i] * decay;
+    const float G = g[i];
+    const float M = m[i] + (G - m[i]) * (1.f - b1);
+    const float V = v[i] * b2 + (1.f - b2) * G * G;
+    P -= step_size * (M / (sqrtf(V) * inv_sqrt_bc2 + eps));
+    p[i] = P; m[i] = M; v[i] = V;
+  }
+}
+int adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                   float wd, const long long* step_dev, cudaStream_t s) {
+  ProfScope _ps("adamw", s, 0.0, (double)n * 28.0);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adamw_dev_kernel<<<blocks, 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                float wd, int step, cudaStream_t s) {
   ProfScope _ps("adamw", s, 0.0, (double)n * 28.0);

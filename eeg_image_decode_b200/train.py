@@ -47,7 +47,7 @@ def _adam_hparams(optimizer):
     return dict(lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
 
 
-def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False) -> None:
+def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False, device_steps=None) -> None:
     """torch.optim.AdamW semantics on model.flat_params / model.flat_grads.  Parameters that received no gradient
     this step (the unused half of {subject table, shared token}; the never-used cold parameters) are skipped, as
     torch.optim does for ``grad is None``."""
@@ -61,6 +61,12 @@ def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False) -> N
     segs = [("main", 0, n_main)]
     segs.append(("shared", o_sh, 250) if use_shared else ("table", o_tab, N_SUBJECT_ROWS * 250))
     for name, off, n in segs:
+        if device_steps is not None:
+            # CUDA-graph path: the step number lives in device memory and is advanced inside the captured graph
+            device_steps[name].add_(1)
+            _lib.adamw_step_dev(model.flat_params[off:], model.flat_grads[off:], model._adam_m[off:], model._adam_v[off:], n,
+                                hp["lr"], hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"], device_steps[name])
+            continue
         model._adam_steps[name] += 1
         _lib.adamw_step(model.flat_params[off:], model.flat_grads[off:], model._adam_m[off:], model._adam_v[off:], n,
                         hp["lr"], hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"], model._adam_steps[name])
@@ -101,7 +107,7 @@ class StepEngine:
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
 
-    def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None):
+    def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None, device_steps=None):
         """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024])"""
         m = self.model
         W = self.world
@@ -136,7 +142,7 @@ class StepEngine:
         else:
             m.backprop(d_e)
         if self.fused:
-            fused_adamw_step(m, self.optimizer, use_shared)
+            fused_adamw_step(m, self.optimizer, use_shared, device_steps)
         else:
             self._generic_optimizer_step(use_shared)
         return loss, feats
@@ -164,6 +170,59 @@ class StepEngine:
         self.optimizer.step()
 
 
+class GraphedTrainStep:
+    """The whole training step (forward, 2x InfoNCE, backward, AdamW, train-accuracy scoring: ~90 kernel launches)
+    captured once into a CUDA graph and replayed.  The first two calls run eagerly (they create workspaces, optimiser
+    state and kernel attributes); the third call captures -- capture does not execute -- and replays.  Everything that
+    changes from step to step lives in device memory: inputs are copied into static buffers, the dropout seed is
+    `seed + device counter`, the AdamW step numbers are device counters advanced inside the graph.
+    Falls back to eager execution for data-parallel runs, foreign optimisers and odd batch sizes."""
+
+    def __init__(self, eng: "StepEngine", gallery, use_shared: bool, enabled: bool = True):
+        import os
+        self.eng, self.gallery, self.use_shared = eng, gallery, use_shared
+        self.enabled = enabled and os.environ.get("EEGB200_CUDA_GRAPH", "1") != "0"
+        self.graph = None
+        self.calls = 0
+        self.B = None
+        self.launches_per_replay = 0
+        self.replays = 0
+
+    def _body(self, eeg, sid, img, txt, labels, device_steps):
+        loss, feats = self.eng.step(eeg, sid, img, txt, self.use_shared, device_steps=device_steps)
+        r = _lib.retrieval(feats, self.gallery, self.eng.model.logit_scale.detach(), labels=labels, want_top5=False)
+        return loss, feats, r["correct"]
+
+    def __call__(self, eeg, sid, img, txt, labels):
+        eng = self.eng
+        m = eng.model
+        B = eeg.shape[0]
+        ok = self.enabled and eng.world == 1 and eng.fused
+        if not ok or (self.graph is None and self.calls < 2) or (self.B is not None and B != self.B):
+            self.calls += 1
+            return self._body(eeg, sid, img, txt, labels, None)
+        if self.graph is None:
+            self.B = B
+            self.s = [t.clone() for t in (eeg, sid, img, txt, labels)]
+            self.dev_steps = {k: torch.tensor([v], dtype=torch.int64, device=eeg.device) for k, v in m._adam_steps.items()}
+            torch.cuda.synchronize()
+            n0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = self._body(*self.s, self.dev_steps)
+                m._seed_ctr.add_(1)
+            self.launches_per_replay = _lib.launch_count() - n0
+            self.graph = g
+        else:
+            for dst, src in zip(self.s, (eeg, sid, img, txt, labels)):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        self.replays += 1
+        m._adam_steps["main"] += 1
+        m._adam_steps["shared" if self.use_shared else "table"] += 1
+        return self.out
+
+
 def _BN_SCALE_SHIFT(world: int) -> int:
     """phase-mask bits 8..15 carry the SyncBN world size (0/1 = local statistics)"""
     return (int(world) & 0xFF) << 8
@@ -185,6 +244,7 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
     eng = StepEngine(eeg_model, optimizer, alpha)
     subject_id = extract_id_from_string(sub)
     use_shared = subject_id is None or subject_id >= N_SUBJECT_ROWS or subject_id < 0
+    gstep = GraphedTrainStep(eng, img_features_all, use_shared)
     loss_acc = torch.zeros(3, device=device)
     correct = torch.zeros(1, device=device, dtype=torch.int32)
     total = 0
@@ -218,12 +278,11 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
             t_.record_stream(main_stream)
         batch_size = eeg_data.size(0)
         subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
-        loss, eeg_features = eng.step(eeg_data, subject_ids, img_features, text_features, use_shared)
+        # step + train accuracy against the 1654-way prototype gallery (:241-250, scored with the post-update logit_scale)
+        loss, eeg_features, n_ok = gstep(eeg_data, subject_ids, img_features, text_features, labels)
         loss_acc += loss
         features_list.append(eeg_features.clone())
-        # train accuracy against the 1654-way prototype gallery (:241-250), scored with the post-update logit_scale
-        r = _lib.retrieval(eeg_features, img_features_all, eeg_model.logit_scale.detach(), labels=labels, want_top5=False)
-        correct += r["correct"]
+        correct += n_ok
         total += batch_size
         n_batches += 1
         if step_callback is not None:

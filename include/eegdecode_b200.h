@@ -127,6 +127,8 @@ typedef struct eegb200_atms_io {
   void* workspace;               /* >= eegb200_atms_workspace_bytes(B); holds the saved activations */
   size_t workspace_bytes;
   float* out;                    /* [B,1024] */
+  const uint64_t* seed_offset_dev; /* optional DEVICE counter mixed into `seed` when the kernels run (CUDA-graph replay
+                                      draws new dropout masks without re-capturing); NULL -> `seed` alone */
 } eegb200_atms_io;
 
 size_t eegb200_atms_workspace_bytes(int B);
@@ -177,6 +179,9 @@ int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int 
 /* torch.optim.AdamW semantics on a flat arena (ATMS_retrieval.py:548, :237) */
 int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, void* stream);
+/* same, with the step number read from DEVICE memory when the kernel runs (CUDA-graph friendly) */
+int eegb200_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, const long long* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

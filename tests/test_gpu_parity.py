@@ -482,3 +482,36 @@ def test_data_parallel_equals_single_process():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", script],
                        capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cuda_graph_step_matches_eager(lib):
+    """the captured step (device-side dropout counter / AdamW step counters) reproduces eager training"""
+    from eeg_image_decode_b200.train import GraphedTrainStep, StepEngine
+    B = 8
+    xs = [recipe.make_eeg(B, seed=80 + i).cuda() for i in range(5)]
+    sid = torch.full((B,), 8).cuda()
+    img = recipe.make_targets(B, seed=80, tag="img").cuda()
+    txt = recipe.make_targets(B, seed=80, tag="txt").cuda()
+    lab = recipe.make_labels(B, 50, seed=80).cuda()
+    gal = recipe.make_targets(50, seed=80, tag="gal").cuda()
+    outs = {}
+    for graphed in (False, True):
+        m = make_model(p_drop=0.0).train()
+        eng = StepEngine(m, None)
+        gs = GraphedTrainStep(eng, gal, use_shared=False, enabled=graphed)
+        losses = []
+        for i in range(5):
+            loss, feats, n_ok = gs(xs[i], sid, img, txt, lab)
+            losses.append(loss[0].item())
+        assert (gs.graph is not None) == graphed
+        outs[graphed] = (losses, m.flat_params.clone(), dict(m._adam_steps))
+    assert outs[True][2] == outs[False][2]
+    for a, b in zip(outs[True][0], outs[False][0]):
+        assert abs(a - b) < 2e-4 * abs(b), (outs[True][0], outs[False][0])
+    d = (outs[True][1] - outs[False][1]).abs()
+    assert (d > 1e-4).float().mean().item() < 2e-2      # AdamW sign flips on ~0 gradients only
+    # dropout active: replays must draw different masks (device counter) -> different losses on identical input
+    m = make_model().train()
+    gs = GraphedTrainStep(StepEngine(m, None), gal, use_shared=False)
+    ls = [gs(xs[0], sid, img, txt, lab)[0][0].item() for _ in range(5)]
+    assert gs.graph is not None and len({round(v, 4) for v in ls[2:]}) == 3, ls
