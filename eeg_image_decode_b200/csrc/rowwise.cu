@@ -443,19 +443,31 @@ __global__ void __launch_bounds__(256) dropout_apply_colsum_kernel(const float* 
   const int ld4 = ld >> 2;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c4 < ld4) {
-    for (int r = blockIdx.x * 4 + ry; r < rows; r += gridDim.x * 4) {
-      const size_t i = (size_t)r * ld4 + c4;
-      float4 v = reinterpret_cast<const float4*>(src)[i];
-      if (cfg.p > 0.f) {
-        const uint32_t m = dropout_keep4(cfg, (uint64_t)i * 4);
-        v.x = (m & 1u) ? v.x * cfg.scale : 0.f;
-        v.y = (m & 2u) ? v.y * cfg.scale : 0.f;
-        v.z = (m & 4u) ? v.z * cfg.scale : 0.f;
-        v.w = (m & 8u) ? v.w * cfg.scale : 0.f;
+    const int stride = gridDim.x * 4;
+    for (int r0 = blockIdx.x * 4 + ry; r0 < rows; r0 += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * stride;
+        if (r < rows) v[u] = reinterpret_cast<const float4*>(src)[(size_t)r * ld4 + c4];
       }
-      if (round_tf) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
-      reinterpret_cast<float4*>(dst)[i] = v;
-      if (!(row_mod > 0 && (r % row_mod) == row_skip)) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * stride;
+        if (r >= rows) continue;
+        const size_t i = (size_t)r * ld4 + c4;
+        float4 w = v[u];
+        if (cfg.p > 0.f) {
+          const uint32_t m = dropout_keep4(cfg, (uint64_t)i * 4);
+          w.x = (m & 1u) ? w.x * cfg.scale : 0.f;
+          w.y = (m & 2u) ? w.y * cfg.scale : 0.f;
+          w.z = (m & 4u) ? w.z * cfg.scale : 0.f;
+          w.w = (m & 8u) ? w.w * cfg.scale : 0.f;
+        }
+        if (round_tf) { w.x = tf32_rn(w.x); w.y = tf32_rn(w.y); w.z = tf32_rn(w.z); w.w = tf32_rn(w.w); }
+        reinterpret_cast<float4*>(dst)[i] = w;
+        if (!(row_mod > 0 && (r % row_mod) == row_skip)) { acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w; }
+      }
     }
   }
   part[ry][c4] = acc;
@@ -472,7 +484,7 @@ int dropout_apply_colsum(const float* src, float* dst, int rows, int ld, Dropout
                          int cs_cols, int row_mod, int row_skip, cudaStream_t s) {
   ProfScope _ps("dropout_apply_colsum", s, 0.0, (double)rows * ld * 8.0);
   EEG_REQUIRE((ld & 3) == 0 && ld <= 256, "dropout_apply_colsum: ld %d must be a multiple of 4 and <= 256", ld);
-  int blocks = cdiv(rows, 4 * 8);
+  int blocks = cdiv(rows, 4 * 16);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   dropout_apply_colsum_kernel<<<blocks, 256, 0, s>>>(src, dst, rows, ld, cfg, round_tf, colsum_out, cs_cols, row_mod, row_skip);
