@@ -300,6 +300,11 @@ def bench_ours(args):
             ach = v["bytes"] / v["n"] / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            roof["traffic"] = traffic.get(name)
+        except Exception:
+            pass
         roof["share_of_step"] = v["ms"] / tot
         roof["sum_kernel_ms_per_step"] = tot / n_prof
 
