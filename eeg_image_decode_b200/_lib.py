@@ -271,7 +271,7 @@ def retrieval(eeg, gallery, logit_scale, sel=None, labels=None, want_top5=True):
     ld = (G + 3) // 4 * 4
     dev = eeg.device
     logits = torch.empty(Q, ld, device=dev, dtype=torch.float32)
-    round_ws = torch.empty(2 * (Q + G) * D, device=dev, dtype=torch.float32)
+    round_ws = torch.empty(3 * (Q + G) * D, device=dev, dtype=torch.float32)
     top1 = torch.empty(Q, device=dev, dtype=torch.int64)
     top5 = torch.empty(Q, 5, device=dev, dtype=torch.int32) if want_top5 else None
     correct = torch.zeros(1, device=dev, dtype=torch.int32)

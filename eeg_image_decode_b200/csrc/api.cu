@@ -155,23 +155,19 @@ int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int 
   EEG_REQUIRE(eeg && gallery && logit_scale && logits_ws && round_ws, "retrieval: null pointer");
   EEG_REQUIRE(Q > 0 && G > 0 && D > 0 && (D & 3) == 0 && ld >= G && (ld & 3) == 0, "retrieval: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
-  // 3xTF32: near-fp32 scores so that retrieval ranks match the fp32 reference except for exact ties
-  float* e_hi = reinterpret_cast<float*>(round_ws);
-  float* e_lo = e_hi + (size_t)Q * D;
-  float* g_hi = e_lo + (size_t)Q * D;
-  float* g_lo = g_hi + (size_t)G * D;
-  EEG_TRY(split_tf32(eeg, e_hi, e_lo, (long long)Q * D, s));
-  EEG_TRY(split_tf32(gallery, g_hi, g_lo, (long long)G * D, s));
-  const float* As[3] = {e_lo, e_hi, e_hi};
-  const float* Bs[3] = {g_hi, g_lo, g_hi};
-  for (int i = 0; i < 3; ++i) {                    // small terms first
+  // 3xTF32 (hi.hi + hi.lo + lo.hi) as one GEMM over K = 3*D: near-fp32 scores, so retrieval ranks match the fp32
+  // reference except for exact ties
+  float* a3 = reinterpret_cast<float*>(round_ws);
+  float* b3 = a3 + (size_t)Q * 3 * D;
+  EEG_TRY(split3_tf32(eeg, a3, Q, D, 0, s));
+  EEG_TRY(split3_tf32(gallery, b3, G, D, 1, s));
+  {
     GemmArgs g;
-    g.M = Q; g.N = G; g.K = D;
-    g.A = {As[i], D, 0};
-    g.B = {Bs[i], D, 0};
+    g.M = Q; g.N = G; g.K = 3 * D;
+    g.A = {a3, 3 * D, 0};
+    g.B = {b3, 3 * D, 0};
     g.epi.C = logits_ws; g.epi.ldc = ld;
     g.epi.alpha_dev = logit_scale;
-    g.epi.store_mode = i == 0 ? EPI_STORE : EPI_ADD;
     EEG_TRY(gemm_launch(g, s));
   }
   const float* scores = logits_ws;

@@ -481,11 +481,20 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                      pick_split(N_FILT, K_SPAT, R), s));
     unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(w.dWs_p, GR[EEGB200_P_WS]);
     count_launch();
-    // dA1 = dY2 . Ws
-    EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, epi_out(w.dA1, K_SPAT), 1, s));
+    // dA1 = dY2 . Ws, then dz1 = dA1 * ELU'(BN1(y1)) and the two BN1-backward reductions
     EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
-    EEG_TRY(bn1_bwd_reduce(w.dA1, w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.bn1_bsums,
-                           (long long)R * K_SPAT, s));
+    if (RT) {
+      // tensor-core path: ELU', the y1 read and both reductions ride in the GEMM epilogue (no separate 1.1 GB pass)
+      Epilogue e = epi_out(w.dA1, K_SPAT);
+      e.bn_y = w.Y1; e.ld_bn_y = K_SPAT;
+      e.bn_mean_rstd = w.bn1_mr; e.bn_gamma = P[EEGB200_P_BN1_G]; e.bn_beta = P[EEGB200_P_BN1_B];
+      e.bn_sums = w.bn1_bsums;
+      EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, e, 1, s));
+    } else {
+      EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, epi_out(w.dA1, K_SPAT), 1, s));
+      EEG_TRY(bn1_bwd_reduce(w.dA1, w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.bn1_bsums,
+                             (long long)R * K_SPAT, s));
+    }
   }
   if (phases & EEGB200_PHASE_C) {
     EEG_TRY(conv_temporal_bwd(w.dA1, w.Y1, w.X3, P[EEGB200_P_WT], w.bn1_mr, P[EEGB200_P_BN1_G], w.bn1_bsums,

@@ -35,6 +35,15 @@ struct Epilogue {
   int ld_res = 0;
   int round_tf32 = 0;
   int store_mode = EPI_STORE;
+  // fused BatchNorm(train)+ELU backward of the conv stack (tcgen05 vector path only):
+  //   v *= ELU'(gamma[c]*yhat + beta[c]),  yhat = (bn_y[row,col] - mean[c]) * rstd[c],  c = col % 40
+  //   bn_sums[c] += v,  bn_sums[40+c] += v*yhat      (the two reductions the BatchNorm backward needs)
+  const float* bn_y = nullptr;
+  int ld_bn_y = 0;
+  const float* bn_mean_rstd = nullptr;   // [2][40]
+  const float* bn_gamma = nullptr;
+  const float* bn_beta = nullptr;
+  double* bn_sums = nullptr;             // [2][40]
 };
 
 struct GemmArgs {
@@ -98,11 +107,25 @@ __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int co
   L.bias = L.mul = L.resid = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
   if (e.mul_in) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
+  if (e.bn_y) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
   if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
   return L;
 }
-__device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a) {
+__device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
+                                            float* bn_s1 = nullptr, float* bn_s2 = nullptr) {
   float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
+  if (e.bn_y) {
+    const int c = col % 40;
+    const float yv[4] = {L.mul.x, L.mul.y, L.mul.z, L.mul.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float yh = (yv[i] - __ldg(e.bn_mean_rstd + c + i)) * __ldg(e.bn_mean_rstd + 40 + c + i);
+      const float z = fmaf(yh, __ldg(e.bn_gamma + c + i), __ldg(e.bn_beta + c + i));
+      v[i] *= elu1_grad(z);
+      bn_s1[i] += v[i];
+      bn_s2[i] = fmaf(v[i], yh, bn_s2[i]);
+    }
+  }
   if (e.bias) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
   if (e.aux_out) *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
   if (e.act == EPI_ACT_GELU) {
@@ -142,6 +165,7 @@ static inline bool epi_vec_ok(const Epilogue& e) {
   if (e.mul_in) ok = ok && al(e.mul_in) && (e.ld_mul & 3) == 0;
   if (e.resid) ok = ok && al(e.resid) && (e.ld_res & 3) == 0;
   if (e.drop.p > 0.f) ok = ok && (e.drop_ld & 3) == 0;
+  if (e.bn_y) ok = ok && al(e.bn_y) && (e.ld_bn_y & 3) == 0;
   return ok;
 }
 

@@ -38,7 +38,7 @@ static constexpr int EPI_SLD = 36;   // staging row stride in floats (16-byte al
 // segment, and the loads of 4 row groups are in flight before the first is consumed.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t tmem_acc, float* stage, int tile_m,
-                                              int tile_n, int warp, int lane, bool has_acc) {
+                                              int tile_n, int warp, int lane, bool has_acc, float* sred) {
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
   const Epilogue& e = p.epi;
@@ -64,20 +64,34 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
     __syncwarp();
     const int col = col0 + cq;
     const int row0 = tile_m * BM + q * 32 + r_sub;
-    if (p.vec_ok && col0 + 32 <= p.N) {
+    if (p.vec_ok) {                                  // N % 4 == 0: a lane's 4 columns are all in range or all out
+      const bool lane_ok = col < p.N;
+      float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int g4 = 0; g4 < 2; ++g4) {
         EpiLoads L[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M) L[u] = epi_load4(e, row, col);
+          if (row < p.M && lane_ok) L[u] = epi_load4(e, row, col);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int rl = (g4 * 4 + u) * 4 + r_sub;
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha);
+          if (row < p.M && lane_ok) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2);
+        }
+      }
+      if (e.bn_y) {     // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 8);  bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 16);
+          bs2[i] += __shfl_xor_sync(0xffffffffu, bs2[i], 8);  bs2[i] += __shfl_xor_sync(0xffffffffu, bs2[i], 16);
+        }
+        if (r_sub == 0 && lane_ok) {
+          const int c = col % 40;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { atomicAdd(&sred[c + i], bs1[i]); atomicAdd(&sred[40 + c + i], bs2[i]); }
         }
       }
     } else {
@@ -165,6 +179,8 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+  __shared__ float sred[80];
+  if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -252,7 +268,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = j & 1;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true);
+      epilogue_tile<BN>(p, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -261,6 +277,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (p.epi.bn_sums != nullptr && threadIdx.x < 80) atomicAdd(&p.epi.bn_sums[threadIdx.x], (double)sred[threadIdx.x]);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -283,6 +300,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  __shared__ float sred[80];
+  if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
@@ -375,11 +394,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
     }
     float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_SLD;
-    epilogue_tile<BN>(p, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0);
+    epilogue_tile<BN>(p, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.epi.bn_sums != nullptr && threadIdx.x < 80) atomicAdd(&p.epi.bn_sums[threadIdx.x], (double)sred[threadIdx.x]);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -468,7 +488,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   if (stages < 1) stages = 1;
   p.stages = stages;
   p.epi = g.epi;
-  p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
+  p.vec_ok = (epi_vec_ok(g.epi) && (g.N & 3) == 0) ? 1 : 0;
   p.a_3d = a3; p.b_3d = b3;
   {
     const Epilogue& e = g.epi;
@@ -478,7 +498,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   size_t tile_bytes = (size_t)stages * stage_bytes;
   if (tile_bytes < 36864) tile_bytes = 36864;      // epilogue staging (8 warps x 32 x 36 floats) reuses the tile area
   p.epi = g.epi;
-  p.vec_ok = epi_vec_ok(g.epi) ? 1 : 0;
+  p.vec_ok = (epi_vec_ok(g.epi) && (g.N & 3) == 0) ? 1 : 0;
   p.a_3d = a3; p.b_3d = b3;
   {
     const Epilogue& e = g.epi;

@@ -105,6 +105,7 @@ int infonce_col_reduce(const float* part_max, const float* part_sum, int n_parts
                        float* out_sum, float* out_lse, cudaStream_t s);
 int gather_cols(const float* logits, int ld, const int* sel, int Q, int k, float* out, cudaStream_t s);
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s);
+int split3_tf32(const float* x, float* out, long long rows, int D, int is_b, cudaStream_t s);
 // loss_partial[0] += alpha*..., per rank partial of the global loss (sum over ranks = loss)
 int infonce_loss(const InfoNceArgs& a, const float* row_lse, const float* diag, const float* col_lse, float w_img,
                  float w_txt, float* loss_out, cudaStream_t s);

@@ -288,6 +288,33 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
     lo[i] = tf32_if(v - h, rt);
   }
 }
+// 3xTF32 as ONE GEMM with K tripled:  A' = [hi | hi | lo],  B' = [hi | lo | hi]   (rows of length 3*D)
+__global__ void split3_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int D, int is_b,
+                                   int rt) {
+  const long long n = rows * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int c = (int)(i % D);
+    const float v = x[i];
+    const float h = tf32_if(v, rt);
+    const float l = tf32_if(v - h, rt);
+    float* o = out + r * 3 * D + c;
+    o[0] = h;
+    o[D] = is_b ? l : h;
+    o[2 * D] = is_b ? h : l;
+  }
+}
+int split3_tf32(const float* x, float* out, long long rows, int D, int is_b, cudaStream_t s) {
+  ProfScope _ps("split_tf32", s, 0.0, (double)rows * D * 16.0);
+  const long long n = rows * D;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  split3_tf32_kernel<<<blocks, 256, 0, s>>>(x, out, rows, D, is_b, tf32_rounding());
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s) {
   ProfScope _ps("split_tf32", s, 0.0, (double)n * 12.0);
   int blocks = (int)((n + 255) / 256);

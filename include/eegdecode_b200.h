@@ -172,7 +172,7 @@ int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
  * (evaluate_model, :306-320).  `sel` (int32 [Q,k] or NULL) restricts each query to its own candidate
  * list: results are positions into that list. */
 int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int D, const float* logit_scale,
-                      float* logits_ws, int ld, void* round_ws /* (Q+G)*D floats */,
+                      float* logits_ws, int ld, void* round_ws /* 3*(Q+G)*D floats */,
                       const int32_t* sel, int k, float* sel_ws /* [Q,k] */,
                       const int64_t* labels, int* correct, int64_t* top1, int32_t* top5, void* stream);
 
