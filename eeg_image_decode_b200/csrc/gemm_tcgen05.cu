@@ -517,7 +517,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   // epilogue memory latency and run faster as two co-resident CTAs per SM (16 epilogue warps) -- measured on B200
   if (persistent && total_kb > 0 && p.k_blocks_per_split >= 16) {
     // one CTA per SM: stages fill what is left of the 227 KB after the dedicated epilogue staging
-    int pst = (227 * 1024 - 1024 - 8 * 32 * EPI_SLD * 4 - 512) / stage_bytes;
+    int pst = (226 * 1024 - 1024 - 8 * 32 * EPI_SLD * 4 - 512) / stage_bytes;   // 1 KB of the 227 KB is static smem
     if (pst > 8) pst = 8;
     if (pst > 2 * p.k_blocks_per_split) pst = 2 * p.k_blocks_per_split;    // ring streams across items
     if (pst < 2) pst = 2;
@@ -527,7 +527,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
     auto pk = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
     static bool pconf = false;
     if (!pconf) {
-      EEG_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      EEG_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       pconf = true;
     }
     const int items = cdiv(g.N, BN) * cdiv(g.M, BM) * split;
