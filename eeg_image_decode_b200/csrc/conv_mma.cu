@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_fwd_mma_kernel(const
 // ------------------------------------------------------------------------------------------------
 // backward: BN1 backward apply fused in (dz1, y1 -> dy on the fly); outputs dX3, dWt, dbt (+ BN1 dgamma/dbeta)
 // ------------------------------------------------------------------------------------------------
-static constexpr int DY_LD = 40;              // dz1 is staged by cp.async straight into the dy tile and transformed in place
+static constexpr int DY_LD = 44;
 static constexpr int DY_ROWS = 52;           // 4 zero rows in front (shifted reads m-a), 36 data rows, 12 zero rows
 static constexpr int DPZ = 320;              // 50 leading zeros + dp[0..199] + zero tail
 static constexpr int RAW = N_POOL * N_FILT;  // 1440 floats of dz1 / y1 per (sample, row), staged with cp.async
@@ -166,10 +166,13 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // stage dz1 / y1 of (b, r): 36 segments of 40 floats each, laid out [j][k] in smem
-__device__ __forceinline__ void prefetch_row(const float* __restrict__ src, int b, int r, float* dst, int lane) {
+__device__ __forceinline__ void prefetch_row(const float* __restrict__ dz1, const float* __restrict__ y1, int b, int r,
+                                             float* rawdz, float* rawy, int lane) {
   for (int f = lane; f < N_POOL * 10; f += 32) {
     const int j = f / 10, k4 = (f % 10) * 4;
-    cp_async16(dst + f * 4, src + (((size_t)b * N_POOL + j) * N_CH + r) * N_FILT + k4);
+    const size_t idx = (((size_t)b * N_POOL + j) * N_CH + r) * N_FILT + k4;
+    cp_async16(rawdz + f * 4, dz1 + idx);
+    cp_async16(rawy + f * 4, y1 + idx);
   }
   cp_async_commit();
 }
@@ -191,19 +194,15 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x;
-  // per-warp smem: [xs | dpz share 320 floats] [ps 272] [dy tile 52 x 40 (+16 slack)] [raw y1 1440]
-  constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + RAW;
+  constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DPZ + 2 * RAW;
   float* xs = per_warp + (size_t)warp * PW;
-  float* dpz = xs;                                 // the input row is dead once the pooled sums exist
   float* ps = xs + XS_LEN;
   float* dys = ps + PS_LEN;
-  float* rawdz = dys + 4 * DY_LD;                  // data rows 4..39 of the dy tile
-  float* rawy = dys + DY_ROWS * DY_LD + 16;
-  for (int i = lane; i < PW - RAW; i += 32) xs[i] = 0.f;
-  if (warp < N_CH) {
-    prefetch_row(dz1, b, warp, rawdz, lane);
-    prefetch_row(y1, b, warp, rawy, lane);
-  }
+  float* dpz = dys + DY_ROWS * DY_LD + 16;
+  float* rawdz = dpz + DPZ;
+  float* rawy = rawdz + RAW;
+  for (int i = lane; i < PW - 2 * RAW; i += 32) xs[i] = 0.f;
+  if (warp < N_CH) prefetch_row(dz1, y1, b, warp, rawdz, rawy, lane);
   for (int i = threadIdx.x; i < N_FILT * 26; i += CW_THREADS) wred[i] = 0.f;
   if (threadIdx.x < N_FILT) {
     const int k = threadIdx.x;
@@ -252,12 +251,10 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
         const float yh = (yy[q] - c_mu[k]) * c_rs[k];
         o[q] = tf32_rn(c_gr[k] * (dzv[q] - c_m1[k] - yh * c_m2[k]));
       }
-      *reinterpret_cast<float4*>(dys + (j + 4) * DY_LD + k4) = make_float4(o[0], o[1], o[2], o[3]);   // in place
+      *reinterpret_cast<float4*>(dys + (j + 4) * DY_LD + k4) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    // the row buffer now becomes the dp accumulator: restore its zero borders (dp occupies [50, 250))
-    for (int i = lane; i < 50 + (DPZ - 250); i += 32) dpz[i < 50 ? i : 200 + i] = 0.f;
     __syncwarp();
-    if (r + CW_WARPS < N_CH) prefetch_row(y1, b, r + CW_WARPS, rawy, lane);   // y1 staging is free again: overlaps the MMAs
+    if (r + CW_WARPS < N_CH) prefetch_row(dz1, y1, b, r + CW_WARPS, rawdz, rawy, lane);   // overlaps the MMAs below
     // ---- dW[k][i] += sum_j dy[j][k] * p[5j+i]   (column i == 25 carries a ones-vector: the bias gradient) ----
 #pragma unroll
     for (int kt = 0; kt < 5; ++kt) {
@@ -327,8 +324,6 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
       dst[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
     __syncwarp();
-    // next row's dz1 / y1: issued once this row's dy tile is dead; lands while the next row is pooled
-    if (r + CW_WARPS < N_CH) prefetch_row(dz1, b, r + CW_WARPS, rawdz, lane);
   }
   // token 63 (channel 62) never reaches the conv stack (enc_out[:, :63], ATMS_retrieval.py:91)
   for (int i = threadIdx.x; i < D_PAD; i += CW_THREADS) dx3[((size_t)b * N_TOK + N_CH) * D_PAD + i] = 0.f;
@@ -371,7 +366,7 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
   if (!tf32_rounding())
     return conv_temporal_bwd_simt(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt, dgamma, dbeta, B, gscale, s);
   ProfScope _ps("conv_temporal_bwd", s, (double)B * 63 * 36 * 40 * 100.0, (double)B * (36 * 2520 * 8.0 + 63 * 2000.0));
-  constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + RAW;
+  constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DPZ + 2 * RAW;
   const size_t smem = (size_t)(5 * N_FILT + N_FILT * 26 + 8 + CW_WARPS * PW) * sizeof(float);
   static bool configured = false;
   if (!configured) {

@@ -92,6 +92,8 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, 
   if (e.round_tf32) v = tf32_rn(v);
   return v;
 }
+// scalar tail path (ragged N / unaligned outputs): rare, kept out of line
+static __device__ __noinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N);
 __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, float v) {
   float* p = e.C + (size_t)row * e.ldc + col;
   if (e.store_mode == EPI_STORE) *p = v;
@@ -107,14 +109,18 @@ __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int co
   L.bias = L.mul = L.resid = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
   if (e.mul_in) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
-  if (e.bn_y) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
+  else if (e.bn_y) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
   if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
   return L;
 }
-__device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
+// NOT inlined on purpose: the epilogue calls it 8x per 32-column chunk, and inlining the whole generic path that often
+// made the GEMM kernels ~100 KB of SASS (instruction-cache misses were the #3 stall reason in ncu).  `e` lives in
+// shared memory (copied from the kernel parameters at start) so that a real function can take its address.
+template <bool BNF = false>   // BNF: the fused BatchNorm+ELU backward flavour (only the dA1 GEMM of the conv stack pays for it)
+__device__ __noinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
                                             float* bn_s1 = nullptr, float* bn_s2 = nullptr) {
   float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
-  if (e.bn_y) {
+  if (BNF) {
     const int c = col % 40;
     const float yv[4] = {L.mul.x, L.mul.y, L.mul.z, L.mul.w};
 #pragma unroll
@@ -155,6 +161,10 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
   } else {
     red_add_v4(p, v[0], v[1], v[2], v[3]);
   }
+}
+static __device__ __noinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N) {
+  const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+  for (int i = 0; i < 4 && col + i < N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
 }
 // host-side: can the vector path be used for this epilogue?
 static inline bool epi_vec_ok(const Epilogue& e) {

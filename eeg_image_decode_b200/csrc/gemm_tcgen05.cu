@@ -36,12 +36,11 @@ static constexpr int EPI_SLD = 36;   // staging row stride in floats (16-byte al
 // split the 32-column chunks).  TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns:
 // every global access of the fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row
 // segment, and the loads of 4 row groups are in flight before the first is consumed.
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t tmem_acc, float* stage, int tile_m,
-                                              int tile_n, int warp, int lane, bool has_acc, float* sred) {
+template <int BN, bool BNF>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const Epilogue& e, uint32_t tmem_acc, float* stage,
+                                              int tile_m, int tile_n, int warp, int lane, bool has_acc, float* sred) {
   const int q = warp & 3;
   const int half = (warp - 2) >> 2;
-  const Epilogue& e = p.epi;
   constexpr int SLD = EPI_SLD;
   const int r_sub = lane >> 3;      // 4 rows per pass
   const int cq = (lane & 7) * 4;    // 4 consecutive columns per lane
@@ -67,7 +66,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
     if (p.vec_ok) {                                  // N % 4 == 0: a lane's 4 columns are all in range or all out
       const bool lane_ok = col < p.N;
       float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
       for (int g4 = 0; g4 < 2; ++g4) {
         EpiLoads L[4];
 #pragma unroll
@@ -79,10 +78,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_
         for (int u = 0; u < 4; ++u) {
           const int rl = (g4 * 4 + u) * 4 + r_sub;
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M && lane_ok) epi_finish4(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2);
+          if (row < p.M && lane_ok) epi_finish4<BNF>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2);
         }
       }
-      if (e.bn_y) {     // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
+      if (BNF) {        // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 8);  bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 16);
@@ -180,7 +179,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   __shared__ float sred[80];
+  __shared__ Epilogue s_epi;
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) s_epi = p.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -268,7 +269,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = j & 1;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
+      epilogue_tile<BN, false>(p, s_epi, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -277,11 +278,10 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (p.epi.bn_sums != nullptr && threadIdx.x < 80) atomicAdd(&p.epi.bn_sums[threadIdx.x], (double)sred[threadIdx.x]);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, bool BNF = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
@@ -301,7 +301,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   __shared__ float sred[80];
+  __shared__ Epilogue s_epi;
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) s_epi = p.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
@@ -394,12 +396,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
     }
     float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_SLD;
-    epilogue_tile<BN>(p, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
+    epilogue_tile<BN, BNF>(p, s_epi, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.epi.bn_sums != nullptr && threadIdx.x < 80) atomicAdd(&p.epi.bn_sums[threadIdx.x], (double)sred[threadIdx.x]);
+  if (BNF && threadIdx.x < 80) atomicAdd(&p.epi.bn_sums[threadIdx.x], (double)sred[threadIdx.x]);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -515,7 +517,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   }
   // persistent (1 CTA/SM, overlapped epilogue) pays off when the main loop is long; the short-K token GEMMs are bound by
   // epilogue memory latency and run faster as two co-resident CTAs per SM (16 epilogue warps) -- measured on B200
-  if (persistent && total_kb > 0 && p.k_blocks_per_split >= 16) {
+  if (persistent && total_kb > 0 && p.k_blocks_per_split >= 16 && g.epi.bn_y == nullptr) {
     // one CTA per SM: stages fill what is left of the 227 KB after the dedicated epilogue staging
     int pst = (226 * 1024 - 1024 - 8 * 32 * EPI_SLD * 4 - 512) / stage_bytes;   // 1 KB of the 227 KB is static smem
     if (pst > 8) pst = 8;
@@ -539,13 +541,32 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   }
   const size_t smem = tile_bytes + 1024 + 256;
   p.tile_bytes = (int)tile_bytes;
+  dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), split);
+  if (g.epi.bn_y != nullptr) {
+    if constexpr (BN == 256 && A_MN == 0 && B_MN == 1) {
+      EEG_REQUIRE(p.vec_ok && g.epi.bn_sums && g.epi.bn_mean_rstd && g.epi.bn_gamma && g.epi.bn_beta && split == 1,
+                  "gemm: the fused BatchNorm-backward epilogue needs the vector path and all BN pointers");
+      auto kb = gemm_tf32_kernel<256, 0, 1, true>;
+      static bool cb = false;
+      if (!cb) {
+        EEG_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        cb = true;
+      }
+      kb<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+      EEG_CUDA_OK(cudaGetLastError());
+      count_launch();
+      return 0;
+    } else {
+      set_error("gemm: the fused BatchNorm-backward epilogue is only built for the 256-wide K-major x MN-major kernel");
+      return 2;
+    }
+  }
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static size_t configured = 0;   // per template instantiation
   if (smem > configured) {
     EEG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
   }
-  dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), split);
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
