@@ -92,8 +92,6 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, 
   if (e.round_tf32) v = tf32_rn(v);
   return v;
 }
-// scalar tail path (ragged N / unaligned outputs): rare, kept out of line
-static __device__ __noinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N);
 __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, float v) {
   float* p = e.C + (size_t)row * e.ldc + col;
   if (e.store_mode == EPI_STORE) *p = v;
@@ -113,11 +111,10 @@ __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int co
   if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
   return L;
 }
-// NOT inlined on purpose: the epilogue calls it 8x per 32-column chunk, and inlining the whole generic path that often
-// made the GEMM kernels ~100 KB of SASS (instruction-cache misses were the #3 stall reason in ncu).  `e` lives in
-// shared memory (copied from the kernel parameters at start) so that a real function can take its address.
+// (an out-of-line version of this function was tried to shrink the ~100 KB kernels: the call overhead and the
+// shared-memory copy of the parameters cost more than the instruction-cache misses they saved: 95 -> 125 us per GEMM)
 template <bool BNF = false>   // BNF: the fused BatchNorm+ELU backward flavour (only the dA1 GEMM of the conv stack pays for it)
-__device__ __noinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
+__device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
                                             float* bn_s1 = nullptr, float* bn_s2 = nullptr) {
   float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
   if (BNF) {
@@ -162,7 +159,7 @@ __device__ __noinline__ void epi_finish4(const Epilogue& e, int row, int col, fl
     red_add_v4(p, v[0], v[1], v[2], v[3]);
   }
 }
-static __device__ __noinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N) {
+__device__ __forceinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N) {
   const float av[4] = {a4.x, a4.y, a4.z, a4.w};
   for (int i = 0; i < 4 && col + i < N; ++i) epi_store(e, row, col + i, epi_value(e, row, col + i, av[i]));
 }

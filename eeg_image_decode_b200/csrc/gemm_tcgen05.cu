@@ -67,7 +67,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
       const bool lane_ok = col < p.N;
       float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int g4 = 0; g4 < 2; ++g4) {
+      for (int g4 = 0; g4 < 2; ++g4) {     // not unrolled: halves the epilogue's SASS footprint (I-cache)
         EpiLoads L[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -179,9 +179,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   __shared__ float sred[80];
-  __shared__ Epilogue s_epi;
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
-  if (threadIdx.x == 0) s_epi = p.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -269,7 +267,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = j & 1;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      epilogue_tile<BN, false>(p, s_epi, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
+      epilogue_tile<BN, false>(p, p.epi, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -301,9 +299,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   __shared__ float sred[80];
-  __shared__ Epilogue s_epi;
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
-  if (threadIdx.x == 0) s_epi = p.epi;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;
@@ -396,7 +392,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
     }
     float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_SLD;
-    epilogue_tile<BN, BNF>(p, s_epi, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
+    epilogue_tile<BN, BNF>(p, p.epi, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
   }
 
   tc_fence_before();
@@ -591,6 +587,7 @@ int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   EEG_REQUIRE(g.split_k <= 1 || g.epi.store_mode == EPI_ATOMIC, "gemm: split-K needs the atomic store mode");
   EEG_TRY(resolve_encode());
   // widest tile that still yields >= ~one wave of CTAs (small-M problems: projector, logits, retrieval)
+  if (g.epi.bn_y != nullptr) return launch_bn<256>(g, stream);     // the fused BatchNorm-backward flavour is built for BN = 256
   const int mt = cdiv(g.M, BM);
   const int split = g.split_k > 1 ? g.split_k : 1;
   auto ctas = [&](int bn) { return mt * cdiv(g.N, bn) * split; };
