@@ -48,7 +48,7 @@ __device__ __forceinline__ void qk_scores(const float* __restrict__ Q, const flo
                                           float s[8][4]) {
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
+#pragma unroll 2
   for (int kt = 0; kt < 8; ++kt) {
     uint32_t ah[4], al[4];
 #pragma unroll
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_bwd_mma_kernel(const flo
     float dv[8][4], dk[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int kt = 0; kt < 8; ++kt) {
       uint32_t ap[4], as[4];
 #pragma unroll

@@ -115,15 +115,16 @@ __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int co
 // shared-memory copy of the parameters cost more than the instruction-cache misses they saved: 95 -> 125 us per GEMM)
 template <bool BNF = false>   // BNF: the fused BatchNorm+ELU backward flavour (only the dA1 GEMM of the conv stack pays for it)
 __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
-                                            float* bn_s1 = nullptr, float* bn_s2 = nullptr) {
+                                            float* bn_s1 = nullptr, float* bn_s2 = nullptr, const float* bn_tab = nullptr,
+                                            int bn_c = 0) {
   float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
   if (BNF) {
-    const int c = col % 40;
+    // bn_tab (shared memory, built once per CTA): [0][c] = mean, [1][c] = rstd, [2][c] = gamma, [3][c] = beta
     const float yv[4] = {L.mul.x, L.mul.y, L.mul.z, L.mul.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float yh = (yv[i] - __ldg(e.bn_mean_rstd + c + i)) * __ldg(e.bn_mean_rstd + 40 + c + i);
-      const float z = fmaf(yh, __ldg(e.bn_gamma + c + i), __ldg(e.bn_beta + c + i));
+      const float yh = (yv[i] - bn_tab[bn_c + i]) * bn_tab[40 + bn_c + i];
+      const float z = fmaf(yh, bn_tab[80 + bn_c + i], bn_tab[120 + bn_c + i]);
       v[i] *= elu1_grad(z);
       bn_s1[i] += v[i];
       bn_s2[i] = fmaf(v[i], yh, bn_s2[i]);

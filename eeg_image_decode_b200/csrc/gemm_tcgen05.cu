@@ -66,6 +66,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
     if (p.vec_ok) {                                  // N % 4 == 0: a lane's 4 columns are all in range or all out
       const bool lane_ok = col < p.N;
       float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
+      const int bn_c = BNF ? col % 40 : 0;
 #pragma unroll 1
       for (int g4 = 0; g4 < 2; ++g4) {     // not unrolled: halves the epilogue's SASS footprint (I-cache)
         EpiLoads L[4];
@@ -78,7 +79,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
         for (int u = 0; u < 4; ++u) {
           const int rl = (g4 * 4 + u) * 4 + r_sub;
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M && lane_ok) epi_finish4<BNF>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2);
+          if (row < p.M && lane_ok) epi_finish4<BNF>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2, sred + 80, bn_c);
         }
       }
       if (BNF) {        // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
@@ -88,7 +89,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
           bs2[i] += __shfl_xor_sync(0xffffffffu, bs2[i], 8);  bs2[i] += __shfl_xor_sync(0xffffffffu, bs2[i], 16);
         }
         if (r_sub == 0 && lane_ok) {
-          const int c = col % 40;
+          const int c = bn_c;
 #pragma unroll
           for (int i = 0; i < 4; ++i) { atomicAdd(&sred[c + i], bs1[i]); atomicAdd(&sred[40 + c + i], bs2[i]); }
         }
@@ -298,8 +299,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  __shared__ float sred[80];
+  __shared__ float sred[BNF ? 240 : 80];     // [0,80): BN-backward reductions; [80,240): mean | rstd | gamma | beta
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
+  if (BNF && threadIdx.x < 160) {
+    const int k = threadIdx.x % 40, w = threadIdx.x / 40;
+    sred[80 + threadIdx.x] = w == 0 ? p.epi.bn_mean_rstd[k] : (w == 1 ? p.epi.bn_mean_rstd[40 + k] : (w == 2 ? p.epi.bn_gamma[k] : p.epi.bn_beta[k]));
+  }
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_n = blockIdx.x, tile_m = blockIdx.y;

@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(1024) colsum_vec_kernel(const float* __restric
   if (c4 * 4 < cols) {
     const int stride = gridDim.x * 16;
     int r = blockIdx.x * 16 + ry;
-    for (; r + 3 * stride < rows; r += 4 * stride) {
-      float4 v[4];
+    for (; r + 7 * stride < rows; r += 8 * stride) {
+      float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(x + (size_t)(r + u * stride) * ld + c4 * 4);
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(x + (size_t)(r + u * stride) * ld + c4 * 4);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         if (row_mod > 0 && ((r + u * stride) % row_mod) == row_skip) continue;
         acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
       }
@@ -366,7 +366,7 @@ int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, 
   for (int c0 = 0; c0 < cols; c0 += 256) {
     const int w = cols - c0 < 256 ? cols - c0 : 256;
     if (vec) {
-      int blocks = cdiv(rows, 16 * 4);
+      int blocks = cdiv(rows, 16 * 8);
       if (blocks > 148 * 2) blocks = 148 * 2;
       if (blocks < 1) blocks = 1;
       colsum_vec_kernel<<<blocks, dim3(64, 16), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
