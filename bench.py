@@ -276,6 +276,15 @@ def bench_ours(args):
     e2e_val = world * B * K / float(tt.item())
     h2d = B * 63 * 250 * 4 + 2 * B * 1024 * 4 + B * 8
     d2h = 4
+    # diagnostic: pinned host -> device bandwidth of this box (e2e is H2D-bound below ~21 GB/s at this step time)
+    hb = host_eeg[0]
+    dstb = torch.empty_like(eegs[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        dstb.copy_(hb, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbs = 5 * hb.numel() * 4 / (time.perf_counter() - t0) / 1e9
 
     if rank != 0:
         if world > 1:
@@ -337,6 +346,7 @@ def bench_ours(args):
                    "precision": "fp32 storage, TF32 tensor-core operands (RN pre-rounded), fp32 accumulate",
                    "cuda_graph": bool(gstep.graph is not None)},
         "e2e": {"value": e2e_val, "unit": "trials/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "pinned_h2d_gbs_measured": h2d_gbs,
                 "api": "train_model(sub, model, pinned-host dataloader, torch.optim.AdamW, ...) + per-step loss read-back; best of 2 passes"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "top_kernels": top, "final_loss": final_loss,

@@ -282,29 +282,39 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
       }
     }
     // ---- dp[5m+rho] = sum_{a,k} dy[m-a][k] * w[k][rho+5a]/51 ----
-#pragma unroll 1
-    for (int mt = 0; mt < 3; ++mt) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
+    // 6 independent accumulator chains (3 m-tiles x even/odd k-tile): a single chain of 25 dependent MMAs per m-tile
+    // left the tensor pipe idle most of the time ("wait" was the top stall reason in ncu)
+    {
+      float c[3][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) c[mt][e][0] = c[mt][e][1] = c[mt][e][2] = c[mt][e][3] = 0.f;
 #pragma unroll
       for (int a = 0; a < 5; ++a)
 #pragma unroll
         for (int kk = 0; kk < 5; ++kk) {
-          uint32_t af[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const int m = mt * 16 + g + 8 * (h & 1), k = kk * 8 + t + 4 * (h >> 1);
-            af[h] = __float_as_uint(dys[(m - a + 4) * DY_LD + k]);
+          for (int mt = 0; mt < 3; ++mt) {
+            uint32_t af[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int m = mt * 16 + g + 8 * (h & 1), k = kk * 8 + t + 4 * (h >> 1);
+              af[h] = __float_as_uint(dys[(m - a + 4) * DY_LD + k]);
+            }
+            mma_tf32(c[mt][(a * 5 + kk) & 1], af, bw[a * 5 + kk][0], bw[a * 5 + kk][1]);
           }
-          mma_tf32(c, af, bw[a * 5 + kk][0], bw[a * 5 + kk][1]);
         }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int m = mt * 16 + g + 8 * h;
-        if (m < 40) {
-          if (2 * t < 5) dpz[50 + 5 * m + 2 * t] = c[2 * h];
-          if (2 * t + 1 < 5) dpz[50 + 5 * m + 2 * t + 1] = c[2 * h + 1];
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = mt * 16 + g + 8 * h;
+          if (m < 40) {
+            if (2 * t < 5) dpz[50 + 5 * m + 2 * t] = c[mt][0][2 * h] + c[mt][1][2 * h];
+            if (2 * t + 1 < 5) dpz[50 + 5 * m + 2 * t + 1] = c[mt][0][2 * h + 1] + c[mt][1][2 * h + 1];
+          }
         }
-      }
     }
     __syncwarp();
     // ---- dx[t] = sum_{s=t-50}^{t} dp[s]  (sliding window, 8 outputs per lane) ----
