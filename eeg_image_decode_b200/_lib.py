@@ -238,10 +238,6 @@ def ws_tensor(workspace, B: int, name: str):
     off = p.value - workspace.data_ptr()
     if name.endswith("_sums"):
         return workspace[off:off + 80 * 8].view(torch.float64)
-    if name == "y1" and lib().eegb200_get_gemm_backend() == 0:
-        # tensor-core path keeps the conv output as fp16
-        n = r.value * ld.value
-        return workspace[off:off + n * 2].view(torch.float16).view(r.value, ld.value)[:, :c.value].float()
     n = r.value * ld.value
     return workspace[off:off + n * 4].view(torch.float32).view(r.value, ld.value)[:, :c.value]
 

@@ -390,7 +390,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
   if (phases & EEGB200_PHASE_B) {
     BnState bn1{w.bn1_sums, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], BUF[EEGB200_BUF_BN1_RM], BUF[EEGB200_BUF_BN1_RV]};
     EEG_TRY(bn_finalize(bn1, wmul * B * N_CH * N_POOL, train, train && io->update_running_stats, s));
-    EEG_TRY(bn_elu_apply(w.Y1, RT, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
+    EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
     {
       Epilogue e = epi_out(w.Y2, N_FILT);        // spatial conv (63,1) == GEMM over (r,k1)  (ATMS_retrieval.py:106)
       e.bias = P[EEGB200_P_BS];

@@ -6,7 +6,6 @@
 // Layouts: y1 / a1 : [B*36 (b,j), 63 (r), 40 (k)]  == row-major [B*36, 2520], the A operand of the spatial-conv GEMM
 //          y2      : [B*36, 40];   feat : [B, 36*40] (index j*40 + e, the reference's flatten order)
 #include "kernels.h"
-#include <cuda_fp16.h>
 
 namespace eegb200 {
 
@@ -124,44 +123,15 @@ __global__ void bn_elu_apply_kernel(const float4* __restrict__ y, const float* _
     a[i] = v;
   }
 }
-// same with fp16 input (tensor-core path storage of y1)
-__global__ void bn_elu_apply_half_kernel(const uint2* __restrict__ y, const float* __restrict__ mean_rstd,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                         float4* __restrict__ a, long long n4, int round_tf) {
-  __shared__ float sc[N_FILT], sh[N_FILT];
-  if (threadIdx.x < N_FILT) {
-    const float r = mean_rstd[N_FILT + threadIdx.x] * gamma[threadIdx.x];
-    sc[threadIdx.x] = r;
-    sh[threadIdx.x] = beta[threadIdx.x] - mean_rstd[threadIdx.x] * r;
-  }
-  __syncthreads();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % N_FILT);
-    const uint2 raw = y[i];
-    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    float4 v;
-    v.x = elu1(fmaf(lo.x, sc[c], sh[c]));
-    v.y = elu1(fmaf(lo.y, sc[c + 1], sh[c + 1]));
-    v.z = elu1(fmaf(hi.x, sc[c + 2], sh[c + 2]));
-    v.w = elu1(fmaf(hi.y, sc[c + 3], sh[c + 3]));
-    if (round_tf) { v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w); }
-    a[i] = v;
-  }
-}
-int bn_elu_apply(const void* y, int y_is_half, const float* mean_rstd, const float* gamma, const float* beta, float* a,
-                 long long n, int round_tf, cudaStream_t s) {
-  ProfScope _ps("bn_elu_apply", s, 0.0, (double)n * (y_is_half ? 6.0 : 8.0));
+int bn_elu_apply(const float* y, const float* mean_rstd, const float* gamma, const float* beta, float* a, long long n,
+                 int round_tf, cudaStream_t s) {
+  ProfScope _ps("bn_elu_apply", s, 0.0, (double)n * 8.0);
   const long long n4 = n / 4;
   int blocks = (int)((n4 + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  if (y_is_half)
-    bn_elu_apply_half_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint2*>(y), mean_rstd, gamma, beta,
-                                                    reinterpret_cast<float4*>(a), n4, round_tf);
-  else
-    bn_elu_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(y), mean_rstd, gamma, beta,
-                                               reinterpret_cast<float4*>(a), n4, round_tf);
+  bn_elu_apply_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(y), mean_rstd, gamma, beta,
+                                             reinterpret_cast<float4*>(a), n4, round_tf);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

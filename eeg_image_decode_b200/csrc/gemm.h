@@ -3,8 +3,6 @@
 // kernel used to verify it on device (tests only, selected with eegb200_set_gemm_backend).
 #pragma once
 #include "common.cuh"
-#include <cuda_fp16.h>
-#include <cuda_bf16.h>
 
 namespace eegb200 {
 
@@ -40,7 +38,7 @@ struct Epilogue {
   // fused BatchNorm(train)+ELU backward of the conv stack (tcgen05 vector path only):
   //   v *= ELU'(gamma[c]*yhat + beta[c]),  yhat = (bn_y[row,col] - mean[c]) * rstd[c],  c = col % 40
   //   bn_sums[c] += v,  bn_sums[40+c] += v*yhat      (the two reductions the BatchNorm backward needs)
-  const void* bn_y = nullptr;            // fp16 [rows, ld_bn_y]; the output C is then written as bf16 (ldc in elements)
+  const float* bn_y = nullptr;
   int ld_bn_y = 0;
   const float* bn_mean_rstd = nullptr;   // [2][40]
   const float* bn_gamma = nullptr;
@@ -109,12 +107,7 @@ __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int co
   L.bias = L.mul = L.resid = make_float4(0.f, 0.f, 0.f, 0.f);
   if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
   if (e.mul_in) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
-  else if (e.bn_y) {     // fp16 storage of the conv output: 4 values = 8 bytes
-    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(e.bn_y) + (size_t)row * e.ld_bn_y + col);
-    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    L.mul = make_float4(lo.x, lo.y, hi.x, hi.y);
-  }
+  else if (e.bn_y) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
   if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
   return L;
 }
@@ -136,13 +129,6 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
       bn_s1[i] += v[i];
       bn_s2[i] = fmaf(v[i], yh, bn_s2[i]);
     }
-    // dz1 leaves as bf16 (only conv_temporal_bwd reads it); ldc counts bf16 elements
-    __nv_bfloat162 p01 = __floats2bfloat162_rn(v[0], v[1]), p23 = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&p01);
-    pk.y = *reinterpret_cast<uint32_t*>(&p23);
-    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.C) + (size_t)row * e.ldc + col) = pk;
-    return;
   }
   if (e.bias) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
   if (e.aux_out) *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);

@@ -68,10 +68,9 @@ struct BnState {          // one BatchNorm2d(40); all device pointers
   const float* gamma; const float* beta;
   float* running_mean; float* running_var;   // updated in train mode (momentum 0.1, unbiased variance)
 };
-// y1 / dz1 element types depend on the backend: fp16 / bf16 on the tensor-core path, fp32 on the verification path
-int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, void* y1, double* sums, int B, cudaStream_t s);
+int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s);
 int bn_finalize(BnState bn, long long count, int train, int update_running, cudaStream_t s);
-int bn_elu_apply(const void* y, int y_is_half, const float* mean_rstd, const float* gamma, const float* beta, float* a, long long n,
+int bn_elu_apply(const float* y, const float* mean_rstd, const float* gamma, const float* beta, float* a, long long n,
                  int round_tf, cudaStream_t s);
 int colstats(const float* y, int ld, int rows, int cols, double* sums, cudaStream_t s);
 int conv_head_fwd(const float* y2, const float* mean_rstd, const float* gamma, const float* beta, const float* wc,
@@ -86,7 +85,7 @@ int bn_bwd_apply(const float* dz, const float* y, const float* mean_rstd, const 
 // dz1 = da1 * ELU'(bn1(y1)) in place + reduction sums for the BN1 backward
 int bn1_bwd_reduce(float* da1, const float* y1, const float* mean_rstd, const float* gamma, const float* beta,
                    double* bwd_sums, long long n, cudaStream_t s);
-int conv_temporal_bwd(const void* dz1, const void* y1, const float* x3, const float* wt, const float* mean_rstd,
+int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
                       float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s);
 

@@ -138,8 +138,7 @@ int eegb200_atms_forward(const eegb200_atms_io* io, int phase_mask, void* stream
 int eegb200_atms_backward(const eegb200_atms_io* io, const float* d_out, float* const* grads, int phase_mask, void* stream);
 /* intermediates inside the workspace, for stage-level parity tests and SyncBN exchange.
  * name: "h0","qkv","attn_o","x1","ffn_u","x3","y1","a1","y2","feat","z1","z2",
- *       "bn1_sums","bn2_sums","bn1_bwd_sums","bn2_bwd_sums" (the last four are double[80]).
- * Note: on the tensor-core backend "y1" is stored as fp16 (same shape) and "da1" as bf16. */
+ *       "bn1_sums","bn2_sums","bn1_bwd_sums","bn2_bwd_sums" (the last four are double[80]). */
 int eegb200_atms_ws_tensor(void* workspace, int B, const char* name, void** ptr, int* rows, int* cols, int* ld);
 
 /* ------------------------------------------------------------------------------------------------
