@@ -27,3 +27,13 @@ print("y2", rel(m.ws_tensor("y2").reshape(B, 36, 40).permute(0, 2, 1), ref["y2"]
 print("feat", rel(m.ws_tensor("feat"), ref["feat"]))
 print("z1", rel(m.ws_tensor("z1"), ref["z1"]))
 print("out (global, worst row)", rel(out, ref["out"]))
+
+# ---- train mode (batch-statistics BatchNorm), small batch, dropout off: the tightest parity case in the test-suite ----
+for Bt, seed in ((8, 21), (8, 41), (16, 61), (64, 13)):
+    xt = recipe.make_eeg(Bt, seed=seed)
+    sidt = torch.full((Bt,), 8)
+    reft = O.atms_forward(recipe.make_state_dict(), xt, sidt, train=True, dtype=torch.float64)
+    mt = ATMS(); mt.load_state_dict(recipe.make_state_dict()); mt = mt.cuda().train(); mt.dropout_p = [0.0] * 8
+    outt = mt.encode(xt.cuda(), sidt.cuda(), train=True, seed=1)
+    print(f"train B={Bt} seed={seed}: x3", rel(mt.ws_tensor("x3").reshape(Bt, 64, -1)[:, :, :250], reft["x3"]),
+          "feat", rel(mt.ws_tensor("feat"), reft["feat"]), "out", rel(outt, reft["out"]))
