@@ -5,6 +5,7 @@
 #include "../../include/eegdecode_b200.h"
 #include "kernels.h"
 #include <string.h>
+#include <stdlib.h>
 
 namespace eegb200 {
 
@@ -431,6 +432,46 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// The weight / bias gradient kernels (split-K GEMMs over all tokens, column sums, unpack) are off the critical path:
+// only the optimiser needs them.  They are forked onto a side stream as soon as their inputs exist and joined before
+// the call returns, so they fill the SMs / HBM bandwidth the latency-bound dX chain leaves idle.  Works the same under
+// CUDA-graph capture (fork / join become parallel graph branches).
+struct SideStream {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool used = false;
+  int init() {
+    if (side) return 0;
+    EEG_CUDA_OK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    EEG_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    EEG_CUDA_OK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    return 0;
+  }
+  // everything enqueued on `main` so far becomes visible to the side stream
+  int sync_from(cudaStream_t main) {
+    EEG_CUDA_OK(cudaEventRecord(fork, main));
+    EEG_CUDA_OK(cudaStreamWaitEvent(side, fork, 0));
+    used = true;
+    return 0;
+  }
+  int join_into(cudaStream_t main) {
+    if (!used) return 0;
+    EEG_CUDA_OK(cudaEventRecord(join, side));
+    EEG_CUDA_OK(cudaStreamWaitEvent(main, join, 0));
+    used = false;
+    return 0;
+  }
+};
+static SideStream g_side;
+static int side_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("EEGB200_SIDE_STREAM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on;
+}
+
 static int backward(const eegb200_atms_io* io, const float* d_out, float* const* GR, int phases, cudaStream_t s) {
   Ws w;
   EEG_TRY(check_io(io, &w));
@@ -445,6 +486,10 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
   const Cfg cfg = make_cfg(io);
   const int RT = tf32_rounding();
   const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;
+  const bool use_side = side_enabled() && !prof_enabled();
+  if (use_side) EEG_TRY(g_side.init());
+  cudaStream_t ws = use_side ? g_side.side : s;      // stream of the weight-gradient work
+#define FORK() do { if (use_side) EEG_TRY(g_side.sync_from(s)); } while (0)
 
   if (phases & EEGB200_PHASE_A) {
     EEG_REQUIRE(d_out != nullptr, "null d_out");
@@ -452,9 +497,10 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     EEG_TRY(layernorm_bwd(d_out, D_OUT, w.Z2, D_OUT, B, D_OUT, P[EEGB200_P_LNP_G], P[EEGB200_P_LNP_B], w.stp, nullptr,
                           nullptr, w.dZ2, D_OUT, GR[EEGB200_P_LNP_G], GR[EEGB200_P_LNP_B], nullptr, nullptr, 0, s));
     EEG_TRY(dropout_apply(w.dZ2, w.dZ2d, B, D_OUT, cfg.d[EEGB200_SITE_PROJ], RT, s));
-    EEG_TRY(colsum(w.dZ2d, D_OUT, B, D_OUT, GR[EEGB200_P_BP2], 0, 0, s));
+    FORK();
+    EEG_TRY(colsum(w.dZ2d, D_OUT, B, D_OUT, GR[EEGB200_P_BP2], 0, 0, ws));
     EEG_TRY(run_gemm(D_OUT, D_OUT, B, w.dZ2d, D_OUT, 1, w.G, D_OUT, 1, epi_wgrad(GR[EEGB200_P_WP2], D_OUT),
-                     pick_split(D_OUT, D_OUT, B), s));
+                     pick_split(D_OUT, D_OUT, B), ws));
     {
       Epilogue e = epi_out(w.dZ1, D_OUT);        // dZ1 = dZ2 + (dZ2d . Wp2) * GELU'(Z1)
       e.mul_in = w.Z1; e.ld_mul = D_OUT;
@@ -462,9 +508,10 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       e.round_tf32 = RT;
       EEG_TRY(run_gemm(B, D_OUT, D_OUT, w.dZ2d, D_OUT, 0, w.Wp2_r, D_OUT, 1, e, 1, s));
     }
-    EEG_TRY(colsum(w.dZ1, D_OUT, B, D_OUT, GR[EEGB200_P_BP1], 0, 0, s));
+    FORK();
+    EEG_TRY(colsum(w.dZ1, D_OUT, B, D_OUT, GR[EEGB200_P_BP1], 0, 0, ws));
     EEG_TRY(run_gemm(D_OUT, D_FEAT, B, w.dZ1, D_OUT, 1, w.feat, D_FEAT, 1, epi_wgrad(GR[EEGB200_P_WP1], D_FEAT),
-                     pick_split(D_OUT, D_FEAT, B), s));
+                     pick_split(D_OUT, D_FEAT, B), ws));
     EEG_TRY(run_gemm(B, D_FEAT, D_OUT, w.dZ1, D_OUT, 0, w.Wp1_r, D_FEAT, 1, epi_out(w.dfeat, D_FEAT), 1, s));
     // ---- conv head backward down to d(BN2 out) + BN2 reductions ----
     EEG_CUDA_OK(cudaMemsetAsync(w.bn2_bsums, 0, 2 * N_FILT * sizeof(double), s));
@@ -474,12 +521,13 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
   if (phases & EEGB200_PHASE_B) {
     EEG_TRY(bn_bwd_apply(w.dz2, w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], w.bn2_bsums, wmul * R, w.dY2, GR[EEGB200_P_BN2_G],
                          GR[EEGB200_P_BN2_B], (long long)R * N_FILT, RT, 1.f / (float)wmul, s));
-    EEG_TRY(colsum(w.dY2, N_FILT, R, N_FILT, GR[EEGB200_P_BS], 0, 0, s));
+    FORK();
+    EEG_TRY(colsum(w.dY2, N_FILT, R, N_FILT, GR[EEGB200_P_BS], 0, 0, ws));
     // dWs[k2][(r,k1)] = sum_{(b,j)} dY2[(b,j)][k2] * A1[(b,j)][(r,k1)]
-    EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), s));
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), ws));
     EEG_TRY(run_gemm(N_FILT, K_SPAT, R, w.dY2, N_FILT, 1, w.A1, K_SPAT, 1, epi_wgrad(w.dWs_p, K_SPAT),
-                     pick_split(N_FILT, K_SPAT, R), s));
-    unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, s>>>(w.dWs_p, GR[EEGB200_P_WS]);
+                     pick_split(N_FILT, K_SPAT, R), ws));
+    unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, ws>>>(w.dWs_p, GR[EEGB200_P_WS]);
     count_launch();
     // dA1 = dY2 . Ws, then dz1 = dA1 * ELU'(BN1(y1)) and the two BN1-backward reductions
     EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
@@ -506,7 +554,8 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                           GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
     // ---- FFN ----
     EEG_TRY(dropout_apply_colsum(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, GR[EEGB200_P_B2], N_T, 0, 0, s));
-    EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), s));
+    FORK();
+    EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), ws));
     {
       Epilogue e = epi_out(w.dU, 256);           // dU = dropout_ffn1(T1 . W2) * GELU'(U)
       e.drop = cfg.d[EEGB200_SITE_FFN1]; e.drop_ld = 256;
@@ -514,8 +563,9 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       e.round_tf32 = RT;
       EEG_TRY(run_gemm(M, 256, 256, w.T1, 256, 0, w.W2_p, 256, 1, e, 1, s));
     }
-    EEG_TRY(colsum(w.dU, 256, M, D_FF, GR[EEGB200_P_B1], 0, 0, s));
-    EEG_TRY(run_gemm(D_FF, N_T, M, w.dU, 256, 1, w.X1, 256, 1, epi_wgrad(GR[EEGB200_P_W1], N_T), pick_split(D_FF, N_T, M), s));
+    FORK();
+    EEG_TRY(colsum(w.dU, 256, M, D_FF, GR[EEGB200_P_B1], 0, 0, ws));
+    EEG_TRY(run_gemm(D_FF, N_T, M, w.dU, 256, 1, w.X1, 256, 1, epi_wgrad(GR[EEGB200_P_W1], N_T), pick_split(D_FF, N_T, M), ws));
     {
       Epilogue e = epi_out(w.dX1, 256);          // dX1 = dR2 + dU . W1
       e.resid = w.dR2; e.ld_res = 256;
@@ -526,18 +576,20 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                           w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
     // ---- attention ----
     EEG_TRY(dropout_apply_colsum(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, GR[EEGB200_P_BO], N_T, 0, 0, s));
-    EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), s));
-    EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), s));
-    unpack_wo_grad_kernel<<<256, 256, 0, s>>>(w.dWo_p, GR[EEGB200_P_WO]);
+    FORK();
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), ws));
+    EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), ws));
+    unpack_wo_grad_kernel<<<256, 256, 0, ws>>>(w.dWo_p, GR[EEGB200_P_WO]);
     count_launch();
     EEG_TRY(run_gemm(M, 256, 256, w.T2, 256, 0, w.Wo_p, 256, 1, epi_out(w.dO, 256), 1, s));
     EEG_TRY(attention_bwd(w.QKV, w.dO, w.dQKV, B, cfg.d[EEGB200_SITE_ATTN], s));
-    EEG_CUDA_OK(cudaMemsetAsync(w.dWqkv_p, 0, 768 * 256 * sizeof(float), s));
-    EEG_CUDA_OK(cudaMemsetAsync(w.dbqkv_p, 0, 768 * sizeof(float), s));
-    EEG_TRY(colsum(w.dQKV, 768, M, 768, w.dbqkv_p, 0, 0, s));
-    EEG_TRY(run_gemm(768, 256, M, w.dQKV, 768, 1, w.H0, 256, 1, epi_wgrad(w.dWqkv_p, 256), pick_split(768, 256, M), s));
-    unpack_qkv_grad_kernel<<<768, 256, 0, s>>>(w.dWqkv_p, w.dbqkv_p, GR[EEGB200_P_WQ], GR[EEGB200_P_WK], GR[EEGB200_P_WV],
-                                               GR[EEGB200_P_BQ], GR[EEGB200_P_BK], GR[EEGB200_P_BV]);
+    FORK();
+    EEG_CUDA_OK(cudaMemsetAsync(w.dWqkv_p, 0, 768 * 256 * sizeof(float), ws));
+    EEG_CUDA_OK(cudaMemsetAsync(w.dbqkv_p, 0, 768 * sizeof(float), ws));
+    EEG_TRY(colsum(w.dQKV, 768, M, 768, w.dbqkv_p, 0, 0, ws));
+    EEG_TRY(run_gemm(768, 256, M, w.dQKV, 768, 1, w.H0, 256, 1, epi_wgrad(w.dWqkv_p, 256), pick_split(768, 256, M), ws));
+    unpack_qkv_grad_kernel<<<768, 256, 0, ws>>>(w.dWqkv_p, w.dbqkv_p, GR[EEGB200_P_WQ], GR[EEGB200_P_WK], GR[EEGB200_P_WV],
+                                                GR[EEGB200_P_BQ], GR[EEGB200_P_BK], GR[EEGB200_P_BV]);
     count_launch();
     {
       Epilogue e = epi_out(w.dH0, 256);          // dH0 = dR1 + dQKV . Wqkv
@@ -547,13 +599,16 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     // ---- DataEmbedding ----
     // token-0 rows carry no value embedding -> excluded from the bias gradient
     EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
-    EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), s));
+    FORK();
+    EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), ws));
     EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,
                 "subject-token gradients need both the table and the shared-token grad buffers");
     EEG_TRY(subject_token_bwd(reinterpret_cast<const long long*>(io->subject_ids), w.flag, w.dH0, GR[EEGB200_P_SUBJ_TABLE],
                               GR[EEGB200_P_SUBJ_SHARED], B, cfg.d[EEGB200_SITE_EMBED], s));
     EEG_CUDA_OK(cudaGetLastError());
   }
+  if (use_side) EEG_TRY(g_side.join_into(s));      // gradients are complete when the caller's stream continues
+#undef FORK
   return 0;
 }
 

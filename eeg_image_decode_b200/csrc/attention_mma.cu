@@ -7,6 +7,7 @@
 // limit of this kernel, see conv_mma.cu).  Backward: P and dS are exchanged through shared memory for the two
 // products that reduce over the query index.
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace eegb200 {
 
@@ -141,6 +142,7 @@ __device__ __forceinline__ void pv_product(const float p[8][4], const float* __r
   }
 }
 
+template <int XP>
 __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o,
                                                                        DropoutCfg drop) {
   extern __shared__ __align__(16) float sm[];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const flo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
   float s[8][4];
-  qk_scores<1>(Q, K, row0, g, t, s);
+  qk_scores<XP>(Q, K, row0, g, t, s);
   softmax_rows(s);
   if (drop.p > 0.f) {
     float kf[8][4];
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const flo
       for (int q = 0; q < 4; ++q) s[nt][q] *= kf[nt][q];
   }
   float acc[8][4];
-  pv_product<1>(s, V, g, t, acc);
+  pv_product<XP>(s, V, g, t, acc);
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     float* orow = o + ((size_t)b * 64 + row0 + g + 8 * hrow) * 256 + h * 64;
@@ -295,12 +297,15 @@ int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream
   if (!tf32_rounding()) return attention_fwd_simt(qkv, o, B, drop, s);     // exact-fp32 verification path
   ProfScope _ps("attention_fwd", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
   const size_t smem = 3 * 64 * AL * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  static int xp = -1;
+  if (xp < 0) {
+    const char* e = getenv("EEGB200_ATTN_XP");
+    xp = (e && e[0] == '3') ? 3 : 1;
+    EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  attention_fwd_mma_kernel<<<B * N_HEAD, AT_THREADS, smem, s>>>(qkv, o, drop);
+  if (xp == 3) attention_fwd_mma_kernel<3><<<B * N_HEAD, AT_THREADS, smem, s>>>(qkv, o, drop);
+  else attention_fwd_mma_kernel<1><<<B * N_HEAD, AT_THREADS, smem, s>>>(qkv, o, drop);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

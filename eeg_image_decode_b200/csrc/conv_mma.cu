@@ -6,10 +6,12 @@
 //   dP      : dp[5m+rho] = sum_{a<5,k} dY[m-a][k] * w[k][rho+5a]/51   (1-D transposed conv written as a GEMM over (a,k))
 // so one warp owns a row, keeps the weight fragments (and the dW accumulators) in registers and streams the row
 // through shared memory.  The hand-written tcgen05 path is reserved for the large GEMMs; these row problems are far
-// below one 128-row UMMA tile.  Plain TF32 (RN-rounded operands) in both directions: the legacy mma.sync pipe issues one m16n8k8 per ~16 cycles
-// per SM sub-partition on B200, so a 3xTF32 split would make the forward issue-bound for ~1e-4 of accuracy
-// (measured end-to-end embedding error stays < 4e-4 relative, budget 1e-3); the 3x variant is kept as a template.
+// below one 128-row UMMA tile.  Forward: 3xTF32 split (hi.hi + hi.lo + lo.hi).  The conv output feeds a train-mode BatchNorm that
+// subtracts the batch mean, so rounding errors count relative to the CENTRED signal: with plain TF32 the train-mode
+// embedding error was 1.0e-3 (at the parity gate), with the split 6.5e-4 (tools/gpu_error_budget.py); cost ~55 us
+// per step (the legacy mma.sync pipe issues one m16n8k8 per ~16 cycles per SM sub-partition).  Backward: plain TF32.
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace eegb200 {
 
@@ -364,7 +366,10 @@ int conv_temporal_bwd_simt(const float* dz1, const float* y1, const float* x3, c
 int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s) {
   if (!tf32_rounding()) return conv_temporal_fwd_simt(x3, wt, bt, y1, sums, B, s);   // exact-fp32 verification path
   ProfScope _ps("conv_temporal_fwd", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * (63 * 1000.0 + 36 * 2520 * 4.0));
-  conv_temporal_fwd_mma_kernel<1><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
+  static int xp = -1;
+  if (xp < 0) { const char* e = getenv("EEGB200_CONV_XP"); xp = (e && e[0] == '1') ? 1 : 3; }
+  if (xp == 3) conv_temporal_fwd_mma_kernel<3><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
+  else conv_temporal_fwd_mma_kernel<1><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
