@@ -232,8 +232,9 @@ def _BN_SCALE_SHIFT(world: int) -> int:
 def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
                 step_callback=None):
     """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254.
-    ``step_callback(step_index, loss_tensor[3])`` (optional, keyword only) is invoked after every step, e.g. to read
-    the loss back to the host like the reference does (:238)."""
+    ``step_callback(step_index, loss[3] on the HOST)`` (optional, keyword only) receives every step's loss (mix, image,
+    text share), read back from the device like the reference does (:238) but delivered one step late so that the
+    read-back does not stall the next launch."""
     eeg_model.train()
     device = torch.device(device)
     if device.type != "cuda":
@@ -264,6 +265,16 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
             ev.record(copy_stream)
         return t, ev
 
+    # per-step loss read-back (step_callback): the value is copied to pinned host memory right after the step and handed
+    # to the callback one step later, so the host never stalls the launch of the next step
+    pending = []            # (step index, pinned tensor, event)
+
+    def flush(keep: int):
+        while len(pending) > keep:
+            i_, host_, ev_ = pending.pop(0)
+            ev_.synchronize()
+            step_callback(i_, host_)
+
     it = iter(dataloader)
     nxt = next(it, None)
     staged = stage(nxt) if nxt is not None else None
@@ -286,7 +297,14 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
         total += batch_size
         n_batches += 1
         if step_callback is not None:
-            step_callback(batch_idx, loss)
+            host = torch.empty(3, dtype=torch.float32, pin_memory=True)
+            host.copy_(loss, non_blocking=True)
+            ev_l = torch.cuda.Event()
+            ev_l.record(main_stream)
+            pending.append((batch_idx, host, ev_l))
+            flush(keep=1)
+    if step_callback is not None:
+        flush(keep=0)
     if n_batches == 0:
         raise RuntimeError("train_model: empty dataloader")
     if eng.world > 1:
