@@ -268,12 +268,13 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
     # per-step loss read-back (step_callback): the value is copied to pinned host memory right after the step and handed
     # to the callback one step later, so the host never stalls the launch of the next step
     pending = []            # (step index, pinned tensor, event)
+    pin_ring = torch.empty(8, 3, dtype=torch.float32, pin_memory=True) if step_callback is not None else None
 
     def flush(keep: int):
         while len(pending) > keep:
             i_, host_, ev_ = pending.pop(0)
             ev_.synchronize()
-            step_callback(i_, host_)
+            step_callback(i_, host_.clone())
 
     it = iter(dataloader)
     nxt = next(it, None)
@@ -297,7 +298,7 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
         total += batch_size
         n_batches += 1
         if step_callback is not None:
-            host = torch.empty(3, dtype=torch.float32, pin_memory=True)
+            host = pin_ring[batch_idx % 8]          # at most 2 copies are in flight (flush(keep=1) below)
             host.copy_(loss, non_blocking=True)
             ev_l = torch.cuda.Event()
             ev_l.record(main_stream)
