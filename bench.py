@@ -117,6 +117,41 @@ def cpu_step_runner(batch, threads):
     return run
 
 
+def torch_eager_cuda_baseline(batch=1024, steps=5):
+    """context number: the same step body as stock PyTorch eager ops on this GPU (the oracle port moved to cuda:0 --
+    cuDNN/cuBLAS/ATen library kernels, fp32 with TF32 matmuls allowed), i.e. what the reference would run on a B200"""
+    import torch
+    import recipe
+    from oracle import atms_oracle as O
+    dev = torch.device("cuda")
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    sd = {k: v.to(dev) for k, v in recipe.make_state_dict().items()}
+    opt_state = {}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 63, 250, generator=g).to(dev)
+    sid = torch.full((batch,), 8, device=dev)
+    img = torch.nn.functional.normalize(torch.randn(batch, 1024, generator=g), dim=-1).to(dev)
+    txt = torch.nn.functional.normalize(torch.randn(batch, 1024, generator=g), dim=-1).to(dev)
+    gal = torch.nn.functional.normalize(torch.randn(N_GALLERY, 1024, generator=g), dim=-1).to(dev)
+    labels = torch.randint(0, N_GALLERY, (batch,), generator=g).to(dev)
+
+    def masks():
+        return {site: (torch.rand((batch,) + tuple(shape), device=dev) >= p).float() for site, (shape, p) in O.DROPOUT_SITES.items()}
+
+    def run(step):
+        loss, grads, r = O.train_step(sd, opt_state, x, sid, img, txt, step, masks=masks())
+        O.train_accuracy_counts(r["out"].detach(), gal, labels, sd["logit_scale"])
+
+    run(1); run(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        run(3 + i)
+    torch.cuda.synchronize()
+    return batch * steps / (time.perf_counter() - t0)
+
+
 def pick_cpu_threads(batch):
     """torch's intra-op pool does not scale to every core of a large host for this model (128 threads on a 128-core
     box ran 30x slower than 8 threads on 8 cores), so take the best of a short scan -- the baseline gets its best shot."""
@@ -353,7 +388,12 @@ def bench_ours(args):
             run()
             n += 1
         dtc = time.perf_counter() - t0
-        cpu = {"value": args.cpu_batch * n / dtc, "unit": "trials/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+        try:
+            eager = torch_eager_cuda_baseline()
+        except Exception as ex:   # context only: never fail the bench line on it
+            eager = f"unavailable: {type(ex).__name__}"
+        cpu = {"torch_eager_cuda_trials_s": eager,
+               "value": args.cpu_batch * n / dtc, "unit": "trials/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
                "sample": f"{n} train steps at batch {args.cpu_batch} of the same step body (oracle port, torch {torch.__version__} CPU fp32)"}
 
     line = {

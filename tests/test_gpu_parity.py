@@ -516,3 +516,24 @@ def test_cuda_graph_step_matches_eager(lib):
     gs = GraphedTrainStep(StepEngine(m, None), gal, use_shared=False)
     ls = [gs(xs[0], sid, img, txt, lab)[0][0].item() for _ in range(5)]
     assert gs.graph is not None and len({round(v, 4) for v in ls[2:]}) == 3, ls
+
+
+def test_resident_data_path_feeds_train_model(lib):
+    """the HBM-resident loader and a host loader drive train_model to the same result"""
+    from eeg_image_decode_b200.data import ResidentEEGData
+    from eeg_image_decode_b200.train import train_model
+    n_cls, n = 4, 4 * 40
+    eeg = recipe.make_eeg(n, seed=91)
+    labels = (torch.arange(n) % (n_cls * 40)) // 40
+    txt_all = recipe.make_targets(n_cls, seed=91, tag="txt")
+    img_all = recipe.make_targets(n_cls * 10, seed=91, tag="img")
+    res = []
+    for resident in (False, True):
+        m = make_model(p_drop=0.0)
+        opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+        ds = ResidentEEGData(eeg, labels, txt_all, img_all, train=True, n_cls=n_cls, device="cuda" if resident else "cpu")
+        loader = ds.loader(32, shuffle=False, drop_last=True)
+        res.append(train_model("sub-08", m, loader, opt, torch.device("cuda"), txt_all, img_all, _Cfg()))
+    assert abs(res[0][0] - res[1][0]) < 3e-3 * abs(res[0][0])
+    assert res[0][2].shape == res[1][2].shape == (n // 32 * 32, 1024)
+    assert rows_rel(res[1][2][:32], res[0][2][:32]) < 1e-5
