@@ -536,4 +536,6 @@ def test_resident_data_path_feeds_train_model(lib):
         res.append(train_model("sub-08", m, loader, opt, torch.device("cuda"), txt_all, img_all, _Cfg()))
     assert abs(res[0][0] - res[1][0]) < 3e-3 * abs(res[0][0])
     assert res[0][2].shape == res[1][2].shape == (n // 32 * 32, 1024)
-    assert rows_rel(res[1][2][:32], res[0][2][:32]) < 1e-5
+    # not bit-identical: BatchNorm batch sums are accumulated with atomics (order-dependent in the last bits) and a
+    # 1e-8 change can flip the TF32 rounding of individual activations downstream (tools/gpu_determinism.py)
+    assert rows_rel(res[1][2][:32], res[0][2][:32]) < 5e-4
