@@ -176,12 +176,14 @@ class GraphedTrainStep:
     state and kernel attributes); the third call captures -- capture does not execute -- and replays.  Everything that
     changes from step to step lives in device memory: inputs are copied into static buffers, the dropout seed is
     `seed + device counter`, the AdamW step numbers are device counters advanced inside the graph.
-    Falls back to eager execution for data-parallel runs, foreign optimisers and odd batch sizes."""
+    Data-parallel steps (NCCL all-gather / all-reduce inside the step) are captured as well.  Falls back to eager
+    execution for foreign optimisers and odd batch sizes."""
 
     def __init__(self, eng: "StepEngine", gallery, use_shared: bool, enabled: bool = True):
         import os
         self.eng, self.gallery, self.use_shared = eng, gallery, use_shared
         self.enabled = enabled and os.environ.get("EEGB200_CUDA_GRAPH", "1") != "0"
+        self.dp_ok = os.environ.get("EEGB200_CUDA_GRAPH_DP", "1") != "0"
         self.graph = None
         self.calls = 0
         self.B = None
@@ -197,7 +199,8 @@ class GraphedTrainStep:
         eng = self.eng
         m = eng.model
         B = eeg.shape[0]
-        ok = self.enabled and eng.world == 1 and eng.fused
+        # data-parallel steps are captured too (NCCL collectives are graph-capturable); EEGB200_CUDA_GRAPH_DP=0 opts out
+        ok = self.enabled and eng.fused and (eng.world == 1 or self.dp_ok)
         if not ok or (self.graph is None and self.calls < 2) or (self.B is not None and B != self.B):
             self.calls += 1
             return self._body(eeg, sid, img, txt, labels, None)

@@ -89,6 +89,24 @@ def main():
     if rank == 0:
         print(f"dropout step finite={fin}", flush=True)
     ok = ok and fin
+    # CUDA-graph captured data-parallel step (NCCL collectives inside the graph) vs eager data-parallel, 5 steps
+    from eeg_image_decode_b200.train import GraphedTrainStep
+    gal = recipe.make_targets(50, seed=71, tag="gal").cuda()
+    lab = recipe.make_labels(Bl, 50, seed=71).cuda()
+    finals = {}
+    for graphed in (False, True):
+        mg = make_model(0.0)
+        gs = GraphedTrainStep(StepEngine(mg, None), gal, use_shared=False, enabled=graphed)
+        ls = []
+        for i in range(5):
+            l, f, c = gs(x[sl], sid[sl], img[sl], txt[sl], lab)
+            t_ = l.clone(); dist.all_reduce(t_); ls.append(t_[0].item())
+        finals[graphed] = (ls, mg.flat_params.clone(), gs.graph is not None)
+    gerr = max(abs(a - b) / abs(b) for a, b in zip(finals[True][0], finals[False][0]))
+    gok = finals[True][2] and not finals[False][2] and gerr < 5e-3
+    if rank == 0:
+        print(f"graphed DP: captured={finals[True][2]} loss rel diff vs eager={gerr:.2e} -> {'PASS' if gok else 'FAIL'}", flush=True)
+    ok = ok and gok
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
