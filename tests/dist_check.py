@@ -107,11 +107,12 @@ def main():
     if rank == 0:
         print(f"graphed DP: captured={finals[True][2]} loss rel diff vs eager={gerr:.2e} -> {'PASS' if gok else 'FAIL'}", flush=True)
     ok = ok and gok
-    dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
     if rank == 0:
         print("DIST_CHECK " + ("PASS" if ok else "FAIL"), flush=True)
-    sys.exit(0 if ok else 1)
+    # no destroy_process_group(): tearing down NCCL with captured collectives alive hung on this stack
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
