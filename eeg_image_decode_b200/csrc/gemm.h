@@ -101,24 +101,40 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, f
 
 // 4 consecutive columns of one row (col % 4 == 0, col + 4 <= N, every used pointer 16-byte aligned with ld % 4 == 0).
 // Split in two so the caller can issue the global loads of several rows before consuming any (latency hiding).
+// Compile-time epilogue feature masks.  EF_GENERIC keeps every feature behind a runtime check (one kernel serves any
+// Epilogue); the hot token GEMMs dispatch to kernels specialised on exactly the features they use, which removes the
+// dead paths from the unrolled epilogue (the generic kernel is ~60 KB of SASS and stalls on instruction fetch).
+enum : uint32_t {
+  EF_BIAS = 1, EF_BIAS_TABLE = 2, EF_AUX = 4, EF_GELU = 8, EF_DROP = 16, EF_MUL = 32, EF_RESID = 64, EF_ROUND = 128,
+  EF_BNF = 256, EF_GENERIC = 0x80000000u
+};
+#define EPI_ON(bit, runtime_cond) ((F & EF_GENERIC) ? (runtime_cond) : ((F & (bit)) != 0))
+
 struct EpiLoads { float4 bias, mul, resid; };
+template <uint32_t F>
 __device__ __forceinline__ EpiLoads epi_load4(const Epilogue& e, int row, int col) {
   EpiLoads L;
   L.bias = L.mul = L.resid = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
-  if (e.mul_in) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
-  else if (e.bn_y) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
-  if (e.resid) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
+  if (F & EF_GENERIC) {
+    if (e.bias) L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (e.bias_period ? (size_t)(row % e.bias_period) * e.ld_bias : 0) + col));
+  } else if (F & EF_BIAS_TABLE) {
+    L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + (size_t)(row & 63) * e.ld_bias + col));   // period 64 (tokens)
+  } else if (F & EF_BIAS) {
+    L.bias = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  }
+  if (EPI_ON(EF_MUL, e.mul_in != nullptr)) L.mul = *reinterpret_cast<const float4*>(e.mul_in + (size_t)row * e.ld_mul + col);
+  else if (EPI_ON(EF_BNF, false)) L.mul = *reinterpret_cast<const float4*>(e.bn_y + (size_t)row * e.ld_bn_y + col);
+  if (EPI_ON(EF_RESID, e.resid != nullptr)) L.resid = *reinterpret_cast<const float4*>(e.resid + (size_t)row * e.ld_res + col);
   return L;
 }
-// (an out-of-line version of this function was tried to shrink the ~100 KB kernels: the call overhead and the
-// shared-memory copy of the parameters cost more than the instruction-cache misses they saved: 95 -> 125 us per GEMM)
-template <bool BNF = false>   // BNF: the fused BatchNorm+ELU backward flavour (only the dA1 GEMM of the conv stack pays for it)
+// (an out-of-line version of this function was tried to shrink the kernels: the call overhead and the shared-memory
+// copy of the parameters cost more than the instruction-cache misses they saved: 95 -> 125 us per GEMM)
+template <uint32_t F>
 __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col, float4 acc, const EpiLoads& L, float a,
                                             float* bn_s1 = nullptr, float* bn_s2 = nullptr, const float* bn_tab = nullptr,
                                             int bn_c = 0) {
   float v[4] = {acc.x * a, acc.y * a, acc.z * a, acc.w * a};
-  if (BNF) {
+  if (F & EF_BNF) {
     // bn_tab (shared memory, built once per CTA): [0][c] = mean, [1][c] = rstd, [2][c] = gamma, [3][c] = beta
     const float yv[4] = {L.mul.x, L.mul.y, L.mul.z, L.mul.w};
 #pragma unroll
@@ -130,27 +146,28 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
       bn_s2[i] = fmaf(v[i], yh, bn_s2[i]);
     }
   }
-  if (e.bias) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
-  if (e.aux_out) *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
-  if (e.act == EPI_ACT_GELU) {
+  if (EPI_ON(EF_BIAS | EF_BIAS_TABLE, e.bias != nullptr)) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
+  if (EPI_ON(EF_AUX, e.aux_out != nullptr))
+    *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
+  if (EPI_ON(EF_GELU, e.act == EPI_ACT_GELU)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = gelu_exact(v[i]);
   }
-  if (e.drop.p > 0.f) {
+  if (EPI_ON(EF_DROP, e.drop.p > 0.f)) {
     const uint32_t m = dropout_keep4(e.drop, (uint64_t)row * e.drop_ld + col);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (m >> i) & 1u ? v[i] * e.drop.scale : 0.f;
   }
-  if (e.mul_in) {
+  if (EPI_ON(EF_MUL, e.mul_in != nullptr)) {
     v[0] *= gelu_grad(L.mul.x); v[1] *= gelu_grad(L.mul.y); v[2] *= gelu_grad(L.mul.z); v[3] *= gelu_grad(L.mul.w);
   }
-  if (e.resid) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
-  if (e.round_tf32) {
+  if (EPI_ON(EF_RESID, e.resid != nullptr)) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
+  if (EPI_ON(EF_ROUND, e.round_tf32 != 0)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = tf32_rn(v[i]);
   }
   float* p = e.C + (size_t)row * e.ldc + col;
-  if (e.store_mode == EPI_STORE) {
+  if (!(F & EF_GENERIC) || e.store_mode == EPI_STORE) {          // specialised flavours always store
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   } else if (e.store_mode == EPI_ADD) {
     float4 o = *reinterpret_cast<float4*>(p);
@@ -159,6 +176,19 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
   } else {
     red_add_v4(p, v[0], v[1], v[2], v[3]);
   }
+}
+// feature mask of an epilogue (host side); specialised kernels exist for some masks only
+static inline uint32_t epi_feature_mask(const Epilogue& e) {
+  uint32_t m = 0;
+  if (e.bias) m |= e.bias_period ? EF_BIAS_TABLE : EF_BIAS;
+  if (e.aux_out) m |= EF_AUX;
+  if (e.act == EPI_ACT_GELU) m |= EF_GELU;
+  if (e.drop.p > 0.f) m |= EF_DROP;
+  if (e.mul_in) m |= EF_MUL;
+  if (e.resid) m |= EF_RESID;
+  if (e.round_tf32) m |= EF_ROUND;
+  if (e.bn_y) m |= EF_BNF;
+  return m;
 }
 __device__ __forceinline__ void epi_scalar4(const Epilogue& e, int row, int col, float4 a4, int N) {
   const float av[4] = {a4.x, a4.y, a4.z, a4.w};

@@ -36,7 +36,7 @@ static constexpr int EPI_SLD = 36;   // staging row stride in floats (16-byte al
 // split the 32-column chunks).  TMEM -> registers (thread = row) -> per-warp smem transpose -> lanes along columns:
 // every global access of the fused epilogue (bias / aux / GELU' input / residual / output) is a coalesced 128-byte row
 // segment, and the loads of 4 row groups are in flight before the first is consumed.
-template <int BN, bool BNF>
+template <int BN, uint32_t F>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const Epilogue& e, uint32_t tmem_acc, float* stage,
                                               int tile_m, int tile_n, int warp, int lane, bool has_acc, float* sred) {
   const int q = warp & 3;
@@ -63,26 +63,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
     __syncwarp();
     const int col = col0 + cq;
     const int row0 = tile_m * BM + q * 32 + r_sub;
-    if (p.vec_ok) {                                  // N % 4 == 0: a lane's 4 columns are all in range or all out
+    if (!(F & EF_GENERIC) || p.vec_ok) {             // N % 4 == 0: a lane's 4 columns are all in range or all out
       const bool lane_ok = col < p.N;
       float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
-      const int bn_c = BNF ? col % 40 : 0;
+      const int bn_c = (F & EF_BNF) ? col % 40 : 0;
 #pragma unroll 1
       for (int g4 = 0; g4 < 2; ++g4) {     // not unrolled: halves the epilogue's SASS footprint (I-cache)
         EpiLoads L[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M && lane_ok) L[u] = epi_load4(e, row, col);
+          if (row < p.M && lane_ok) L[u] = epi_load4<F>(e, row, col);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int rl = (g4 * 4 + u) * 4 + r_sub;
           const int row = row0 + (g4 * 4 + u) * 4;
-          if (row < p.M && lane_ok) epi_finish4<BNF>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2, sred + 80, bn_c);
+          if (row < p.M && lane_ok) epi_finish4<F>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2, sred + 80, bn_c);
         }
       }
-      if (BNF) {        // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
+      if (F & EF_BNF) {  // same 4 columns for every row of this lane: reduce over the 4 row lanes, then 8 lanes publish
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 8);  bs1[i] += __shfl_xor_sync(0xffffffffu, bs1[i], 16);
@@ -268,7 +268,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = j & 1;
       mbar_wait(&tmem_full_bar[acc], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      epilogue_tile<BN, false>(p, p.epi, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
+      epilogue_tile<BN, EF_GENERIC>(p, p.epi, tmem_base + (uint32_t)(acc * BN), stage, tm, tn, warp, lane, true, sred);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -280,7 +280,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int A_MN, int B_MN, bool BNF = false>
+template <int BN, int A_MN, int B_MN, uint32_t F = EF_GENERIC>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
@@ -299,6 +299,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  constexpr bool BNF = (F & EF_BNF) != 0;
   __shared__ float sred[BNF ? 240 : 80];     // [0,80): BN-backward reductions; [80,240): mean | rstd | gamma | beta
   if (threadIdx.x < 80) sred[threadIdx.x] = 0.f;
   if (BNF && threadIdx.x < 160) {
@@ -397,7 +398,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
     }
     float* stage = reinterpret_cast<float*>(tiles) + (size_t)(warp - 2) * 32 * EPI_SLD;
-    epilogue_tile<BN, BNF>(p, p.epi, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
+    epilogue_tile<BN, F>(p, p.epi, tmem_base, stage, tile_m, tile_n, warp, lane, num_kb > 0, sred);
   }
 
   tc_fence_before();
@@ -543,24 +544,45 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
   const size_t smem = tile_bytes + 1024 + 256;
   p.tile_bytes = (int)tile_bytes;
   dim3 grid(cdiv(g.N, BN), cdiv(g.M, BM), split);
-  if (g.epi.bn_y != nullptr) {
-    if constexpr (BN == 256 && A_MN == 0 && B_MN == 1) {
-      EEG_REQUIRE(p.vec_ok && g.epi.bn_sums && g.epi.bn_mean_rstd && g.epi.bn_gamma && g.epi.bn_beta && split == 1,
-                  "gemm: the fused BatchNorm-backward epilogue needs the vector path and all BN pointers");
-      auto kb = gemm_tf32_kernel<256, 0, 1, true>;
-      static bool cb = false;
-      if (!cb) {
-        EEG_CUDA_OK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        cb = true;
-      }
-      kb<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
-      EEG_CUDA_OK(cudaGetLastError());
-      count_launch();
-      return 0;
-    } else {
-      set_error("gemm: the fused BatchNorm-backward epilogue is only built for the 256-wide K-major x MN-major kernel");
-      return 2;
+  // kernels specialised on the exact epilogue feature set of the hot 256-wide GEMMs (everything else: generic kernel)
+  if constexpr (BN == 256 && A_MN == 0) {
+    const uint32_t fm = epi_feature_mask(g.epi);
+    const bool spec_ok = p.vec_ok && g.epi.store_mode == EPI_STORE && split == 1 && (g.N % 32) == 0 &&
+                         (!(fm & EF_BIAS_TABLE) || g.epi.bias_period == 64);
+    if (fm & EF_BNF) {
+      EEG_REQUIRE(B_MN == 1 && p.vec_ok && fm == EF_BNF && g.epi.bn_sums && g.epi.bn_mean_rstd && g.epi.bn_gamma &&
+                  g.epi.bn_beta && split == 1, "gemm: unsupported use of the fused BatchNorm-backward epilogue");
     }
+#define EEG_SPEC(MASK)                                                                                        \
+    if (fm == (MASK)) {                                                                                       \
+      auto ks = gemm_tf32_kernel<256, 0, B_MN, (MASK)>;                                                       \
+      static bool cs = false;                                                                                 \
+      if (!cs) {                                                                                              \
+        EEG_CUDA_OK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       \
+        cs = true;                                                                                            \
+      }                                                                                                       \
+      ks<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);                                                    \
+      EEG_CUDA_OK(cudaGetLastError());                                                                        \
+      count_launch();                                                                                         \
+      return 0;                                                                                               \
+    }
+    if (spec_ok || (fm & EF_BNF)) {
+      if constexpr (B_MN == 0) {
+        EEG_SPEC(EF_BIAS_TABLE | EF_DROP | EF_ROUND)                       // value embedding (train)
+        EEG_SPEC(EF_BIAS)                                                   // QKV projection
+        EEG_SPEC(EF_BIAS | EF_DROP | EF_RESID)                              // out-projection / FFN2 + residual (train)
+        EEG_SPEC(EF_BIAS | EF_AUX | EF_GELU | EF_DROP | EF_ROUND)           // FFN1 (train)
+      } else {
+        EEG_SPEC(EF_DROP | EF_MUL | EF_ROUND)                               // dU = dropout(T1.W2) * GELU'(U)
+        EEG_SPEC(EF_RESID)                                                  // dX1, dH0
+        EEG_SPEC(0u)                                                        // dO
+        EEG_SPEC(EF_BNF)                                                    // dA1 with the BatchNorm1+ELU backward
+      }
+    }
+#undef EEG_SPEC
+    EEG_REQUIRE(!(fm & EF_BNF), "gemm: the fused BatchNorm-backward epilogue has no generic fallback");
+  } else {
+    EEG_REQUIRE(g.epi.bn_y == nullptr, "gemm: the fused BatchNorm-backward epilogue is only built for the 256-wide K-major x MN-major kernel");
   }
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static size_t configured = 0;   // per template instantiation

@@ -484,8 +484,10 @@ int dropout_apply_colsum(const float* src, float* dst, int rows, int ld, Dropout
                          int cs_cols, int row_mod, int row_skip, cudaStream_t s) {
   ProfScope _ps("dropout_apply_colsum", s, 0.0, (double)rows * ld * 8.0);
   EEG_REQUIRE((ld & 3) == 0 && ld <= 256, "dropout_apply_colsum: ld %d must be a multiple of 4 and <= 256", ld);
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("EEGB200_DACS_BLOCKS"); cap = e ? atoi(e) : 148 * 4; }
   int blocks = cdiv(rows, 4 * 16);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dropout_apply_colsum_kernel<<<blocks, 256, 0, s>>>(src, dst, rows, ld, cfg, round_tf, colsum_out, cs_cols, row_mod, row_skip);
   EEG_CUDA_OK(cudaGetLastError());
