@@ -472,6 +472,16 @@ static int side_enabled() {
   return on;
 }
 
+// EEGB200_LN_FUSED=0 falls back to the separate LayerNorm-backward + dropout passes (A/B switch)
+static int ln_fused() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("EEGB200_LN_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on;
+}
+
 static int backward(const eegb200_atms_io* io, const float* d_out, float* const* GR, int phases, cudaStream_t s) {
   Ws w;
   EEG_TRY(check_io(io, &w));
@@ -549,11 +559,18 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                               wmul * B * N_CH * N_POOL, w.dX3, GR[EEGB200_P_WT], GR[EEGB200_P_BT],
                               GR[EEGB200_P_BN1_G], GR[EEGB200_P_BN1_B], B, 1.f / (float)wmul, s));
     // ---- final norm + norm2 ----
-    EEG_TRY(layernorm_bwd(w.dX3, 256, w.R2, 256, M, N_T, P[EEGB200_P_LN2_G], P[EEGB200_P_LN2_B], w.st2,
-                          P[EEGB200_P_LNF_G], w.stf, w.dR2, 256, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B],
-                          GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
+    // (the LayerNorm backward also emits T1 = dropout_ffn2(dR2), the operand of the FFN GEMMs, and db2 = colsum(T1))
+    if (ln_fused()) {
+      EEG_TRY(layernorm_bwd_tok(w.dX3, w.R2, M, N_T, P[EEGB200_P_LN2_G], P[EEGB200_P_LN2_B], w.st2, P[EEGB200_P_LNF_G],
+                                w.stf, w.dR2, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B], GR[EEGB200_P_LNF_G],
+                                GR[EEGB200_P_LNF_B], w.T1, cfg.d[EEGB200_SITE_FFN2], RT, GR[EEGB200_P_B2], s));
+    } else {
+      EEG_TRY(layernorm_bwd(w.dX3, 256, w.R2, 256, M, N_T, P[EEGB200_P_LN2_G], P[EEGB200_P_LN2_B], w.st2,
+                            P[EEGB200_P_LNF_G], w.stf, w.dR2, 256, GR[EEGB200_P_LN2_G], GR[EEGB200_P_LN2_B],
+                            GR[EEGB200_P_LNF_G], GR[EEGB200_P_LNF_B], 0, s));
+      EEG_TRY(dropout_apply_colsum(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, GR[EEGB200_P_B2], N_T, 0, 0, s));
+    }
     // ---- FFN ----
-    EEG_TRY(dropout_apply_colsum(w.dR2, w.T1, M, 256, cfg.d[EEGB200_SITE_FFN2], RT, GR[EEGB200_P_B2], N_T, 0, 0, s));
     FORK();
     EEG_TRY(run_gemm(N_T, D_FF, M, w.T1, 256, 1, w.Hf, 256, 1, epi_wgrad(GR[EEGB200_P_W2], D_FF), pick_split(N_T, D_FF, M), ws));
     {
@@ -572,10 +589,16 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
       EEG_TRY(run_gemm(M, 256, 256, w.dU, 256, 0, w.W1_p, 256, 1, e, 1, s));
     }
     // ---- norm1 ----
-    EEG_TRY(layernorm_bwd(w.dX1, 256, w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr,
-                          w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
+    if (ln_fused()) {
+      EEG_TRY(layernorm_bwd_tok(w.dX1, w.R1, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr, w.dR1,
+                                GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, w.T2,
+                                cfg.d[EEGB200_SITE_RES1], RT, GR[EEGB200_P_BO], s));
+    } else {
+      EEG_TRY(layernorm_bwd(w.dX1, 256, w.R1, 256, M, N_T, P[EEGB200_P_LN1_G], P[EEGB200_P_LN1_B], w.st1, nullptr, nullptr,
+                            w.dR1, 256, GR[EEGB200_P_LN1_G], GR[EEGB200_P_LN1_B], nullptr, nullptr, 0, s));
+      EEG_TRY(dropout_apply_colsum(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, GR[EEGB200_P_BO], N_T, 0, 0, s));
+    }
     // ---- attention ----
-    EEG_TRY(dropout_apply_colsum(w.dR1, w.T2, M, 256, cfg.d[EEGB200_SITE_RES1], RT, GR[EEGB200_P_BO], N_T, 0, 0, s));
     FORK();
     EEG_CUDA_OK(cudaMemsetAsync(w.dWo_p, 0, 256 * 256 * sizeof(float), ws));
     EEG_TRY(run_gemm(256, 256, M, w.T2, 256, 1, w.O, 256, 1, epi_wgrad(w.dWo_p, 256), pick_split(256, 256, M), ws));

@@ -48,6 +48,11 @@ int layernorm_fwd(const float* x, int ld, int rows, int D, const float* g1, cons
 int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, int D, const float* g1, const float* b1,
                   const float* stats1, const float* g2, const float* stats2, float* dx, int ld_dx, float* dg1,
                   float* db1, float* dg2, float* db2, int round_tf, cudaStream_t s);
+// token-stream form (every ld = 256): dx, plus optionally drop_out = tf32?(dropout(dx)) and colsum_out += colsum(drop_out)
+int layernorm_bwd_tok(const float* dy, const float* x, int rows, int D, const float* g1, const float* b1,
+                      const float* stats1, const float* g2, const float* stats2, float* dx, float* dg1, float* db1,
+                      float* dg2, float* db2, float* drop_out, DropoutCfg cfg, int drop_round, float* colsum_out,
+                      cudaStream_t s);
 int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s);
 int dropout_mask(DropoutCfg cfg, int rows, int cols, int ld, float* out, cudaStream_t s);
 // dst[r*ld+c] = tf32?(keep(r*ld+c) ? src*scale : 0) over [rows, ld]

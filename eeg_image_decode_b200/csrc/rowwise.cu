@@ -301,6 +301,150 @@ int layernorm_bwd(const float* dy, int ld_dy, const float* x, int ld, int rows, 
   return 0;
 }
 
+// Token-stream LayerNorm backward (all leading dimensions 256, D <= 256): one warp per row, each lane owns the column
+// quads [4*lane, 4*lane+4) and [128+4*lane, ...), so every access is a 16-byte vector.  Optionally also writes
+// drop_out = tf32?(dropout(dx)) -- the A operand of the next backward GEMM -- and accumulates its column sums (the
+// bias gradient of the layer in front of that dropout); this replaces a separate 134 MB pass over dx.
+template <bool TWO>
+__global__ void __launch_bounds__(256) layernorm_bwd_tok_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, int rows, int D, const float* __restrict__ g1,
+    const float* __restrict__ b1, const float* __restrict__ stats1, const float* __restrict__ g2,
+    const float* __restrict__ stats2, float* __restrict__ dx, float* __restrict__ dg1, float* __restrict__ db1,
+    float* __restrict__ dg2, float* __restrict__ db2, float* __restrict__ drop_out, DropoutCfg cfg, int drop_round,
+    float* __restrict__ colsum) {
+  __shared__ float sh[5][256];
+  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) (&sh[0][0])[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int col[8];
+  float gm1[8], bt1[8], gm2[8];
+  bool ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    col[i] = (i < 4 ? 0 : 128) + 4 * lane + (i & 3);
+    ok[i] = col[i] < D;
+    gm1[i] = ok[i] ? g1[col[i]] : 0.f;
+    bt1[i] = (TWO && ok[i]) ? b1[col[i]] : 0.f;
+    gm2[i] = (TWO && ok[i]) ? g2[col[i]] : 0.f;
+  }
+  float acc_g1[8], acc_b1[8], acc_g2[8], acc_b2[8], acc_cs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc_g1[i] = acc_b1[i] = acc_g2[i] = acc_b2[i] = acc_cs[i] = 0.f;
+  const float invD = 1.f / (float)D;
+
+  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * 256);
+    const float4* dyr = reinterpret_cast<const float4*>(dy + (size_t)row * 256);
+    const float4 xa = xr[lane], xb = xr[32 + lane], ga = dyr[lane], gb = dyr[32 + lane];
+    const float2 st1 = *reinterpret_cast<const float2*>(stats1 + 2 * row);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    float xh1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh1[i] = ok[i] ? (xv[i] - st1.x) * st1.y : 0.f;
+      g[i] = ok[i] ? g[i] : 0.f;
+    }
+    if (TWO) {
+      const float2 st2 = *reinterpret_cast<const float2*>(stats2 + 2 * row);
+      float s1 = 0.f, s2 = 0.f, xh2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(xh1[i], gm1[i], bt1[i]);
+        xh2[i] = ok[i] ? (u - st2.x) * st2.y : 0.f;
+        acc_g2[i] = fmaf(g[i], xh2[i], acc_g2[i]);
+        acc_b2[i] += g[i];
+        g[i] *= gm2[i];
+        s1 += g[i];
+        s2 = fmaf(g[i], xh2[i], s2);
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = ok[i] ? st2.y * (g[i] - s1 - xh2[i] * s2) : 0.f;
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc_g1[i] = fmaf(g[i], xh1[i], acc_g1[i]);
+      acc_b1[i] += g[i];
+      g[i] *= gm1[i];
+      s1 += g[i];
+      s2 = fmaf(g[i], xh1[i], s2);
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ok[i] ? st1.y * (g[i] - s1 - xh1[i] * s2) : 0.f;
+    float4* dxr = reinterpret_cast<float4*>(dx + (size_t)row * 256);
+    dxr[lane] = make_float4(v[0], v[1], v[2], v[3]);
+    dxr[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+    if (drop_out != nullptr) {
+      if (cfg.p > 0.f) {
+        const uint32_t m0 = dropout_keep4(cfg, (uint64_t)row * 256 + 4 * lane);
+        const uint32_t m1 = dropout_keep4(cfg, (uint64_t)row * 256 + 128 + 4 * lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] = (m0 >> i) & 1u ? v[i] * cfg.scale : 0.f;
+          v[4 + i] = (m1 >> i) & 1u ? v[4 + i] * cfg.scale : 0.f;
+        }
+      }
+      if (drop_round) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tf32_rn(v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc_cs[i] += v[i];
+      float4* dr = reinterpret_cast<float4*>(drop_out + (size_t)row * 256);
+      dr[lane] = make_float4(v[0], v[1], v[2], v[3]);
+      dr[32 + lane] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (!ok[i]) continue;
+    atomicAdd(&sh[0][col[i]], acc_g1[i]);
+    atomicAdd(&sh[1][col[i]], acc_b1[i]);
+    if (TWO) {
+      atomicAdd(&sh[2][col[i]], acc_g2[i]);
+      atomicAdd(&sh[3][col[i]], acc_b2[i]);
+    }
+    if (drop_out != nullptr) atomicAdd(&sh[4][col[i]], acc_cs[i]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(&dg1[c], sh[0][c]);
+    atomicAdd(&db1[c], sh[1][c]);
+    if (TWO) {
+      atomicAdd(&dg2[c], sh[2][c]);
+      atomicAdd(&db2[c], sh[3][c]);
+    }
+    if (colsum != nullptr) atomicAdd(&colsum[c], sh[4][c]);
+  }
+}
+
+int layernorm_bwd_tok(const float* dy, const float* x, int rows, int D, const float* g1, const float* b1,
+                      const float* stats1, const float* g2, const float* stats2, float* dx, float* dg1, float* db1,
+                      float* dg2, float* db2, float* drop_out, DropoutCfg cfg, int drop_round, float* colsum_out,
+                      cudaStream_t s) {
+  ProfScope _ps(g2 ? "layernorm2x_bwd" : "layernorm_bwd", s, 0.0, (double)rows * 256 * (drop_out ? 16.0 : 12.0));
+  EEG_REQUIRE(D <= 256 && D > 0, "layernorm_bwd_tok: D=%d unsupported", D);
+  EEG_REQUIRE(!g2 || (stats2 && dg2 && db2), "layernorm_bwd_tok: the chained form needs stats2/dg2/db2");
+  int blocks = cdiv(rows, 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  if (g2)
+    layernorm_bwd_tok_kernel<true><<<blocks, 256, 0, s>>>(dy, x, rows, D, g1, b1, stats1, g2, stats2, dx, dg1, db1, dg2, db2,
+                                                         drop_out, cfg, drop_round, colsum_out);
+  else
+    layernorm_bwd_tok_kernel<false><<<blocks, 256, 0, s>>>(dy, x, rows, D, g1, b1, stats1, g2, stats2, dx, dg1, db1, dg2,
+                                                          db2, drop_out, cfg, drop_round, colsum_out);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[c] += sum_r x[r*ld + c] (c < cols); optional dropout mask on the fly (bias grads of layers whose
 // output passes through a dropout before the residual).
