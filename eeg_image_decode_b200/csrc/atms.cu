@@ -24,7 +24,10 @@ struct Ws {
   // backward temporaries
   float *dZ2, *dZ2d, *dZ1, *dfeat, *dz2, *dY2, *dA1, *dX3, *dR2, *T1, *dU, *dX1, *dR1, *T2, *dO, *dQKV, *dH0, *T3;
   float *dWqkv_p, *dbqkv_p, *dWo_p, *dWs_p;
+  // joint-subject variant: one packed value embedding / token-bias table per subject slot
+  float *Wv_j, *tokbias_j;
 };
+constexpr int MAX_JOINT_SUBJECTS = 16;
 
 struct Carver {
   uint8_t* base;
@@ -106,6 +109,8 @@ static size_t carve(void* base, int B, Ws* w) {
   t.dbqkv_p = c.take<float>(768);
   t.dWo_p = c.take<float>(256 * 256);
   t.dWs_p = c.take<float>((size_t)N_FILT * K_SPAT);
+  t.Wv_j = c.take<float>((size_t)MAX_JOINT_SUBJECTS * 256 * 256);
+  t.tokbias_j = c.take<float>((size_t)MAX_JOINT_SUBJECTS * 64 * 256);
   if (w) *w = t;
   return align_up(c.off, 256);
 }
@@ -244,6 +249,47 @@ __global__ void pack_all_kernel(PackArgs a, int rt) {
   }
 }
 
+// joint-subject variant: value embedding of one subject [250,250] -> [256,256] (TF32) and its token-bias table
+// (bias + positional row, Embed.py:144-149); token 0 is the subject slot
+__global__ void pack_value_joint_kernel(const float* __restrict__ vw, const float* __restrict__ vb,
+                                        const float* __restrict__ pe, float* __restrict__ Wv_p,
+                                        float* __restrict__ tokbias, int rt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 256 * 256) {
+    const int r = idx >> 8, c = idx & 255;
+    Wv_p[idx] = (r < N_T && c < N_T) ? tf32_if(vw[r * N_T + c], rt) : 0.f;
+  }
+  if (idx < 64 * 256) {
+    const int t = idx >> 8, c = idx & 255;
+    tokbias[idx] = (t > 0 && c < N_T) ? vb[c] + pe[(t - 1) * N_T + c] : 0.f;
+  }
+}
+
+static int check_joint(const eegb200_atms_io* io, bool backward) {
+  if (!io->joint_value_w) return 0;
+  EEG_REQUIRE(io->joint_value_b && io->group_offsets && io->group_subject, "joint variant: null pointer");
+  EEG_REQUIRE(io->n_subjects >= 1 && io->n_subjects <= MAX_JOINT_SUBJECTS, "joint variant: n_subjects %d outside [1,%d]",
+              io->n_subjects, MAX_JOINT_SUBJECTS);
+  EEG_REQUIRE(io->n_groups >= 1 && io->n_groups <= io->n_subjects, "joint variant: n_groups %d outside [1,%d]", io->n_groups,
+              io->n_subjects);
+  EEG_REQUIRE(io->group_offsets[0] == 0 && io->group_offsets[io->n_groups] == io->B,
+              "joint variant: group_offsets must run from 0 to B=%d", io->B);
+  unsigned seen = 0;
+  for (int g = 0; g < io->n_groups; ++g) {
+    const int sj = io->group_subject[g];
+    EEG_REQUIRE(io->group_offsets[g + 1] > io->group_offsets[g], "joint variant: empty or unordered group %d", g);
+    EEG_REQUIRE(sj >= 0 && sj < io->n_subjects, "joint variant: no value embedding for subject id %d (KeyError '%d' in the "
+                "reference, Embed.py:144)", sj, sj);
+    EEG_REQUIRE(!(seen & (1u << sj)), "joint variant: subject %d appears in two groups (sort the batch by subject)", sj);
+    seen |= 1u << sj;
+    EEG_REQUIRE(io->joint_value_w[sj] && io->joint_value_b[sj], "joint variant: null value embedding for subject %d", sj);
+    if (backward)
+      EEG_REQUIRE(io->joint_value_dw && io->joint_value_db && io->joint_value_dw[sj] && io->joint_value_db[sj],
+                  "joint variant: null gradient buffer for subject %d", sj);
+  }
+  return 0;
+}
+
 static int pack_weights(const float* const* P, float* const* BUF, const Ws& w, cudaStream_t s) {
   const int RT = tf32_rounding();
   ProfScope _ps("pack_weights", s, 0.0, 3.2e6 * 8.0);
@@ -339,12 +385,31 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
     EEG_TRY(pack_weights(P, BUF, w, s));
     // ---- DataEmbedding (Embed.py:141-162) ----
     EEG_TRY(pad_input(io->x, w.Xp, B, s));
-    {
+    if (!io->joint_value_w) {
       Epilogue e = epi_out(w.H0, 256);
       e.bias = w.tokbias; e.bias_period = 64; e.ld_bias = 256;
       e.drop = cfg.d[EEGB200_SITE_EMBED]; e.drop_ld = 256;
       e.round_tf32 = RT;
       EEG_TRY(run_gemm(M, 256, 256, w.Xp, 256, 0, w.Wv_p, 256, 0, e, 1, s));
+    } else {
+      // joint-subject variant (Embed.py:144): one grouped GEMM per subject present in the batch, each with its own
+      // packed weights / token-bias table, into T3 (a backward temporary, free here); then one pass applies the embed
+      // dropout with the same element indexing as the fused epilogue above (+ TF32 rounding) into H0
+      EEG_TRY(check_joint(io, false));
+      for (int g = 0; g < io->n_groups; ++g) {
+        const int sj = io->group_subject[g];
+        const size_t r0 = (size_t)io->group_offsets[g] * N_TOK;
+        const int rows = (io->group_offsets[g + 1] - io->group_offsets[g]) * N_TOK;
+        float* Wj = w.Wv_j + (size_t)sj * 256 * 256;
+        float* bj = w.tokbias_j + (size_t)sj * 64 * 256;
+        pack_value_joint_kernel<<<256, 256, 0, s>>>(io->joint_value_w[sj], io->joint_value_b[sj], BUF[EEGB200_BUF_PE], Wj, bj, RT);
+        EEG_CUDA_OK(cudaGetLastError());
+        count_launch();
+        Epilogue e = epi_out(w.T3 + r0 * 256, 256);
+        e.bias = bj; e.bias_period = 64; e.ld_bias = 256;
+        EEG_TRY(run_gemm(rows, 256, 256, w.Xp + r0 * 256, 256, 0, Wj, 256, 0, e, 1, s));
+      }
+      EEG_TRY(dropout_apply(w.T3, w.H0, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
     }
     EEG_TRY(subject_token(reinterpret_cast<const long long*>(io->subject_ids), P[EEGB200_P_SUBJ_TABLE],
                           P[EEGB200_P_SUBJ_SHARED], io->n_subjects, w.flag, w.H0, B, cfg.d[EEGB200_SITE_EMBED], RT, s));
@@ -621,9 +686,24 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     }
     // ---- DataEmbedding ----
     // token-0 rows carry no value embedding -> excluded from the bias gradient
-    EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
-    FORK();
-    EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), ws));
+    if (!io->joint_value_w) {
+      EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
+      FORK();
+      EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), ws));
+    } else {
+      // joint-subject variant: every subject's value embedding gets the gradient of its own trials only
+      EEG_TRY(check_joint(io, true));
+      EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
+      FORK();
+      for (int g = 0; g < io->n_groups; ++g) {
+        const int sj = io->group_subject[g];
+        const size_t r0 = (size_t)io->group_offsets[g] * N_TOK;
+        const int rows = (io->group_offsets[g + 1] - io->group_offsets[g]) * N_TOK;
+        EEG_TRY(colsum(w.T3 + r0 * 256, 256, rows, N_T, io->joint_value_db[sj], N_TOK, 0, ws));
+        EEG_TRY(run_gemm(N_T, N_T, rows, w.T3 + r0 * 256, 256, 1, w.Xp + r0 * 256, 256, 1,
+                         epi_wgrad(io->joint_value_dw[sj], N_T), pick_split(N_T, N_T, rows), ws));
+      }
+    }
     EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,
                 "subject-token gradients need both the table and the shared-token grad buffers");
     EEG_TRY(subject_token_bwd(reinterpret_cast<const long long*>(io->subject_ids), w.flag, w.dH0, GR[EEGB200_P_SUBJ_TABLE],

@@ -120,6 +120,10 @@ int infonce_grad(const InfoNceArgs& a, float* logits_inout, const float* row_lse
 int argmax_count(const float* logits, int ld, int rows, int cols, const long long* labels, int* correct,
                  long long* pred_out, cudaStream_t s);
 int topk5(const float* logits, int ld, int rows, int cols, int* top5_out /*[rows][5]*/, cudaStream_t s);
+// weight * MSE(eeg, tgt) share of this rank (mean over n_total*D elements): loss / loss_term += (either may be null),
+// d_eeg += weight*grad_out * d MSE / d eeg (null: loss only)
+int mse_loss(const float* eeg, const float* tgt, int B, int D, long long n_total, float weight, float grad_out, float* loss,
+             float* loss_term, float* d_eeg, cudaStream_t s);
 
 // ---- optim.cu ----
 int adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

@@ -326,4 +326,52 @@ int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Regression term of the reconstruction-training variant: nn.MSELoss()(eeg_features, img_features)
+// (Generation/ATMS_reconstruction.py:201, 227-228): mean over ALL n_total*D elements of the global batch.
+// This rank's rows add   loss += weight * sum (e-t)^2 / (n_total*D)   and   d_eeg += g_scale * (e-t),
+// g_scale = weight * grad_out * 2 / (n_total*D).  float4 grid-stride; one double atomic per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_kernel(const float4* __restrict__ e, const float4* __restrict__ t, long long n4,
+                                                  float loss_scale, float g_scale, float* __restrict__ loss,
+                                                  float* __restrict__ loss_term, float4* d_eeg) {
+  __shared__ float part[8];
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = e[i], b = t[i];
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    acc = fmaf(dx, dx, acc); acc = fmaf(dy, dy, acc); acc = fmaf(dz, dz, acc); acc = fmaf(dw, dw, acc);
+    if (d_eeg != nullptr) {
+      float4 g = d_eeg[i];
+      g.x = fmaf(g_scale, dx, g.x); g.y = fmaf(g_scale, dy, g.y); g.z = fmaf(g_scale, dz, g.z); g.w = fmaf(g_scale, dw, g.w);
+      d_eeg[i] = g;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += part[i];
+    tot *= loss_scale;
+    if (loss != nullptr) atomicAdd(loss, tot);
+    if (loss_term != nullptr) atomicAdd(loss_term, tot);
+  }
+}
+int mse_loss(const float* eeg, const float* tgt, int B, int D, long long n_total, float weight, float grad_out, float* loss,
+             float* loss_term, float* d_eeg, cudaStream_t s) {
+  ProfScope _ps("mse_loss", s, 0.0, (double)B * D * (d_eeg ? 16.0 : 8.0));
+  const long long n4 = (long long)B * D / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks < 1) blocks = 1;
+  const double inv = 1.0 / ((double)n_total * (double)D);
+  mse_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(eeg), reinterpret_cast<const float4*>(tgt), n4,
+                                    (float)(weight * inv), (float)(2.0 * weight * grad_out * inv), loss, loss_term,
+                                    reinterpret_cast<float4*>(d_eeg));
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace eegb200

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define EEGB200_ABI_VERSION 1
+#define EEGB200_ABI_VERSION 2
 
 int eegb200_abi_version(void);
 const char* eegb200_last_error(void);
@@ -129,6 +129,20 @@ typedef struct eegb200_atms_io {
   float* out;                    /* [B,1024] */
   const uint64_t* seed_offset_dev; /* optional DEVICE counter mixed into `seed` when the kernels run (CUDA-graph replay
                                       draws new dropout masks without re-capturing); NULL -> `seed` alone */
+  /* ---- joint-subject variant (ABI v2): per-subject value embeddings, DataEmbedding(joint_train=True)
+   * (models/subject_layers/Embed.py:128-130, 144; model built at Retrieval/ATMS_retrieval_joint_train.py:173-176).
+   * joint_value_w == NULL selects the single shared embedding params[EEGB200_P_VALUE_W / _B] (all fields below
+   * ignored).  Otherwise the trials must be ordered so that trials of one subject are contiguous: group g covers
+   * trials [group_offsets[g], group_offsets[g+1]) and uses value embedding group_subject[g] -- one grouped GEMM per
+   * subject instead of the reference's per-trial Python loop.  params[EEGB200_P_VALUE_W / _B] must still be
+   * non-NULL (any valid pointer) and are not read; grads of those two slots are not written. */
+  const float* const* joint_value_w;   /* [n_subjects] device pointers, each [250,250] */
+  const float* const* joint_value_b;   /* [n_subjects] device pointers, each [250] */
+  float* const* joint_value_dw;        /* backward: += gradients, same indexing (subjects absent from the batch untouched) */
+  float* const* joint_value_db;
+  const int32_t* group_offsets;        /* HOST int32[n_groups+1], group_offsets[0] = 0, group_offsets[n_groups] = B */
+  const int32_t* group_subject;        /* HOST int32[n_groups], each in [0, n_subjects), pairwise distinct */
+  int n_groups;
 } eegb200_atms_io;
 
 size_t eegb200_atms_workspace_bytes(int B);
@@ -166,6 +180,16 @@ typedef struct eegb200_infonce_io {
 } eegb200_infonce_io;
 size_t eegb200_infonce_workspace_bytes(int B, int N, int D, int n_targets);
 int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
+
+/* Regression term of the reconstruction-training variant (replaces nn.MSELoss()(eeg_features, img_features),
+ * Generation/ATMS_reconstruction.py:201, 227-228 and :264, 285-286; the step loss there is
+ * alpha*10*MSE + (1-alpha)*10*ClipLoss(img)).  MSE is the mean over all n_total_rows*D elements of the (global) batch;
+ * this rank's B rows contribute
+ *     *loss, *loss_term += weight * sum_{b,d} (eeg-tgt)^2 / (n_total_rows*D)          (either may be NULL)
+ *     d_eeg[b,d]        += weight * grad_out * 2 (eeg-tgt)[b,d] / (n_total_rows*D)     (NULL: loss only)
+ * so it composes with eegb200_infonce, whose phase B writes loss[0] and d_eeg first. */
+int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_total_rows, float weight, float grad_out,
+                float* loss, float* loss_term, float* d_eeg, void* stream);
 
 /* scores = logit_scale * eeg @ gallery^T into logits_ws [Q, ld >= G rounded up to 4]; optional argmax
  * count against labels (train accuracy, ATMS_retrieval.py:241-250), top-1 / top-5 indices

@@ -122,6 +122,36 @@ def positional_embedding(n_tok: int, d_model: int = N_T, dtype=torch.float32) ->
     return pe.to(dtype)
 
 
+JOINT_VALUE_PREFIX = "encoder.enc_embedding.value_embedding."   # + "<subject>.weight" / ".bias" (ModuleDict, Embed.py:128-130)
+
+
+def joint_value_keys(sd) -> list:
+    """state_dict keys of the per-subject value embeddings of the joint-train variant, [] for the plain model"""
+    out = []
+    for k in sd:
+        if k.startswith(JOINT_VALUE_PREFIX):
+            tail = k[len(JOINT_VALUE_PREFIX):].split(".")
+            if len(tail) == 2 and tail[0].isdigit():
+                out.append(k)
+    return out
+
+
+def value_embedding(sd, P, x, subject_ids, dtype):
+    """DataEmbedding value path (Embed.py:142-146).  Plain model: one Linear(250,250) over the time axis.
+    joint_train=True (model of Retrieval/ATMS_retrieval_joint_train.py:173-176): every trial goes through the Linear of
+    its own subject, ``self.value_embedding[str(subject_id.item())](x[i])``; an id without an entry is the reference's
+    KeyError."""
+    if "Wv" in P:
+        return F.linear(x, P["Wv"], P["bv"])
+    rows = []
+    for i, sj in enumerate(subject_ids.tolist()):
+        kw, kb = f"{JOINT_VALUE_PREFIX}{sj}.weight", f"{JOINT_VALUE_PREFIX}{sj}.bias"
+        if kw not in sd:
+            raise KeyError(str(sj))
+        rows.append(F.linear(x[i], sd[kw].to(dtype), sd[kb].to(dtype)))
+    return torch.stack(rows)
+
+
 def atms_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, subject_ids: torch.Tensor,
                  train: bool = False, masks: Optional[Dict[str, torch.Tensor]] = None,
                  dtype=torch.float32, update_running_stats: bool = False) -> Dict[str, torch.Tensor]:
@@ -136,7 +166,7 @@ def atms_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, subject_ids: torc
     r: Dict[str, torch.Tensor] = {}
 
     # ---- DataEmbedding.forward  (Embed.py:141-162) ----
-    v = F.linear(x, P["Wv"], P["bv"])                       # :146  (B,63,250), Linear over the time axis
+    v = value_embedding(sd, P, x, subject_ids, dtype)       # :143-146  (B,63,250), Linear over the time axis
     v = v + P["pe"][:, :N_CH]                               # :149  pe indexed by channel-token
     # SubjectEmbedding.forward (Embed.py:116-121): ANY id >= num_embeddings -> shared token for the whole batch
     n_subj = P["subj"].shape[0]
@@ -246,6 +276,13 @@ def contrastive_loss(eeg, img, txt, logit_scale, alpha: float = 0.99):
     return alpha * clip_loss(eeg, img, logit_scale) + (1 - alpha) * clip_loss(eeg, txt, logit_scale)
 
 
+def reconstruction_loss(eeg, img, logit_scale, alpha: float = 0.90):
+    """loss of the reconstruction-training variant (Generation/ATMS_reconstruction.py:198-201, 224-228; evaluate_model
+    uses the same expression with alpha = 0.99, :259, :283-286): alpha*10*MSE(eeg, img) + (1-alpha)*10*ClipLoss(eeg, img).
+    The text ClipLoss is computed by the reference but not used."""
+    return alpha * F.mse_loss(eeg, img) * 10 + (1 - alpha) * clip_loss(eeg, img, logit_scale) * 10
+
+
 def train_accuracy_counts(eeg, gallery, labels, logit_scale):
     """train_model accuracy bookkeeping (ATMS_retrieval.py:241-250): argmax over the gallery."""
     logits = logit_scale * eeg @ gallery.T
@@ -279,7 +316,7 @@ TRAINED_KEYS = [k for a, k in K.items() if a not in ("pe", "bn1_rm", "bn1_rv", "
 
 
 def train_step(sd, opt_state, x, subject_ids, img, txt, step: int, masks=None, lr=3e-4,
-               dtype=torch.float32, alpha=0.99):
+               dtype=torch.float32, alpha=0.99, variant: str = "retrieval"):
     """One body of the hot loop (ATMS_retrieval.py:215-237): forward, loss mix, backward, AdamW.
 
     ``sd`` (reference-keyed tensors) and ``opt_state`` ({key: (m, v)}) are updated in place.
@@ -287,13 +324,16 @@ def train_step(sd, opt_state, x, subject_ids, img, txt, step: int, masks=None, l
     Returns (loss, grads dict, forward intermediates)."""
     leaves = {}
     sd_g = dict(sd)
-    for k in TRAINED_KEYS:
+    for k in TRAINED_KEYS + joint_value_keys(sd):
         if k in sd:
             t = sd[k].detach().to(dtype).clone().requires_grad_(True)
             leaves[k] = t
             sd_g[k] = t
     r = atms_forward(sd_g, x, subject_ids, train=True, masks=masks, dtype=dtype)
-    loss = contrastive_loss(r["out"], img.to(dtype), txt.to(dtype), sd_g["logit_scale"], alpha)
+    if variant == "reconstruction":     # Generation/ATMS_reconstruction.py:224-228 (alpha = 0.90 there)
+        loss = reconstruction_loss(r["out"], img.to(dtype), sd_g["logit_scale"], alpha)
+    else:
+        loss = contrastive_loss(r["out"], img.to(dtype), txt.to(dtype), sd_g["logit_scale"], alpha)
     grads_list = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
     grads = {k: g for k, g in zip(leaves.keys(), grads_list)}
     # BN running statistics (momentum 0.1, unbiased variance)

@@ -203,8 +203,147 @@ def gen_loops():
     save("loops", **arrs)
 
 
+# ---------------------------------------------------------------- F: joint-subject variant (per-subject value embeddings)
+def _set_dropout(m, p):
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = p
+
+
+def gen_joint():
+    from ref_import import import_reference_joint
+    J = import_reference_joint()
+
+    def joint_model():
+        m = J.ATMS(joint_train=True)
+        r = m.load_state_dict(recipe.make_joint_state_dict(), strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        return m
+
+    arrs = {}
+    # eval forward, mixed subjects in one batch (Embed.py:144 picks the Linear per trial)
+    m = joint_model().eval()
+    cap = {}
+    h = m.encoder.enc_embedding.register_forward_hook(lambda mod, i, o: cap.__setitem__("h0", o.detach()))
+    x = recipe.make_eeg(5, seed=51)
+    sid = torch.tensor([3, 0, 3, 9, 0])
+    with torch.no_grad():
+        out = m(x, sid)
+    arrs["eval_out"], arrs["eval_sid"], arrs["eval_h0"] = out, sid, cap["h0"]
+    h.remove()
+    # two AdamW steps, dropout p = 0, mixed subjects: only the value embeddings of subjects in the batch get gradients
+    B = 8
+    m = joint_model().train()
+    _set_dropout(m, 0.0)
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+    x = recipe.make_eeg(B, seed=52)
+    sid = torch.tensor([2, 2, 5, 5, 5, 2, 7, 7])
+    img = recipe.make_targets(B, seed=52, tag="img")
+    txt = recipe.make_targets(B, seed=52, tag="txt")
+    arrs["train_sid"] = sid
+    for step in (1, 2):
+        opt.zero_grad()
+        out = m(x, sid).float()
+        loss = 0.99 * m.loss_func(out, img, m.logit_scale) + 0.01 * m.loss_func(out, txt, m.logit_scale)
+        loss.backward()
+        if step == 1:
+            arrs["out1"] = out.detach().clone()
+            for k, p in m.named_parameters():
+                if p.grad is None:
+                    arrs["gradnone/" + k] = np.asarray(1)
+                else:
+                    arrs["graddig/" + k] = recipe.digest(p.grad)
+        arrs[f"loss{step}"] = loss.detach()
+        opt.step()
+        for k, v in m.state_dict().items():
+            if v.dtype.is_floating_point and not k.endswith(".pe"):
+                arrs[f"paramdig{step}/" + k] = recipe.digest(v)
+    # the script's own train_model / evaluate_model (every trial carries the id parsed from `sub`)
+    n_cls, n_per = 40, 10
+    m = joint_model()
+    _set_dropout(m, 0.0)
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+    n = 16
+    eeg = recipe.make_eeg(n, seed=53)
+    labels = recipe.make_labels(n, n_cls, seed=53)
+    img_all = recipe.make_targets(n_cls * n_per, seed=53, tag="img_all")
+    txt_all = recipe.make_targets(n_cls, seed=53, tag="txt_all")
+    loader = _Loader(eeg, labels, txt_all[labels], img_all[labels * n_per], 8)
+    avg_loss, acc, feats = J.train_model("sub-03", m, loader, opt, torch.device("cpu"), txt_all, img_all, _Cfg())
+    arrs.update(train_avg_loss=np.float64(avg_loss), train_acc=np.float64(acc), train_feats=feats.detach())
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point and not k.endswith(".pe"):
+            arrs["loop_paramdig/" + k] = recipe.digest(v)
+    n_cls_t = 200
+    teeg = recipe.make_eeg(10, seed=54)
+    tlabels = recipe.make_labels(10, n_cls_t, seed=54)
+    timg_all = recipe.make_targets(n_cls_t, seed=54, tag="timg")
+    ttxt_all = recipe.make_targets(n_cls_t, seed=54, tag="ttxt")
+    tl = _Loader(teeg, tlabels, ttxt_all[tlabels], timg_all[tlabels], 1)
+    for k in (200, 10):
+        random.seed(2000 + k)
+        arrs[f"eval_k{k}"] = np.asarray(J.evaluate_model("sub-03", m, tl, torch.device("cpu"), ttxt_all, timg_all, k, _Cfg()),
+                                        dtype=np.float64)
+    save("joint", **arrs)
+
+
+# ---------------------------------------------------------------- G: reconstruction-training variant (MSE + InfoNCE)
+def gen_reconstruction():
+    from ref_import import import_reference_reconstruction
+    G = import_reference_reconstruction()
+
+    def model():
+        m = G.ATMS()
+        r = m.load_state_dict(recipe.make_state_dict(), strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        _set_dropout(m, 0.0)
+        return m
+
+    arrs = {}
+    # one step of the loss mix of ATMS_reconstruction.py:224-228 (alpha = 0.90) with gradient digests
+    B = 8
+    m = model().train()
+    x = recipe.make_eeg(B, seed=61)
+    sid = torch.full((B,), 8)
+    img = recipe.make_targets(B, seed=61, tag="img")
+    out = m(x, sid).float()
+    mse = torch.nn.MSELoss()(out, img)
+    il = m.loss_func(out, img, m.logit_scale)
+    loss = 0.90 * mse * 10 + (1 - 0.90) * il * 10
+    loss.backward()
+    arrs.update(step_out=out.detach(), step_loss=loss.detach(), step_mse=mse.detach(), step_img_loss=il.detach())
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            arrs["graddig/" + k] = recipe.digest(p.grad)
+    # the script's own train_model / evaluate_model
+    n_cls, n_per = 40, 10
+    m = model()
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+    n = 24
+    eeg = recipe.make_eeg(n, seed=62)
+    labels = recipe.make_labels(n, n_cls, seed=62)
+    img_all = recipe.make_targets(n_cls * n_per, seed=62, tag="img_all")
+    txt_all = recipe.make_targets(n_cls, seed=62, tag="txt_all")
+    loader = _Loader(eeg, labels, txt_all[labels], img_all[labels * n_per], 8)
+    avg_loss, acc, feats = G.train_model("sub-08", m, loader, opt, torch.device("cpu"), txt_all, img_all, _Cfg())
+    arrs.update(train_avg_loss=np.float64(avg_loss), train_acc=np.float64(acc), train_feats=feats.detach())
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point and not k.endswith(".pe"):
+            arrs["loop_paramdig/" + k] = recipe.digest(v)
+    n_cls_t = 200
+    teeg = recipe.make_eeg(10, seed=63)
+    tlabels = recipe.make_labels(10, n_cls_t, seed=63)
+    timg_all = recipe.make_targets(n_cls_t, seed=63, tag="timg")
+    ttxt_all = recipe.make_targets(n_cls_t, seed=63, tag="ttxt")
+    tl = _Loader(teeg, tlabels, ttxt_all[tlabels], timg_all[tlabels], 1)
+    random.seed(3000)
+    arrs["eval_k200"] = np.asarray(G.evaluate_model("sub-08", m, tl, torch.device("cpu"), ttxt_all, timg_all, 200, _Cfg()),
+                                   dtype=np.float64)
+    save("reconstruction", **arrs)
+
+
 if __name__ == "__main__":
-    gen_eval_forward()
-    gen_train_step()
-    gen_cliploss()
-    gen_loops()
+    gens = {"eval_forward": gen_eval_forward, "train_step": gen_train_step, "cliploss": gen_cliploss, "loops": gen_loops,
+            "joint": gen_joint, "reconstruction": gen_reconstruction}
+    for name in (sys.argv[1:] or list(gens)):
+        gens[name]()

@@ -81,10 +81,35 @@ def positional_table() -> torch.Tensor:
     return pe.unsqueeze(0)
 
 
-def make_state_dict(seed: int = 0) -> dict:
+def joint_state_shapes(num_subjects: int = 10) -> dict:
+    """state_dict of ATMS(joint_train=True) in Retrieval/ATMS_retrieval_joint_train.py:173-176 (probed): the value
+    embedding is a ModuleDict of per-subject Linear(250,250) and there are num_subjects subject_wise_linear layers"""
+    shapes = {}
+    for key, shape in STATE_SHAPES.items():
+        if key.startswith("encoder.enc_embedding.value_embedding."):
+            if key.endswith("weight"):
+                for sj in range(num_subjects):
+                    shapes[f"encoder.enc_embedding.value_embedding.{sj}.weight"] = (250, 250)
+                    shapes[f"encoder.enc_embedding.value_embedding.{sj}.bias"] = (250,)
+            continue
+        if key.startswith("subject_wise_linear."):
+            if key == "subject_wise_linear.0.weight":
+                for sj in range(num_subjects):
+                    shapes[f"subject_wise_linear.{sj}.weight"] = (250, 250)
+                    shapes[f"subject_wise_linear.{sj}.bias"] = (250,)
+            continue
+        shapes[key] = shape
+    return shapes
+
+
+def make_joint_state_dict(seed: int = 0, num_subjects: int = 10) -> dict:
+    return make_state_dict(seed, joint_state_shapes(num_subjects))
+
+
+def make_state_dict(seed: int = 0, shapes: dict = None) -> dict:
     """Reference-keyed fp32 state_dict with non-trivial affine/BN values."""
     sd = {}
-    for key, shape in STATE_SHAPES.items():
+    for key, shape in (shapes or STATE_SHAPES).items():
         g = _gen(key, seed)
         if key.endswith("num_batches_tracked"):
             sd[key] = torch.tensor(0, dtype=torch.long)

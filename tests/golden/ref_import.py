@@ -70,3 +70,31 @@ def import_reference():
             sys.path.insert(0, p)
     import ATMS_retrieval  # noqa: E402
     return ATMS_retrieval
+
+
+def _import_file(mod_name: str, path: str):
+    """import one reference script under its own module name (two of them are both called ATMS_*.py with a class ATMS)"""
+    import importlib.util
+    if mod_name in sys.modules:
+        return sys.modules[mod_name]
+    spec = importlib.util.spec_from_file_location(mod_name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[mod_name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def import_reference_joint():
+    """Retrieval/ATMS_retrieval_joint_train.py (per-subject value embeddings), unmodified"""
+    import_reference()          # installs the stubs and sys.path entries
+    class _Dummy:
+        def __init__(self, *a, **k):
+            raise RuntimeError("stubbed third-party class")
+    _stub("eegdatasets_joint_subjects", EEGDataset=_Dummy)
+    return _import_file("ATMS_retrieval_joint_train", os.path.join(REF_ROOT, "Retrieval", "ATMS_retrieval_joint_train.py"))
+
+
+def import_reference_reconstruction():
+    """Generation/ATMS_reconstruction.py (MSE + InfoNCE loss mix), unmodified"""
+    import_reference()
+    return _import_file("ATMS_reconstruction", os.path.join(REF_ROOT, "Generation", "ATMS_reconstruction.py"))
