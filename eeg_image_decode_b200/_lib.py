@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libeegdecode_b200.so")
 _lib = None
+ABI_VERSION = 2      # include/eegdecode_b200.h EEGB200_ABI_VERSION
 
 
 class GemmDesc(ctypes.Structure):
@@ -39,8 +40,9 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.eegb200_last_error.restype = ctypes.c_char_p
         _lib.eegb200_launch_count.restype = ctypes.c_longlong
-        if _lib.eegb200_abi_version() != 1:
-            raise RuntimeError("libeegdecode_b200.so ABI version mismatch")
+        if _lib.eegb200_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libeegdecode_b200.so ABI version mismatch (library {_lib.eegb200_abi_version()}, "
+                               f"binding {ABI_VERSION}): rebuild with `python -m eeg_image_decode_b200.build`")
     return _lib
 
 
@@ -167,6 +169,14 @@ class AtmsIO(ctypes.Structure):
         ("workspace_bytes", ctypes.c_size_t),
         ("out", ctypes.c_void_p),
         ("seed_offset_dev", ctypes.c_void_p),
+        # joint-subject variant (ABI v2); joint_value_w == NULL selects the single shared value embedding
+        ("joint_value_w", ctypes.POINTER(ctypes.c_void_p)),
+        ("joint_value_b", ctypes.POINTER(ctypes.c_void_p)),
+        ("joint_value_dw", ctypes.POINTER(ctypes.c_void_p)),
+        ("joint_value_db", ctypes.POINTER(ctypes.c_void_p)),
+        ("group_offsets", ctypes.POINTER(ctypes.c_int32)),
+        ("group_subject", ctypes.POINTER(ctypes.c_int32)),
+        ("n_groups", ctypes.c_int),
     ]
 
 
@@ -207,6 +217,8 @@ def _sig():
     L.eegb200_adamw_step_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_longlong, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                           ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    L.eegb200_mse.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                              ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.eegb200_dropout_mask.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     L._eeg_sig_done = True
@@ -254,6 +266,14 @@ def adamw_step(p, g, m, v, n, lr, b1, b2, eps, wd, step) -> None:
 def adamw_step_dev(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev) -> None:
     check(_sig().eegb200_adamw_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, ptr(step_dev),
                                         stream_ptr()), "adamw_step_dev")
+
+
+def mse(eeg, tgt, n_total_rows: int, weight: float, grad_out: float, loss=None, loss_term=None, d_eeg=None) -> None:
+    """weight * MSE(eeg, tgt) share of these rows (mean over n_total_rows*D elements): loss / loss_term (1-element device
+    tensors) += ; d_eeg += weight*grad_out * dMSE/deeg"""
+    B, D = eeg.shape
+    check(_sig().eegb200_mse(ptr(eeg), ptr(tgt), B, D, int(n_total_rows), float(weight), float(grad_out), ptr(loss),
+                             ptr(loss_term), ptr(d_eeg), stream_ptr()), "mse")
 
 
 def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int):

@@ -1,0 +1,100 @@
+"""Reconstruction-training variant and embedding export.
+
+Drop-in for ``train_model`` / ``evaluate_model`` of Generation/ATMS_reconstruction.py (:193-249, :251-317) -- the ATM-S
+encoder trained with ``alpha*10*MSE(eeg, img) + (1-alpha)*10*ClipLoss(eeg, img)`` (alpha 0.90 in training, :198, :224-228;
+0.99 in evaluation, :259, :283-286) so that the embedding regresses onto the un-normalised CLIP image embedding the
+frozen diffusion prior / SDXL + IP-Adapter stage consumes -- and for the notebooks' ``get_eegfeatures``
+(Generation/Generation_metrics_sub8.ipynb, cell defining it) which dumps the eval-mode embeddings to
+``ATM_S_eeg_features_{sub}.pt``.  The model class is the same ``ATMS`` (ATMS_reconstruction.py:162-183 is identical to
+the retrieval one).  The MSE term runs as ``eegb200_mse`` right after the InfoNCE kernels (include/eegdecode_b200.h);
+everything else is the shared step engine (CUDA-graph captured, data-parallel capable).
+"""
+from __future__ import annotations
+
+import os
+import random
+
+import torch
+
+from . import _lib
+from .atms import ATMS, N_SUBJECT_ROWS  # noqa: F401
+from .train import StepEngine, _train_epoch, extract_id_from_string
+
+
+def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
+                step_callback=None):
+    """One epoch of ATMS_reconstruction.py:193-249.  Returns (average_loss, accuracy, features[n_seen,1024])."""
+    return _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config,
+                        variant="reconstruction", alpha=0.90, step_callback=step_callback)
+
+
+def _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, alpha, keep_features):
+    eeg_model.eval()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("this implementation runs on CUDA only (no CPU fallback)")
+    text_features_all = text_features_all.to(device).float()
+    img_features_all = img_features_all.to(device).float().contiguous()
+    all_labels = set(range(text_features_all.size(0)))
+    eng = StepEngine(eeg_model, None, alpha, "reconstruction")
+    subject_id = extract_id_from_string(sub)
+    total_loss = torch.zeros(3, device=device)
+    n_batches = 0
+    pend, feats, labels = [], [], None
+    with torch.no_grad():
+        for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
+            eeg_data = eeg_data.to(device)
+            img_features = img_features.to(device).float()
+            batch_size = eeg_data.size(0)
+            subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
+            eeg_features = eeg_model.encode(eeg_data, subject_ids, train=False)
+            loss, _, _ = eng.loss_and_grad(eeg_features, img_features.contiguous(), None, need_grad=False)
+            total_loss += loss
+            n_batches += 1
+            if keep_features:
+                feats.append(eeg_features.clone())
+            # host side: the reference's per-trial candidate draw (ATMS_reconstruction.py:290-293)
+            label_list = labels.tolist()
+            sel_rows = []
+            for label in label_list:
+                possible_classes = list(all_labels - {label})
+                sel_rows.append(random.sample(possible_classes, k - 1) + [label])
+            pend.append((eeg_features, torch.tensor(sel_rows, dtype=torch.int32), label_list))
+        correct = total = 0
+        for eeg_features, sel, label_list in pend:
+            r = _lib.retrieval(eeg_features, img_features_all, eeg_model.logit_scale.detach(), sel=sel, want_top5=False)
+            top1 = r["top1"].tolist()
+            sel_l = sel.tolist()
+            for i, label in enumerate(label_list):
+                correct += int(sel_l[i][top1[i]] == label)
+                total += 1
+    average_loss = float(total_loss[0].item()) / max(n_batches, 1)
+    return average_loss, correct, total, labels, (torch.cat(feats, dim=0) if feats else None)
+
+
+def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, config):
+    """200-way zero-shot retrieval with the reconstruction loss mix (alpha = 0.99), ATMS_reconstruction.py:251-317.
+    Returns (average_loss, accuracy, top5_acc); top5_acc is always 0.0 there (never counted, :262, :316).  Any k other
+    than 200 makes the reference print "Error." per trial and then divide by zero (:310-315); here that is a
+    ZeroDivisionError raised up front."""
+    if k != 200:
+        print("Error.")
+        raise ZeroDivisionError("division by zero (the reconstruction script's evaluate_model only scores k == 200)")
+    average_loss, correct, total, _, _ = _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_features_all,
+                                                   k, 0.99, False)
+    return average_loss, correct / total, 0.0
+
+
+def get_eegfeatures(sub, eegmodel, dataloader, device, text_features_all, img_features_all, k, *, save_features=True,
+                    out_dir="."):
+    """Embedding export of the generation notebooks (``get_eegfeatures(sub, eegmodel, dataloader, device,
+    text_features_all, img_features_all, k)``): eval-mode embeddings of every trial, k-way accuracy, loss mix with
+    alpha = 0.9.  Returns (average_loss, accuracy, labels of the last batch, features.cpu()) and writes
+    ``ATM_S_eeg_features_{sub}.pt`` (the file the diffusion prior / SDXL stage loads) unless ``save_features=False``."""
+    average_loss, correct, total, labels, feats = _evaluate(sub, eegmodel, dataloader, device, text_features_all,
+                                                            img_features_all, k, 0.9, True)
+    features_tensor = feats.cpu()
+    if save_features:
+        print("features_tensor", features_tensor.shape)
+        torch.save(features_tensor, os.path.join(out_dir, f"ATM_S_eeg_features_{sub}.pt"))
+    return average_loss, correct / total, labels, features_tensor

@@ -47,20 +47,15 @@ def _adam_hparams(optimizer):
     return dict(lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
 
 
-def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False, device_steps=None) -> None:
+def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False, device_steps=None, subjects=None) -> None:
     """torch.optim.AdamW semantics on model.flat_params / model.flat_grads.  Parameters that received no gradient
-    this step (the unused half of {subject table, shared token}; the never-used cold parameters) are skipped, as
-    torch.optim does for ``grad is None``."""
+    this step (the unused half of {subject table, shared token}; in the joint-subject model the value embeddings of
+    subjects outside ``subjects``; the never-used cold parameters) are skipped, as torch.optim does for ``grad is None``."""
     hp = _adam_hparams(optimizer)
     if model._adam_m is None:
         model._adam_m = torch.zeros_like(model.flat_grads)
         model._adam_v = torch.zeros_like(model.flat_grads)
-    n_main = model._n_main
-    o_tab = model._offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]
-    o_sh = model._offs[_lib.P_NAMES[_lib.P_SUBJ_SHARED]]
-    segs = [("main", 0, n_main)]
-    segs.append(("shared", o_sh, 250) if use_shared else ("table", o_tab, N_SUBJECT_ROWS * 250))
-    for name, off, n in segs:
+    for name, off, n in model.adam_segments(use_shared, subjects):
         if device_steps is not None:
             # CUDA-graph path: the step number lives in device memory and is advanced inside the captured graph
             device_steps[name].add_(1)
@@ -77,11 +72,9 @@ def publish_optimizer_state(model: ATMS, optimizer) -> None:
     if optimizer is None or model._adam_m is None:
         return
     named = dict(model.named_parameters())
-    tab, sh = _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]
     for n in model._hot_order():
         p = named[n]
-        which = "table" if n == tab else ("shared" if n == sh else "main")
-        steps = model._adam_steps[which]
+        steps = model._adam_steps[model.adam_segment_of(n)]
         if steps == 0:
             continue
         o = model._offs[n]
@@ -96,10 +89,17 @@ def publish_optimizer_state(model: ATMS, optimizer) -> None:
 # one contrastive step (forward, 2x InfoNCE, backward, optimiser), optionally data-parallel
 # ------------------------------------------------------------------------------------------------
 class StepEngine:
-    def __init__(self, model: ATMS, optimizer=None, alpha: float = 0.99):
+    """``variant``: "retrieval" -- alpha*ClipLoss(img) + (1-alpha)*ClipLoss(txt), alpha = 0.99 (ATMS_retrieval.py:229-234);
+    "reconstruction" -- alpha*10*MSE(eeg, img) + (1-alpha)*10*ClipLoss(img), alpha = 0.90
+    (Generation/ATMS_reconstruction.py:198, 224-228)."""
+
+    def __init__(self, model: ATMS, optimizer=None, alpha: float = 0.99, variant: str = "retrieval"):
+        if variant not in ("retrieval", "reconstruction"):
+            raise ValueError(f"unknown step variant {variant!r}")
         self.model = model
         self.optimizer = optimizer
         self.alpha = alpha
+        self.variant = variant
         self.nce = _InfoNCE()
         self.world, self.rank = _world()
         self.fused = optimizer is None or type(optimizer).__name__ in ("AdamW", "FusedAdamW")
@@ -107,8 +107,26 @@ class StepEngine:
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
 
-    def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None, device_steps=None):
-        """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024])"""
+    def loss_and_grad(self, feats, img_feat, txt_feat, need_grad=True):
+        """this rank's share of the step loss ([3] device tensor: total, ClipLoss(img), second term) and d loss / d feats,
+        d loss / d logit_scale.  Targets are the LOCAL rows; the global-batch gather happens here."""
+        m, W = self.model, self.world
+        img_all = gather_targets(img_feat, W)
+        row0 = self.rank * feats.shape[0]
+        if self.variant == "retrieval":
+            txt_all = gather_targets(txt_feat, W)
+            return fused_contrastive(self.nce, feats, img_all, txt_all, m.logit_scale.detach(), self.alpha,
+                                     row_offset=row0, need_grad=need_grad, world_size=W)
+        w_clip, w_mse = (1.0 - self.alpha) * 10.0, self.alpha * 10.0
+        loss, d_e, d_s = self.nce.run(feats, img_all, None, m.logit_scale.detach(), w_clip, 0.0, row0, need_grad,
+                                      world_size=W)
+        # nn.MSELoss() is the mean over the whole (global) batch; each rank adds the share of its own rows
+        _lib.mse(feats, img_feat.contiguous(), img_all.shape[0], w_mse, 1.0, loss=loss[0:1], loss_term=loss[2:3], d_eeg=d_e)
+        return loss, d_e, d_s
+
+    def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None, device_steps=None,
+             known_subject: Optional[int] = None):
+        """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024]).  ``known_subject``: see ATMS.encode."""
         m = self.model
         W = self.world
         m.zero_flat_grads()
@@ -116,7 +134,7 @@ class StepEngine:
         if W > 1:
             seed ^= (self.rank + 1) * 0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF     # decorrelate the ranks' dropout masks
             # SyncBN: all-reduce the batch statistics between the forward phases
-            m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A)
+            m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A, known_subject=known_subject)
             self._allreduce(m.ws_tensor("bn1_sums"))
             out = m._last[3]
             self._phase(_lib.PHASE_B, fwd=True, batch_scale=W)
@@ -126,11 +144,8 @@ class StepEngine:
                 bn.num_batches_tracked.add_(1)
             feats = out
         else:
-            feats = m.encode(eeg, subject_ids, train=True, seed=seed)
-        img_all = gather_targets(img_feat, W)
-        txt_all = gather_targets(txt_feat, W)
-        loss, d_e, d_s = fused_contrastive(self.nce, feats, img_all, txt_all, m.logit_scale.detach(), self.alpha,
-                                           row_offset=self.rank * feats.shape[0], need_grad=True, world_size=W)
+            feats = m.encode(eeg, subject_ids, train=True, seed=seed, known_subject=known_subject)
+        loss, d_e, d_s = self.loss_and_grad(feats, img_feat, txt_feat)
         m.grad_view("logit_scale").add_(d_s)
         if W > 1:
             m.backprop(d_e, phases=_lib.PHASE_A)
@@ -141,10 +156,14 @@ class StepEngine:
             self._allreduce(m.flat_grads)
         else:
             m.backprop(d_e)
+        subjects = m._last_subjects          # joint-subject model: whose value embeddings got a gradient
+        if W > 1 and subjects is not None and known_subject is None:
+            raise NotImplementedError("data-parallel steps of the joint-subject model need known_subject (every rank must "
+                                      "update the same value embeddings)")
         if self.fused:
-            fused_adamw_step(m, self.optimizer, use_shared, device_steps)
+            fused_adamw_step(m, self.optimizer, use_shared, device_steps, subjects)
         else:
-            self._generic_optimizer_step(use_shared)
+            self._generic_optimizer_step(use_shared, subjects)
         return loss, feats
 
     def _phase(self, phase, fwd, batch_scale):
@@ -155,18 +174,17 @@ class StepEngine:
         if fwd:
             _lib.atms_forward(io, phase | (_BN_SCALE_SHIFT(batch_scale)))
         else:
-            _, G, _ = m._pointers()
+            G = m._pointers()[1]
             import ctypes
             _lib.check(_lib._sig().eegb200_atms_backward(ctypes.byref(io), None, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)),
                                                          phase | (_BN_SCALE_SHIFT(batch_scale)), _lib.stream_ptr()),
                        "atms_backward")
 
-    def _generic_optimizer_step(self, use_shared):
+    def _generic_optimizer_step(self, use_shared, subjects=None):
         named = dict(self.model.named_parameters())
-        tab, sh = _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]
+        live = {seg[0] for seg in self.model.adam_segments(use_shared, subjects)}
         for n in self.model._hot_order():
-            skip = (n == tab and use_shared) or (n == sh and not use_shared)
-            named[n].grad = None if skip else self.model.grad_view(n)
+            named[n].grad = self.model.grad_view(n) if self.model.adam_segment_of(n) in live else None
         self.optimizer.step()
 
 
@@ -179,9 +197,13 @@ class GraphedTrainStep:
     Data-parallel steps (NCCL all-gather / all-reduce inside the step) are captured as well.  Falls back to eager
     execution for foreign optimisers and odd batch sizes."""
 
-    def __init__(self, eng: "StepEngine", gallery, use_shared: bool, enabled: bool = True):
+    def __init__(self, eng: "StepEngine", gallery, use_shared: bool, enabled: bool = True, known_subject: Optional[int] = None):
         import os
         self.eng, self.gallery, self.use_shared = eng, gallery, use_shared
+        # joint-subject model: the graph bakes in which value embedding is used, so the caller must pin the subject
+        self.known_subject = known_subject
+        if eng.model.joint_train and known_subject is None:
+            enabled = False
         self.enabled = enabled and os.environ.get("EEGB200_CUDA_GRAPH", "1") != "0"
         self.dp_ok = os.environ.get("EEGB200_CUDA_GRAPH_DP", "1") != "0"
         self.graph = None
@@ -191,7 +213,8 @@ class GraphedTrainStep:
         self.replays = 0
 
     def _body(self, eeg, sid, img, txt, labels, device_steps):
-        loss, feats = self.eng.step(eeg, sid, img, txt, self.use_shared, device_steps=device_steps)
+        loss, feats = self.eng.step(eeg, sid, img, txt, self.use_shared, device_steps=device_steps,
+                                    known_subject=self.known_subject)
         r = _lib.retrieval(feats, self.gallery, self.eng.model.logit_scale.detach(), labels=labels, want_top5=False)
         return loss, feats, r["correct"]
 
@@ -221,8 +244,8 @@ class GraphedTrainStep:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
         self.replays += 1
-        m._adam_steps["main"] += 1
-        m._adam_steps["shared" if self.use_shared else "table"] += 1
+        for name, _, _ in m.adam_segments(self.use_shared, m._last_subjects):
+            m._adam_steps[name] += 1
         return self.out
 
 
@@ -237,18 +260,30 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
     """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254.
     ``step_callback(step_index, loss[3] on the HOST)`` (optional, keyword only) receives every step's loss (mix, image,
     text share), read back from the device like the reference does (:238) but delivered one step late so that the
-    read-back does not stall the next launch."""
+    read-back does not stall the next launch.
+    Also serves the joint-subject model (Retrieval/ATMS_retrieval_joint_train.py:201-254, same body): every trial then
+    goes through the value embedding of the subject parsed from ``sub``."""
+    return _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config,
+                        variant="retrieval", alpha=0.99, step_callback=step_callback)
+
+
+def _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
+                 variant, alpha, step_callback=None):
     eeg_model.train()
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("train_model: this implementation runs on CUDA only (no CPU fallback)")
     text_features_all = text_features_all.to(device).float()
     img_features_all = (img_features_all[::10]).to(device).float().contiguous()       # :202 class-prototype gallery
-    alpha = 0.99
-    eng = StepEngine(eeg_model, optimizer, alpha)
+    eng = StepEngine(eeg_model, optimizer, alpha, variant)
     subject_id = extract_id_from_string(sub)
     use_shared = subject_id is None or subject_id >= N_SUBJECT_ROWS or subject_id < 0
-    gstep = GraphedTrainStep(eng, img_features_all, use_shared)
+    known_subject = None
+    if eeg_model.joint_train:
+        if use_shared:
+            raise KeyError(str(subject_id))     # the reference: self.value_embedding[str(subject_id.item())] (Embed.py:144)
+        known_subject = subject_id
+    gstep = GraphedTrainStep(eng, img_features_all, use_shared, known_subject=known_subject)
     loss_acc = torch.zeros(3, device=device)
     correct = torch.zeros(1, device=device, dtype=torch.int32)
     total = 0
@@ -340,6 +375,11 @@ def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_fe
     total = 0
     n_batches = 0
     subject_id = extract_id_from_string(sub)
+    known_subject = None
+    if eeg_model.joint_train:
+        if subject_id is None or not 0 <= subject_id < N_SUBJECT_ROWS:
+            raise KeyError(str(subject_id))
+        known_subject = subject_id
     pend = []
     with torch.no_grad():
         for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
@@ -348,7 +388,7 @@ def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_fe
             img_features = img_features.to(device).float()
             batch_size = eeg_data.size(0)
             subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
-            eeg_features = eeg_model.encode(eeg_data, subject_ids, train=False)
+            eeg_features = eeg_model.encode(eeg_data, subject_ids, train=False, known_subject=known_subject)
             loss, _, _ = fused_contrastive(nce, eeg_features, img_features.contiguous(), text_features.contiguous(),
                                            eeg_model.logit_scale.detach(), alpha, need_grad=False)
             total_loss += loss

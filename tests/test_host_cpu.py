@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in sorted(names):
         assert hasattr(L, n), f"{n} declared in the header but not exported"
-    assert L.eegb200_abi_version() == 1
+    assert L.eegb200_abi_version() == _lib.ABI_VERSION == 2
     assert _lib.atms_workspace_bytes(4) > 0
     assert _lib.infonce_workspace_bytes(8, 8, 1024, 2) > 0
 
@@ -71,3 +71,84 @@ def test_default_init_is_rng_identical_to_reference():
         assert torch.equal(ref[k], ours[k]), k
     # a reference checkpoint loads strictly, and ours loads into the reference
     R.ATMS().load_state_dict(ours, strict=True)
+
+
+# ---------------------------------------------------------------- joint-subject / reconstruction variants (host logic)
+def test_joint_model_state_dict_and_segments():
+    from eeg_image_decode_b200.joint import ATMS
+    m = ATMS(joint_train=True)
+    shapes = recipe.joint_state_shapes()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())
+    for k, shp in shapes.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    r = m.load_state_dict(recipe.make_joint_state_dict(), strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    # plain constructor call of that script == single value embedding, ten subject_wise_linear layers
+    p = ATMS()
+    assert "encoder.enc_embedding.value_embedding.weight" in p.state_dict() and "subject_wise_linear.9.bias" in p.state_dict()
+    # AdamW segments: always-trained prefix, table or shared token, one segment per subject present in the batch
+    segs = m.adam_segments(False, [7, 2, 2])
+    assert [s[0] for s in segs] == ["main", "table", "ve2", "ve7"]
+    named = dict(m.named_parameters())
+    for name, off, n in segs[2:]:
+        sj = name[2:]
+        w, b = named[f"encoder.enc_embedding.value_embedding.{sj}.weight"], named[f"encoder.enc_embedding.value_embedding.{sj}.bias"]
+        base = m.flat_params.data_ptr()
+        assert w.data_ptr() == base + 4 * off and b.data_ptr() + 4 * 250 == base + 4 * (off + n)
+    assert m.adam_segment_of("encoder.enc_embedding.value_embedding.4.bias") == "ve4"
+    assert m.adam_segment_of("proj_eeg.0.weight") == "main"
+    # every trainable tensor on the hot path lies inside the gradient arena; the never-used ones do not
+    assert m._offs["subject_wise_linear.0.weight"] >= m._n_hot
+    assert m._offs["encoder.enc_embedding.value_embedding.9.bias"] + 250 <= m._n_hot
+
+
+def test_joint_grouping_by_subject():
+    from eeg_image_decode_b200.joint import ATMS
+    m = ATMS(joint_train=True)
+    x = torch.arange(5, dtype=torch.float32).reshape(5, 1, 1).expand(5, 63, 250).contiguous()
+    sid = torch.tensor([3, 0, 3, 9, 0])
+    xs, sids, perm, groups = m._group_by_subject(x, sid, None)
+    assert perm.tolist() == [1, 4, 0, 2, 3] and sids.tolist() == [0, 0, 3, 3, 9]
+    assert xs[:, 0, 0].tolist() == [1.0, 4.0, 0.0, 2.0, 3.0]
+    assert groups == [(0, 0), (2, 3), (4, 9)]
+    # already ordered / single subject: no permutation, no copy
+    _, _, perm, groups = m._group_by_subject(x, torch.tensor([1, 1, 4, 4, 8]), None)
+    assert perm is None and groups == [(0, 1), (2, 4), (4, 8)]
+    _, _, perm, groups = m._group_by_subject(x, sid, 6)          # caller vouches for the subject: ids are not read
+    assert perm is None and groups == [(0, 6)]
+    with pytest.raises(KeyError):       # Embed.py:144: self.value_embedding['10']
+        m._group_by_subject(x, torch.tensor([1, 10, 2, 3, 4]), None)
+    with pytest.raises(KeyError):
+        m._group_by_subject(x, sid, 10)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Retrieval"), reason="live reference not mounted")
+def test_joint_default_init_is_rng_identical_to_reference():
+    from ref_import import import_reference_joint
+    from eeg_image_decode_b200.joint import ATMS
+    J = import_reference_joint()
+    for jt in (True, False):
+        torch.manual_seed(11)
+        ref = J.ATMS(joint_train=jt).state_dict()
+        torch.manual_seed(11)
+        ours = ATMS(joint_train=jt).state_dict()
+        assert list(ref.keys()) == list(ours.keys())
+        for k in ref:
+            assert torch.equal(ref[k], ours[k]), k
+        J.ATMS(joint_train=jt).load_state_dict(ours, strict=True)
+
+
+def test_variant_modules_mirror_reference_signatures():
+    import inspect
+    from eeg_image_decode_b200 import joint, reconstruction
+    assert list(inspect.signature(joint.ATMS.__init__).parameters)[1:] == ["sequence_length", "num_subjects", "joint_train"]
+    for mod in (joint, reconstruction):
+        assert list(inspect.signature(mod.train_model).parameters)[:8] == [
+            "sub", "eeg_model", "dataloader", "optimizer", "device", "text_features_all", "img_features_all", "config"]
+        assert list(inspect.signature(mod.evaluate_model).parameters) == [
+            "sub", "eeg_model", "dataloader", "device", "text_features_all", "img_features_all", "k", "config"]
+    assert list(inspect.signature(reconstruction.get_eegfeatures).parameters)[:7] == [
+        "sub", "eegmodel", "dataloader", "device", "text_features_all", "img_features_all", "k"]
+    with pytest.raises(RuntimeError):       # no CPU fallback in the variants either
+        reconstruction.train_model("sub-08", reconstruction.ATMS(), [], None, "cpu", torch.zeros(4, 1024), torch.zeros(40, 1024), None)
