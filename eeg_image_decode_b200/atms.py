@@ -199,6 +199,8 @@ class ATMS(nn.Module):
             self._adam_steps.update({f"ve{sj}": 0 for sj in range(N_SUBJECT_ROWS)})
         self._ptr_cache = None
         self._ws = {}
+        self._ws_pinned = set()         # batch sizes whose workspace a captured CUDA graph points into
+        self._gstep_cache = {}          # captured training steps, reused across train_model() calls (train.py)
         # device counter mixed into the dropout seed by the kernels (0 unless a captured CUDA graph advances it)
         self._seed_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
 
@@ -262,7 +264,9 @@ class ATMS(nn.Module):
         ws = self._ws.get(B)
         if ws is None:
             ws = torch.empty(_lib.atms_workspace_bytes(B), dtype=torch.uint8, device=self.flat_params.device)
-            self._ws = {B: ws}          # keep only the latest batch size resident
+            # keep only the latest batch size resident, plus the ones a live CUDA graph was captured on
+            self._ws = {b: t for b, t in self._ws.items() if b in self._ws_pinned}
+            self._ws[B] = ws
         return ws
 
     # ---------------------------------------------------------------- engine-level API (no autograd)

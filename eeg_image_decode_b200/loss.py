@@ -28,8 +28,9 @@ class _InfoNCE:
     """workspace + two-phase call into eegb200_infonce; shared by ClipLoss and the fused train step."""
 
     def __init__(self):
-        self._ws = None
-        self._key = None
+        # one workspace per problem shape, never replaced: a captured CUDA graph may hold pointers into any of them
+        # (e.g. the full-batch shape) while a ragged last batch runs eagerly with another
+        self._ws_by_key = {}
 
     def run(self, eeg, tgt_img, tgt_txt, logit_scale, w_img, w_txt, row_offset, need_grad, grad_out=1.0, group=None,
             world_size=1):
@@ -38,9 +39,14 @@ class _InfoNCE:
         N = tgt_img.shape[0]
         nt = 2 if tgt_txt is not None else 1
         key = (B, N, D, nt, eeg.device)
-        if self._key != key:
-            self._ws = torch.empty(_lib.infonce_workspace_bytes(B, N, D, nt), dtype=torch.uint8, device=eeg.device)
-            self._key = key
+        ws = self._ws_by_key.get(key)
+        if ws is None:
+            if len(self._ws_by_key) >= 8 and not torch.cuda.is_current_stream_capturing():
+                self._ws_by_key.pop(next(k for k in self._ws_by_key if k != getattr(self, "_graph_key", None)))
+            ws = torch.empty(_lib.infonce_workspace_bytes(B, N, D, nt), dtype=torch.uint8, device=eeg.device)
+            self._ws_by_key[key] = ws
+        if torch.cuda.is_current_stream_capturing():
+            self._graph_key = key           # never evicted
         dev = eeg.device
         col_stats = torch.empty(2, nt * N, device=dev, dtype=torch.float32)
         loss = torch.zeros(3, device=dev, dtype=torch.float32)
@@ -52,7 +58,7 @@ class _InfoNCE:
         io.B, io.N, io.D, io.row_offset = B, N, D, row_offset
         io.logit_scale = logit_scale.data_ptr()
         io.w_img, io.w_txt, io.grad_out = w_img, w_txt, grad_out
-        io.workspace, io.workspace_bytes = self._ws.data_ptr(), self._ws.numel()
+        io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
         io.col_stats = col_stats.data_ptr()
         io.col_parts, io.n_parts = None, 1
         io.loss = loss.data_ptr()

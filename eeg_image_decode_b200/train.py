@@ -229,8 +229,11 @@ class GraphedTrainStep:
             return self._body(eeg, sid, img, txt, labels, None)
         if self.graph is None:
             self.B = B
+            m._ws_pinned.add(B)          # the graph bakes in pointers into this workspace: it must outlive other batch sizes
+            self._ws_keep = m.workspace(B)
             self.s = [t.clone() for t in (eeg, sid, img, txt, labels)]
             self.dev_steps = {k: torch.tensor([v], dtype=torch.int64, device=eeg.device) for k, v in m._adam_steps.items()}
+            self._dev_host = dict(m._adam_steps)     # what the device counters hold, mirrored on the host
             torch.cuda.synchronize()
             n0 = _lib.launch_count()
             g = torch.cuda.CUDAGraph()
@@ -242,11 +245,37 @@ class GraphedTrainStep:
         else:
             for dst, src in zip(self.s, (eeg, sid, img, txt, labels)):
                 dst.copy_(src, non_blocking=True)
+        # steps taken outside this graph (a ragged last batch run eagerly, another captured step on the same model) moved
+        # the host-side AdamW step numbers: bring the device counters back in line before replaying
+        for name, v in m._adam_steps.items():
+            if self._dev_host.get(name) != v:
+                self.dev_steps[name].fill_(v)
         self.graph.replay()
         self.replays += 1
-        for name, _, _ in m.adam_segments(self.use_shared, m._last_subjects):
+        for name, _, _ in m.adam_segments(self.use_shared, [self.known_subject] if self.known_subject is not None else None):
             m._adam_steps[name] += 1
+        self._dev_host = dict(m._adam_steps)
         return self.out
+
+
+def _cached_graphed_step(model: ATMS, optimizer, alpha, variant, use_shared, known_subject, gallery) -> "GraphedTrainStep":
+    """The captured step survives across train_model() calls (one per epoch in main_train_loop): everything the graph
+    bakes in is part of the key -- optimiser object and hyper-parameters, loss variant, token branch, dropout rates,
+    gallery shape -- and the gallery itself is copied into the graph's static buffer.  Without this every epoch paid two
+    eager steps plus a re-capture (~9 ms, 12 % of a 20-step epoch at B = 1024)."""
+    world, _ = _world()
+    hp = _adam_hparams(optimizer)
+    key = (id(optimizer), type(optimizer).__name__, variant, float(alpha), bool(use_shared), known_subject,
+           tuple(gallery.shape), tuple(model.dropout_p), hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], world)
+    gstep = model._gstep_cache.get(key)
+    if gstep is None:
+        model._gstep_cache.clear()          # one live graph per model: drop the previous configuration
+        eng = StepEngine(model, optimizer, alpha, variant)
+        gstep = GraphedTrainStep(eng, gallery.clone(), use_shared, known_subject=known_subject)
+        model._gstep_cache[key] = gstep
+    else:
+        gstep.gallery.copy_(gallery)
+    return gstep
 
 
 def _BN_SCALE_SHIFT(world: int) -> int:
@@ -275,7 +304,6 @@ def _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_al
         raise RuntimeError("train_model: this implementation runs on CUDA only (no CPU fallback)")
     text_features_all = text_features_all.to(device).float()
     img_features_all = (img_features_all[::10]).to(device).float().contiguous()       # :202 class-prototype gallery
-    eng = StepEngine(eeg_model, optimizer, alpha, variant)
     subject_id = extract_id_from_string(sub)
     use_shared = subject_id is None or subject_id >= N_SUBJECT_ROWS or subject_id < 0
     known_subject = None
@@ -283,7 +311,8 @@ def _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_al
         if use_shared:
             raise KeyError(str(subject_id))     # the reference: self.value_embedding[str(subject_id.item())] (Embed.py:144)
         known_subject = subject_id
-    gstep = GraphedTrainStep(eng, img_features_all, use_shared, known_subject=known_subject)
+    gstep = _cached_graphed_step(eeg_model, optimizer, alpha, variant, use_shared, known_subject, img_features_all)
+    eng = gstep.eng
     loss_acc = torch.zeros(3, device=device)
     correct = torch.zeros(1, device=device, dtype=torch.int32)
     total = 0
