@@ -264,9 +264,11 @@ def _cached_graphed_step(model: ATMS, optimizer, alpha, variant, use_shared, kno
     gallery shape -- and the gallery itself is copied into the graph's static buffer.  Without this every epoch paid two
     eager steps plus a re-capture (~9 ms, 12 % of a 20-step epoch at B = 1024)."""
     world, _ = _world()
-    hp = _adam_hparams(optimizer)
+    fused = optimizer is None or type(optimizer).__name__ in ("AdamW", "FusedAdamW")
+    hp = _adam_hparams(optimizer) if fused else None      # foreign optimisers step eagerly: nothing of theirs is baked in
+    hp_key = (hp["lr"], tuple(hp["betas"]), hp["eps"], hp["weight_decay"]) if hp else None
     key = (id(optimizer), type(optimizer).__name__, variant, float(alpha), bool(use_shared), known_subject,
-           tuple(gallery.shape), tuple(model.dropout_p), hp["lr"], hp["betas"], hp["eps"], hp["weight_decay"], world)
+           tuple(gallery.shape), tuple(model.dropout_p), hp_key, world)
     gstep = model._gstep_cache.get(key)
     if gstep is None:
         model._gstep_cache.clear()          # one live graph per model: drop the previous configuration
