@@ -59,3 +59,17 @@ def sync_batch_stats(y_local):
     mean = sums[0] / count
     var = sums[1] / count - mean * mean
     return mean.float(), var.float(), count
+
+
+def reconstruction_share(e_local, img_local, logit_scale, alpha=0.90):
+    """data-parallel form of the reconstruction-training loss (Generation/ATMS_reconstruction.py:227-228) as
+    StepEngine.loss_and_grad(variant="reconstruction") composes it: (1-alpha)*10 x the row-block ClipLoss(img) share plus
+    alpha*10 x this rank's rows of the global-batch MSE mean.  Returns (loss share, d loss / d e_local)."""
+    W = dist.get_world_size()
+    n_total = W * e_local.shape[0]
+    # single-target row-block InfoNCE == row_block_infonce with all the weight on the image target
+    share, d_e, _ = row_block_infonce(e_local, img_local, img_local, logit_scale, alpha=1.0)
+    w_clip, w_mse = (1.0 - alpha) * 10.0, alpha * 10.0
+    diff = e_local - img_local
+    mse_share = (diff * diff).sum() / (n_total * e_local.shape[1])
+    return w_clip * share[1] + w_mse * mse_share, w_clip * d_e + w_mse * 2.0 * diff / (n_total * e_local.shape[1])

@@ -53,6 +53,15 @@ def _worker(rank, world, port, q):
             "dE": ((d_e - Eg.grad[sl]).norm() / Eg.grad[sl].norm()).item(),
             "ds": abs(ds_tot.item() - sg.grad.item()) / abs(sg.grad.item()),
         }
+        # reconstruction-training variant: MSE is a mean over the GLOBAL batch, every rank adds its rows' share
+        r_share, r_de = DP.reconstruction_share(E[sl], img[sl], s, alpha=0.90)
+        r_tot = r_share.clone()
+        dist.all_reduce(r_tot)
+        Er = E.clone().requires_grad_(True)
+        r_ref = O.reconstruction_loss(Er, img, s, 0.90)
+        r_ref.backward()
+        res["recon_loss"] = abs(r_tot.item() - r_ref.item()) / abs(r_ref.item())
+        res["recon_dE"] = ((r_de - Er.grad[sl]).norm() / Er.grad[sl].norm()).item()
         # SyncBN statistics == statistics of the global batch
         y = torch.randn(N, 40, 63, 36, generator=g)
         mean, var, count = DP.sync_batch_stats(y[sl])
@@ -78,6 +87,7 @@ def test_two_rank_protocol_equals_single_process():
     res = q.get()
     assert res["loss"] < 1e-5 and res["loss_vs_gathered"] < 1e-6, res
     assert res["dE"] < 1e-4 and res["ds"] < 1e-4, res
+    assert res["recon_loss"] < 1e-5 and res["recon_dE"] < 1e-4, res
     assert res["bn_mean"] < 1e-5 and res["bn_var"] < 1e-4 and res["bn_count"] == 0, res
 
 
