@@ -152,3 +152,30 @@ def test_variant_modules_mirror_reference_signatures():
         "sub", "eegmodel", "dataloader", "device", "text_features_all", "img_features_all", "k"]
     with pytest.raises(RuntimeError):       # no CPU fallback in the variants either
         reconstruction.train_model("sub-08", reconstruction.ATMS(), [], None, "cpu", torch.zeros(4, 1024), torch.zeros(40, 1024), None)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """the Python binding's struct layouts are checked against the header with the C compiler (sizeof / offsetof)"""
+    import shutil
+    import subprocess
+    from eeg_image_decode_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"eegb200_atms_io": _lib.AtmsIO, "eegb200_infonce_io": _lib.InfoNceIO, "eegb200_gemm_desc": _lib.GemmDesc}
+    lines = []
+    for cname, st in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void){%s return 0;}\n'
+                   % (os.path.join(ROOT, "include", "eegdecode_b200.h"), "".join(lines)))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {l.split()[0]: int(l.split()[1]) for l in out if l.strip()}
+    for cname, st in structs.items():
+        assert got[cname] == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert got[f"{cname}.{fname}"] == getattr(st, fname).offset, f"{cname}.{fname}"
