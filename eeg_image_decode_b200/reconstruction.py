@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .atms import ATMS, N_SUBJECT_ROWS  # noqa: F401
-from .train import StepEngine, _train_epoch, extract_id_from_string
+from .train import StepEngine, _evaluate_epoch, _train_epoch, extract_id_from_string
 
 
 def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
@@ -28,7 +28,7 @@ def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all
                         variant="reconstruction", alpha=0.90, step_callback=step_callback)
 
 
-def _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, alpha, keep_features):
+def _export(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, alpha, keep_features):
     eeg_model.eval()
     device = torch.device(device)
     if device.type != "cuda":
@@ -37,6 +37,7 @@ def _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_feature
     img_features_all = img_features_all.to(device).float().contiguous()
     all_labels = set(range(text_features_all.size(0)))
     eng = StepEngine(eeg_model, None, alpha, "reconstruction")
+    eng.world, eng.rank = 1, 0          # export / evaluation is per process, no collectives
     subject_id = extract_id_from_string(sub)
     total_loss = torch.zeros(3, device=device)
     n_batches = 0
@@ -53,7 +54,7 @@ def _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_feature
             n_batches += 1
             if keep_features:
                 feats.append(eeg_features.clone())
-            # host side: the reference's per-trial candidate draw (ATMS_reconstruction.py:290-293)
+            # host side: the notebook's per-trial candidate draw (one draw, top-1 only, any k)
             label_list = labels.tolist()
             sel_rows = []
             for label in label_list:
@@ -73,16 +74,10 @@ def _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_feature
 
 
 def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, config):
-    """200-way zero-shot retrieval with the reconstruction loss mix (alpha = 0.99), ATMS_reconstruction.py:251-317.
-    Returns (average_loss, accuracy, top5_acc); top5_acc is always 0.0 there (never counted, :262, :316).  Any k other
-    than 200 makes the reference print "Error." per trial and then divide by zero (:310-315); here that is a
-    ZeroDivisionError raised up front."""
-    if k != 200:
-        print("Error.")
-        raise ZeroDivisionError("division by zero (the reconstruction script's evaluate_model only scores k == 200)")
-    average_loss, correct, total, _, _ = _evaluate(sub, eeg_model, dataloader, device, text_features_all, img_features_all,
-                                                   k, 0.99, False)
-    return average_loss, correct / total, 0.0
+    """k-way zero-shot retrieval with the reconstruction loss mix at alpha = 0.99 (ATMS_reconstruction.py:251-353).
+    Returns (average_loss, accuracy, top5_acc); candidate draws as in the reference (same body as the retrieval script)."""
+    return _evaluate_epoch(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, config,
+                           variant="reconstruction", alpha=0.99)
 
 
 def get_eegfeatures(sub, eegmodel, dataloader, device, text_features_all, img_features_all, k, *, save_features=True,
@@ -91,7 +86,7 @@ def get_eegfeatures(sub, eegmodel, dataloader, device, text_features_all, img_fe
     text_features_all, img_features_all, k)``): eval-mode embeddings of every trial, k-way accuracy, loss mix with
     alpha = 0.9.  Returns (average_loss, accuracy, labels of the last batch, features.cpu()) and writes
     ``ATM_S_eeg_features_{sub}.pt`` (the file the diffusion prior / SDXL stage loads) unless ``save_features=False``."""
-    average_loss, correct, total, labels, feats = _evaluate(sub, eegmodel, dataloader, device, text_features_all,
+    average_loss, correct, total, labels, feats = _export(sub, eegmodel, dataloader, device, text_features_all,
                                                             img_features_all, k, 0.9, True)
     features_tensor = feats.cpu()
     if save_features:

@@ -280,9 +280,7 @@ def test_reconstruction_loops_and_feature_export(lib, tmp_path):
     loss, a, t5 = evaluate_model("sub-08", m, tl, torch.device("cuda"), ttxt_all, timg_all, 200, _Cfg())
     ref = g["eval_k200"]
     assert abs(loss - ref[0]) < 5e-3 * abs(ref[0]) + 1e-4          # the MSE term dominates (B=1: ClipLoss == 0)
-    assert abs(a - ref[1]) <= 0.1 + 1e-9 and t5 == ref[2] == 0.0
-    with pytest.raises(ZeroDivisionError):
-        evaluate_model("sub-08", m, tl, torch.device("cuda"), ttxt_all, timg_all, 10, _Cfg())
+    assert abs(a - ref[1]) <= 0.1 + 1e-9 and abs(t5 - ref[2]) <= 0.1 + 1e-9, (a, t5, ref)
     # embedding export consumed by the diffusion prior / SDXL stage
     big = _Loader(teeg, tlabels, ttxt_all[tlabels], timg_all[tlabels], 5)
     random.seed(1)
