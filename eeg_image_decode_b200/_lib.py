@@ -26,7 +26,7 @@ class GemmDesc(ctypes.Structure):
         ("drop_ld", ctypes.c_int),
         ("mul_in", ctypes.c_void_p), ("ld_mul", ctypes.c_int),
         ("resid", ctypes.c_void_p), ("ld_res", ctypes.c_int),
-        ("round_tf32", ctypes.c_int), ("store_mode", ctypes.c_int), ("split_k", ctypes.c_int),
+        ("round_tf32", ctypes.c_int), ("store_mode", ctypes.c_int), ("split_k", ctypes.c_int), ("tile_n", ctypes.c_int),
     ]
 
 
@@ -76,7 +76,7 @@ def set_gemm_backend(backend: int) -> None:
 
 def gemm(A, B, C, M, N, K, *, lda=None, ldb=None, ldc=None, a_mn=False, b_mn=False, alpha=1.0, bias=None,
          bias_period=0, ld_bias=0, aux_out=None, ld_aux=0, act=0, drop_seed=0, drop_site=0, drop_p=0.0, drop_ld=0,
-         mul_in=None, ld_mul=0, resid=None, ld_res=0, round_tf32=False, store_mode=0, split_k=1):
+         mul_in=None, ld_mul=0, resid=None, ld_res=0, round_tf32=False, store_mode=0, split_k=1, tile_n=0):
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.A, d.lda, d.a_mn_major = ptr(A), int(lda if lda is not None else A.stride(0)), int(a_mn)
@@ -89,7 +89,7 @@ def gemm(A, B, C, M, N, K, *, lda=None, ldb=None, ldc=None, a_mn=False, b_mn=Fal
     d.drop_seed, d.drop_site, d.drop_p, d.drop_ld = drop_seed, drop_site, drop_p, drop_ld
     d.mul_in, d.ld_mul = ptr(mul_in), ld_mul
     d.resid, d.ld_res = ptr(resid), ld_res
-    d.round_tf32, d.store_mode, d.split_k = int(round_tf32), store_mode, split_k
+    d.round_tf32, d.store_mode, d.split_k, d.tile_n = int(round_tf32), store_mode, split_k, tile_n
     check(lib().eegb200_gemm(ctypes.byref(d), stream_ptr()), "gemm")
 
 

@@ -316,11 +316,22 @@ static int run_gemm(int M, int N, int K, const float* A, int lda, int amn, const
   g.split_k = split;
   return gemm_launch(g, s);
 }
-// split-K factor for the weight-gradient GEMMs (tiny outputs, reduction over all tokens)
+// split-K factor for the weight-gradient GEMMs (tiny outputs, reduction over all tokens).  Measured on B200
+// (tools/gemm_sweep.py): the work items (tiles x splits) must fit ONE wave of the 148 persistent CTAs -- 150 items ran
+// 45 % slower than 140 (dWs: 126 -> 87 us, dWqkv: 107 -> 74 us) -- and large outputs prefer few splits because every
+// split adds a full pass of red.global traffic over the output (dWp2 1024x1024: split 5 -> 41 us, split 2 -> 19 us).
 static int pick_split(int M, int N, int K) {
+  static int forced = -2;
+  if (forced == -2) { const char* e = getenv("EEGB200_WGRAD_SPLIT"); forced = e ? atoi(e) : -1; }
   const int tiles = cdiv(M, 128) * cdiv(N, N <= 64 ? 64 : (N <= 128 ? 128 : 256));
   const int kb = cdiv(K, 32);
-  int split = cdiv(148, tiles);          // ~one deep-pipelined CTA per SM: halves the L2 atomic traffic of the reduction
+  int split;
+  if (forced == 0) split = cdiv(148, tiles);          // round-1 rule (A/B)
+  else {
+    split = 148 / tiles;
+    if ((long long)M * N >= 512 * 1024 && split > 2) split = 2;
+    if (split >= 64) split /= 2;
+  }
   if (split > kb / 4) split = kb / 4;
   if (split < 1) split = 1;
   return split;
@@ -587,7 +598,15 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     EEG_TRY(colsum(w.dZ1, D_OUT, B, D_OUT, GR[EEGB200_P_BP1], 0, 0, ws));
     EEG_TRY(run_gemm(D_OUT, D_FEAT, B, w.dZ1, D_OUT, 1, w.feat, D_FEAT, 1, epi_wgrad(GR[EEGB200_P_WP1], D_FEAT),
                      pick_split(D_OUT, D_FEAT, B), ws));
-    EEG_TRY(run_gemm(B, D_FEAT, D_OUT, w.dZ1, D_OUT, 0, w.Wp1_r, D_FEAT, 1, epi_out(w.dfeat, D_FEAT), 1, s));
+    {
+      GemmArgs g;                                // dfeat = dZ1 . Wp1 (128-wide tiles: 25 vs 34 us at B = 1024)
+      g.M = B; g.N = D_FEAT; g.K = D_OUT;
+      g.A = {w.dZ1, D_OUT, 0};
+      g.B = {w.Wp1_r, D_FEAT, 1};
+      g.epi = epi_out(w.dfeat, D_FEAT);
+      g.tile_n = 128;
+      EEG_TRY(gemm_launch(g, s));
+    }
     // ---- conv head backward down to d(BN2 out) + BN2 reductions ----
     EEG_CUDA_OK(cudaMemsetAsync(w.bn2_bsums, 0, 2 * N_FILT * sizeof(double), s));
     EEG_TRY(conv_head_bwd(w.dfeat, w.Y2, w.bn2_mr, P[EEGB200_P_BN2_G], P[EEGB200_P_BN2_B], P[EEGB200_P_WC], w.dz2,
@@ -679,21 +698,39 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     unpack_qkv_grad_kernel<<<768, 256, 0, ws>>>(w.dWqkv_p, w.dbqkv_p, GR[EEGB200_P_WQ], GR[EEGB200_P_WK], GR[EEGB200_P_WV],
                                                 GR[EEGB200_P_BQ], GR[EEGB200_P_BK], GR[EEGB200_P_BV]);
     count_launch();
-    {
-      Epilogue e = epi_out(w.dH0, 256);          // dH0 = dR1 + dQKV . Wqkv
+    // ---- dH0 = dR1 + dQKV . Wqkv, then the DataEmbedding backward ----
+    // Only T3 = tf32(dropout_embed(dH0)) is consumed downstream (value-embedding weight / bias gradients; the subject-token
+    // gradient reads its rows with the same mask), so the GEMM epilogue applies residual -> dropout -> rounding and writes
+    // T3 directly: the separate 134 MB dropout pass (51 us on the critical path) is gone and the bias column sums run on
+    // the side stream.  EEGB200_DH0_FUSED=0 restores the two-pass form (A/B switch).
+    static int dh0_fused = -1;
+    if (dh0_fused < 0) { const char* e_ = getenv("EEGB200_DH0_FUSED"); dh0_fused = (e_ && e_[0] == '0') ? 0 : 1; }
+    const DropoutCfg no_drop = make_dropout(0, 0, 0.f, false);
+    if (dh0_fused) {
+      Epilogue e = epi_out(w.T3, 256);
+      e.resid = w.dR1; e.ld_res = 256; e.resid_before_drop = 1;
+      e.drop = cfg.d[EEGB200_SITE_EMBED]; e.drop_ld = 256;
+      e.round_tf32 = RT;
+      EEG_TRY(run_gemm(M, 256, 768, w.dQKV, 768, 0, w.Wqkv_p, 256, 1, e, 1, s));
+    } else {
+      Epilogue e = epi_out(w.dH0, 256);
       e.resid = w.dR1; e.ld_res = 256;
       EEG_TRY(run_gemm(M, 256, 768, w.dQKV, 768, 0, w.Wqkv_p, 256, 1, e, 1, s));
     }
-    // ---- DataEmbedding ----
     // token-0 rows carry no value embedding -> excluded from the bias gradient
     if (!io->joint_value_w) {
-      EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
-      FORK();
+      if (dh0_fused) {
+        FORK();
+        EEG_TRY(colsum(w.T3, 256, M, N_T, GR[EEGB200_P_VALUE_B], N_TOK, 0, ws));
+      } else {
+        EEG_TRY(dropout_apply_colsum(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, GR[EEGB200_P_VALUE_B], N_T, N_TOK, 0, s));
+        FORK();
+      }
       EEG_TRY(run_gemm(N_T, N_T, M, w.T3, 256, 1, w.Xp, 256, 1, epi_wgrad(GR[EEGB200_P_VALUE_W], N_T), pick_split(N_T, N_T, M), ws));
     } else {
       // joint-subject variant: every subject's value embedding gets the gradient of its own trials only
       EEG_TRY(check_joint(io, true));
-      EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
+      if (!dh0_fused) EEG_TRY(dropout_apply(w.dH0, w.T3, M, 256, cfg.d[EEGB200_SITE_EMBED], RT, s));
       FORK();
       for (int g = 0; g < io->n_groups; ++g) {
         const int sj = io->group_subject[g];
@@ -706,8 +743,10 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
     }
     EEG_REQUIRE(GR[EEGB200_P_SUBJ_TABLE] != nullptr && GR[EEGB200_P_SUBJ_SHARED] != nullptr,
                 "subject-token gradients need both the table and the shared-token grad buffers");
-    EEG_TRY(subject_token_bwd(reinterpret_cast<const long long*>(io->subject_ids), w.flag, w.dH0, GR[EEGB200_P_SUBJ_TABLE],
-                              GR[EEGB200_P_SUBJ_SHARED], B, cfg.d[EEGB200_SITE_EMBED], s));
+    // (fused form: the token-0 rows of T3 already carry the embed dropout mask and scale)
+    EEG_TRY(subject_token_bwd(reinterpret_cast<const long long*>(io->subject_ids), w.flag, dh0_fused ? w.T3 : w.dH0,
+                              GR[EEGB200_P_SUBJ_TABLE], GR[EEGB200_P_SUBJ_SHARED], B,
+                              dh0_fused ? no_drop : cfg.d[EEGB200_SITE_EMBED], s));
     EEG_CUDA_OK(cudaGetLastError());
   }
   if (use_side) EEG_TRY(g_side.join_into(s));      // gradients are complete when the caller's stream continues

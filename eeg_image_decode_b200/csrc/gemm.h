@@ -15,7 +15,7 @@ struct GemmOperand {
 enum { EPI_ACT_NONE = 0, EPI_ACT_GELU = 1 };
 enum { EPI_STORE = 0, EPI_ADD = 1, EPI_ATOMIC = 2 };
 
-// order: v = alpha*acc; +bias; aux_out=v; act; dropout; *gelu'(mul_in); +resid; tf32 round; store
+// order: v = alpha*acc; +bias; [+resid if resid_before_drop]; aux_out=v; act; dropout; *gelu'(mul_in); +resid; tf32 round; store
 struct Epilogue {
   float* C = nullptr;
   int ldc = 0;
@@ -33,6 +33,7 @@ struct Epilogue {
   int ld_mul = 0;
   const float* resid = nullptr;
   int ld_res = 0;
+  int resid_before_drop = 0;     // add the residual right after the bias (before activation / dropout) instead of last
   int round_tf32 = 0;
   int store_mode = EPI_STORE;
   // fused BatchNorm(train)+ELU backward of the conv stack (tcgen05 vector path only):
@@ -51,6 +52,7 @@ struct GemmArgs {
   GemmOperand A{nullptr, 0, 0}, B{nullptr, 0, 0};
   Epilogue epi;
   int split_k = 1;   // >1 requires epi.store_mode == EPI_ATOMIC and a pre-zeroed C
+  int tile_n = 0;    // 0: heuristic; 64 / 128 / 256: force the N tile of the tcgen05 kernel
 };
 
 enum { GEMM_BACKEND_TCGEN05 = 0, GEMM_BACKEND_SIMT_FP32 = 1 };
@@ -84,11 +86,12 @@ __device__ __forceinline__ float epi_value(const Epilogue& e, int row, int col, 
   float v = e.alpha * acc;
   if (e.alpha_dev) v *= __ldg(e.alpha_dev);
   if (e.bias) v += e.bias_period ? e.bias[(size_t)(row % e.bias_period) * e.ld_bias + col] : e.bias[col];
+  if (e.resid && e.resid_before_drop) v += e.resid[(size_t)row * e.ld_res + col];
   if (e.aux_out) e.aux_out[(size_t)row * e.ld_aux + col] = v;
   if (e.act == EPI_ACT_GELU) v = gelu_exact(v);
   if (e.drop.p > 0.f) v = dropout_keep(e.drop, (uint64_t)row * e.drop_ld + col) ? v * e.drop.scale : 0.f;
   if (e.mul_in) v *= gelu_grad(e.mul_in[(size_t)row * e.ld_mul + col]);
-  if (e.resid) v += e.resid[(size_t)row * e.ld_res + col];
+  if (e.resid && !e.resid_before_drop) v += e.resid[(size_t)row * e.ld_res + col];
   if (e.round_tf32) v = tf32_rn(v);
   return v;
 }
@@ -106,7 +109,7 @@ __device__ __forceinline__ void epi_store(const Epilogue& e, int row, int col, f
 // dead paths from the unrolled epilogue (the generic kernel is ~60 KB of SASS and stalls on instruction fetch).
 enum : uint32_t {
   EF_BIAS = 1, EF_BIAS_TABLE = 2, EF_AUX = 4, EF_GELU = 8, EF_DROP = 16, EF_MUL = 32, EF_RESID = 64, EF_ROUND = 128,
-  EF_BNF = 256, EF_GENERIC = 0x80000000u
+  EF_BNF = 256, EF_RESID_FIRST = 512 /* generic kernel only */, EF_GENERIC = 0x80000000u
 };
 #define EPI_ON(bit, runtime_cond) ((F & EF_GENERIC) ? (runtime_cond) : ((F & (bit)) != 0))
 
@@ -147,6 +150,8 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
     }
   }
   if (EPI_ON(EF_BIAS | EF_BIAS_TABLE, e.bias != nullptr)) { v[0] += L.bias.x; v[1] += L.bias.y; v[2] += L.bias.z; v[3] += L.bias.w; }
+  const bool resid_first = (F & EF_GENERIC) ? (e.resid != nullptr && e.resid_before_drop != 0) : false;
+  if (resid_first) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
   if (EPI_ON(EF_AUX, e.aux_out != nullptr))
     *reinterpret_cast<float4*>(e.aux_out + (size_t)row * e.ld_aux + col) = make_float4(v[0], v[1], v[2], v[3]);
   if (EPI_ON(EF_GELU, e.act == EPI_ACT_GELU)) {
@@ -161,7 +166,7 @@ __device__ __forceinline__ void epi_finish4(const Epilogue& e, int row, int col,
   if (EPI_ON(EF_MUL, e.mul_in != nullptr)) {
     v[0] *= gelu_grad(L.mul.x); v[1] *= gelu_grad(L.mul.y); v[2] *= gelu_grad(L.mul.z); v[3] *= gelu_grad(L.mul.w);
   }
-  if (EPI_ON(EF_RESID, e.resid != nullptr)) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
+  if (EPI_ON(EF_RESID, e.resid != nullptr) && !resid_first) { v[0] += L.resid.x; v[1] += L.resid.y; v[2] += L.resid.z; v[3] += L.resid.w; }
   if (EPI_ON(EF_ROUND, e.round_tf32 != 0)) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = tf32_rn(v[i]);
@@ -186,6 +191,7 @@ static inline uint32_t epi_feature_mask(const Epilogue& e) {
   if (e.drop.p > 0.f) m |= EF_DROP;
   if (e.mul_in) m |= EF_MUL;
   if (e.resid) m |= EF_RESID;
+  if (e.resid && e.resid_before_drop) m |= EF_RESID_FIRST;     // no specialised kernel carries this: generic path
   if (e.round_tf32) m |= EF_ROUND;
   if (e.bn_y) m |= EF_BNF;
   return m;

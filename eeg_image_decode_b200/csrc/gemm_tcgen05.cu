@@ -615,6 +615,10 @@ int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   EEG_TRY(resolve_encode());
   // widest tile that still yields >= ~one wave of CTAs (small-M problems: projector, logits, retrieval)
   if (g.epi.bn_y != nullptr) return launch_bn<256>(g, stream);     // the fused BatchNorm-backward flavour is built for BN = 256
+  if (g.tile_n == 256) return launch_bn<256>(g, stream);
+  if (g.tile_n == 128) return launch_bn<128>(g, stream);
+  if (g.tile_n == 64) return launch_bn<64>(g, stream);
+  EEG_REQUIRE(g.tile_n == 0, "gemm: tile_n must be 0, 64, 128 or 256 (got %d)", g.tile_n);
   const int mt = cdiv(g.M, BM);
   const int split = g.split_k > 1 ? g.split_k : 1;
   auto ctas = [&](int bn) { return mt * cdiv(g.N, bn) * split; };

@@ -449,40 +449,45 @@ int layernorm_bwd_tok(const float* dy, const float* x, int rows, int D, const fl
 // out[c] += sum_r x[r*ld + c] (c < cols); optional dropout mask on the fly (bias grads of layers whose
 // output passes through a dropout before the residual).
 // ------------------------------------------------------------------------------------------------
-// float4 columns x 16 row lanes per block; rows strided over the grid, 4 rows in flight per thread
+// float4 columns x 16 row lanes per block.  blockIdx.y selects a 256-column chunk (one launch covers wide matrices such
+// as dQKV [M,768]); every block owns a contiguous band of rows and keeps 8 predicated 16-byte loads in flight per thread
+// (the former grid-strided version fell into a one-row-at-a-time tail loop for most of its rows: 2.3 TB/s).
 __global__ void __launch_bounds__(1024) colsum_vec_kernel(const float* __restrict__ x, int ld, int rows, int cols,
                                                           float* __restrict__ out, int row_mod, int row_skip) {
   __shared__ float4 part[16][64];
   const int c4 = threadIdx.x;            // 64 float4 columns = 256 floats
   const int ry = threadIdx.y;            // 16 row lanes
+  const int c0 = blockIdx.y * 256;
+  const int w = cols - c0 < 256 ? cols - c0 : 256;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (c4 * 4 < cols) {
-    const int stride = gridDim.x * 16;
-    int r = blockIdx.x * 16 + ry;
-    for (; r + 7 * stride < rows; r += 8 * stride) {
+  if (c4 * 4 < w) {
+    const int per = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * per;
+    const int r_end = min(rows, r_begin + per);
+    const float* base = x + c0 + c4 * 4;
+    for (int r = r_begin + ry; r < r_end; r += 16 * 8) {
       float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(x + (size_t)(r + u * stride) * ld + c4 * 4);
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r + u * 16;
+        v[u] = rr < r_end ? *reinterpret_cast<const float4*>(base + (size_t)rr * ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        if (row_mod > 0 && ((r + u * stride) % row_mod) == row_skip) continue;
+        const int rr = r + u * 16;
+        if (row_mod > 0 && (rr % row_mod) == row_skip) continue;
         acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
       }
-    }
-    for (; r < rows; r += stride) {
-      if (row_mod > 0 && (r % row_mod) == row_skip) continue;
-      const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * ld + c4 * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
   part[ry][c4] = acc;
   __syncthreads();
-  if (ry == 0 && c4 * 4 < cols) {
+  if (ry == 0 && c4 * 4 < w) {
     float4 t = part[0][c4];
     for (int i = 1; i < 16; ++i) { t.x += part[i][c4].x; t.y += part[i][c4].y; t.z += part[i][c4].z; t.w += part[i][c4].w; }
     const float tv[4] = {t.x, t.y, t.z, t.w};
     for (int q = 0; q < 4; ++q)
-      if (c4 * 4 + q < cols) atomicAdd(&out[c4 * 4 + q], tv[q]);
+      if (c4 * 4 + q < w) atomicAdd(&out[c0 + c4 * 4 + q], tv[q]);
   }
 }
 __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int cols, float* __restrict__ out,
@@ -507,21 +512,25 @@ __global__ void colsum_kernel(const float* __restrict__ x, int ld, int rows, int
 int colsum(const float* x, int ld, int rows, int cols, float* out, int row_mod, int row_skip, cudaStream_t s) {
   ProfScope _ps("colsum", s, 0.0, (double)rows * cols * 4.0);
   const bool vec = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld >= (cols + 3) / 4 * 4;
+  if (vec) {
+    const int chunks = cdiv(cols, 256);
+    int blocks = cdiv(rows, 16 * 8);
+    const int cap = chunks >= 2 ? 148 : 148 * 2;      // 2 blocks of 1024 threads per SM; wide matrices fill the y dimension
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    colsum_vec_kernel<<<dim3(blocks, chunks), dim3(64, 16), 0, s>>>(x, ld, rows, cols, out, row_mod, row_skip);
+    count_launch();
+    EEG_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   for (int c0 = 0; c0 < cols; c0 += 256) {
     const int w = cols - c0 < 256 ? cols - c0 : 256;
-    if (vec) {
-      int blocks = cdiv(rows, 16 * 8);
-      if (blocks > 148 * 2) blocks = 148 * 2;
-      if (blocks < 1) blocks = 1;
-      colsum_vec_kernel<<<blocks, dim3(64, 16), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
-    } else {
-      const int tx = (w + 31) / 32 * 32;
-      const int ty = 1024 / tx > 8 ? 8 : 1024 / tx;
-      int blocks = cdiv(rows, ty * 8);
-      if (blocks > 148 * 2) blocks = 148 * 2;
-      if (blocks < 1) blocks = 1;
-      colsum_kernel<<<blocks, dim3(tx, ty), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
-    }
+    const int tx = (w + 31) / 32 * 32;
+    const int ty = 1024 / tx > 8 ? 8 : 1024 / tx;
+    int blocks = cdiv(rows, ty * 8);
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    colsum_kernel<<<blocks, dim3(tx, ty), 0, s>>>(x + c0, ld, rows, w, out + c0, row_mod, row_skip);
     count_launch();
   }
   EEG_CUDA_OK(cudaGetLastError());

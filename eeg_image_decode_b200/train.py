@@ -125,8 +125,10 @@ class StepEngine:
         return loss, d_e, d_s
 
     def step(self, eeg, subject_ids, img_feat, txt_feat, use_shared: bool, seed: Optional[int] = None, device_steps=None,
-             known_subject: Optional[int] = None):
-        """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024]).  ``known_subject``: see ATMS.encode."""
+             known_subject: Optional[int] = None, after_forward=None, before_update=None):
+        """returns (loss[3] device tensor -- this rank's share, embeddings [B,1024]).  ``known_subject``: see ATMS.encode.
+        ``after_forward(feats)`` / ``before_update()``: optional hooks right after the embeddings exist and right before the
+        optimiser touches the parameters (GraphedTrainStep scores the train accuracy on a side stream between them)."""
         m = self.model
         W = self.world
         m.zero_flat_grads()
@@ -145,6 +147,8 @@ class StepEngine:
             feats = out
         else:
             feats = m.encode(eeg, subject_ids, train=True, seed=seed, known_subject=known_subject)
+        if after_forward is not None:
+            after_forward(feats)
         loss, d_e, d_s = self.loss_and_grad(feats, img_feat, txt_feat)
         m.grad_view("logit_scale").add_(d_s)
         if W > 1:
@@ -160,6 +164,8 @@ class StepEngine:
         if W > 1 and subjects is not None and known_subject is None:
             raise NotImplementedError("data-parallel steps of the joint-subject model need known_subject (every rank must "
                                       "update the same value embeddings)")
+        if before_update is not None:
+            before_update()
         if self.fused:
             fused_adamw_step(m, self.optimizer, use_shared, device_steps, subjects)
         else:
@@ -206,6 +212,8 @@ class GraphedTrainStep:
             enabled = False
         self.enabled = enabled and os.environ.get("EEGB200_CUDA_GRAPH", "1") != "0"
         self.dp_ok = os.environ.get("EEGB200_CUDA_GRAPH_DP", "1") != "0"
+        self.acc_overlap = os.environ.get("EEGB200_ACC_OVERLAP", "1") != "0"
+        self._side = None
         self.graph = None
         self.calls = 0
         self.B = None
@@ -213,10 +221,34 @@ class GraphedTrainStep:
         self.replays = 0
 
     def _body(self, eeg, sid, img, txt, labels, device_steps):
+        # Train accuracy (ATMS_retrieval.py:241-250): argmax over the class-prototype gallery.  The reference scores after
+        # optimizer.step() with the updated logit_scale, but argmax is invariant under a positive scale and the embeddings
+        # are the pre-update ones (:223), so the 3xTF32 scoring GEMM (~105 us) runs on a side stream right after the
+        # forward, overlapped with the backward, instead of extending the critical path after AdamW; it is joined before
+        # the optimiser writes logit_scale.  (A non-positive logit_scale would flip the ranking: init is ln(1/0.07) = 2.66
+        # and the reference would equally break there.)  EEGB200_ACC_OVERLAP=0 restores the serial order.
+        model = self.eng.model
+        if not self.acc_overlap:
+            loss, feats = self.eng.step(eeg, sid, img, txt, self.use_shared, device_steps=device_steps,
+                                        known_subject=self.known_subject)
+            r = _lib.retrieval(feats, self.gallery, model.logit_scale.detach(), labels=labels, want_top5=False)
+            return loss, feats, r["correct"]
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=eeg.device)
+        side, box = self._side, {}
+
+        def after_forward(feats):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                box["r"] = _lib.retrieval(feats, self.gallery, model.logit_scale.detach(), labels=labels, want_top5=False)
+
+        def before_update():
+            main.wait_stream(side)
+
         loss, feats = self.eng.step(eeg, sid, img, txt, self.use_shared, device_steps=device_steps,
-                                    known_subject=self.known_subject)
-        r = _lib.retrieval(feats, self.gallery, self.eng.model.logit_scale.detach(), labels=labels, want_top5=False)
-        return loss, feats, r["correct"]
+                                    known_subject=self.known_subject, after_forward=after_forward, before_update=before_update)
+        return loss, feats, box["r"]["correct"]
 
     def __call__(self, eeg, sid, img, txt, labels):
         eng = self.eng

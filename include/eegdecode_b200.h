@@ -55,6 +55,7 @@ typedef struct eegb200_gemm_desc {
   int round_tf32;                                   /* round the stored value to TF32 (RN) */
   int store_mode;                                   /* 0 store, 1 C += v, 2 atomicAdd (split-K) */
   int split_k;
+  int tile_n;                                       /* 0 = heuristic; 64 / 128 / 256 force the N tile (tuning, tests) */
 } eegb200_gemm_desc;
 int eegb200_gemm(const eegb200_gemm_desc* d, void* stream);
 
