@@ -54,7 +54,7 @@ __device__ __forceinline__ void warp_load_row_pool(const float* __restrict__ xro
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int XP>   // 3: 3xTF32 split (near fp32), 1: plain TF32
+template <int XP>   // 3: 3xTF32 split (near fp32), 2: activations split / weights rounded (p_hi.w + p_lo.w), 1: plain TF32
 __global__ void __launch_bounds__(CW_THREADS) conv_temporal_fwd_mma_kernel(const float* __restrict__ x3,
                                                                            const float* __restrict__ wt,
                                                                            const float* __restrict__ bt,
@@ -108,14 +108,12 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_fwd_mma_kernel(const
           const int j = mt * 16 + g + 8 * (h & 1), i = kt * 8 + t + 4 * (h >> 1);
           const float p = ps[5 * j + i];
           ah[h] = tf32_bits(p);
-          if (XP == 3) al[h] = tf32_bits(p - __uint_as_float(ah[h]));
+          if (XP >= 2) al[h] = tf32_bits(p - __uint_as_float(ah[h]));
         }
 #pragma unroll
         for (int nt = 0; nt < 5; ++nt) {
-          if (XP == 3) {
-            mma_tf32(c[nt], al, bh[kt][nt][0], bh[kt][nt][1]);
-            mma_tf32(c[nt], ah, bl[kt][nt][0], bl[kt][nt][1]);
-          }
+          if (XP >= 2) mma_tf32(c[nt], al, bh[kt][nt][0], bh[kt][nt][1]);
+          if (XP == 3) mma_tf32(c[nt], ah, bl[kt][nt][0], bl[kt][nt][1]);
           mma_tf32(c[nt], ah, bh[kt][nt][0], bh[kt][nt][1]);
         }
       }
@@ -367,8 +365,9 @@ int conv_temporal_fwd(const float* x3, const float* wt, const float* bt, float* 
   if (!tf32_rounding()) return conv_temporal_fwd_simt(x3, wt, bt, y1, sums, B, s);   // exact-fp32 verification path
   ProfScope _ps("conv_temporal_fwd", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * (63 * 1000.0 + 36 * 2520 * 4.0));
   static int xp = -1;
-  if (xp < 0) { const char* e = getenv("EEGB200_CONV_XP"); xp = (e && e[0] == '1') ? 1 : 3; }
+  if (xp < 0) { const char* e = getenv("EEGB200_CONV_XP"); xp = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
   if (xp == 3) conv_temporal_fwd_mma_kernel<3><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
+  else if (xp == 2) conv_temporal_fwd_mma_kernel<2><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
   else conv_temporal_fwd_mma_kernel<1><<<B, CW_THREADS, 0, s>>>(x3, wt, bt, y1, sums);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();

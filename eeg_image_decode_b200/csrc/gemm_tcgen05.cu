@@ -67,18 +67,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const E
       const bool lane_ok = col < p.N;
       float bs1[4] = {0.f, 0.f, 0.f, 0.f}, bs2[4] = {0.f, 0.f, 0.f, 0.f};
       const int bn_c = (F & EF_BNF) ? col % 40 : 0;
+      // 4 row groups have their global loads issued before the first is consumed.  (8 in flight for the BatchNorm-backward
+      // flavour -- one 16-byte load per group, long-scoreboard bound in ncu -- measured SLOWER on B200: 244 -> 267 us.)
+      constexpr int U = 4;
 #pragma unroll 1
-      for (int g4 = 0; g4 < 2; ++g4) {     // not unrolled: halves the epilogue's SASS footprint (I-cache)
-        EpiLoads L[4];
+      for (int g4 = 0; g4 < 8 / U; ++g4) {
+        EpiLoads L[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int row = row0 + (g4 * 4 + u) * 4;
+        for (int u = 0; u < U; ++u) {
+          const int row = row0 + (g4 * U + u) * 4;
           if (row < p.M && lane_ok) L[u] = epi_load4<F>(e, row, col);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int rl = (g4 * 4 + u) * 4 + r_sub;
-          const int row = row0 + (g4 * 4 + u) * 4;
+        for (int u = 0; u < U; ++u) {
+          const int rl = (g4 * U + u) * 4 + r_sub;
+          const int row = row0 + (g4 * U + u) * 4;
           if (row < p.M && lane_ok) epi_finish4<F>(e, row, col, *reinterpret_cast<const float4*>(stage + rl * SLD + cq), L[u], alpha, bs1, bs2, sred + 80, bn_c);
         }
       }
