@@ -33,14 +33,23 @@ __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
 }
 
 // 64 rows x 64 floats of one head -> smem tile with row stride AL (128 threads, float4)
+// ROUND: store the values already rounded to TF32 (RN) so that the fragment gathers of the plain-TF32 kernels need no
+// cvt per use (2 of the ~5 instructions per MMA in the first version; every tile element is used 16-64 times)
+template <bool ROUND>
 __device__ __forceinline__ void load_tile(const float* __restrict__ base, int ld, float* __restrict__ dst) {
   const int r0 = threadIdx.x >> 4, c4 = threadIdx.x & 15;
+  float4 v[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p) v[p] = *reinterpret_cast<const float4*>(base + (size_t)(r0 + 8 * p) * ld + c4 * 4);
 #pragma unroll
   for (int p = 0; p < 8; ++p) {
-    const int r = r0 + 8 * p;
-    *reinterpret_cast<float4*>(dst + r * AL + c4 * 4) = *reinterpret_cast<const float4*>(base + (size_t)r * ld + c4 * 4);
+    if (ROUND) { v[p].x = tf32_rn(v[p].x); v[p].y = tf32_rn(v[p].y); v[p].z = tf32_rn(v[p].z); v[p].w = tf32_rn(v[p].w); }
+    *reinterpret_cast<float4*>(dst + (r0 + 8 * p) * AL + c4 * 4) = v[p];
   }
 }
+// operand bits of a value that is either pre-rounded (XP == 1 tiles) or still fp32
+template <int XP>
+__device__ __forceinline__ uint32_t opb(float x) { return XP == 1 ? __float_as_uint(x) : tfb(x); }
 
 // scores of 16 query rows (warp tile) against 64 keys.  XP = 3 -> 3xTF32, XP = 1 -> TF32.
 // s[nt][0..3]: rows (g, g+8) x keys (nt*8+2t, +1)
@@ -55,7 +64,7 @@ __device__ __forceinline__ void qk_scores(const float* __restrict__ Q, const flo
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const float v = Q[(row0 + g + 8 * (h & 1)) * AL + kt * 8 + t + 4 * (h >> 1)];
-      if (XP == 3) split(v, ah[h], al[h]); else ah[h] = tfb(v);
+      if (XP == 3) split(v, ah[h], al[h]); else ah[h] = __float_as_uint(v);
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -68,7 +77,7 @@ __device__ __forceinline__ void qk_scores(const float* __restrict__ Q, const flo
         mma8(s[nt], ah, l0, l1);
         mma8(s[nt], ah, h0, h1);
       } else {
-        mma8(s[nt], ah, tfb(k0), tfb(k1));
+        mma8(s[nt], ah, __float_as_uint(k0), __float_as_uint(k1));
       }
     }
   }
@@ -136,7 +145,7 @@ __device__ __forceinline__ void pv_product(const float p[8][4], const float* __r
         mma8(o[nt], ah, l0, l1);
         mma8(o[nt], ah, h0, h1);
       } else {
-        mma8(o[nt], ah, tfb(b0), tfb(b1));
+        mma8(o[nt], ah, __float_as_uint(b0), __float_as_uint(b1));
       }
     }
   }
@@ -151,9 +160,9 @@ __global__ void __launch_bounds__(AT_THREADS) attention_fwd_mma_kernel(const flo
   float* V = K + 64 * AL;
   const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
   const float* base = qkv + (size_t)b * 64 * 768 + h * 64;
-  load_tile(base, 768, Q);
-  load_tile(base + 256, 768, K);
-  load_tile(base + 512, 768, V);
+  load_tile<XP == 1>(base, 768, Q);
+  load_tile<XP == 1>(base + 256, 768, K);
+  load_tile<XP == 1>(base + 512, 768, V);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
@@ -195,10 +204,10 @@ __global__ void __launch_bounds__(AT_THREADS) attention_bwd_mma_kernel(const flo
   float* DS = Pd + 64 * PL;     // d scores [i][j], stride PL
   const int b = blockIdx.x >> 2, h = blockIdx.x & 3;
   const float* base = qkv + (size_t)b * 64 * 768 + h * 64;
-  load_tile(base, 768, Q);
-  load_tile(base + 256, 768, K);
-  load_tile(base + 512, 768, V);
-  load_tile(d_o + (size_t)b * 64 * 256 + h * 64, 256, DO);
+  load_tile<true>(base, 768, Q);
+  load_tile<true>(base + 256, 768, K);
+  load_tile<true>(base + 512, 768, V);
+  load_tile<true>(d_o + (size_t)b * 64 * 256 + h * 64, 256, DO);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16;
@@ -236,8 +245,8 @@ __global__ void __launch_bounds__(AT_THREADS) attention_bwd_mma_kernel(const flo
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int i = row0 + g + 8 * hrow, j = nt * 8 + 2 * t;
       const float k0 = drop.p > 0.f ? kf[nt][2 * hrow] : 1.f, k1 = drop.p > 0.f ? kf[nt][2 * hrow + 1] : 1.f;
-      *reinterpret_cast<float2*>(Pd + i * PL + j) = make_float2(p[nt][2 * hrow] * k0, p[nt][2 * hrow + 1] * k1);
-      *reinterpret_cast<float2*>(DS + i * PL + j) = make_float2(ds[nt][2 * hrow], ds[nt][2 * hrow + 1]);
+      *reinterpret_cast<float2*>(Pd + i * PL + j) = make_float2(tf32_rn(p[nt][2 * hrow] * k0), tf32_rn(p[nt][2 * hrow + 1] * k1));
+      *reinterpret_cast<float2*>(DS + i * PL + j) = make_float2(tf32_rn(ds[nt][2 * hrow]), tf32_rn(ds[nt][2 * hrow + 1]));
     }
   // dQ[i][e] = sum_j dS[i][j] K[j][e]   (rows owned by this warp)
   {
@@ -266,14 +275,14 @@ __global__ void __launch_bounds__(AT_THREADS) attention_bwd_mma_kernel(const flo
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) {
         const int j = row0 + g + 8 * (hh & 1), i = kt * 8 + t + 4 * (hh >> 1);
-        ap[hh] = tfb(Pd[i * PL + j]);
-        as[hh] = tfb(DS[i * PL + j]);
+        ap[hh] = __float_as_uint(Pd[i * PL + j]);      // stored pre-rounded
+        as[hh] = __float_as_uint(DS[i * PL + j]);
       }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int e = nt * 8 + g;
-        mma8(dv[nt], ap, tfb(DO[(kt * 8 + t) * AL + e]), tfb(DO[(kt * 8 + t + 4) * AL + e]));
-        mma8(dk[nt], as, tfb(Q[(kt * 8 + t) * AL + e]), tfb(Q[(kt * 8 + t + 4) * AL + e]));
+        mma8(dv[nt], ap, __float_as_uint(DO[(kt * 8 + t) * AL + e]), __float_as_uint(DO[(kt * 8 + t + 4) * AL + e]));
+        mma8(dk[nt], as, __float_as_uint(Q[(kt * 8 + t) * AL + e]), __float_as_uint(Q[(kt * 8 + t + 4) * AL + e]));
       }
     }
 #pragma unroll
