@@ -356,6 +356,259 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, second version.  Same math and the same two MMA phases as conv_temporal_bwd_mma_kernel; what changed is
+// everything around them, following the ncu source view of the first version (profiles/r01_conv_temporal_bwd.ncu-rep:
+// 24 % of the stall samples in the dz/y -> dy transform, 20 % in the two serial 51-term sliding sums, 7.5 % on the
+// un-prefetched token-row load, ~5 % in per-use cvt.rna of the pooled sums):
+//   * the token row is prefetched with cp.async together with dz / y of the next row;
+//   * box-51 sums and the transposed pooling are differences of a warp-scanned prefix sum (8 values per lane, 5 shuffle
+//     steps) instead of 51 dependent adds per lane;
+//   * the BatchNorm backward is folded into three per-channel constants dy = A*dz + B*y + C kept in registers: 30 lanes
+//     cover exactly 3 rows x 10 float4, so a lane's channel quad never changes (was 20 shared loads per float4);
+//   * pooled sums are stored TF32-rounded once instead of converted at every fragment gather.
+// ------------------------------------------------------------------------------------------------
+static constexpr int XRAW = 256;     // token row staging (cp.async)
+static constexpr int CS_LEN = 272;   // prefix sums C[0..256]
+static constexpr int DP_LEN = 256;   // dp[0..199] + zero tail
+
+// v[0..7]: 8 consecutive values of lane `lane`.  Returns the exclusive-prefix form E[i] = sum of all elements before
+// element 8*lane+i, plus the inclusive total of the lane in *last.
+__device__ __forceinline__ void warp_excl_scan8(float v[8], int lane, float* last) {
+#pragma unroll
+  for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
+  const float tot = v[7];
+  float inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  const float excl = inc - tot;
+  *last = inc;
+#pragma unroll
+  for (int i = 7; i >= 1; --i) v[i] = v[i - 1] + excl;
+  v[0] = excl;
+}
+
+__device__ __forceinline__ void prefetch_row2(const float* __restrict__ dz1, const float* __restrict__ y1,
+                                              const float* __restrict__ x3, int b, int r, float* rawdz, float* rawy,
+                                              float* xraw, int lane) {
+  const float* xrow = x3 + ((size_t)b * N_TOK + r) * D_PAD;
+  cp_async16(xraw + lane * 4, xrow + lane * 4);
+  cp_async16(xraw + 128 + lane * 4, xrow + 128 + lane * 4);
+  for (int f = lane; f < N_POOL * 10; f += 32) {
+    const int j = f / 10, k4 = (f % 10) * 4;
+    const size_t idx = (((size_t)b * N_POOL + j) * N_CH + r) * N_FILT + k4;
+    cp_async16(rawdz + f * 4, dz1 + idx);
+    cp_async16(rawy + f * 4, y1 + idx);
+  }
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma2_kernel(
+    const float* __restrict__ dz1, const float* __restrict__ y1, const float* __restrict__ x3,
+    const float* __restrict__ wt, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+    const double* __restrict__ bwd_sums, long long count, float* __restrict__ dx3, float* __restrict__ dwt,
+    float* __restrict__ dbt, float* __restrict__ dgamma, float* __restrict__ dbeta, float gscale) {
+  extern __shared__ __align__(16) float smem[];
+  // CTA-shared: folded BatchNorm-backward constants [3][40], dW reduction [40][26]
+  float* c_A = smem;
+  float* c_B = c_A + N_FILT;
+  float* c_C = c_B + N_FILT;
+  float* wred = c_C + N_FILT;                        // [40][26]
+  float* per_warp = wred + N_FILT * 26;              // 120 + 1040 = 1160 floats: 16-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x;
+  constexpr int PW = XRAW + CS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DP_LEN + 2 * RAW;
+  float* xraw = per_warp + (size_t)warp * PW;
+  float* cs = xraw + XRAW;
+  float* ps = cs + CS_LEN;
+  float* dys = ps + PS_LEN;
+  float* dps = dys + DY_ROWS * DY_LD + 16;
+  float* rawdz = dps + DP_LEN;
+  float* rawy = rawdz + RAW;
+  for (int i = lane; i < PW - 2 * RAW - XRAW; i += 32) cs[i] = 0.f;          // cs, ps (zero tail), dys (zero rows), dps
+  if (warp < N_CH) prefetch_row2(dz1, y1, x3, b, warp, rawdz, rawy, xraw, lane);
+  for (int i = threadIdx.x; i < N_FILT * 26; i += CW_THREADS) wred[i] = 0.f;
+  if (threadIdx.x < N_FILT) {
+    const int k = threadIdx.x;
+    const float mu = mean_rstd[k], rs = mean_rstd[N_FILT + k];
+    const float gr = gamma[k] * rs;
+    const float m1 = (float)(bwd_sums[k] / (double)count), m2 = (float)(bwd_sums[N_FILT + k] / (double)count);
+    // dy = gr*(dz - m1 - (y-mu)*rs*m2) = A*dz + B*y + C
+    c_A[k] = gr;
+    c_B[k] = -gr * m2 * rs;
+    c_C[k] = gr * (m2 * rs * mu - m1);
+    if (b == 0) {
+      dgamma[k] += gscale * (float)bwd_sums[N_FILT + k];
+      dbeta[k] += gscale * (float)bwd_sums[k];
+    }
+  }
+  // B fragments of the dp GEMM: W'[(a,kk*8+k)][rho] = w[k][rho+5a]/51  (n = rho = g, valid for g < 5)
+  uint32_t bw[25][2];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int kk = 0; kk < 5; ++kk)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = kk * 8 + t + 4 * h, i = g + 5 * a;
+        bw[a * 5 + kk][h] = g < 5 ? tf32_bits(wt[k * K_TEMP + i] * (1.f / K_POOL)) : 0u;
+      }
+  float accw[3][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) accw[mt][nt][0] = accw[mt][nt][1] = accw[mt][nt][2] = accw[mt][nt][3] = 0.f;
+  __syncthreads();
+  // this lane's channel quad in the transform (lanes 0..29: 3 rows x 10 float4 per pass)
+  const int tr_j = lane / 10, tr_k4 = (lane % 10) * 4;
+  float kA[4], kB[4], kC[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { kA[q] = c_A[tr_k4 + q]; kB[q] = c_B[tr_k4 + q]; kC[q] = c_C[tr_k4 + q]; }
+
+  for (int r = warp; r < N_CH; r += CW_WARPS) {
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- box-51 sums of the token row: ps[s] = C[s+51] - C[s], C = prefix sums (TF32-rounded: dW operand only) ----
+    {
+      const float4 x0 = *reinterpret_cast<const float4*>(xraw + 8 * lane), x1 = *reinterpret_cast<const float4*>(xraw + 8 * lane + 4);
+      float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float last;
+      warp_excl_scan8(v, lane, &last);
+      *reinterpret_cast<float4*>(cs + 8 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(cs + 8 * lane + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (lane == 31) cs[256] = last;
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const int sidx = lane + 32 * q;
+        if (sidx < N_PSUM) ps[sidx] = tf32_rn(cs[sidx + K_POOL] - cs[sidx]);
+      }
+    }
+    // ---- dy[j][k] = A*dz + B*y + C for this (b, r) -> smem (TF32-rounded), rows offset by 4 ----
+    if (lane < 30) {
+#pragma unroll 4
+      for (int it = 0; it < 12; ++it) {
+        const int j = it * 3 + tr_j;
+        const float4 dz = *reinterpret_cast<const float4*>(rawdz + j * N_FILT + tr_k4);
+        const float4 yv = *reinterpret_cast<const float4*>(rawy + j * N_FILT + tr_k4);
+        float4 o;
+        o.x = tf32_rn(fmaf(kA[0], dz.x, fmaf(kB[0], yv.x, kC[0])));
+        o.y = tf32_rn(fmaf(kA[1], dz.y, fmaf(kB[1], yv.y, kC[1])));
+        o.z = tf32_rn(fmaf(kA[2], dz.z, fmaf(kB[2], yv.z, kC[2])));
+        o.w = tf32_rn(fmaf(kA[3], dz.w, fmaf(kB[3], yv.w, kC[3])));
+        *reinterpret_cast<float4*>(dys + (j + 4) * DY_LD + tr_k4) = o;
+      }
+    }
+    __syncwarp();
+    if (r + CW_WARPS < N_CH) prefetch_row2(dz1, y1, x3, b, r + CW_WARPS, rawdz, rawy, xraw, lane);   // overlaps the MMAs below
+    // ---- dW[k][i] += sum_j dy[j][k] * p[5j+i]   (column i == 25 carries a ones-vector: the bias gradient) ----
+#pragma unroll
+    for (int kt = 0; kt < 5; ++kt) {
+      uint32_t bp[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = kt * 8 + t + 4 * h, i = nt * 8 + g;
+          float v = 0.f;
+          if (i < K_TEMP) v = ps[5 * j + i];                      // already TF32
+          else if (i == K_TEMP) v = j < N_POOL ? 1.f : 0.f;
+          bp[nt][h] = __float_as_uint(v);
+        }
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {
+        uint32_t a[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int k = mt * 16 + g + 8 * (h & 1), j = kt * 8 + t + 4 * (h >> 1);
+          a[h] = __float_as_uint(dys[(j + 4) * DY_LD + k]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(accw[mt][nt], a, bp[nt][0], bp[nt][1]);
+      }
+    }
+    // ---- dp[5m+rho] = sum_{a,k} dy[m-a][k] * w[k][rho+5a]/51 : 6 independent accumulator chains ----
+    {
+      float c[3][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) c[mt][e][0] = c[mt][e][1] = c[mt][e][2] = c[mt][e][3] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) {
+#pragma unroll
+          for (int mt = 0; mt < 3; ++mt) {
+            uint32_t af[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int m = mt * 16 + g + 8 * (h & 1), k = kk * 8 + t + 4 * (h >> 1);
+              af[h] = __float_as_uint(dys[(m - a + 4) * DY_LD + k]);
+            }
+            mma_tf32(c[mt][(a * 5 + kk) & 1], af, bw[a * 5 + kk][0], bw[a * 5 + kk][1]);
+          }
+        }
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = mt * 16 + g + 8 * h;
+          if (m < 40) {
+            if (2 * t < 5) dps[5 * m + 2 * t] = c[mt][0][2 * h] + c[mt][1][2 * h];
+            if (2 * t + 1 < 5) dps[5 * m + 2 * t + 1] = c[mt][0][2 * h + 1] + c[mt][1][2 * h + 1];
+          }
+        }
+    }
+    __syncwarp();
+    // ---- dx[t] = sum_{s=max(t-50,0)}^{min(t,199)} dp[s] = D[min(t,199)+1] - D[max(t-50,0)], D = prefix sums of dp ----
+    {
+      const float4 d0 = *reinterpret_cast<const float4*>(dps + 8 * lane), d1 = *reinterpret_cast<const float4*>(dps + 8 * lane + 4);
+      float v[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float last;
+      warp_excl_scan8(v, lane, &last);
+      *reinterpret_cast<float4*>(cs + 8 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(cs + 8 * lane + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      if (lane == 31) cs[256] = last;
+      __syncwarp();
+      const int t0 = lane * 8;
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int tt = t0 + q;
+        const int hi = (tt < N_PSUM ? tt : N_PSUM - 1) + 1, lo = tt > K_POOL - 1 ? tt - (K_POOL - 1) : 0;
+        o[q] = tt < N_T ? cs[hi] - cs[lo] : 0.f;
+      }
+      float4* dst = reinterpret_cast<float4*>(dx3 + ((size_t)b * N_TOK + r) * D_PAD + t0);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    __syncwarp();
+  }
+  // token 63 (channel 62) never reaches the conv stack (enc_out[:, :63], ATMS_retrieval.py:91)
+  for (int i = threadIdx.x; i < D_PAD; i += CW_THREADS) dx3[((size_t)b * N_TOK + N_CH) * D_PAD + i] = 0.f;
+  // reduce the dW accumulators of the 4 warps, then one atomic per entry per CTA
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int k = mt * 16 + g + 8 * (h >> 1), i = nt * 8 + 2 * t + (h & 1);
+        if (k < N_FILT && i <= K_TEMP) atomicAdd(&wred[k * 26 + i], accw[mt][nt][h]);
+      }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N_FILT * 26; idx += CW_THREADS) {
+    const int k = idx / 26, i = idx % 26;
+    if (i < K_TEMP) atomicAdd(&dwt[k * K_TEMP + i], wred[idx] * (1.f / K_POOL));
+    else atomicAdd(&dbt[k], wred[idx]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 int conv_temporal_fwd_simt(const float* x3, const float* wt, const float* bt, float* y1, double* sums, int B, cudaStream_t s);
 int conv_temporal_bwd_simt(const float* dz1, const float* y1, const float* x3, const float* wt, const float* mean_rstd,
                            const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
@@ -380,6 +633,22 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
   if (!tf32_rounding())
     return conv_temporal_bwd_simt(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt, dgamma, dbeta, B, gscale, s);
   ProfScope _ps("conv_temporal_bwd", s, (double)B * 63 * 36 * 40 * 100.0, (double)B * (36 * 2520 * 8.0 + 63 * 2000.0));
+  static int version = -1;
+  if (version < 0) { const char* e = getenv("EEGB200_CONV_BWD"); version = (e && e[0] == '1') ? 1 : 2; }
+  if (version == 2) {
+    constexpr int PW2 = XRAW + CS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DP_LEN + 2 * RAW;
+    const size_t smem2 = (size_t)(3 * N_FILT + N_FILT * 26 + CW_WARPS * PW2) * sizeof(float);
+    static bool configured2 = false;
+    if (!configured2) {
+      EEG_CUDA_OK(cudaFuncSetAttribute(conv_temporal_bwd_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured2 = true;
+    }
+    conv_temporal_bwd_mma2_kernel<<<B, CW_THREADS, smem2, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt,
+                                                              dbt, dgamma, dbeta, gscale);
+    EEG_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DPZ + 2 * RAW;
   const size_t smem = (size_t)(5 * N_FILT + N_FILT * 26 + 8 + CW_WARPS * PW) * sizeof(float);
   static bool configured = false;
