@@ -367,6 +367,15 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma_kernel(
 //     cover exactly 3 rows x 10 float4, so a lane's channel quad never changes (was 20 shared loads per float4);
 //   * pooled sums are stored TF32-rounded once instead of converted at every fragment gather.
 // ------------------------------------------------------------------------------------------------
+// A fragment (16 rows x 8 tf32) of a row-major smem tile with one ldmatrix.x4: viewed as b16, an 8x8 matrix is 8 rows
+// of 4 floats; lane L supplies the address of row (L%8) + 8*((L/8)&1), column 4*(L/16), and receives element
+// (row L/4, col L%4) of each of the four 8x4 float blocks = a0..a3 of mma.m16n8k8.tf32.  Rows must be 16-byte aligned.
+__device__ __forceinline__ void ldsm_a_tf32(uint32_t a[4], const float* lane_row_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(smem_u32(lane_row_ptr)));
+}
+
 static constexpr int XRAW = 256;     // token row staging (cp.async)
 static constexpr int CS_LEN = 272;   // prefix sums C[0..256]
 static constexpr int DP_LEN = 256;   // dp[0..199] + zero tail
@@ -532,6 +541,8 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma2_kernel(
     }
     // ---- dp[5m+rho] = sum_{a,k} dy[m-a][k] * w[k][rho+5a]/51 : 6 independent accumulator chains ----
     {
+      // ldmatrix row address of this lane: tile row (lane%8) + 8*((lane/8)&1) (+4 zero rows in front), column 4*(lane/16)
+      const float* dys_lane = dys + ((lane & 7) + 8 * ((lane >> 3) & 1) + 4) * DY_LD + 4 * (lane >> 4);
       float c[3][2][4];
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt)
@@ -543,12 +554,8 @@ __global__ void __launch_bounds__(CW_THREADS) conv_temporal_bwd_mma2_kernel(
         for (int kk = 0; kk < 5; ++kk) {
 #pragma unroll
           for (int mt = 0; mt < 3; ++mt) {
-            uint32_t af[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              const int m = mt * 16 + g + 8 * (h & 1), k = kk * 8 + t + 4 * (h >> 1);
-              af[h] = __float_as_uint(dys[(m - a + 4) * DY_LD + k]);
-            }
+            uint32_t af[4];      // rows m - a (m = mt*16 .. +15), columns kk*8 .. +7 of dy: one ldmatrix.x4
+            ldsm_a_tf32(af, dys_lane + ((mt * 16 - a) * DY_LD + kk * 8));
             mma_tf32(c[mt][(a * 5 + kk) & 1], af, bw[a * 5 + kk][0], bw[a * 5 + kk][1]);
           }
         }
