@@ -428,6 +428,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
     {
       Epilogue e = epi_out(w.QKV, 768);
       e.bias = w.bqkv_p;
+      if (RT && attention_tc_enabled()) e.round_tf32 = 1;     // tcgen05 reads Q/K/V as they are (kind::tf32 truncates)
       EEG_TRY(run_gemm(M, 768, 256, w.H0, 256, 0, w.Wqkv_p, 256, 0, e, 1, s));
     }
     EEG_TRY(attention_fwd(w.QKV, w.O, B, cfg.d[EEGB200_SITE_ATTN], s));

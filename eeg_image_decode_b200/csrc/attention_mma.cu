@@ -304,6 +304,7 @@ int attention_bwd_simt(const float* qkv, const float* d_o, float* dqkv, int B, D
 
 int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s) {
   if (!tf32_rounding()) return attention_fwd_simt(qkv, o, B, drop, s);     // exact-fp32 verification path
+  if (attention_tc_enabled()) return attention_fwd_tc(qkv, o, B, drop, s); // tcgen05 path (default)
   ProfScope _ps("attention_fwd", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
   const size_t smem = 3 * 64 * AL * sizeof(float);
   static int xp = -1;

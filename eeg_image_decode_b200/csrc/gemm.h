@@ -63,6 +63,7 @@ int gemm_get_backend();
 int gemm_launch(const GemmArgs& g, cudaStream_t stream);           // dispatches on the backend switch
 int gemm_launch_tcgen05(const GemmArgs& g, cudaStream_t stream);
 int gemm_launch_simt(const GemmArgs& g, cudaStream_t stream);
+int gemm_make_tmap(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int box_rows, int* is_3d);
 long long gemm_launch_count();                                      // kernels launched so far (bench bookkeeping)
 void count_launch(int n = 1);
 long long total_launch_count();

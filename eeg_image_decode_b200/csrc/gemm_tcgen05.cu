@@ -476,6 +476,13 @@ static int make_operand_map(CUtensorMap* tm, const GemmOperand& op, int rows, in
   return 0;
 }
 
+// tensor map of a GEMM-style operand for kernels outside this file (attention_tc.cu): box = 32 k x box_rows rows
+// (K-major, SWIZZLE_128B) or (32 mn, 32 k, box_rows/32 slabs) (MN-major, SWIZZLE_128B_ATOM_32B)
+int gemm_make_tmap(CUtensorMap* tm, const GemmOperand& op, int rows, int K, int box_rows, int* is_3d) {
+  EEG_TRY(resolve_encode());
+  return make_operand_map(tm, op, rows, K, box_rows, is_3d);
+}
+
 template <int BN, int A_MN, int B_MN>
 static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMap& tb, int a3, int b3, cudaStream_t stream) {
   const int total_kb = cdiv(g.K, BK);
@@ -573,6 +580,7 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
       if constexpr (B_MN == 0) {
         EEG_SPEC(EF_BIAS_TABLE | EF_DROP | EF_ROUND)                       // value embedding (train)
         EEG_SPEC(EF_BIAS)                                                   // QKV projection
+        EEG_SPEC(EF_BIAS | EF_ROUND)                                        // QKV projection, TF32-rounded for the tcgen05 attention
         EEG_SPEC(EF_BIAS | EF_DROP | EF_RESID)                              // out-projection / FFN2 + residual (train)
         EEG_SPEC(EF_BIAS | EF_AUX | EF_GELU | EF_DROP | EF_ROUND)           // FFN1 (train)
       } else {

@@ -65,6 +65,9 @@ int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int l
 // ---- attention.cu ----  qkv [B*64, 768] (Q|K|V, head h at columns h*64..h*64+61), o [B*64, 256]
 int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s);
 int attention_bwd(const float* qkv, const float* d_o, float* dqkv, int B, DropoutCfg drop, cudaStream_t s);
+// attention_tc.cu: forward on tcgen05 (two samples of one head per 128-row UMMA tile); needs TF32-rounded qkv
+int attention_fwd_tc(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s);
+int attention_tc_enabled();     // default on, EEGB200_ATTN_TC=0 disables
 
 // ---- convstack.cu ----
 struct BnState {          // one BatchNorm2d(40); all device pointers
