@@ -198,7 +198,7 @@ def bench_reference(args):
         "e2e": {"value": val, "unit": "trials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -412,7 +412,7 @@ def bench_ours(args):
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "top_kernels": top, "final_loss": final_loss,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     _hard_exit()
 
 
@@ -424,7 +424,27 @@ def _hard_exit():
     os._exit(0)
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 behind Python's back
+    (the 'NCCL version ...' banner of multi-GPU runs) are pointed at stderr, the result goes to the original stdout"""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
