@@ -26,6 +26,8 @@ struct Ws {
   float *dWqkv_p, *dbqkv_p, *dWo_p, *dWs_p;
   // joint-subject variant: one packed value embedding / token-bias table per subject slot
   float *Wv_j, *tokbias_j;
+  // experimental tcgen05 conv stack: spatial weights packed per channel
+  float* Ws_tc;
 };
 constexpr int MAX_JOINT_SUBJECTS = 16;
 
@@ -111,6 +113,7 @@ static size_t carve(void* base, int B, Ws* w) {
   t.dWs_p = c.take<float>((size_t)N_FILT * K_SPAT);
   t.Wv_j = c.take<float>((size_t)MAX_JOINT_SUBJECTS * 256 * 256);
   t.tokbias_j = c.take<float>((size_t)MAX_JOINT_SUBJECTS * 64 * 256);
+  t.Ws_tc = c.take<float>(conv_tc_ws_floats());
   if (w) *w = t;
   return align_up(c.off, 256);
 }
@@ -463,13 +466,22 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
                           P[EEGB200_P_LNF_B], w.stf, w.X3, 256, 0, s));
     // ---- PatchEmbedding temporal conv + pool (ATMS_retrieval.py:102-103) on tokens 0..62 ----
     if (train) EEG_CUDA_OK(cudaMemsetAsync(w.bn1_sums, 0, 2 * N_FILT * sizeof(double), s));
-    EEG_TRY(conv_temporal_fwd(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.Y1, train ? w.bn1_sums : nullptr, B, s));
+    if (RT && conv_tc_enabled()) {
+      // experimental fused tcgen05 path (conv_tc.cu): statistics pass only; Y1 is produced by the apply pass in phase B
+      if (train) EEG_TRY(conv_tc_stats(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_sums, B, s));
+    } else {
+      EEG_TRY(conv_temporal_fwd(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.Y1, train ? w.bn1_sums : nullptr, B, s));
+    }
   }
   if (phases & EEGB200_PHASE_B) {
     BnState bn1{w.bn1_sums, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], BUF[EEGB200_BUF_BN1_RM], BUF[EEGB200_BUF_BN1_RV]};
     EEG_TRY(bn_finalize(bn1, wmul * B * N_CH * N_POOL, train, train && io->update_running_stats, s));
-    EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
-    {
+    if (RT && conv_tc_enabled()) {
+      // conv + pool + BN1 + ELU + spatial conv in one kernel; Y1 / A1 are still stored for the unfused backward
+      EEG_TRY(conv_tc_apply(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B],
+                            P[EEGB200_P_WS], P[EEGB200_P_BS], w.Ws_tc, w.Y1, w.A1, w.Y2, B, s));
+    } else {
+      EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
       Epilogue e = epi_out(w.Y2, N_FILT);        // spatial conv (63,1) == GEMM over (r,k1)  (ATMS_retrieval.py:106)
       e.bias = P[EEGB200_P_BS];
       EEG_TRY(run_gemm(R, N_FILT, K_SPAT, w.A1, K_SPAT, 0, w.Ws_p, K_SPAT, 0, e, 1, s));

@@ -97,6 +97,14 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
                       float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s);
 
+// ---- conv_tc.cu (EXPERIMENTAL, EEGB200_CONV_TC=1): temporal conv + pool + BatchNorm1 + ELU + spatial conv on tcgen05 ----
+int conv_tc_enabled();
+size_t conv_tc_ws_floats();     // packed spatial weights [63][48][64]
+int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s);
+int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                  const float* beta, const float* ws, const float* bs, float* ws_packed, float* y1, float* a1, float* y2,
+                  int B, cudaStream_t s);
+
 // ---- loss.cu ----
 struct InfoNceArgs {
   const float* logits;   // [B, ld] = s * E * Tcat^T, Tcat = [img ; txt] (2N columns)
