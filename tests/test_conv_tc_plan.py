@@ -15,3 +15,12 @@ def test_conv_tc_plan_matches_autograd():
 def test_conv_tc_plan_ragged_last_tile():
     import conv_tc_plan
     assert conv_tc_plan.main(B=5, seed=1) == 0        # 5 = 3 + 2: the second tile has 72 valid rows
+
+
+def test_conv_tc_kernel_protocol_has_no_deadlock_or_hazard():
+    """mbarrier / commit / TMA protocol of csrc/conv_tc.cu replayed with randomised timing (tools/conv_tc_protocol_sim.py)"""
+    import random
+    import conv_tc_protocol_sim as S
+    for mode in ("stats", "apply"):
+        for seed in range(40):
+            S.Sim(mode, random.Random(seed)).run()
