@@ -24,3 +24,9 @@ def test_conv_tc_kernel_protocol_has_no_deadlock_or_hazard():
     for mode in ("stats", "apply"):
         for seed in range(40):
             S.Sim(mode, random.Random(seed)).run()
+
+
+def test_attention_block_diagonal_plan_matches_autograd():
+    """two samples of a head as one 128-row UMMA problem (attention_tc.cu forward; backward = round-2 plan)"""
+    import attn_tc_plan
+    assert attn_tc_plan.main(seed=0) == 0 and attn_tc_plan.main(seed=3, p_drop=0.0) == 0
