@@ -208,6 +208,11 @@ int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n
 int eegb200_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                            float eps, float weight_decay, const long long* step_dev, void* stream);
 
+/* Debug probe (tools/gpu_tma_layout_probe.py): shared-memory image (4096 floats, verbatim) that TMA writes for the first
+ * [128 rows x 32 k] k-block of a GEMM operand, K-major (src[row*ld + k], SWIZZLE_128B) or MN-major (src[k*ld + row],
+ * SWIZZLE_128B_ATOM_32B).  Used to validate the layouts thread-written UMMA operands must follow. */
+int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
