@@ -62,8 +62,20 @@ def ptr(t) -> ctypes.c_void_p:
 
 
 def stream_ptr():
+    """the CURRENT device's current stream: call inside ``on_device(...)`` so that it is the tensors' device"""
     import torch
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device(t):
+    """Context manager making the device of tensor ``t`` (or a torch.device / index) current for a library call.  The
+    library launches on the current device and keeps per-device state (side streams, kernel attributes, SM count) keyed
+    by it, so a model on cuda:1 works while the caller's current device is 0 (the reference's ``--gpu cuda:N`` usage)."""
+    import torch
+    dev = t.device if torch.is_tensor(t) else torch.device(t) if not isinstance(t, int) else torch.device("cuda", t)
+    if dev.type != "cuda":
+        raise RuntimeError("eegdecode_b200: expected a CUDA tensor (this path has no CPU implementation)")
+    return torch.cuda.device(dev)
 
 
 def launch_count() -> int:
@@ -90,7 +102,8 @@ def gemm(A, B, C, M, N, K, *, lda=None, ldb=None, ldc=None, a_mn=False, b_mn=Fal
     d.mul_in, d.ld_mul = ptr(mul_in), ld_mul
     d.resid, d.ld_res = ptr(resid), ld_res
     d.round_tf32, d.store_mode, d.split_k, d.tile_n = int(round_tf32), store_mode, split_k, tile_n
-    check(lib().eegb200_gemm(ctypes.byref(d), stream_ptr()), "gemm")
+    with on_device(C):
+        check(lib().eegb200_gemm(ctypes.byref(d), stream_ptr()), "gemm")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,12 +246,14 @@ def infonce_workspace_bytes(B: int, N: int, D: int, nt: int) -> int:
     return int(_sig().eegb200_infonce_workspace_bytes(int(B), int(N), int(D), int(nt)))
 
 
-def atms_forward(io: AtmsIO, phases: int = PHASE_ALL) -> None:
-    check(_sig().eegb200_atms_forward(ctypes.byref(io), phases, stream_ptr()), "atms_forward")
+def atms_forward(io: AtmsIO, phases: int, device) -> None:
+    with on_device(device):
+        check(_sig().eegb200_atms_forward(ctypes.byref(io), phases, stream_ptr()), "atms_forward")
 
 
-def atms_backward(io: AtmsIO, d_out, grads_array, phases: int = PHASE_ALL) -> None:
-    check(_sig().eegb200_atms_backward(ctypes.byref(io), ptr(d_out), grads_array, phases, stream_ptr()), "atms_backward")
+def atms_backward(io: AtmsIO, d_out, grads_array, phases: int, device) -> None:
+    with on_device(device):
+        check(_sig().eegb200_atms_backward(ctypes.byref(io), ptr(d_out), grads_array, phases, stream_ptr()), "atms_backward")
 
 
 def ws_tensor(workspace, B: int, name: str):
@@ -254,32 +269,37 @@ def ws_tensor(workspace, B: int, name: str):
     return workspace[off:off + n * 4].view(torch.float32).view(r.value, ld.value)[:, :c.value]
 
 
-def infonce(io: InfoNceIO, phases: int) -> None:
-    check(_sig().eegb200_infonce(ctypes.byref(io), phases, stream_ptr()), "infonce")
+def infonce(io: InfoNceIO, phases: int, device) -> None:
+    with on_device(device):
+        check(_sig().eegb200_infonce(ctypes.byref(io), phases, stream_ptr()), "infonce")
 
 
 def adamw_step(p, g, m, v, n, lr, b1, b2, eps, wd, step) -> None:
-    check(_sig().eegb200_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, int(step), stream_ptr()),
-          "adamw_step")
+    with on_device(p):
+        check(_sig().eegb200_adamw_step(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, int(step),
+                                        stream_ptr()), "adamw_step")
 
 
 def adamw_step_dev(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev) -> None:
-    check(_sig().eegb200_adamw_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, ptr(step_dev),
-                                        stream_ptr()), "adamw_step_dev")
+    with on_device(p):
+        check(_sig().eegb200_adamw_step_dev(ptr(p), ptr(g), ptr(m), ptr(v), int(n), lr, b1, b2, eps, wd, ptr(step_dev),
+                                            stream_ptr()), "adamw_step_dev")
 
 
 def mse(eeg, tgt, n_total_rows: int, weight: float, grad_out: float, loss=None, loss_term=None, d_eeg=None) -> None:
     """weight * MSE(eeg, tgt) share of these rows (mean over n_total_rows*D elements): loss / loss_term (1-element device
     tensors) += ; d_eeg += weight*grad_out * dMSE/deeg"""
     B, D = eeg.shape
-    check(_sig().eegb200_mse(ptr(eeg), ptr(tgt), B, D, int(n_total_rows), float(weight), float(grad_out), ptr(loss),
-                             ptr(loss_term), ptr(d_eeg), stream_ptr()), "mse")
+    with on_device(eeg):
+        check(_sig().eegb200_mse(ptr(eeg), ptr(tgt), B, D, int(n_total_rows), float(weight), float(grad_out), ptr(loss),
+                                 ptr(loss_term), ptr(d_eeg), stream_ptr()), "mse")
 
 
-def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int):
+def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int, device="cuda"):
     import torch
-    out = torch.empty(rows, cols, device="cuda", dtype=torch.float32)
-    check(_sig().eegb200_dropout_mask(seed, site, p, rows, cols, ld, ptr(out), stream_ptr()), "dropout_mask")
+    out = torch.empty(rows, cols, device=device, dtype=torch.float32)
+    with on_device(out):
+        check(_sig().eegb200_dropout_mask(seed, site, p, rows, cols, ld, ptr(out), stream_ptr()), "dropout_mask")
     return out
 
 
@@ -303,9 +323,10 @@ def retrieval(eeg, gallery, logit_scale, sel=None, labels=None, want_top5=True):
         sel_ws = torch.empty(Q, k, device=dev, dtype=torch.float32)
     if labels is not None:
         labels = labels.to(device=dev, dtype=torch.int64).contiguous()
-    check(_sig().eegb200_retrieval(ptr(eeg.contiguous()), ptr(gallery.contiguous()), Q, G, D, ptr(logit_scale), ptr(logits),
-                                   ld, ptr(round_ws), ptr(sel), k, ptr(sel_ws), ptr(labels), ptr(correct), ptr(top1),
-                                   ptr(top5), stream_ptr()), "retrieval")
+    with on_device(eeg):
+        check(_sig().eegb200_retrieval(ptr(eeg.contiguous()), ptr(gallery.contiguous()), Q, G, D, ptr(logit_scale),
+                                       ptr(logits), ld, ptr(round_ws), ptr(sel), k, ptr(sel_ws), ptr(labels), ptr(correct),
+                                       ptr(top1), ptr(top5), stream_ptr()), "retrieval")
     return {"top1": top1, "top5": top5, "correct": correct, "logits": logits[:, :G]}
 
 

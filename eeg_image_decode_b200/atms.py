@@ -360,7 +360,7 @@ class ATMS(nn.Module):
         if out is None or perm is not None:
             out = torch.empty(x.shape[0], 1024, device=x.device, dtype=torch.float32)
         io = self._make_io(x, subject_ids, train, seed, out, groups)
-        _lib.atms_forward(io, phases)
+        _lib.atms_forward(io, phases, x.device)
         if train and (phases & _lib.PHASE_C):
             for bn in (self.enc_eeg[0].tsconv[2], self.enc_eeg[0].tsconv[5]):
                 bn.num_batches_tracked.add_(1)
@@ -380,7 +380,7 @@ class ATMS(nn.Module):
         G = self._pointers()[1]
         if d_out is not None:
             d_out = d_out.contiguous() if perm is None else d_out.index_select(0, perm)
-        _lib.atms_backward(io, d_out, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)), phases)
+        _lib.atms_backward(io, d_out, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)), phases, self.flat_params.device)
 
     def zero_flat_grads(self) -> None:
         self.flat_grads.zero_()

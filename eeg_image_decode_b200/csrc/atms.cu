@@ -551,7 +551,7 @@ struct SideStream {
     return 0;
   }
 };
-static SideStream g_side;
+static SideStream g_side_by_dev[64];      // side stream + events belong to a device
 static int side_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -586,6 +586,7 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
   const int RT = tf32_rounding();
   const long long wmul = ((phases >> 8) & 0xFF) > 1 ? ((phases >> 8) & 0xFF) : 1;
   const bool use_side = side_enabled() && !prof_enabled();
+  SideStream& g_side = g_side_by_dev[current_device()];
   if (use_side) EEG_TRY(g_side.init());
   cudaStream_t ws = use_side ? g_side.side : s;      // stream of the weight-gradient work
 #define FORK() do { if (use_side) EEG_TRY(g_side.sync_from(s)); } while (0)

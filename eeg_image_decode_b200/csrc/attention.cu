@@ -183,10 +183,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const float*
 int attention_fwd_simt(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream_t s) {
   ProfScope _ps("attention_fwd_simt", s, (double)B * 4 * 4.0 * 64 * 64 * 62, (double)B * 64 * 1024 * 4.0);
   const size_t smem = 4 * 64 * LDS * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   attention_fwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, o, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());
@@ -197,10 +196,9 @@ int attention_fwd_simt(const float* qkv, float* o, int B, DropoutCfg drop, cudaS
 int attention_bwd_simt(const float* qkv, const float* d_o, float* dqkv, int B, DropoutCfg drop, cudaStream_t s) {
   ProfScope _ps("attention_bwd_simt", s, (double)B * 4 * 12.0 * 64 * 64 * 62, (double)B * 64 * 1792 * 4.0);
   const size_t smem = 5 * 64 * LDS * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   attention_bwd_kernel<<<B * N_HEAD, ATT_THREADS, smem, s>>>(qkv, d_o, dqkv, drop, tf32_rounding());
   EEG_CUDA_OK(cudaGetLastError());

@@ -311,6 +311,9 @@ int attention_fwd(const float* qkv, float* o, int B, DropoutCfg drop, cudaStream
   if (xp < 0) {
     const char* e = getenv("EEGB200_ATTN_XP");
     xp = (e && e[0] == '3') ? 3 : 1;
+  }
+  static PerDeviceOnce once_fwd;
+  if (once_fwd.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -325,10 +328,9 @@ int attention_bwd(const float* qkv, const float* d_o, float* dqkv, int B, Dropou
   if (!tf32_rounding()) return attention_bwd_simt(qkv, d_o, dqkv, B, drop, s);
   ProfScope _ps("attention_bwd", s, (double)B * 4 * 12.0 * 64 * 64 * 62, (double)B * 64 * 1792 * 4.0);
   const size_t smem = (4 * 64 * AL + 2 * 64 * PL) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   attention_bwd_mma_kernel<<<B * N_HEAD, AT_THREADS, smem, s>>>(qkv, d_o, dqkv, drop);
   EEG_CUDA_OK(cudaGetLastError());

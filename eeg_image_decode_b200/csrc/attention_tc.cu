@@ -188,10 +188,9 @@ int attention_fwd_tc(const float* qkv, float* o, int B, DropoutCfg drop, cudaStr
   EEG_TRY(gemm_make_tmap(&tv, GemmOperand{qkv, 768, 1}, 768, m_tok, 64, &d3));
   EEG_REQUIRE(d3 == 1, "attention_fwd_tc: the V operand map must be 3-D");
   const size_t smem = 4 * TILE_KB + 4 * V_KB + 64 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(attention_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   attention_fwd_tc_kernel<<<cdiv(B, 2) * N_HEAD, TC_THREADS, smem, s>>>(tq, tv, o, m_tok, drop);
   EEG_CUDA_OK(cudaGetLastError());

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <atomic>
 
 namespace eegb200 {
 
@@ -38,6 +39,19 @@ const char* get_error();
     int _rc = (expr);            \
     if (_rc != 0) return _rc;    \
   } while (0)
+
+// One-time setup that is per DEVICE (cudaFuncSetAttribute, side streams, SM count): first() is true exactly once per
+// (call site, current device).  The Python binding makes the tensors' device current around every library call.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    return (done.fetch_or(bit) & bit) == 0;
+  }
+};
+static inline int current_device() { int d = 0; cudaGetDevice(&d); return d & 63; }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

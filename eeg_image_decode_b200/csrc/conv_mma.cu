@@ -645,11 +645,9 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
   if (version == 2) {
     constexpr int PW2 = XRAW + CS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DP_LEN + 2 * RAW;
     const size_t smem2 = (size_t)(3 * N_FILT + N_FILT * 26 + CW_WARPS * PW2) * sizeof(float);
-    static bool configured2 = false;
-    if (!configured2) {
+    static PerDeviceOnce once2;
+    if (once2.first())
       EEG_CUDA_OK(cudaFuncSetAttribute(conv_temporal_bwd_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      configured2 = true;
-    }
     conv_temporal_bwd_mma2_kernel<<<B, CW_THREADS, smem2, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt,
                                                               dbt, dgamma, dbeta, gscale);
     EEG_CUDA_OK(cudaGetLastError());
@@ -658,10 +656,9 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
   }
   constexpr int PW = XS_LEN + PS_LEN + DY_ROWS * DY_LD + 16 + DPZ + 2 * RAW;
   const size_t smem = (size_t)(5 * N_FILT + N_FILT * 26 + 8 + CW_WARPS * PW) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(conv_temporal_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   conv_temporal_bwd_mma_kernel<<<B, CW_THREADS, smem, s>>>(dz1, y1, x3, wt, mean_rstd, gamma, bwd_sums, count, dx3, dwt, dbt,
                                                            dgamma, dbeta, gscale);

@@ -415,10 +415,9 @@ size_t conv_tc_ws_floats() { return (size_t)N_CH * N48 * 64; }
 // BatchNorm1 batch statistics of the temporal conv output without materialising it (kernel F1)
 int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s) {
   ProfScope _ps("conv_tc_stats", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * 63 * 1000.0);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-    configured = true;
   }
   ConvTcParams p{x3, wt, bt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B};
   CUtensorMap dummy;
@@ -441,10 +440,9 @@ int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float
   CUtensorMap tw;
   int d3 = 0;
   EEG_TRY(gemm_make_tmap(&tw, GemmOperand{ws_packed, 64, 0}, N_CH * N48, 64, N48, &d3));
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-    configured = true;
   }
   ConvTcParams p{x3, wt, bt, mean_rstd, gamma, beta, bs, y1, a1, y2, nullptr, B};
   conv_tc_fwd_kernel<MODE_APPLY><<<cdiv(B, TILE_S), CTC_THREADS, CTC_SMEM, s>>>(tw, p);

@@ -39,10 +39,9 @@ extern "C" int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, fl
   // logical operand [128 rows, K = 32]: K-major reads src[row*ld + k], MN-major reads src[k*ld + row]
   EEG_TRY(gemm_make_tmap(&tm, GemmOperand{src, ld, mn_major}, 128, 32, 128, &d3));
   EEG_REQUIRE(!mn_major || d3 == 1, "debug_tma_tile: expected a 3-D map for the MN-major operand");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.first()) {
     EEG_CUDA_OK(cudaFuncSetAttribute(tma_tile_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 64 + 1024));
-    configured = true;
   }
   tma_tile_dump_kernel<<<1, 128, 16384 + 64 + 1024, (cudaStream_t)stream>>>(tm, d3, out);
   EEG_CUDA_OK(cudaGetLastError());

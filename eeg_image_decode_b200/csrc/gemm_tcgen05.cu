@@ -519,14 +519,19 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
     p.pair_atomic = (e.store_mode == EPI_ATOMIC && !e.bias && !e.aux_out && !e.mul_in && !e.resid && e.act == EPI_ACT_NONE &&
                      e.drop.p <= 0.f && !e.round_tf32 && (e.ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(e.C) & 7) == 0) ? 1 : 0;
   }
-  static int persistent = -1, num_sms = 148;
+  static int persistent = -1;
+  static int sms_by_dev[64] = {0};
   if (persistent < 0) {
     const char* env = getenv("EEGB200_GEMM_PERSISTENT");
     persistent = (env && env[0] == '0') ? 0 : 1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int dev = current_device();
+  if (sms_by_dev[dev] == 0) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_by_dev[dev] = n > 0 ? n : 148;
+  }
+  const int num_sms = sms_by_dev[dev];
   // persistent (1 CTA/SM, overlapped epilogue) pays off when the main loop is long; the short-K token GEMMs are bound by
   // epilogue memory latency and run faster as two co-resident CTAs per SM (16 epilogue warps) -- measured on B200
   if (persistent && total_kb > 0 && p.k_blocks_per_split >= 16 && g.epi.bn_y == nullptr) {
@@ -539,11 +544,8 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
     p.tile_bytes = pst * stage_bytes;
     const size_t psmem = (size_t)p.tile_bytes + 8 * 32 * EPI_SLD * 4 + 1024 + 512;
     auto pk = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
-    static bool pconf = false;
-    if (!pconf) {
-      EEG_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      pconf = true;
-    }
+    static PerDeviceOnce pconf;
+    if (pconf.first()) EEG_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     const int items = cdiv(g.N, BN) * cdiv(g.M, BM) * split;
     const int grid_p = items < num_sms ? items : num_sms;
     pk<<<grid_p, GEMM_THREADS, psmem, stream>>>(ta, tb, p);
@@ -566,11 +568,9 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
 #define EEG_SPEC(MASK)                                                                                        \
     if (fm == (MASK)) {                                                                                       \
       auto ks = gemm_tf32_kernel<256, 0, B_MN, (MASK)>;                                                       \
-      static bool cs = false;                                                                                 \
-      if (!cs) {                                                                                              \
+      static PerDeviceOnce cs;                                                                                \
+      if (cs.first())                                                                                         \
         EEG_CUDA_OK(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       \
-        cs = true;                                                                                            \
-      }                                                                                                       \
       ks<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);                                                    \
       EEG_CUDA_OK(cudaGetLastError());                                                                        \
       count_launch();                                                                                         \
@@ -596,11 +596,8 @@ static int launch_cfg(const GemmArgs& g, const CUtensorMap& ta, const CUtensorMa
     EEG_REQUIRE(g.epi.bn_y == nullptr, "gemm: the fused BatchNorm-backward epilogue is only built for the 256-wide K-major x MN-major kernel");
   }
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
-  static size_t configured = 0;   // per template instantiation
-  if (smem > configured) {
-    EEG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
-  }
+  static PerDeviceOnce kconf;     // per template instantiation and device
+  if (kconf.first()) EEG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -65,14 +65,14 @@ class _InfoNCE:
         io.d_eeg = d_eeg.data_ptr() if need_grad else None
         io.d_logit_scale = d_scale.data_ptr() if need_grad else None
         if _dist_ready(world_size):
-            _lib.infonce(io, _lib.PHASE_A)
+            _lib.infonce(io, _lib.PHASE_A, dev)
             parts = torch.empty(world_size, 2, nt * N, device=dev, dtype=torch.float32)
             torch.distributed.all_gather_into_tensor(parts, col_stats, group=group)
             io.col_parts, io.n_parts = parts.data_ptr(), world_size
-            _lib.infonce(io, _lib.PHASE_B)
+            _lib.infonce(io, _lib.PHASE_B, dev)
             self._keep = parts
         else:
-            _lib.infonce(io, _lib.PHASE_A | _lib.PHASE_B)
+            _lib.infonce(io, _lib.PHASE_A | _lib.PHASE_B, dev)
         return loss, d_eeg, d_scale
 
 

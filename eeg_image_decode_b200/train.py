@@ -177,14 +177,14 @@ class StepEngine:
         # W*B samples, so the count must be scaled.  B is patched in the io for the BN-count only.
         m = self.model
         io = m._last[0]
+        dev = m.flat_params.device
         if fwd:
-            _lib.atms_forward(io, phase | (_BN_SCALE_SHIFT(batch_scale)))
+            _lib.atms_forward(io, phase | (_BN_SCALE_SHIFT(batch_scale)), dev)
         else:
             G = m._pointers()[1]
             import ctypes
-            _lib.check(_lib._sig().eegb200_atms_backward(ctypes.byref(io), None, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)),
-                                                         phase | (_BN_SCALE_SHIFT(batch_scale)), _lib.stream_ptr()),
-                       "atms_backward")
+            _lib.atms_backward(io, None, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)),
+                               phase | (_BN_SCALE_SHIFT(batch_scale)), dev)
 
     def _generic_optimizer_step(self, use_shared, subjects=None):
         named = dict(self.model.named_parameters())

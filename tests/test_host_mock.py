@@ -29,14 +29,14 @@ def fake(monkeypatch):
             return None
         return ([io.group_offsets[i] for i in range(io.n_groups + 1)], [io.group_subject[i] for i in range(io.n_groups)])
 
-    def atms_forward(io, phases=7):
+    def atms_forward(io, phases=7, device=None):
         x = _view(io.x, io.B * 63 * 250).reshape(io.B, 63, 250)
         sid = _view(io.subject_ids, io.B, ctypes.c_int64, np.int64)
         out = _view(io.out, io.B * 1024).reshape(io.B, 1024)
         out[:] = x[:, 0, :1] + 100.0 * sid[:, None]          # row b identifies (trial, subject id) it was computed from
         calls.append(("fwd", io.B, phases, io.train, groups_of(io), sid.copy()))
 
-    def atms_backward(io, d_out, grads, phases=7):
+    def atms_backward(io, d_out, grads, phases=7, device=None):
         d = None if d_out is None else _view(d_out.data_ptr(), io.B * 1024).reshape(io.B, 1024).copy()
         if io.joint_value_w:
             for sj in groups_of(io)[1]:                       # mark the gradient buffers the library would write
@@ -46,7 +46,7 @@ def fake(monkeypatch):
             _view(grads[0], 1)[0] += 1.0
         calls.append(("bwd", io.B, phases, groups_of(io), d))
 
-    def infonce(io, phases):
+    def infonce(io, phases, device=None):
         if phases & 2:
             _view(io.loss, 3)[:] = (1.0 * io.w_img + 2.0 * io.w_txt, 1.0, 2.0 if io.tgt_txt else 0.0)
             if io.d_eeg:
