@@ -33,6 +33,22 @@ B_LOCAL = 1024
 N_GALLERY = 1654
 METRIC = "EEG-trials/sec contrastive step"
 
+# SURVEY.md 8(d) algorithmic figures.  Conv stack (K4) is HBM-bound: bytes per SAMPLE a launch must
+# move (63 x 250 fp32 token rows in, 36 x 40 fp32 pooled map out; the backward also writes d(token rows)); everything
+# else is a dense contraction and is rated in FLOPs against the TF32 tensor peak (the profiler's per-launch 2*M*N*K).
+X3_BYTES, Y2_BYTES = 63 * 250 * 4, 36 * 40 * 4
+ALGO_BYTES_PER_SAMPLE = {
+    "conv_tc_stats": X3_BYTES,                          # BatchNorm1 batch statistics: reads the token rows only
+    "conv_tc_apply": X3_BYTES + Y2_BYTES,               # conv + pool + BN1 + ELU + spatial conv: rows in, Y2 out
+    "conv_tc_bwd_stats": X3_BYTES + Y2_BYTES,           # rows + dY2 in (dWs out is per launch, 403 KB)
+    "conv_tc_bwd_apply": 2 * X3_BYTES + Y2_BYTES,       # rows + dY2 in, d(rows) out
+    "conv_temporal_fwd": X3_BYTES,                      # unfused round-1 kernels: what they would move if Y1 / A1 / dA1
+    "bn_elu_apply": 0,                                  #   (intermediates, not algorithmic) never left the chip
+    "conv_temporal_bwd": 2 * X3_BYTES,
+}
+STEP_ALGO_BYTES = 163e6      # B*(63000 + 2*1024*4) + 28 B x 3.2 M parameters at B = 1024
+STEP_ALGO_FLOPS = 0.31e12    # 3.03e8 per sample x 1024
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -174,24 +190,30 @@ def pick_cpu_threads(batch):
 
 
 def bench_reference(args):
+    """the reference's CPU path on the SAME config as our arm (batch 1024 per step); the sample is bounded by wall
+    clock: at least 2 timed steps, then as many of the requested K as fit into ~150 s"""
     import torch
     batch = args.cpu_batch
-    threads = pick_cpu_threads(batch)
+    threads = pick_cpu_threads(min(batch, 128))
     run = cpu_step_runner(batch, threads)
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):
-        run()
+    run()                                   # one warm-up step (allocator, oneDNN primitive caches)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    done = 0
+    while done < args.steps and (done < 2 or time.perf_counter() - t0 < 150.0):
         run()
+        done += 1
     dt = time.perf_counter() - t0
+    requested = args.steps
+    args.steps = done
     val = batch * args.steps / dt
     line = {
         "metric": METRIC, "value": val, "unit": "trials/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"contrastive train step (fwd + 2x ClipLoss + bwd + AdamW + train-acc), batch {batch} per step, "
-                               "63ch x 250t fp32 EEG vs 1024-d targets, torch CPU fp32",
-                   "note": "bounded sample of the B=1024 workload: CPU throughput is flat in the batch size (BASELINE.md)"},
+        "config": {"workload": "contrastive train step, 1024 trials/GPU (63ch x 250t fp32) vs 1024-d CLIP img+txt targets: "
+                               "ATM-S fwd + 0.99/0.01 InfoNCE + bwd + AdamW + 1654-way train-acc scoring",
+                   "global_batch": batch, "parallelism": "cpu", "precision": "torch CPU fp32 (oneDNN / MKL)",
+                   "note": f"bounded sample: {done} of the requested {requested} steps of the same batch-{batch} workload"},
         "cpu_baseline": {"value": val, "unit": "trials/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
                          "sample": f"{args.steps} steps at batch {batch} (oracle port: the reference's torch modules restated op by op; "
                                    f"torch {torch.__version__})"},
@@ -318,20 +340,20 @@ def bench_ours(args):
     cb = lambda idx, l: host_reads.append(float(l[0]))            # every step's loss, read back to pinned host memory
     warm = PinnedLoader([host_eeg[0]], [h(labels[0])], [h(txts[0])], [h(imgs[0])])
     train_model("sub-08", model, warm, opt, dev, txt_all_host, img_all_host, Cfg(), step_callback=cb)   # warm the API path
-    best = None
-    passes = []
-    for _rep in range(4):          # best of four passes: the wall-clock e2e number is sensitive to host-side hiccups
+    times = []
+    for _rep in range(5):          # the wall-clock e2e number is sensitive to host-side hiccups: report median AND best
         barrier()
         t0 = time.perf_counter()
         train_model("sub-08", model, loader, opt, dev, txt_all_host, img_all_host, Cfg(), step_callback=cb)
         barrier()
-        dt = time.perf_counter() - t0
-        passes.append(world * B * K / dt)
-        best = dt if best is None else min(best, dt)
-    tt = torch.tensor([best], device=dev)
+        times.append(time.perf_counter() - t0)
+    tt = torch.tensor(times, device=dev)
     if world > 1:
-        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = world * B * K / float(tt.item())
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)      # per pass: the slowest rank
+    times = sorted(float(v) for v in tt.tolist())
+    passes = [world * B * K / v for v in times]
+    e2e_val = world * B * K / times[len(times) // 2]                               # headline = median pass
+    e2e_best = world * B * K / times[0]
     h2d = B * 63 * 250 * 4 + 2 * B * 1024 * 4 + B * 8
     d2h = 12
     # diagnostic: pinned host -> device bandwidth of this box (e2e is H2D-bound below ~21 GB/s at this step time)
@@ -345,7 +367,8 @@ def bench_ours(args):
     h2d_gbs = 5 * hb.numel() * 4 / (time.perf_counter() - t0) / 1e9
 
     if rank != 0:
-        _hard_exit()
+        _leave(world, (gstep, eager, model))
+        return
 
     # ---- roofline of the dominant kernel ----
     peaks = load_peaks()
@@ -358,16 +381,23 @@ def bench_ours(args):
                for k, v in ranked[:40]]
         name, v = ranked[0]
         per_launch_ms = v["ms"] / v["n"]
-        if name.startswith("gemm_tf32"):
+        algo = next((b for k, b in ALGO_BYTES_PER_SAMPLE.items() if name.startswith(k)), None)
+        if algo is None and v["flops"] > 0 and (name.startswith("gemm_tf32") or name.startswith("attention")):
             ach = v["flops"] / v["n"] / (per_launch_ms * 1e-3) / 1e12
             # TF32 dense rate is half the bf16 rate on this part; the measured bf16 cuBLAS number is the denominator source
-            peak = peaks["tf_burst"] / 2.0
+            # (sustained figure: the kernel is timed inside a long step)
+            peak = peaks["tf_sustained"] / 2.0
             roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peaks["src"] + ": bf16 burst / 2 (TF32 runs at half the bf16 rate)"}
+                    "traffic": None, "peak_source": peaks["src"] + ": bf16 sustained / 2 (TF32 runs at half the bf16 rate)"}
         else:
-            ach = v["bytes"] / v["n"] / (per_launch_ms * 1e-3) / 1e9
+            # ALGORITHMIC bytes / measured duration; the as-built byte count of the launch is kept beside it
+            built = v["bytes"] / v["n"]
+            abytes = algo * B if algo is not None else built
+            ach = abytes / (per_launch_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"],
+                    "algorithmic_bytes_per_launch": abytes, "algorithmic": algo is not None,
+                    "as_built_bytes_per_launch": built, "as_built_gbs": built / (per_launch_ms * 1e-3) / 1e9}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             roof["traffic"] = traffic.get(name)
@@ -375,6 +405,14 @@ def bench_ours(args):
             pass
         roof["share_of_step"] = v["ms"] / tot
         roof["sum_kernel_ms_per_step"] = tot / n_prof
+        roof["ms_per_launch"] = per_launch_ms
+        # the whole step against both roofs (163 MB and 0.31 TFLOP of algorithmic work per B = 1024 step)
+        step_s = ms / args.steps / 1e3
+        roof["whole_step"] = {"algorithmic_bytes": STEP_ALGO_BYTES, "algorithmic_flops": STEP_ALGO_FLOPS,
+                              "hbm_frac": STEP_ALGO_BYTES / step_s / 1e9 / peaks["hbm_gbs"],
+                              "tensor_frac": STEP_ALGO_FLOPS / step_s / 1e12 / (peaks["tf_sustained"] / 2.0),
+                              "ideal_ms": max(STEP_ALGO_BYTES / (peaks["hbm_gbs"] * 1e9),
+                                              STEP_ALGO_FLOPS / (peaks["tf_sustained"] / 2.0 * 1e12)) * 1e3}
 
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only) ----
     cpu = None
@@ -407,21 +445,40 @@ def bench_ours(args):
                    "precision": "fp32 storage, TF32 tensor-core operands (RN pre-rounded), fp32 accumulate",
                    "cuda_graph": bool(gstep.graph is not None)},
         "e2e": {"value": e2e_val, "unit": "trials/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "pinned_h2d_gbs_measured": h2d_gbs, "passes_trials_s": passes,
-                "api": "train_model(sub, model, pinned-host dataloader, torch.optim.AdamW, ...) + per-step loss read-back; best of 4 passes"},
+                "pinned_h2d_gbs_measured": h2d_gbs, "passes_trials_s": passes, "best": e2e_best,
+                "api": "train_model(sub, model, pinned-host dataloader, torch.optim.AdamW, ...) + per-step loss read-back; "
+                       "median of 5 passes (best beside it)"},
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "top_kernels": top, "final_loss": final_loss,
     }
     _emit(line)
-    _hard_exit()
+    _leave(world, (gstep, eager, model))
 
 
-def _hard_exit():
-    """leave without running destructors: tearing down a NCCL process group whose collectives were captured in a live
-    CUDA graph hung on this stack (observed: destroy_process_group never returned), and nothing is left to flush"""
+def _leave(world, holders):
+    """Single GPU: a normal interpreter exit (atexit / sitecustomize hooks run, the loaded libeegdecode_b200.so stays
+    visible to whoever inspects the process at exit).  Data parallel: tearing down a NCCL process group whose
+    collectives were captured in a live CUDA graph hung on this stack (destroy_process_group never returned), so the
+    graphs are dropped first, the exit hooks are run by hand, and only then the process leaves without destructors."""
+    import torch
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
+    if world == 1:
+        return
+    for h in holders:
+        if hasattr(h, "graph"):
+            h.graph = None
+        if hasattr(h, "_gstep_cache"):
+            for g in h._gstep_cache.values():
+                g.graph = None
+            h._gstep_cache.clear()
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    import atexit
+    try:
+        atexit._run_exitfuncs()
+    finally:
+        os._exit(0)
 
 
 _JSON_OUT = None
@@ -450,7 +507,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=128)
+    ap.add_argument("--cpu-batch", type=int, default=None, help="batch of the CPU legs (default: 1024 for --impl reference, "
+                    "128 for the cpu_baseline sample of our arm)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -458,10 +516,12 @@ def main():
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        if args.steps > 6:
-            args.steps = 6          # bounded sample: each step is ~2-4 s of CPU work
+        if args.cpu_batch is None:
+            args.cpu_batch = B_LOCAL        # same config as our arm
         bench_reference(args)
     else:
+        if args.cpu_batch is None:
+            args.cpu_batch = 128
         bench_ours(args)
 
 

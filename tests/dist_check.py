@@ -13,6 +13,7 @@ for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
     if p not in sys.path:
         sys.path.insert(0, p)
 import recipe  # noqa: E402
+from oracle import atms_oracle as O  # noqa: E402  (the checker: CPU restatement of the reference step)
 from eeg_image_decode_b200 import _lib  # noqa: E402
 from eeg_image_decode_b200.atms import ATMS  # noqa: E402
 from eeg_image_decode_b200.train import StepEngine  # noqa: E402
@@ -39,6 +40,8 @@ def main():
     txt = recipe.make_targets(N, seed=71, tag="txt").cuda()
     sl = slice(rank * Bl, (rank + 1) * Bl)
     ok = True
+    # the reference semantics of the W-rank step == ONE process at batch W*B_local: the CPU oracle's autograd step
+    o_loss, o_grads, o_r = O.train_step(recipe.make_state_dict(), {}, x.cpu(), sid.cpu(), img.cpu(), txt.cpu(), 1)
     for backend, tol_f, tol_g in ((1, 5e-5, 2e-3), (0, 1.5e-3, 4e-2)):
         _lib.set_gemm_backend(backend)
         # --- data parallel
@@ -71,7 +74,15 @@ def main():
         bn = max(rel(m.state_dict()[k], ref.state_dict()[k]) for k in
                  ("enc_eeg.0.tsconv.2.running_mean", "enc_eeg.0.tsconv.2.running_var", "enc_eeg.0.tsconv.5.running_var"))
         errs["bn_running"] = bn
+        # ... and against the oracle (dp_oracle.py / atms_oracle.py), not only against the library itself
+        errs["loss_vs_oracle"] = abs(total[0].item() - o_loss.item()) / abs(o_loss.item())
+        errs["feats_vs_oracle"] = rel(feats.cpu(), o_r["out"].detach()[sl])
+        errs["grads_vs_oracle"] = max(rel(m.grad_view(k).cpu(), g) for k, g in o_grads.items()
+                                      if g is not None and k not in ("enc_eeg.0.tsconv.0.bias", "enc_eeg.0.tsconv.4.bias",
+                                                                     "encoder.encoder.attn_layers.0.attention.key_projection.bias"))
         good = errs["loss"] < tol_f * 10 and errs["feats"] < tol_f and errs["grads"] < tol_g and bn < tol_f * 10
+        good = good and errs["loss_vs_oracle"] < max(tol_f * 10, 2e-4) and errs["feats_vs_oracle"] < max(tol_f, 2e-5) \
+            and errs["grads_vs_oracle"] < tol_g
         # ranks stay in sync after the update
         w = m.state_dict()["proj_eeg.0.weight"].clone()
         w0 = w.clone()
@@ -110,8 +121,14 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         print("DIST_CHECK " + ("PASS" if ok else "FAIL"), flush=True)
-    # no destroy_process_group(): tearing down NCCL with captured collectives alive hung on this stack
+    # destroy_process_group() with captured collectives alive hung on this stack: drop the graphs, run the interpreter's
+    # exit hooks by hand (so that whoever records loaded libraries at exit still does), then leave without destructors
+    del gs, mg, finals
+    torch.cuda.synchronize()
+    dist.barrier()
     sys.stdout.flush()
+    import atexit
+    atexit._run_exitfuncs()
     os._exit(0 if ok else 1)
 
 

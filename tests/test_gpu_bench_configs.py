@@ -1,0 +1,332 @@
+"""GPU parity at the configurations the benchmark numbers are quoted on (BASELINE.json configs[1..3]):
+
+  cfg2  1xB200, batch 1024: eval forward + one full train step (dropout off) against the CPU oracle
+        (reference: ATMS.forward Retrieval/ATMS_retrieval.py:182-191, train_model step body :215-237)
+  cfg3  8-rank data parallel, B_local 1024, N_global 8192: the row-block InfoNCE with ``row_offset`` and the column
+        statistics exchange, every rank emulated in turn on one GPU, against the full N x N ClipLoss
+        (models/loss.py:100-141 with world_size > 1, local_loss=False)
+  cfg4  10 subjects x 200 test trials against 200-way and 1654-way galleries: exact top-1 / top-5 equality on a gallery
+        with an enforced score margin, plus the random-gallery stress case (evaluate_model, :258-362)
+
+These sizes exercise what the small-batch tests never reach: split-K heuristics, 256-wide tiles, the persistent GEMM,
+the InfoNCE column-split path (ncol >= 1024), BatchNorm atomics over 2.3 M elements.
+"""
+import random
+
+import pytest
+import torch
+
+import recipe
+from oracle import atms_oracle as O
+
+pytestmark = pytest.mark.gpu
+NOISE_GRADS = ("enc_eeg.0.tsconv.0.bias", "enc_eeg.0.tsconv.4.bias",
+               "encoder.encoder.attn_layers.0.attention.key_projection.bias")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from eeg_image_decode_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def make_model(p_drop=None):
+    from eeg_image_decode_b200.atms import ATMS
+    m = ATMS()
+    m.load_state_dict(recipe.make_state_dict(), strict=True)
+    m = m.cuda()
+    if p_drop is not None:
+        m.dropout_p = [p_drop] * 8
+    return m
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rows_rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm(dim=-1) / b.norm(dim=-1)).max().item()
+
+
+# ------------------------------------------------------------------------------------------------ cfg2
+def test_cfg2_b1024_eval_forward(lib):
+    """forward embeddings at the benchmark batch within 1e-3 relative (north_star) of the fp64 oracle, every row"""
+    B = 1024
+    x = recipe.make_eeg(B, seed=1234)
+    sid = torch.full((B,), 8)
+    ref = O.atms_forward(recipe.make_state_dict(), x, sid, dtype=torch.float64)["out"]
+    m = make_model().eval()
+    out = m.encode(x.cuda(), sid.cuda(), train=False)
+    assert rows_rel(out, ref) < 1e-3
+    # the reference-facing call (model(x, ids)) is the same path
+    with torch.no_grad():
+        out2 = m(x.cuda(), sid.cuda())
+    assert rows_rel(out2, ref) < 1e-3
+
+
+def test_cfg2_b1024_train_step(lib):
+    """one full step at B = 1024 (dropout off): embeddings, loss, EVERY parameter gradient, BatchNorm running statistics
+    and the AdamW update against the oracle's autograd step on the CPU (fp32)"""
+    from eeg_image_decode_b200.train import StepEngine
+    B = 1024
+    x = recipe.make_eeg(B, seed=1234)
+    sid = torch.full((B,), 8)
+    img = recipe.make_targets(B, seed=1234, tag="img")
+    txt = recipe.make_targets(B, seed=1234, tag="txt")
+    sd = recipe.make_state_dict()
+    lo, grads, r = O.train_step(sd, {}, x, sid, img, txt, 1)
+    m = make_model(p_drop=0.0).train()
+    loss, feats = StepEngine(m, None).step(x.cuda(), sid.cuda(), img.cuda(), txt.cuda(), use_shared=False)
+    assert rows_rel(feats, r["out"].detach()) < 1e-3
+    assert abs(loss[0].item() - lo.item()) < 3e-3 * abs(lo.item())
+    for k, gr in grads.items():
+        if gr is None:
+            continue
+        got = m.grad_view(k)
+        if k in NOISE_GRADS:
+            assert got.abs().max().item() < 1e-2
+            continue
+        assert rel_l2(got, gr) < 3e-2, f"grad {k}: rel l2 {rel_l2(got, gr)}"
+    new = m.state_dict()
+    for k in ("enc_eeg.0.tsconv.2.running_mean", "enc_eeg.0.tsconv.2.running_var",
+              "enc_eeg.0.tsconv.5.running_mean", "enc_eeg.0.tsconv.5.running_var"):
+        assert (new[k].cpu() - sd[k]).abs().max().item() < 2e-3, k
+    for k, gr in grads.items():
+        if gr is None or k in NOISE_GRADS:
+            continue
+        d = (new[k].cpu() - sd[k]).abs()
+        assert int((d > 1e-5).sum().item()) <= max(2, int(2e-2 * d.numel())), k
+
+
+def test_cfg2_b1024_batchnorm_sums_run_to_run(lib):
+    """BatchNorm batch sums are accumulated with atomics: two runs on the same input may differ in the last bits only"""
+    B = 1024
+    x = recipe.make_eeg(B, seed=99).cuda()
+    sid = torch.full((B,), 8).cuda()
+    m = make_model(p_drop=0.0).train()
+    outs = []
+    for _ in range(2):
+        outs.append(m.encode(x, sid, train=True, seed=1).clone())
+    assert rows_rel(outs[0], outs[1]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ cfg3
+def _infonce_rank(lib, ws, E, img_all, txt_all, s, row_offset, col_parts, n_parts, alpha=0.99):
+    """one rank's call sequence of loss.py::_InfoNCE.run, phase by phase, without the NCCL all-gather in between"""
+    B, D = E.shape
+    N = img_all.shape[0]
+    dev = E.device
+    st = {"col_stats": torch.empty(2, 2 * N, device=dev), "loss": torch.zeros(3, device=dev),
+          "d_eeg": torch.empty_like(E), "d_scale": torch.zeros((), device=dev)}
+    io = lib.InfoNceIO()
+    io.eeg, io.tgt_img, io.tgt_txt = E.data_ptr(), img_all.data_ptr(), txt_all.data_ptr()
+    io.B, io.N, io.D, io.row_offset = B, N, D, row_offset
+    io.logit_scale = s.data_ptr()
+    io.w_img, io.w_txt, io.grad_out = alpha, 1.0 - alpha, 1.0
+    io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
+    io.col_stats = st["col_stats"].data_ptr()
+    io.col_parts, io.n_parts = (col_parts.data_ptr() if col_parts is not None else None), n_parts
+    io.loss, io.d_eeg, io.d_logit_scale = st["loss"].data_ptr(), st["d_eeg"].data_ptr(), st["d_scale"].data_ptr()
+    return io, st
+
+
+def test_cfg3_infonce_row_blocks_n8192(lib):
+    """8 ranks x 1024 local rows against 8192 gathered targets: loss, dE and d(logit_scale) of every rank's row block
+    (row_offset = rank * 1024, column statistics merged across ranks) against the single-process N x N ClipLoss"""
+    W, Bl, D = 8, 1024, 1024
+    N = W * Bl
+    gen = torch.Generator().manual_seed(11)
+    E = torch.randn(N, D, generator=gen)                     # LayerNorm-like embeddings (unit variance, |e| ~ 32)
+    img = recipe.make_targets(N, seed=77, tag="img")
+    txt = recipe.make_targets(N, seed=77, tag="txt")
+    s = torch.tensor(2.659)
+    # oracle: full N x N problem, autograd (fp32 matmuls; the loss reductions in double)
+    Eo = E.clone().requires_grad_(True)
+    so = s.clone().requires_grad_(True)
+    lo = O.contrastive_loss(Eo, img, txt, so)
+    lo.backward()
+    Ed, imgd, txtd, sd_ = E.cuda(), img.cuda(), txt.cuda(), s.cuda()
+    wss = [torch.empty(lib.infonce_workspace_bytes(Bl, N, D, 2), dtype=torch.uint8, device="cuda") for _ in range(W)]
+    ios = []
+    for rk in range(W):                                      # phase A on every "rank": logits, row LSE, column partials
+        io, st = _infonce_rank(lib, wss[rk], Ed[rk * Bl:(rk + 1) * Bl].contiguous(), imgd, txtd, sd_, rk * Bl, None, 1)
+        ios.append((io, st))
+        lib.infonce(io, lib.PHASE_A, Ed.device)
+    parts = torch.stack([st["col_stats"] for _, st in ios]).contiguous()      # what all_gather_into_tensor delivers
+    total = torch.zeros(3, device="cuda")
+    ds = torch.zeros((), device="cuda")
+    for rk, (io, st) in enumerate(ios):
+        io.col_parts, io.n_parts = parts.data_ptr(), W
+        lib.infonce(io, lib.PHASE_B, Ed.device)
+        total += st["loss"]
+        ds += st["d_scale"]
+    torch.cuda.synchronize()
+    assert abs(total[0].item() - lo.item()) < 2e-3 * abs(lo.item())
+    for rk in (0, 3, 7):
+        assert rel_l2(ios[rk][1]["d_eeg"], Eo.grad[rk * Bl:(rk + 1) * Bl]) < 5e-3, rk
+    assert abs(ds.item() - so.grad.item()) < 5e-3 * abs(so.grad.item()) + 1e-5
+
+
+def test_cfg2_infonce_b1024_single_rank(lib):
+    from eeg_image_decode_b200.loss import _InfoNCE, fused_contrastive
+    B = 1024
+    E = torch.randn(B, 1024, generator=torch.Generator().manual_seed(5))
+    img = recipe.make_targets(B, seed=9, tag="img")
+    txt = recipe.make_targets(B, seed=9, tag="txt")
+    s = torch.tensor(2.659)
+    Eo, so = E.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    lo = O.contrastive_loss(Eo, img, txt, so)
+    lo.backward()
+    loss, dE, ds = fused_contrastive(_InfoNCE(), E.cuda(), img.cuda(), txt.cuda(), s.cuda())
+    assert abs(loss[0].item() - lo.item()) < 2e-3 * abs(lo.item())
+    assert rel_l2(dE, Eo.grad) < 5e-3
+    assert abs(ds.item() - so.grad.item()) < 5e-3 * abs(so.grad.item()) + 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ cfg4
+def _margin_gallery(E_ref, n_gallery, seed):
+    """gallery whose fp64 scores against the reference embeddings are prescribed: the six best candidates of every query
+    score 12, 10, 8, 6, 4, 2, everything else lies in [-0.5, 0.5] (rows of pinv(E) are the dual basis: E @ pinv(E) = I)"""
+    Q = E_ref.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    C = torch.rand(n_gallery, Q, generator=g, dtype=torch.float64) - 0.5
+    for q in range(Q):
+        idx = torch.randperm(n_gallery, generator=g)[:6]
+        C[idx, q] = torch.arange(12, 0, -2, dtype=torch.float64)
+    return (C @ torch.linalg.pinv(E_ref).T).float()
+
+
+@pytest.mark.parametrize("n_gallery", [200, 1654])
+def test_cfg4_ten_subjects_exact_ranks(lib, n_gallery):
+    """10 subjects x 200 test trials (THINGS-EEG2 test split shape): top-1 and top-5 index sets identical to the fp64
+    reference scores on an enforced-margin gallery; random (near-tie) gallery as the stress case"""
+    Q = 200
+    sd = recipe.make_state_dict()
+    m = make_model().eval()
+    s = torch.tensor(2.659)
+    for subj in range(1, 11):                          # sub-10 takes the shared-token branch (Embed.py:117-119)
+        x = recipe.make_eeg(Q, seed=400 + subj)
+        sid = torch.full((Q,), subj)
+        ref = O.atms_forward(sd, x, sid, dtype=torch.float64)["out"]
+        e = m.encode(x.cuda(), sid.cuda(), train=False)
+        assert rows_rel(e, ref) < 1e-3
+        gal = _margin_gallery(ref, n_gallery, seed=subj)
+        ref_scores = s.double() * ref @ gal.double().T
+        r = lib.retrieval(e, gal.cuda(), s.cuda())
+        # the construction is only a valid test if the realised score error is far below the enforced margin (1.5 * s)
+        err = (r["logits"].double().cpu() - ref_scores).abs().max().item()
+        assert err < 0.25 * 1.5 * s.item(), err
+        assert torch.equal(r["top1"].cpu(), ref_scores.argmax(1))
+        t5 = torch.topk(ref_scores, 5, dim=1).indices
+        assert torch.equal(r["top5"].cpu().long(), t5)          # same candidates in the same order
+        if subj in (1, 10):
+            # stress: random unit-norm gallery (near ties exist); identical wherever the fp64 margin exceeds the error
+            galr = recipe.make_targets(n_gallery, seed=900 + subj, tag="gal")
+            sc = s.double() * ref @ galr.double().T
+            rr = lib.retrieval(e, galr.cuda(), s.cuda())
+            errr = (rr["logits"].double().cpu() - sc).abs().max().item()
+            top = torch.topk(sc, 6, dim=1).values
+            safe1 = (top[:, 0] - top[:, 1]) > 2.5 * errr
+            assert torch.equal(rr["top1"].cpu()[safe1], sc.argmax(1)[safe1])
+            safe5 = (top[:, 4] - top[:, 5]) > 2.5 * errr
+            got5 = torch.sort(rr["top5"].cpu().long(), dim=1).values
+            assert torch.equal(got5[safe5], torch.sort(torch.topk(sc, 5, dim=1).indices, dim=1).values[safe5])
+            assert (rr["top1"].cpu() == sc.argmax(1)).float().mean().item() > 0.95
+
+
+class _Loader:
+    def __init__(self, eeg, labels, txt, img, bs):
+        self.eeg, self.labels, self.txt, self.img, self.bs = eeg, labels, txt, img, bs
+
+    def __iter__(self):
+        for i in range(0, self.eeg.shape[0], self.bs):
+            sl = slice(i, i + self.bs)
+            yield (self.eeg[sl], self.labels[sl], None, self.txt[sl], None, self.img[sl])
+
+
+class _Cfg:
+    epochs = 1
+    insubject = True
+    encoder_type = "ATMS"
+
+
+def _decided_gallery(E_ref, labels, seed):
+    """200-way test gallery for the k-way protocol: the fp64 score of every query against its OWN class is +8 or -8 (coin
+    flip), three decoy classes score +5, everything else lies in [-0.5, 0.5] -- so whether the true class wins a k-way
+    draw (or makes its top 5) is decided by margins >= 2.5 x logit_scale, far above the TF32 embedding error"""
+    Q = E_ref.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    C = torch.rand(Q, Q, generator=g, dtype=torch.float64) - 0.5             # C[class, query]
+    for q in range(Q):
+        lab = int(labels[q])
+        others = [c for c in torch.randperm(Q, generator=g).tolist() if c != lab][:3]
+        C[others, q] = 5.0
+        C[lab, q] = 8.0 if torch.rand(1, generator=g).item() < 0.5 else -8.0
+    return (C @ torch.linalg.pinv(E_ref).T).float()
+
+
+@pytest.mark.parametrize("k", [200, 50, 4])
+def test_cfg4_evaluate_model_exact_hit_counts(lib, k):
+    """evaluate_model over the 200-trial test split (batch size 1 like the reference's test loader): with a margin
+    gallery the k-way hit counts are EXACT, draw for draw with the reference's random.sample calls"""
+    from eeg_image_decode_b200.train import evaluate_model
+    Q = 200
+    sd = recipe.make_state_dict()
+    x = recipe.make_eeg(Q, seed=555)
+    sid = torch.full((Q,), 8)
+    ref = O.atms_forward(sd, x, sid, dtype=torch.float64)["out"]
+    labels = torch.randperm(Q, generator=torch.Generator().manual_seed(8))
+    img_all = _decided_gallery(ref, labels, seed=3)              # test gallery: one image per class (:262)
+    txt_all = recipe.make_targets(Q, seed=555, tag="txt")
+    s = float(sd["logit_scale"])
+    # oracle hit counts with the reference's candidate draws (:297-300, second draw :323-325 / :340-341)
+    random.seed(1234)
+    hit1 = hit5 = 0
+    all_labels = set(range(Q))
+    for i in range(Q):
+        label = int(labels[i])
+        possible = list(all_labels - {label})
+        sel = random.sample(possible, k - 1) + [label]
+        if k in (2, 4, 10, 50, 100):
+            random.sample(possible, k - 1)
+        sc = s * ref[i] @ img_all[sel].double().T
+        hit1 += int(sel[int(sc.argmax())] == label)
+        if k >= 50:
+            hit5 += int(label in [sel[j] for j in torch.topk(sc, 5).indices.tolist()])
+    assert 0 < hit1 < Q                                          # the case is not degenerate
+    m = make_model().eval()
+    random.seed(1234)
+    loader = _Loader(x, labels, txt_all[labels], img_all[labels], 1)
+    loss, acc, top5 = evaluate_model("sub-08", m, loader, torch.device("cuda"), txt_all, img_all, k, _Cfg())
+    assert round(acc * Q) == hit1
+    if k >= 50:
+        assert round(top5 * Q) == hit5
+
+
+def test_model_on_second_device_with_other_current_device(lib):
+    """the library follows the tensors' device, not the caller's current device (reference: --gpu cuda:N without
+    set_device); needs two GPUs"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from eeg_image_decode_b200.atms import ATMS
+    from eeg_image_decode_b200.train import StepEngine
+    B = 4
+    x = recipe.make_eeg(B, seed=21)
+    sid = torch.full((B,), 8)
+    img, txt = recipe.make_targets(B, seed=21, tag="img"), recipe.make_targets(B, seed=21, tag="txt")
+    res = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)
+        m = ATMS()
+        m.load_state_dict(recipe.make_state_dict())
+        m = m.to(dev).train()
+        m.dropout_p = [0.0] * 8
+        loss, feats = StepEngine(m, None).step(x.to(dev), sid.to(dev), img.to(dev), txt.to(dev), use_shared=False)
+        torch.cuda.synchronize(dev)
+        res.append((loss.cpu(), feats.cpu(), m.grad_view("proj_eeg.0.weight").cpu()))
+    assert rows_rel(res[1][1], res[0][1]) < 2e-4
+    assert abs(res[1][0][0].item() - res[0][0][0].item()) < 1e-3 * abs(res[0][0][0].item())
+    assert rel_l2(res[1][2], res[0][2]) < 5e-3

@@ -472,13 +472,15 @@ def test_dropout_tensorcore_path_matches_fp32_path(lib):
 
 
 def test_data_parallel_equals_single_process():
-    """2 ranks x 8 trials == 1 process x 16 trials (NCCL over NVLink); needs two GPUs, skipped otherwise"""
+    """W ranks x 8 trials == 1 process x 8W trials == the CPU oracle at batch 8W (NCCL over NVLink), W = every GPU of
+    the box up to 8; needs two GPUs, skipped otherwise"""
     import subprocess
     import sys as _sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = os.path.join(os.path.dirname(__file__), "dist_check.py")
-    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    nproc = min(torch.cuda.device_count(), 8)
+    r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                         "--master-addr", "127.0.0.1", "--master-port", "29517", script],
                        capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
