@@ -192,11 +192,18 @@ class ATMS(nn.Module):
         self._n_main = offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]            # always-trained prefix (incl. logit_scale)
         self._n_hot = offs[cold[0]] if cold else off
         self.flat_grads = torch.zeros(self._n_hot, dtype=torch.float32, device=dev)
-        self._adam_m = None
-        self._adam_v = None
-        self._adam_steps = {"main": 0, "table": 0, "shared": 0}
-        if self.joint_train:
-            self._adam_steps.update({f"ve{sj}": 0 for sj in range(N_SUBJECT_ROWS)})
+        # fused-AdamW moments survive .to() / .cuda() / .float() (the arena layout depends on the parameter names only);
+        # they belong to ONE optimizer object (train.py::adopt_optimizer resets / imports them when it changes)
+        old_m, old_v = getattr(self, "_adam_m", None), getattr(self, "_adam_v", None)
+        if old_m is not None and old_m.numel() == self._n_hot:
+            self._adam_m, self._adam_v = old_m.to(dev), old_v.to(dev)
+        else:
+            self._adam_m = None
+            self._adam_v = None
+            self._adam_steps = {"main": 0, "table": 0, "shared": 0}
+            if self.joint_train:
+                self._adam_steps.update({f"ve{sj}": 0 for sj in range(N_SUBJECT_ROWS)})
+            self._adam_owner = None
         self._ptr_cache = None
         self._ws = {}
         self._ws_pinned = set()         # batch sizes whose workspace a captured CUDA graph points into

@@ -2,6 +2,11 @@
 #include "../../include/eegdecode_b200.h"
 #include "gemm.h"
 
+namespace eegb200 {
+static int g_debug_stores = 0;
+int debug_stores() { return g_debug_stores; }
+}  // namespace eegb200
+
 using namespace eegb200;
 
 extern "C" {
@@ -18,6 +23,7 @@ int eegb200_set_gemm_backend(int backend) {
   return 0;
 }
 int eegb200_get_gemm_backend(void) { return gemm_get_backend(); }
+int eegb200_set_debug_stores(int on) { g_debug_stores = on ? 1 : 0; return 0; }
 int eegb200_prof_enable(int on) { prof_enable(on); return 0; }
 int eegb200_prof_report(char* buf, size_t cap) {
   EEG_REQUIRE(buf && cap > 2, "prof_report: bad buffer");

@@ -467,7 +467,7 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
     // ---- PatchEmbedding temporal conv + pool (ATMS_retrieval.py:102-103) on tokens 0..62 ----
     if (train) EEG_CUDA_OK(cudaMemsetAsync(w.bn1_sums, 0, 2 * N_FILT * sizeof(double), s));
     if (RT && conv_tc_enabled()) {
-      // experimental fused tcgen05 path (conv_tc.cu): statistics pass only; Y1 is produced by the apply pass in phase B
+      // fused tcgen05 path (conv_tc.cu): statistics pass only; the activations are recomputed by the apply pass in phase B
       if (train) EEG_TRY(conv_tc_stats(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_sums, B, s));
     } else {
       EEG_TRY(conv_temporal_fwd(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.Y1, train ? w.bn1_sums : nullptr, B, s));
@@ -477,9 +477,10 @@ static int forward(const eegb200_atms_io* io, int phases, cudaStream_t s) {
     BnState bn1{w.bn1_sums, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], BUF[EEGB200_BUF_BN1_RM], BUF[EEGB200_BUF_BN1_RV]};
     EEG_TRY(bn_finalize(bn1, wmul * B * N_CH * N_POOL, train, train && io->update_running_stats, s));
     if (RT && conv_tc_enabled()) {
-      // conv + pool + BN1 + ELU + spatial conv in one kernel; Y1 / A1 are still stored for the unfused backward
+      // conv + pool + BN1 + ELU + spatial conv in one kernel; y1 / a1 never leave the chip (debug stores: stage checks)
+      const bool dbg = debug_stores() != 0;
       EEG_TRY(conv_tc_apply(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B],
-                            P[EEGB200_P_WS], P[EEGB200_P_BS], w.Ws_tc, w.Y1, w.A1, w.Y2, B, s));
+                            P[EEGB200_P_WS], P[EEGB200_P_BS], w.Ws_tc, dbg ? w.Y1 : nullptr, dbg ? w.A1 : nullptr, w.Y2, B, s));
     } else {
       EEG_TRY(bn_elu_apply(w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.A1, (long long)R * K_SPAT, RT, s));
       Epilogue e = epi_out(w.Y2, N_FILT);        // spatial conv (63,1) == GEMM over (r,k1)  (ATMS_retrieval.py:106)
@@ -631,31 +632,44 @@ static int backward(const eegb200_atms_io* io, const float* d_out, float* const*
                          GR[EEGB200_P_BN2_B], (long long)R * N_FILT, RT, 1.f / (float)wmul, s));
     FORK();
     EEG_TRY(colsum(w.dY2, N_FILT, R, N_FILT, GR[EEGB200_P_BS], 0, 0, ws));
-    // dWs[k2][(r,k1)] = sum_{(b,j)} dY2[(b,j)][k2] * A1[(b,j)][(r,k1)]
-    EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), ws));
-    EEG_TRY(run_gemm(N_FILT, K_SPAT, R, w.dY2, N_FILT, 1, w.A1, K_SPAT, 1, epi_wgrad(w.dWs_p, K_SPAT),
-                     pick_split(N_FILT, K_SPAT, R), ws));
-    unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, ws>>>(w.dWs_p, GR[EEGB200_P_WS]);
-    count_launch();
-    // dA1 = dY2 . Ws, then dz1 = dA1 * ELU'(BN1(y1)) and the two BN1-backward reductions
-    EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
-    if (RT) {
-      // tensor-core path: ELU', the y1 read and both reductions ride in the GEMM epilogue (no separate 1.1 GB pass)
-      Epilogue e = epi_out(w.dA1, K_SPAT);
-      e.bn_y = w.Y1; e.ld_bn_y = K_SPAT;
-      e.bn_mean_rstd = w.bn1_mr; e.bn_gamma = P[EEGB200_P_BN1_G]; e.bn_beta = P[EEGB200_P_BN1_B];
-      e.bn_sums = w.bn1_bsums;
-      EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, e, 1, s));
+    if (RT && conv_tc_enabled()) {
+      // fused tcgen05 path: d a1 / a1 are recomputed on chip; this pass delivers the BatchNorm1-backward reductions and dWs
+      EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
+      EEG_TRY(conv_tc_bwd_stats(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B],
+                                P[EEGB200_P_WS], w.dY2, w.Ws_tc, w.bn1_bsums, GR[EEGB200_P_WS], B, s));
     } else {
-      EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, epi_out(w.dA1, K_SPAT), 1, s));
-      EEG_TRY(bn1_bwd_reduce(w.dA1, w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.bn1_bsums,
-                             (long long)R * K_SPAT, s));
+      // dWs[k2][(r,k1)] = sum_{(b,j)} dY2[(b,j)][k2] * A1[(b,j)][(r,k1)]
+      EEG_CUDA_OK(cudaMemsetAsync(w.dWs_p, 0, (size_t)N_FILT * K_SPAT * sizeof(float), ws));
+      EEG_TRY(run_gemm(N_FILT, K_SPAT, R, w.dY2, N_FILT, 1, w.A1, K_SPAT, 1, epi_wgrad(w.dWs_p, K_SPAT),
+                       pick_split(N_FILT, K_SPAT, R), ws));
+      unpack_ws_grad_kernel<<<cdiv(N_FILT * K_SPAT, 256), 256, 0, ws>>>(w.dWs_p, GR[EEGB200_P_WS]);
+      count_launch();
+      // dA1 = dY2 . Ws, then dz1 = dA1 * ELU'(BN1(y1)) and the two BN1-backward reductions
+      EEG_CUDA_OK(cudaMemsetAsync(w.bn1_bsums, 0, 2 * N_FILT * sizeof(double), s));
+      if (RT) {
+        // tensor-core path: ELU', the y1 read and both reductions ride in the GEMM epilogue (no separate 1.1 GB pass)
+        Epilogue e = epi_out(w.dA1, K_SPAT);
+        e.bn_y = w.Y1; e.ld_bn_y = K_SPAT;
+        e.bn_mean_rstd = w.bn1_mr; e.bn_gamma = P[EEGB200_P_BN1_G]; e.bn_beta = P[EEGB200_P_BN1_B];
+        e.bn_sums = w.bn1_bsums;
+        EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, e, 1, s));
+      } else {
+        EEG_TRY(run_gemm(R, K_SPAT, N_FILT, w.dY2, N_FILT, 0, w.Ws_p, K_SPAT, 1, epi_out(w.dA1, K_SPAT), 1, s));
+        EEG_TRY(bn1_bwd_reduce(w.dA1, w.Y1, w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B], w.bn1_bsums,
+                               (long long)R * K_SPAT, s));
+      }
     }
   }
   if (phases & EEGB200_PHASE_C) {
-    EEG_TRY(conv_temporal_bwd(w.dA1, w.Y1, w.X3, P[EEGB200_P_WT], w.bn1_mr, P[EEGB200_P_BN1_G], w.bn1_bsums,
-                              wmul * B * N_CH * N_POOL, w.dX3, GR[EEGB200_P_WT], GR[EEGB200_P_BT],
-                              GR[EEGB200_P_BN1_G], GR[EEGB200_P_BN1_B], B, 1.f / (float)wmul, s));
+    if (RT && conv_tc_enabled()) {
+      EEG_TRY(conv_tc_bwd_apply(w.X3, P[EEGB200_P_WT], P[EEGB200_P_BT], w.bn1_mr, P[EEGB200_P_BN1_G], P[EEGB200_P_BN1_B],
+                                w.dY2, w.Ws_tc, w.bn1_bsums, wmul * B * N_CH * N_POOL, 1.f / (float)wmul, w.dX3,
+                                GR[EEGB200_P_WT], GR[EEGB200_P_BT], GR[EEGB200_P_BN1_G], GR[EEGB200_P_BN1_B], B, s));
+    } else {
+      EEG_TRY(conv_temporal_bwd(w.dA1, w.Y1, w.X3, P[EEGB200_P_WT], w.bn1_mr, P[EEGB200_P_BN1_G], w.bn1_bsums,
+                                wmul * B * N_CH * N_POOL, w.dX3, GR[EEGB200_P_WT], GR[EEGB200_P_BT],
+                                GR[EEGB200_P_BN1_G], GR[EEGB200_P_BN1_B], B, 1.f / (float)wmul, s));
+    }
     // ---- final norm + norm2 ----
     // (the LayerNorm backward also emits T1 = dropout_ffn2(dR2), the operand of the FFN GEMMs, and db2 = colsum(T1))
     if (ln_fused()) {

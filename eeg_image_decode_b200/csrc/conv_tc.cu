@@ -1,26 +1,25 @@
-// PatchEmbedding conv stack forward on tcgen05 (docs/ROUND2_CONV_TCGEN05.md, kernels F1 / F2).
+// PatchEmbedding conv stack (Retrieval/ATMS_retrieval.py:101-116) on tcgen05: temporal conv o avg-pool, BatchNorm1,
+// ELU and the (63,1) spatial conv, forward AND backward, without ever writing the (B,40,63,36) activations
+// (363 KB per sample each for y1 / a1 / d a1) to HBM.  They are recomputed from the 63 KB token tile instead.
 //
-// STATUS: EXPERIMENTAL, OFF BY DEFAULT (EEGB200_CONV_TC=1 selects it).  Written at the end of round 1 after the GPU
-// budget was spent: it compiles for sm_100a and follows the blocking that tools/conv_tc_plan.py checks against autograd
-// on the CPU, but it has NOT run on a GPU yet.  The default path (conv_mma.cu + convstack.cu + the spatial GEMM) is the
-// verified one.  First thing to do in round 2: EEGB200_CONV_TC=1 python -m pytest tests/test_gpu_parity.py -k stages.
+//   ps[b,c,u]  = sum_{v<51} x3[b,c,u+v]                              u < 200   (warp prefix scan)
+//   y[b,c,p,k] = sum_{t<25} ps[b,c,5p+t] wt[k,t]/51 + bt[k]          "conv MMA": rows (s,p), K = 25 -> 32, N = 40 -> 48
+//   a1         = ELU(BN1(y))
+//   y2[b,p,j]  = sum_{c,k} a1[b,c,p,k] Ws[j,k,c] + bs[j]             "spatial MMA": K = (c,k), accumulated over channels
 //
-// One CTA = 3 consecutive samples = one 128-row UMMA tile (rows (s, p): sample s < 3, pooled position p < 36; 108 valid),
-// looping over the 63 channel-tokens:
+// A 128-row UMMA tile = 3 samples x 36 pooled positions (108 valid rows).  Four kernels, all warp-specialised
+// (builder warps: token rows -> pooled sums -> im2col operand in swizzled shared memory; one control thread: TMA of the
+// per-channel spatial weights + every tcgen05.mma; epilogue warps: thread = TMEM lane = tile row):
 //
-//   builders (warps 0-3)  token rows of channel c -> box-51 pooled sums (warp prefix scan) -> im2col tile
-//                         A[(s,p), t] = ps[s][5p+t], t < 25 (K padded to 32), split hi / lo for 3xTF32, written into
-//                         SWIZZLE_128B K-major shared memory (double buffered)
-//   control (warp 8)      conv UMMAs  C1[buf] = A_lo.Bhi + A_hi.Blo + A_hi.Bhi   (M=128, N=48, K=32, TMEM double buffered)
-//                         spatial UMMAs  Y2 += A1_c . Ws_c^T                      (M=128, N=48, K=40; one channel behind)
-//                         TMA of the per-channel spatial weights Ws_c [48 x 64] (pre-packed, 4-deep ring)
-//   epilogue (warps 4-7)  thread = TMEM lane = row: y = C1 + bias
-//                           MODE_STATS: accumulate sum / sum^2 per filter (BatchNorm1 batch statistics, kernel F1)
-//                           MODE_APPLY: a1 = tf32(ELU(BN1(y))) -> next K slice of the spatial A operand in swizzled smem;
-//                                       optionally store y / a1 to HBM for the (not yet fused) backward
-//                         after the last channel: Y2 + bias -> HBM
+//   F1 conv_tc_stats      conv MMA (3xTF32) -> per-filter sum / sum of squares (BatchNorm1 batch statistics)
+//   F2 conv_tc_apply      conv MMA -> BN1 + ELU in registers -> A operand of the spatial MMA -> Y2 (red.add per item)
+//   B1 conv_tc_bwd_stats  conv MMA + dA1 = dY2 . Ws_c (UMMA) -> dz = dA1 * ELU'(z): sum dz, sum dz*yhat (BatchNorm1
+//                         backward reductions) and dWs_c += dY2^T . a1 (UMMA over the rows, accumulated in TMEM)
+//   B2 conv_tc_bwd_apply  same recomputation -> dy = A*dz + B*y + C (folded BatchNorm backward) -> G = dy . wt (UMMA)
+//                         scattered into the pooled positions, prefix-summed into d x3; dwt += dy^T . im2col (UMMA)
 //
-// Y1 / A1 never leave the chip in the target configuration (y1 == a1 == nullptr).
+// F1 / F2 work items are (tile, 21 channels), B1 / B2 CTAs own a group of 4 channels and stride over the tiles, so that
+// the dWs / dwt accumulators stay in TMEM for the whole kernel.
 #include "kernels.h"
 #include <stdlib.h>
 #include <string.h>
@@ -29,45 +28,21 @@ namespace eegb200 {
 
 namespace {
 
-constexpr int CTC_THREADS = 288;
 constexpr int TILE_S = 3;                         // samples per tile
+constexpr int TILE_ROWS = TILE_S * N_POOL;        // 108 valid rows of the 128-row UMMA tile
 constexpr uint32_t KB_A = 128 * 32 * 4;           // [128 rows x 32 floats] K-major k-block: 16 KB
-constexpr uint32_t KB_B = 48 * 32 * 4;            // [48 rows x 32 floats] K-major k-block: 6 KB (6 swizzle atoms)
-constexpr int WS_RING = 4;
+constexpr uint32_t KB_48 = 48 * 32 * 4;           // [48 rows x 32 floats] K-major k-block: 6 KB
+constexpr uint32_t KB_32 = 32 * 32 * 4;           // [32 rows x 32 floats] K-major k-block: 4 KB
+constexpr uint32_t SLAB = 128 * 128;              // MN-major slab [128 k-rows][32 mn floats]: 16 KB
 constexpr int N48 = 48;
-
-// shared-memory map (offsets from the 1024-byte aligned base)
-constexpr uint32_t OFF_IM = 0;                              // [2 buf][hi, lo] x 16 KB
-constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights hi, lo: 2 x 6 KB
-constexpr uint32_t OFF_A1 = OFF_BC + 2 * KB_B;              // [2 buf][2 k-blocks] x 16 KB
-constexpr uint32_t OFF_WS = OFF_A1 + 4 * KB_A;              // [4 ring][2 k-blocks] x 6 KB
-constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_B;    // pooled sums [3][208] + scan scratch [3][264] floats
+constexpr int WS_RING = 4;
+constexpr int F_PARTS = 3, F_LEN = 21;            // forward work item = (tile, 21 of the 63 channels)
+constexpr int GC = 4, N_GROUPS = 16;              // backward: channel groups of 4 (the last one has 3)
 constexpr uint32_t PS_LD = 208, CSX_LD = 264;
-constexpr uint32_t OFF_TAB = OFF_PS + (3 * PS_LD + 3 * CSX_LD) * 4;      // BN scale / shift / bias tables [3][48] floats
-constexpr uint32_t OFF_RED = OFF_TAB + 3 * 48 * 4;                        // statistics reduction [2][40] floats
-constexpr uint32_t OFF_BAR = (OFF_RED + 80 * 4 + 7) & ~7u;                // mbarriers
-constexpr int N_BARS = 2 + 2 + 2 + 2 + 2 + 2 + WS_RING + WS_RING + 1;
-constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
-constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;                        // + alignment slack
 
-enum { MODE_STATS = 0, MODE_APPLY = 1 };
-
-struct ConvTcParams {
-  const float* x3;          // [B*64, 256] token rows (channel c of sample b at row b*64 + c)
-  const float* wt;          // [40, 25]
-  const float* bt;          // [40]
-  const float* mean_rstd;   // [2][40]   (MODE_APPLY)
-  const float* gamma;       // [40]
-  const float* beta;        // [40]
-  const float* bs;          // [40] spatial conv bias
-  float* y1;                // [B*36, 2520] or nullptr
-  float* a1;                // [B*36, 2520] or nullptr
-  float* y2;                // [B*36, 40]
-  double* sums;             // [2][40]   (MODE_STATS)
-  int B;
-};
-
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float v[16]) {
+// ------------------------------------------------------------------------------------------------ small helpers
+// NOTE: the values of the *_nw loads may only be used after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -76,14 +51,29 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float v[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a K-major SWIZZLE_128B k-block
 __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+}
+// byte offset of element (mn index m, k-row k) inside an MN-major SWIZZLE_128B_ATOM_32B tile [slab][128 k][32 mn]
+// (verified against what TMA writes in that mode: tools/gpu_tma_layout_probe.py)
+__device__ __forceinline__ uint32_t mn_off(int m, int k) {
+  return (uint32_t)(m >> 5) * SLAB + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
+         (uint32_t)((((m & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)(m & 7) * 4u;
 }
 __device__ __forceinline__ float tf32_fast(float x) {     // cvt.rna for finite values: add half an ulp of tf32, truncate
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -97,33 +87,111 @@ __device__ __forceinline__ float elu_fast(float z) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// filter index of register slot i (0..19) of an epilogue thread of column half h: {16h .. 16h+15} + {32+4h .. 32+4h+3}
+// (two naturally aligned tcgen05.ld: .x16 at column 16h, .x4 at column 32+4h)
+__device__ __forceinline__ int kidx(int h, int i) { return i < 16 ? 16 * h + i : 32 + 4 * h + (i - 16); }
+
+// box-51 pooled sums of one token row (8 floats per lane): cs[k] = sum of the first k samples, ps[u] = cs[u+51]-cs[u]
+__device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int lane, float* cs, float* ps) {
+  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+  for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
+  const float tot = v[7];
+  float inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float nb = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += nb;
+  }
+  const float excl = inc - tot;
+  cs[8 * lane] = excl;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) cs[8 * lane + 1 + i] = v[i] + excl;
+  if (lane == 31) cs[256] = inc;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    const int u = lane + 32 * q;
+    if (u < N_PSUM) ps[u] = cs[u + K_POOL] - cs[u];
+  }
+}
+
+// =================================================================================================================
+// forward
+// =================================================================================================================
+constexpr int F_THREADS = 13 * 32;                // 4 builder, 8 epilogue, 1 control warp
+constexpr uint32_t OFF_IM = 0;                              // [2 buf][hi, lo] x 16 KB
+constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights hi, lo: 2 x 6 KB
+constexpr uint32_t OFF_A1 = OFF_BC + 2 * KB_48;             // [2 buf][2 k-blocks] x 16 KB
+constexpr uint32_t OFF_WS = OFF_A1 + 4 * KB_A;              // [4 ring][2 k-blocks] x 6 KB
+constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // pooled sums [3][208] + scan scratch [3][264] floats
+constexpr uint32_t OFF_TAB = OFF_PS + (3 * PS_LD + 3 * CSX_LD) * 4;      // BN scale / shift / bias tables [3][48] floats
+constexpr uint32_t OFF_RED = OFF_TAB + 3 * 48 * 4;                        // statistics reduction [2][40] floats
+constexpr uint32_t OFF_BAR = (OFF_RED + 80 * 4 + 7) & ~7u;                // mbarriers
+constexpr int N_BARS = 6 * 2 + 2 * WS_RING + 2 * 2;
+constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
+constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;                        // + alignment slack
+static_assert(OFF_BC % 1024 == 0 && OFF_A1 % 1024 == 0 && OFF_WS % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(CTC_SMEM <= 227 * 1024, "conv forward kernel exceeds the shared memory of an SM");
+
+enum { MODE_STATS = 0, MODE_APPLY = 1 };
+
+struct ConvTcParams {
+  const float* x3;          // [B*64, 256] token rows (channel c of sample b at row b*64 + c)
+  const float* wt;          // [40, 25]
+  const float* bt;          // [40]
+  const float* mean_rstd;   // [2][40]   (MODE_APPLY)
+  const float* gamma;       // [40]
+  const float* beta;        // [40]
+  const float* bs;          // [40] spatial conv bias
+  float* y1;                // [B*36, 2520] or nullptr (debug stores for the stage checks)
+  float* a1;                // [B*36, 2520] or nullptr
+  float* y2;                // [B*36, 40], pre-zeroed: every (tile, part) item adds its share
+  double* sums;             // [2][40]   (MODE_STATS)
+  int B;
+  int n_tiles;
+};
+
+struct FwdIt { int tile, c, l, item_local, part, ns; };
+__device__ __forceinline__ FwdIt fwd_decode(int it, int B) {
+  FwdIt d;
+  d.item_local = it / F_LEN;
+  d.l = it - d.item_local * F_LEN;
+  const int id = blockIdx.x + d.item_local * gridDim.x;
+  d.tile = id / F_PARTS;
+  d.part = id - d.tile * F_PARTS;
+  d.c = d.part * F_LEN + d.l;
+  d.ns = min(TILE_S, B - d.tile * TILE_S);
+  return d;
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(CTC_THREADS, 1)
+__global__ void __launch_bounds__(F_THREADS, 1)
 conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   float* ps_all = reinterpret_cast<float*>(sm + OFF_PS);
   float* cs_all = ps_all + 3 * PS_LD;
-  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);          // [0]: scale, [1]: shift, [2]: conv bias (+ spatial bias at 40..)
+  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);          // [0]: scale, [1]: shift, [2]: conv bias
   float* red = reinterpret_cast<float*>(sm + OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
   uint64_t* tile_full = bars;            // [2] builders -> control
   uint64_t* tile_empty = bars + 2;       // [2] conv UMMAs done -> builders
   uint64_t* c1_full = bars + 4;          // [2] conv UMMAs done -> epilogue
-  uint64_t* c1_empty = bars + 6;         // [2] epilogue read TMEM -> control        (4 arrivals)
-  uint64_t* a1_full = bars + 8;          // [2] epilogue wrote the A1 slice -> control (4 arrivals)
+  uint64_t* c1_empty = bars + 6;         // [2] epilogue read TMEM -> control        (8 arrivals)
+  uint64_t* a1_full = bars + 8;          // [2] epilogue wrote the A1 slice -> control (8 arrivals)
   uint64_t* a1_empty = bars + 10;        // [2] spatial UMMAs done -> epilogue
   uint64_t* ws_full = bars + 12;         // [4] TMA -> control
   uint64_t* ws_empty = bars + 12 + WS_RING;   // [4] spatial UMMAs done -> control (TMA refill)
-  uint64_t* y2_full = bars + 12 + 2 * WS_RING;
+  uint64_t* y2_full = bars + 12 + 2 * WS_RING;       // [2] last spatial UMMA of an item -> epilogue
+  uint64_t* y2_empty = y2_full + 2;                  // [2] epilogue drained Y2 -> control (8 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b0 = blockIdx.x * TILE_S;
-  const int ns = min(TILE_S, p.B - b0);                 // samples of this tile
-  const int rows_valid = ns * N_POOL;
+  const int n_items = p.n_tiles * F_PARTS;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_it = n_my * F_LEN;
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
@@ -131,31 +199,32 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       mbar_init(&tile_full[i], 1);
       mbar_init(&tile_empty[i], 1);
       mbar_init(&c1_full[i], 1);
-      mbar_init(&c1_empty[i], 4);
-      mbar_init(&a1_full[i], 4);
+      mbar_init(&c1_empty[i], 8);
+      mbar_init(&a1_full[i], 8);
       mbar_init(&a1_empty[i], 1);
+      mbar_init(&y2_full[i], 1);
+      mbar_init(&y2_empty[i], 8);
     }
     for (int i = 0; i < WS_RING; ++i) {
       mbar_init(&ws_full[i], 1);
       mbar_init(&ws_empty[i], 1);
     }
-    mbar_init(y2_full, 1);
     mbar_fence_init();
     if (MODE == MODE_APPLY) tma_prefetch_desc(&tmWs);
   }
-  // zero the im2col tiles (pad rows / pad columns stay zero for the whole kernel) and the A1 tiles
-  for (uint32_t i = threadIdx.x * 16; i < 4 * KB_A; i += CTC_THREADS * 16) {
+  // zero the im2col tiles (pad columns stay zero for the whole kernel) and the A1 tiles
+  for (uint32_t i = threadIdx.x * 16; i < 4 * KB_A; i += F_THREADS * 16) {
     *reinterpret_cast<float4*>(sm + OFF_IM + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(sm + OFF_A1 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // conv weights / 51 as the B operand, hi and lo parts: rows k < 40 (48 with padding), columns t < 25 (32)
-  for (int i = threadIdx.x; i < N48 * 32; i += CTC_THREADS) {
+  for (int i = threadIdx.x; i < N48 * 32; i += F_THREADS) {
     const int k = i >> 5, t = i & 31;
     const float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
     const float hi = tf32_fast(w), lo = tf32_fast(w - hi);
     const uint32_t off = sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u;
     *reinterpret_cast<float*>(sm + OFF_BC + off) = hi;
-    *reinterpret_cast<float*>(sm + OFF_BC + KB_B + off) = lo;
+    *reinterpret_cast<float*>(sm + OFF_BC + KB_48 + off) = lo;
   }
   if (threadIdx.x < N48) {
     const int k = threadIdx.x;
@@ -169,8 +238,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     tab[96 + k] = k < N_FILT ? p.bt[k] : 0.f;
   }
   if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
-  if (warp == 8) {
-    tmem_alloc(tmem_slot, 256);          // C1[0]: cols 0..47, C1[1]: cols 64..111, Y2: cols 128..175
+  if (warp == 12) {
+    tmem_alloc(tmem_slot, 256);          // C1[0]: cols 0..47, C1[1]: 64..111, Y2[0]: 128..175, Y2[1]: 192..239
     tmem_relinquish();
   }
   fence_proxy_async_smem();
@@ -183,48 +252,38 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     // =============================== builders ===============================
     const int r = threadIdx.x;                         // tile row 0..127
     const int s_row = r / N_POOL, p_row = r % N_POOL;
-    for (int c = 0; c < N_CH; ++c) {
-      const int bi = c & 1;
-      const uint32_t n = (uint32_t)(c >> 1);
-      // pooled sums of the (up to) three token rows of this channel: warps 0..2, one row each
-      if (warp < ns) {
-        const float* xrow = p.x3 + ((size_t)(b0 + warp) * N_TOK + c) * D_PAD + 8 * lane;
-        const float4 x0 = *reinterpret_cast<const float4*>(xrow), x1 = *reinterpret_cast<const float4*>(xrow + 4);
-        float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
-        const float tot = v[7];
-        float inc = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float nb = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += nb;
-        }
-        const float excl = inc - tot;
-        float* cs = cs_all + warp * CSX_LD;               // C[k] = sum of the first k samples, k = 0..256
-        cs[8 * lane] = excl;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) cs[8 * lane + 1 + i] = v[i] + excl;
-        if (lane == 31) cs[256] = inc;
-        __syncwarp();
-        float* ps = ps_all + warp * PS_LD;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const int u = lane + 32 * q;
-          if (u < N_PSUM) ps[u] = cs[u + K_POOL] - cs[u];
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    auto fetch = [&](int it) {                          // token row of (sample `warp` of the tile, channel) for iteration it
+      if (it < total_it && warp < TILE_S) {
+        const FwdIt d = fwd_decode(it, p.B);
+        if (warp < d.ns) {
+          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + warp) * N_TOK + d.c) * D_PAD + 8 * lane;
+          xa = __ldg(reinterpret_cast<const float4*>(xrow));
+          xb = __ldg(reinterpret_cast<const float4*>(xrow + 4));
         }
       }
+    };
+    fetch(0);
+    for (int it = 0; it < total_it; ++it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      const int rows_valid = d.ns * N_POOL;
+      const float4 x0 = xa, x1 = xb;
+      fetch(it + 1);                                    // the next row travels while this one is processed
+      if (warp < d.ns) pool_row(x0, x1, lane, cs_all + warp * CSX_LD, ps_all + warp * PS_LD);
       named_bar_sync(1, 128);
-      mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of channel c-2 have consumed this buffer
-      if (r < rows_valid) {
+      mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of iteration it-2 have consumed this buffer
+      {
         const float* src = ps_all + s_row * PS_LD + 5 * p_row;
         uint8_t* hi_t = sm + OFF_IM + (uint32_t)bi * 2 * KB_A;
         uint8_t* lo_t = hi_t + KB_A;
+        const bool valid = r < rows_valid;
 #pragma unroll
         for (int ch = 0; ch < 7; ++ch) {                  // chunk 6 = tap 24 + zeros; chunk 7 stays zero
           float a[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = (ch * 4 + q) < K_TEMP ? src[ch * 4 + q] : 0.f;
+          for (int q = 0; q < 4; ++q) a[q] = (valid && (ch * 4 + q) < K_TEMP) ? src[ch * 4 + q] : 0.f;
           float4 h, l;
           h.x = tf32_fast(a[0]); h.y = tf32_fast(a[1]); h.z = tf32_fast(a[2]); h.w = tf32_fast(a[3]);
           l.x = tf32_fast(a[0] - h.x); l.y = tf32_fast(a[1] - h.y); l.z = tf32_fast(a[2] - h.z); l.w = tf32_fast(a[3] - h.w);
@@ -237,159 +296,172 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       named_bar_sync(1, 128);
       if (threadIdx.x == 0) mbar_arrive(&tile_full[bi]);
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // =============================== epilogue ===============================
-    const int q = warp - 4;                              // TMEM lane quarter (== warp % 4)
+    const int q = warp & 3;                              // TMEM lane quarter (== warp % 4)
+    const int h = (warp - 4) >> 2;                       // column half
     const int r = q * 32 + lane;                         // tile row
-    const bool valid = r < rows_valid;
-    const size_t grow = (size_t)b0 * N_POOL + r;         // global (b, p) row
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float s1[N_FILT], s2[N_FILT];
+    float s1[20], s2[20];
     if (MODE == MODE_STATS) {
 #pragma unroll
-      for (int k = 0; k < N_FILT; ++k) s1[k] = s2[k] = 0.f;
+      for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
     }
-    for (int c = 0; c < N_CH; ++c) {
-      const int bi = c & 1;
-      const uint32_t n = (uint32_t)(c >> 1);
+    for (int it = 0; it < total_it; ++it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      const bool valid = r < d.ns * N_POOL;
+      const size_t grow = (size_t)d.tile * TILE_ROWS + r;         // global (b, p) row
       mbar_wait(&c1_full[bi], n & 1u);
       tc_fence_after();
-      float y[48];
-      tmem_ld_32x32(tmem_base + lane_addr + (uint32_t)(bi * 64), y);
-      tmem_ld_32x16(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32), y + 32);
+      float y[20];
+      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
+      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&c1_empty[bi]);         // the accumulator may be overwritten by channel c+2
+      if (lane == 0) mbar_arrive(&c1_empty[bi]);         // the accumulator may be overwritten by iteration it+2
 #pragma unroll
-      for (int k = 0; k < N_FILT; ++k) y[k] += tab[96 + k];
+      for (int i = 0; i < 20; ++i) y[i] += tab[96 + kidx(h, i)];
       if (MODE == MODE_STATS) {
         if (valid) {
 #pragma unroll
-          for (int k = 0; k < N_FILT; ++k) { s1[k] += y[k]; s2[k] = fmaf(y[k], y[k], s2[k]); }
+          for (int i = 0; i < 20; ++i) { s1[i] += y[i]; s2[i] = fmaf(y[i], y[i], s2[i]); }
         }
       } else {
         if (valid && p.y1 != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(p.y1 + grow * K_SPAT + c * N_FILT);
+          float* dst = p.y1 + grow * K_SPAT + d.c * N_FILT;
 #pragma unroll
-          for (int j = 0; j < 10; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          for (int j = 0; j < 5; ++j)
+            *reinterpret_cast<float4*>(dst + kidx(h, 4 * j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
 #pragma unroll
-        for (int k = 0; k < N_FILT; ++k) y[k] = tf32_fast(elu_fast(fmaf(y[k], tab[k], tab[48 + k])));
+        for (int i = 0; i < 20; ++i) {
+          const int k = kidx(h, i);
+          y[i] = valid ? tf32_fast(elu_fast(fmaf(y[i], tab[k], tab[48 + k]))) : 0.f;
+        }
         if (valid && p.a1 != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(p.a1 + grow * K_SPAT + c * N_FILT);
+          float* dst = p.a1 + grow * K_SPAT + d.c * N_FILT;
 #pragma unroll
-          for (int j = 0; j < 10; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          for (int j = 0; j < 5; ++j)
+            *reinterpret_cast<float4*>(dst + kidx(h, 4 * j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
-        // K slice of the spatial A operand: k 0..31 -> k-block 0, k 32..39 -> first two chunks of k-block 1
-        mbar_wait(&a1_empty[bi], (n & 1u) ^ 1u);         // spatial UMMAs of channel c-2 are done with this buffer
+        // K slice of the spatial A operand: k 0..31 -> k-block 0 (chunk k/4), k 32..39 -> chunks 0, 1 of k-block 1
+        mbar_wait(&a1_empty[bi], (n & 1u) ^ 1u);         // spatial UMMAs of iteration it-2 are done with this buffer
         uint8_t* a1t = sm + OFF_A1 + (uint32_t)bi * 2 * KB_A;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<float4*>(a1t + sw128_off(r, ch)) = make_float4(y[4 * ch], y[4 * ch + 1], y[4 * ch + 2], y[4 * ch + 3]);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-          *reinterpret_cast<float4*>(a1t + KB_A + sw128_off(r, ch)) =
-              make_float4(y[32 + 4 * ch], y[33 + 4 * ch], y[34 + 4 * ch], y[35 + 4 * ch]);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(a1t + sw128_off(r, 4 * h + j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        *reinterpret_cast<float4*>(a1t + KB_A + sw128_off(r, h)) = make_float4(y[16], y[17], y[18], y[19]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1_full[bi]);
+        if (d.l == F_LEN - 1) {
+          // ---- last channel of the item: y2 share = accumulated spatial product (+ bias once per tile) ----
+          const int ib = d.item_local & 1;
+          mbar_wait(&y2_full[ib], (uint32_t)(d.item_local >> 1) & 1u);
+          tc_fence_after();
+          float o[20];
+          tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + ib * 64 + 16 * h), o);
+          tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + ib * 64 + 32 + 4 * h), o + 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&y2_empty[ib]);
+          if (valid) {
+            float* dst = p.y2 + grow * N_FILT;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const int k = kidx(h, 4 * j);
+              float4 v = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              if (d.part == 0) { v.x += p.bs[k]; v.y += p.bs[k + 1]; v.z += p.bs[k + 2]; v.w += p.bs[k + 3]; }
+              red_add_v4(dst + k, v.x, v.y, v.z, v.w);
+            }
+          }
+        }
       }
     }
     if (MODE == MODE_STATS) {
       // per-filter sums over the 32 rows of this warp, then shared + one double atomic per filter per CTA
 #pragma unroll
-      for (int k = 0; k < N_FILT; ++k) {
-        const float a = warp_sum(s1[k]), b = warp_sum(s2[k]);
-        if (lane == 0) { atomicAdd(&red[k], a); atomicAdd(&red[N_FILT + k], b); }
+      for (int i = 0; i < 20; ++i) {
+        const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
+        if (lane == 0) { atomicAdd(&red[kidx(h, i)], a); atomicAdd(&red[N_FILT + kidx(h, i)], b); }
       }
-      named_bar_sync(2, 128);
+      named_bar_sync(2, 256);
       const int k = threadIdx.x - 128;
       if (k < 2 * N_FILT) atomicAdd(&p.sums[k], (double)red[k]);
-    } else {
-      // ---- y2 = accumulated spatial product + bias ----
-      mbar_wait(y2_full, 0);
-      tc_fence_after();
-      float o[48];
-      tmem_ld_32x32(tmem_base + lane_addr + 128u, o);
-      tmem_ld_32x16(tmem_base + lane_addr + 160u, o + 32);
-      if (valid) {
-        float4* dst = reinterpret_cast<float4*>(p.y2 + grow * N_FILT);
-#pragma unroll
-        for (int j = 0; j < 10; ++j)
-          dst[j] = make_float4(o[4 * j] + p.bs[4 * j], o[4 * j + 1] + p.bs[4 * j + 1], o[4 * j + 2] + p.bs[4 * j + 2],
-                               o[4 * j + 3] + p.bs[4 * j + 3]);
-      }
     }
   } else if (lane == 0) {
     // =============================== control: TMA + UMMA issue ===============================
     constexpr uint32_t idesc = umma_idesc_tf32(128, N48, 0, 0);
     const uint32_t im = smem_u32(sm + OFF_IM), bc = smem_u32(sm + OFF_BC), a1s = smem_u32(sm + OFF_A1), wss = smem_u32(sm + OFF_WS);
-    auto load_ws = [&](int c) {
-      const int wi = c & (WS_RING - 1);
-      const uint32_t n = (uint32_t)(c / WS_RING);
+    auto load_ws = [&](int it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int wi = it & (WS_RING - 1);
+      const uint32_t n = (uint32_t)(it / WS_RING);
       mbar_wait(&ws_empty[wi], (n & 1u) ^ 1u);
-      mbar_arrive_expect_tx(&ws_full[wi], 2 * KB_B);
-      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_B, 0, c * N48);
-      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_B + KB_B, 32, c * N48);
+      mbar_arrive_expect_tx(&ws_full[wi], 2 * KB_48);
+      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48, 0, d.c * N48);
+      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48 + KB_48, 32, d.c * N48);
     };
-    auto spatial = [&](int c) {
-      const int bi = c & 1, wi = c & (WS_RING - 1);
-      mbar_wait(&a1_full[bi], (uint32_t)(c >> 1) & 1u);
-      mbar_wait(&ws_full[wi], (uint32_t)(c / WS_RING) & 1u);
+    auto spatial = [&](int it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int bi = it & 1, wi = it & (WS_RING - 1), ib = d.item_local & 1;
+      if (d.l == 0) mbar_wait(&y2_empty[ib], ((uint32_t)(d.item_local >> 1) & 1u) ^ 1u);   // Y2[ib] drained (item - 2)
+      mbar_wait(&a1_full[bi], (uint32_t)(it >> 1) & 1u);
+      mbar_wait(&ws_full[wi], (uint32_t)(it / WS_RING) & 1u);
       tc_fence_after();
-      const uint32_t a = a1s + (uint32_t)bi * 2 * KB_A, w = wss + (uint32_t)wi * 2 * KB_B;
+      const uint32_t a = a1s + (uint32_t)bi * 2 * KB_A, w = wss + (uint32_t)wi * 2 * KB_48;
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) {                   // K = 40: four 8-steps of k-block 0 and the first of k-block 1
-        const uint32_t ao = kk < 4 ? (uint32_t)kk * 32u : KB_A, wo = kk < 4 ? (uint32_t)kk * 32u : KB_B;
-        tc_mma_tf32(tmem_base + 128u, umma_smem_desc(a + ao, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(w + wo, 16, 1024, UMMA_LAYOUT_SW128), idesc, (c > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t ao = kk < 4 ? (uint32_t)kk * 32u : KB_A, wo = kk < 4 ? (uint32_t)kk * 32u : KB_48;
+        tc_mma_tf32(tmem_base + 128u + (uint32_t)(ib * 64), umma_smem_desc(a + ao, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(w + wo, 16, 1024, UMMA_LAYOUT_SW128), idesc, (d.l > 0 || kk > 0) ? 1u : 0u);
       }
       tc_commit(&a1_empty[bi]);
       tc_commit(&ws_empty[wi]);
+      if (d.l == F_LEN - 1) tc_commit(&y2_full[ib]);
     };
-    // weights of channel c+2 are requested while channel c is processed: their ring slot was last read by the spatial
-    // UMMAs of channel c-2, issued one iteration earlier
     if (MODE == MODE_APPLY) {
-      load_ws(0);
-      load_ws(1);
+      if (total_it > 0) load_ws(0);
+      if (total_it > 1) load_ws(1);
     }
-    for (int c = 0; c < N_CH; ++c) {
-      const int bi = c & 1;
-      const uint32_t n = (uint32_t)(c >> 1);
+    for (int it = 0; it < total_it; ++it) {
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
       mbar_wait(&tile_full[bi], n & 1u);
       mbar_wait(&c1_empty[bi], (n & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t hi = im + (uint32_t)bi * 2 * KB_A, lo = hi + KB_A;
-      const uint32_t d = tmem_base + (uint32_t)(bi * 64);
+      const uint32_t dcol = tmem_base + (uint32_t)(bi * 64);
       // 3xTF32: lo.hi + hi.lo + hi.hi (small terms first)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(d, umma_smem_desc(lo + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
+        tc_mma_tf32(dcol, umma_smem_desc(lo + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
                     umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, kk > 0 ? 1u : 0u);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(d, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + KB_B + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
+        tc_mma_tf32(dcol, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(bc + KB_48 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(d, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
+        tc_mma_tf32(dcol, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
                     umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
       tc_commit(&tile_empty[bi]);
       tc_commit(&c1_full[bi]);
       if (MODE == MODE_APPLY) {
-        if (c + 2 < N_CH) load_ws(c + 2);
-        if (c > 0) spatial(c - 1);                       // one channel behind: its epilogue ran while these MMAs were issued
+        if (it + 2 < total_it) load_ws(it + 2);
+        if (it > 0) spatial(it - 1);                     // one iteration behind: its epilogue ran while these MMAs were issued
       }
     }
-    if (MODE == MODE_APPLY) {
-      spatial(N_CH - 1);
-      tc_commit(y2_full);
-    }
+    if (MODE == MODE_APPLY && total_it > 0) spatial(total_it - 1);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (warp == 12) tmem_dealloc(tmem_base, 256);
 }
 
 // tsconv.4.weight [j][k][c] -> [c][48 rows j][64 floats k], TF32-rounded, zero padded: B operand of the spatial UMMA
@@ -400,35 +472,637 @@ __global__ void pack_ws_tc_kernel(const float* __restrict__ ws, float* __restric
   out[idx] = (j < N_FILT && k < N_FILT) ? tf32_rn(ws[(j * N_FILT + k) * N_CH + c]) : 0.f;
 }
 
+// =================================================================================================================
+// backward
+// =================================================================================================================
+enum { MODE_BSTATS = 0, MODE_BAPPLY = 1 };
+constexpr int B1_THREADS = 13 * 32;               // 4 builder, 8 epilogue, 1 control warp
+constexpr int B2_THREADS = 17 * 32;               // + 4 scatter warps
+constexpr uint32_t FWD_PACK_FLOATS = N_CH * N48 * 64;        // pack_ws_tc_kernel output
+constexpr uint32_t WST_MAIN_FLOATS = N_CH * N48 * 32;        // [c][48 rows k][32 floats j 0..31]
+constexpr uint32_t WST_TAIL_FLOATS = N_GROUPS * N48 * 32;    // [g][48 rows k][8 ci + (j - 32)]
+// shared-memory map (common part)
+constexpr uint32_t OB_IMK = 0;                               // [2] x 16 KB   im2col, K-major (TF32 hi part only)
+constexpr uint32_t OB_BC = OB_IMK + 2 * KB_A;                // 6 KB          conv weights / 51, K-major
+constexpr uint32_t OB_DYK = OB_BC + KB_48;                   // [2] x 16 KB   dY2 tile columns 0..31, K-major
+constexpr uint32_t OB_TAIL = OB_DYK + 2 * KB_A;              // 16 KB         shared tail k-block, one 8-column k-step each:
+                                                             //   kk = 0, 1: dY2 columns 32..39 of tile buffer 0, 1; kk = 2: dy tail
+constexpr uint32_t OB_WST = OB_TAIL + KB_A;                  // [4] x 6 KB    ring: Ws_c^T rows k, columns j 0..31
+constexpr uint32_t OB_WSTT = OB_WST + WS_RING * KB_48;       // 6 KB          the group's Ws^T tails (j 32..39), k-step ci
+constexpr uint32_t OB_MODE = OB_WSTT + KB_48;                // mode-specific tiles from here
+static_assert(OB_BC % 1024 == 0 && OB_DYK % 1024 == 0 && OB_TAIL % 1024 == 0 && OB_WST % 1024 == 0 &&
+              OB_WSTT % 1024 == 0 && OB_MODE % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+// B1: dY2 MN-major [2][2 slabs], a1 MN-major [2 slabs]
+constexpr uint32_t O1_DYM = OB_MODE;                         // [2] x 32 KB
+constexpr uint32_t O1_A1M = O1_DYM + 4 * SLAB;               // 32 KB  (the M = 128 A operand of the dWs UMMA reads two
+                                                             //   slabs past DYM[tb]: they must stay inside the allocation)
+constexpr uint32_t O1_MISC = O1_A1M + 2 * SLAB;
+// B2: dy MN-major [2 slabs], im2col MN-major [2][1 slab], dy K-major main, wt^T
+constexpr uint32_t O2_DYM = OB_MODE;                         // 32 KB (+ 2 don't-care slabs = the IMM tiles behind it)
+constexpr uint32_t O2_IMM = O2_DYM + 2 * SLAB;               // [2] x 16 KB
+constexpr uint32_t O2_DYK2 = O2_IMM + 2 * SLAB;              // 16 KB
+constexpr uint32_t O2_WTT = O2_DYK2 + KB_A;                  // 8 KB: [32 rows t][32 floats k 0..31] + tail block (k 32..39)
+constexpr uint32_t O2_MISC = O2_WTT + 2 * KB_32;
+// misc area: ps / cs (builders), dps / csd (scatter warps), tables [5][48], red [80], barriers, tmem slot
+constexpr uint32_t M_PS = 0;
+constexpr uint32_t M_DPS = M_PS + (3 * PS_LD + 3 * CSX_LD) * 4;
+constexpr uint32_t M_TAB = M_DPS + (3 * PS_LD + 3 * CSX_LD) * 4;
+constexpr uint32_t M_RED = M_TAB + 5 * 48 * 4;
+constexpr uint32_t M_BAR = (M_RED + 80 * 4 + 7) & ~7u;
+constexpr int NB_BARS = 6 * 2 + 2 * WS_RING + 1 + 4 * 2 + 1;
+constexpr uint32_t M_TMEM = M_BAR + NB_BARS * 8;
+constexpr uint32_t M_END = M_TMEM + 16;
+constexpr uint32_t B1_SMEM = O1_MISC + M_END + 1024;
+constexpr uint32_t B2_SMEM = O2_MISC + M_END + 1024;
+static_assert(B1_SMEM <= 227 * 1024 && B2_SMEM <= 227 * 1024, "conv backward kernels exceed the shared memory of an SM");
+
+struct ConvBwdParams {
+  const float* x3;          // [B*64, 256]
+  const float* wt;          // [40, 25]
+  const float* bt;          // [40]
+  const float* mean_rstd;   // [2][40] BatchNorm1 statistics of the forward
+  const float* gamma;       // [40]
+  const float* beta;        // [40]
+  const float* dy2;         // [B*36, 40] d loss / d (spatial conv output)
+  double* bsums;            // [2][40]: sum dz, sum dz*yhat   (B1 adds, B2 reads)
+  float* dws;               // tsconv.4.weight gradient [j][k][c]   (B1, +=)
+  float* dx3;               // [B*64, 256]                           (B2)
+  float* dwt;               // [40, 25]  (+=)
+  float* dbt;               // [40]      (+=)
+  float* dgamma;            // [40]      (+=)
+  float* dbeta;             // [40]      (+=)
+  long long count;          // BatchNorm element count (global batch under SyncBN)
+  float gscale;             // 1 / world size for the parameters whose gradient every rank computes in full
+  int B;
+  int n_tiles;
+};
+
+struct BwdIt { int tl, ci, c, tile, ns; };
+__device__ __forceinline__ BwdIt bwd_decode(int it, int gc, int g, int slot, int n_slots, int B) {
+  BwdIt d;
+  d.tl = it / gc;
+  d.ci = it - d.tl * gc;
+  d.c = g * GC + d.ci;
+  d.tile = slot + d.tl * n_slots;
+  d.ns = min(TILE_S, B - d.tile * TILE_S);
+  return d;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MODE == MODE_BSTATS ? B1_THREADS : B2_THREADS, 1)
+conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_constant__ CUtensorMap tmWstt, const ConvBwdParams p) {
+  constexpr bool BS = MODE == MODE_BSTATS;
+  constexpr int NTHREADS = BS ? B1_THREADS : B2_THREADS;
+  constexpr int CTRL_WARP = BS ? 12 : 16;
+  constexpr uint32_t O_MISC = BS ? O1_MISC : O2_MISC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* misc = sm + O_MISC;
+  float* ps_all = reinterpret_cast<float*>(misc + M_PS);
+  float* cs_all = ps_all + 3 * PS_LD;
+  float* dps_all = reinterpret_cast<float*>(misc + M_DPS);
+  float* csd_all = dps_all + 3 * PS_LD;
+  float* tab = reinterpret_cast<float*>(misc + M_TAB);       // [0] bt, [1] sc, [2] sh, [3] p1, [4] p2 (see the epilogue)
+  float* red = reinterpret_cast<float*>(misc + M_RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + M_BAR);
+  uint64_t* im_full = bars;              // [2] builders -> control
+  uint64_t* im_empty = bars + 2;         // [2] last UMMA reading the im2col buffer -> builders
+  uint64_t* dyt_full = bars + 4;         // [2] builders wrote the dY2 tile -> control
+  uint64_t* dyt_empty = bars + 6;        // [2] last UMMA reading the dY2 tile -> builders
+  uint64_t* c_full = bars + 8;           // [2] conv + dA1 UMMAs done -> epilogue
+  uint64_t* c_empty = bars + 10;         // [2] epilogue read TMEM -> control (8 arrivals)
+  uint64_t* wst_full = bars + 12;        // [4]
+  uint64_t* wst_empty = bars + 12 + WS_RING;     // [4]
+  uint64_t* wstt_full = bars + 12 + 2 * WS_RING; // [1]
+  uint64_t* op_full = wstt_full + 1;     // [0 used] epilogue wrote a1 (B1) / dy (B2) -> control (8 arrivals)
+  uint64_t* op_empty = op_full + 2;      // [0 used] UMMAs reading it done -> epilogue
+  uint64_t* gg_full = op_empty + 2;      // [2] G UMMAs done -> scatter warps (B2)
+  uint64_t* gg_empty = gg_full + 2;      // [2] scatter warps read TMEM -> control (4 arrivals)
+  uint64_t* final_full = gg_empty + 2;   // everything issued by the control thread has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + M_TMEM);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x % N_GROUPS, slot = blockIdx.x / N_GROUPS, n_slots = gridDim.x / N_GROUPS;
+  const int gc = min(GC, N_CH - g * GC);                         // 4, or 3 for the last group
+  const int n_my_tiles = (p.n_tiles - slot + n_slots - 1) / n_slots;
+  const int total_it = n_my_tiles * gc;
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&im_full[i], 1);
+      mbar_init(&im_empty[i], 1);
+      mbar_init(&dyt_full[i], 1);
+      mbar_init(&dyt_empty[i], 1);
+      mbar_init(&c_full[i], 1);
+      mbar_init(&c_empty[i], 8);
+      mbar_init(&gg_full[i], 1);
+      mbar_init(&gg_empty[i], 4);
+      mbar_init(&op_full[i], 8);
+      mbar_init(&op_empty[i], 1);
+    }
+    for (int i = 0; i < WS_RING; ++i) {
+      mbar_init(&wst_full[i], 1);
+      mbar_init(&wst_empty[i], 1);
+    }
+    mbar_init(wstt_full, 1);
+    mbar_init(final_full, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmWst);
+    tma_prefetch_desc(&tmWstt);
+  }
+  // zero every operand tile and the scan scratch once: pad columns / rows that are never written must be finite zeros
+  for (uint32_t i = threadIdx.x * 16; i < O_MISC + M_TAB; i += NTHREADS * 16)
+    *reinterpret_cast<float4*>(sm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  // conv weights / 51 (TF32) as the B operand of the conv UMMA: rows k < 40 (48), columns t < 25 (32)
+  for (int i = threadIdx.x; i < N48 * 32; i += NTHREADS) {
+    const int k = i >> 5, t = i & 31;
+    const float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
+    *reinterpret_cast<float*>(sm + OB_BC + sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u) = tf32_fast(w);
+  }
+  if (!BS) {
+    // wt^T (unscaled) as the B operand of the G UMMA: rows t < 25 (32), columns k: 0..31 main block, 32..39 tail block
+    for (int i = threadIdx.x; i < 32 * N_FILT; i += NTHREADS) {
+      const int t = i / N_FILT, k = i - t * N_FILT;
+      const float w = t < K_TEMP ? tf32_fast(p.wt[k * K_TEMP + t]) : 0.f;
+      const uint32_t blk = k < 32 ? 0u : KB_32;
+      const int kc = k & 31;
+      *reinterpret_cast<float*>(sm + O2_WTT + blk + sw128_off(t, kc >> 2) + (uint32_t)(kc & 3) * 4u) = w;
+    }
+  }
+  if (threadIdx.x < N48) {
+    const int k = threadIdx.x;
+    float bt = 0.f, sc = 0.f, sh = 0.f, p1 = 0.f, p2 = 0.f;
+    if (k < N_FILT) {
+      const float mu = p.mean_rstd[k], rs = p.mean_rstd[N_FILT + k], ga = p.gamma[k];
+      bt = p.bt[k];
+      sc = ga * rs;                                  // z = sc*y + sh ; also the A of dy = A*dz + Bc*y + Cc
+      sh = p.beta[k] - mu * sc;
+      if (BS) {
+        p1 = rs;                                     // yhat = p1*y + p2
+        p2 = -mu * rs;
+      } else {
+        const float m1 = (float)(p.bsums[k] / (double)p.count);
+        const float m2 = (float)(p.bsums[N_FILT + k] / (double)p.count);
+        p1 = -sc * rs * m2;                          // Bc
+        p2 = sc * (mu * rs * m2 - m1);               // Cc
+      }
+    }
+    tab[k] = bt; tab[48 + k] = sc; tab[96 + k] = sh; tab[144 + k] = p1; tab[192 + k] = p2;
+  }
+  if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
+  if (!BS && blockIdx.x == 0 && threadIdx.x < N_FILT) {
+    // BatchNorm1 affine gradients straight from the reductions of B1
+    atomicAdd(&p.dgamma[threadIdx.x], p.gscale * (float)p.bsums[N_FILT + threadIdx.x]);
+    atomicAdd(&p.dbeta[threadIdx.x], p.gscale * (float)p.bsums[threadIdx.x]);
+  }
+  if (warp == CTRL_WARP) {
+    tmem_alloc(tmem_slot, 512);   // Y[2]: 0, 64; DA[2]: 128, 192; B1: dWs[4] at 256 + 64 ci; B2: G[2] at 256, 288, dwt at 320
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =============================== builders ===============================
+    const int r = threadIdx.x;                         // tile row 0..127
+    const int s_row = r / N_POOL, p_row = r % N_POOL;
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    float4 dyr[10];
+    auto fetch_x = [&](int it) {
+      if (it < total_it && warp < TILE_S) {
+        const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+        if (warp < d.ns) {
+          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + warp) * N_TOK + d.c) * D_PAD + 8 * lane;
+          xa = __ldg(reinterpret_cast<const float4*>(xrow));
+          xb = __ldg(reinterpret_cast<const float4*>(xrow + 4));
+        }
+      }
+    };
+    auto fetch_dy = [&](int tl) {                       // this thread's row of the dY2 tile of local tile tl
+#pragma unroll
+      for (int j = 0; j < 10; ++j) dyr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tl < n_my_tiles) {
+        const int tile = slot + tl * n_slots;
+        const int ns = min(TILE_S, p.B - tile * TILE_S);
+        if (r < ns * N_POOL) {
+          const float4* src = reinterpret_cast<const float4*>(p.dy2 + ((size_t)tile * TILE_ROWS + r) * N_FILT);
+#pragma unroll
+          for (int j = 0; j < 10; ++j) dyr[j] = __ldg(src + j);
+        }
+      }
+    };
+    fetch_x(0);
+    fetch_dy(0);
+    for (int it = 0; it < total_it; ++it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      const int tb = d.tl & 1;
+      const bool valid = r < d.ns * N_POOL;
+      const float4 x0 = xa, x1 = xb;
+      fetch_x(it + 1);
+      if (warp < d.ns) pool_row(x0, x1, lane, cs_all + warp * CSX_LD, ps_all + warp * PS_LD);
+      if (d.ci == 0) {
+        // ---- dY2 rows of this (new) tile: K-major for the dA1 UMMA (+ MN-major for the dWs UMMA in B1) ----
+        mbar_wait(&dyt_empty[tb], ((uint32_t)(d.tl >> 1) & 1u) ^ 1u);
+        uint8_t* dk = sm + OB_DYK + (uint32_t)tb * KB_A;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          float4 v = dyr[j];
+          v.x = tf32_fast(v.x); v.y = tf32_fast(v.y); v.z = tf32_fast(v.z); v.w = tf32_fast(v.w);
+          dyr[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dk + sw128_off(r, j)) = dyr[j];
+        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb)) = dyr[8];
+        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb + 1)) = dyr[9];
+        if (BS) {
+          uint8_t* dm = sm + O1_DYM + (uint32_t)tb * 2 * SLAB;
+#pragma unroll
+          for (int j8 = 0; j8 < 5; ++j8) {               // mn = j: 8 consecutive j per 32-byte chunk
+            const uint32_t off = mn_off(8 * j8, r);
+            *reinterpret_cast<float4*>(dm + off) = dyr[2 * j8];
+            *reinterpret_cast<float4*>(dm + off + 16) = dyr[2 * j8 + 1];
+          }
+        }
+        fetch_dy(d.tl + 1);                             // the next tile's row travels during this tile's iterations
+      }
+      named_bar_sync(1, 128);                             // pooled sums visible
+      mbar_wait(&im_empty[bi], (n & 1u) ^ 1u);
+      {
+        const float* src = ps_all + s_row * PS_LD + 5 * p_row;
+        float a[28];
+#pragma unroll
+        for (int t = 0; t < 28; ++t) a[t] = (valid && t < K_TEMP) ? tf32_fast(src[t]) : 0.f;
+        uint8_t* kt = sm + OB_IMK + (uint32_t)bi * KB_A;
+#pragma unroll
+        for (int ch = 0; ch < 7; ++ch)
+          *reinterpret_cast<float4*>(kt + sw128_off(r, ch)) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
+        if (!BS) {
+          // the same row as k-row r of the MN-major operand (mn = tap t); column 25 = 1 for valid rows: the dwt UMMA
+          // then also delivers sum_rows dy (the conv bias gradient) in output column 25
+          a[25] = valid ? 1.f : 0.f;
+          uint8_t* mt = sm + O2_IMM + (uint32_t)bi * SLAB;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            const uint32_t off = mn_off(8 * j8, r);
+            *reinterpret_cast<float4*>(mt + off) = make_float4(a[8 * j8], a[8 * j8 + 1], a[8 * j8 + 2], a[8 * j8 + 3]);
+            *reinterpret_cast<float4*>(mt + off + 16) =
+                j8 < 3 ? make_float4(a[8 * j8 + 4], a[8 * j8 + 5], a[8 * j8 + 6], a[8 * j8 + 7]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 0) {
+        if (d.ci == 0) mbar_arrive(&dyt_full[tb]);
+        mbar_arrive(&im_full[bi]);
+      }
+    }
+  } else if (warp < 12) {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float s1[BS ? 20 : 1], s2[BS ? 20 : 1];
+    if constexpr (BS) {
+#pragma unroll
+      for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
+    }
+    for (int it = 0; it < total_it; ++it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      const bool valid = r < d.ns * N_POOL;
+      mbar_wait(&c_full[bi], n & 1u);
+      tc_fence_after();
+      float y[20], da[20];
+      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
+      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
+      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 16 * h), da);
+      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 32 + 4 * h), da + 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c_empty[bi]);
+      float o[20];
+#pragma unroll
+      for (int i = 0; i < 20; ++i) {
+        const int k = kidx(h, i);
+        const float yv = y[i] + tab[k];
+        const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
+        const float dz = da[i] * (z > 0.f ? 1.f : __expf(z));          // ELU'(z)
+        if constexpr (BS) {
+          const float yh = fmaf(yv, tab[144 + k], tab[192 + k]);
+          if (valid) { s1[i] += dz; s2[i] = fmaf(dz, yh, s2[i]); }
+          o[i] = valid ? tf32_fast(elu_fast(z)) : 0.f;                  // a1
+        } else {
+          o[i] = valid ? tf32_fast(fmaf(tab[48 + k], dz, fmaf(tab[144 + k], yv, tab[192 + k]))) : 0.f;   // dy
+        }
+      }
+      // ---- operand tiles of the second-stage UMMAs (single buffered: those of iteration it-1 must have completed) ----
+      mbar_wait(&op_empty[0], ((uint32_t)it & 1u) ^ 1u);
+      {
+        uint8_t* mt = sm + (BS ? O1_A1M : O2_DYM);                     // MN-major: mn = filter k, k-row = tile row r
+        const uint32_t o0 = mn_off(16 * h, r), o1 = mn_off(16 * h + 8, r), o2 = mn_off(32 + 4 * h, r);
+        *reinterpret_cast<float4*>(mt + o0) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(mt + o0 + 16) = make_float4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<float4*>(mt + o1) = make_float4(o[8], o[9], o[10], o[11]);
+        *reinterpret_cast<float4*>(mt + o1 + 16) = make_float4(o[12], o[13], o[14], o[15]);
+        *reinterpret_cast<float4*>(mt + o2) = make_float4(o[16], o[17], o[18], o[19]);
+        if (!BS) {
+          uint8_t* kt = sm + O2_DYK2;                                  // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(kt + sw128_off(r, 4 * h + j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 4 + h)) = make_float4(o[16], o[17], o[18], o[19]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&op_full[0]);
+    }
+    // ---- after the loop: the accumulators that lived in TMEM for the whole kernel ----
+    mbar_wait(final_full, 0);
+    tc_fence_after();
+    if constexpr (BS) {
+      if (total_it > 0 && q < 2) {                                     // TMEM lane = j (output filter of the spatial conv)
+        for (int ci = 0; ci < gc; ++ci) {
+          float w[20];
+          tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64 + 16 * h), w);
+          tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64 + 32 + 4 * h), w + 16);
+          tmem_ld_wait();
+          const int c = g * GC + ci;
+          if (r < N_FILT) {
+#pragma unroll
+            for (int i = 0; i < 20; ++i) atomicAdd(&p.dws[((size_t)r * N_FILT + kidx(h, i)) * N_CH + c], w[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 20; ++i) {
+        const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
+        if (lane == 0) { atomicAdd(&red[kidx(h, i)], a); atomicAdd(&red[N_FILT + kidx(h, i)], b); }
+      }
+      named_bar_sync(2, 256);
+      const int k = threadIdx.x - 128;
+      if (k < 2 * N_FILT) atomicAdd(&p.bsums[k], (double)red[k]);
+    } else {
+      if (total_it > 0 && q < 2) {                                     // TMEM lane = filter k, column = tap t (25: ones column)
+        float w[16];
+        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(320 + 16 * h), w);
+        tmem_ld_wait();
+        if (r < N_FILT) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int t = 16 * h + i;
+            if (t < K_TEMP) atomicAdd(&p.dwt[r * K_TEMP + t], w[i] * (1.f / K_POOL));
+            else if (t == K_TEMP) atomicAdd(&p.dbt[r], w[i]);
+          }
+        }
+      }
+    }
+  } else if (!BS && warp < 16) {
+    // =============================== scatter warps (B2): G -> pooled positions -> d x3 ===============================
+    const int q = warp & 3;
+    const int sw = warp - 12;
+    const int r = q * 32 + lane;
+    const int s_row = r / N_POOL, p_row = r % N_POOL;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int it = 0; it < total_it; ++it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bi = it & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      const bool valid = r < d.ns * N_POOL;
+      mbar_wait(&gg_full[bi], n & 1u);
+      tc_fence_after();
+      float gv[32];
+      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32), gv);
+      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32 + 16), gv + 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gg_empty[bi]);
+      if (valid) {
+        float* dp = dps_all + s_row * PS_LD + 5 * p_row;      // dps[u] += G[(s,p), t] at u = 5p + t
+#pragma unroll
+        for (int t = 0; t < K_TEMP; ++t) atomicAdd(dp + t, gv[t]);
+      }
+      named_bar_sync(3, 128);
+      if (sw < d.ns) {
+        // d x3[v] = (1/51) * sum_{u = max(0, v-50)}^{min(v, 199)} dps[u]  via the prefix P: (P[hi+1] - P[lo]) / 51
+        float* dp = dps_all + sw * PS_LD;
+        float* cs = csd_all + sw * CSX_LD;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (lane < 25) {
+          const float4 a = *reinterpret_cast<const float4*>(dp + 8 * lane), b = *reinterpret_cast<const float4*>(dp + 8 * lane + 4);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+          for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
+          *reinterpret_cast<float4*>(dp + 8 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);     // ready for the next iteration
+          *reinterpret_cast<float4*>(dp + 8 * lane + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float tot = v[7];
+        float inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float nb = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += nb;
+        }
+        const float excl = inc - tot;
+        if (lane == 0) cs[0] = 0.f;
+        if (lane < 25) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs[8 * lane + 1 + i] = v[i] + excl;         // P[u+1] = sum of dps[0..u]
+        }
+        __syncwarp();
+        float o8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int t = 8 * lane + i;
+          const int hi = t < N_PSUM - 1 ? t : N_PSUM - 1;
+          const int lo = t - (K_POOL - 1) > 0 ? t - (K_POOL - 1) : 0;
+          o8[i] = t < N_T ? (cs[hi + 1] - cs[lo]) * (1.f / K_POOL) : 0.f;
+        }
+        float* dxr = p.dx3 + ((size_t)(d.tile * TILE_S + sw) * N_TOK + d.c) * D_PAD + 8 * lane;
+        *reinterpret_cast<float4*>(dxr) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+        *reinterpret_cast<float4*>(dxr + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
+        if (d.c == N_CH - 1) {
+          // token 63 (channel 62) never reaches the conv stack (enc_out[:, :63], ATMS_retrieval.py:91): zero gradient
+          float* dz = dxr + D_PAD;
+          *reinterpret_cast<float4*>(dz) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dz + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      named_bar_sync(3, 128);
+    }
+  } else if (warp == CTRL_WARP && lane == 0) {
+    // =============================== control: TMA + UMMA issue ===============================
+    constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0);
+    constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32, 0, 0);
+    constexpr uint32_t idesc48_mn = umma_idesc_tf32(128, N48, 1, 1);
+    constexpr uint32_t idesc32_mn = umma_idesc_tf32(128, 32, 1, 1);
+    const uint32_t s0 = smem_u32(sm);
+    auto load_wst = [&](int it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int wi = it & (WS_RING - 1);
+      const uint32_t n = (uint32_t)(it / WS_RING);
+      mbar_wait(&wst_empty[wi], (n & 1u) ^ 1u);
+      mbar_arrive_expect_tx(&wst_full[wi], KB_48);
+      tma_load_2d(&tmWst, &wst_full[wi], sm + OB_WST + (uint32_t)wi * KB_48, 0, d.c * N48);
+    };
+    auto stage2 = [&](int it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bj = it & 1, tb = d.tl & 1;
+      mbar_wait(&op_full[0], (uint32_t)it & 1u);
+      if (BS) {
+        tc_fence_after();
+        // dWs_c[j, k] += sum_rows dY2[row, j] * a1[row, k]: both operands MN-major, K = the 128 tile rows
+        const uint32_t a = s0 + O1_DYM + (uint32_t)tb * 2 * SLAB, b = s0 + O1_A1M;
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk)
+          tc_mma_tf32(tmem_base + 256u + (uint32_t)(d.ci * 64), umma_smem_desc(a + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
+                      umma_smem_desc(b + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc48_mn,
+                      (d.tl > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&op_empty[0]);
+        if (d.ci == gc - 1) tc_commit(&dyt_empty[tb]);
+      } else {
+        mbar_wait(&gg_empty[bj], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
+        const uint32_t a = s0 + O2_DYK2, b = s0 + O2_WTT;
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) {
+          const uint32_t ao = kk < 4 ? a + (uint32_t)kk * 32u : s0 + OB_TAIL + 2u * 32u;
+          const uint32_t bo = kk < 4 ? b + (uint32_t)kk * 32u : b + KB_32;
+          tc_mma_tf32(tmem_base + 256u + (uint32_t)(bj * 32), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
+                      umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc32, kk > 0 ? 1u : 0u);
+        }
+        tc_commit(&gg_full[bj]);
+        // dwt[k, t] += sum_rows dy[row, k] * im2col[row, t]  (column 25 of the im2col operand is the ones column)
+        const uint32_t am = s0 + O2_DYM, bm = s0 + O2_IMM + (uint32_t)bj * SLAB;
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk)
+          tc_mma_tf32(tmem_base + 320u, umma_smem_desc(am + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
+                      umma_smem_desc(bm + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc32_mn,
+                      (it > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&op_empty[0]);
+        tc_commit(&im_empty[bj]);
+      }
+    };
+    if (total_it > 0) {
+      mbar_arrive_expect_tx(wstt_full, KB_48);
+      tma_load_2d(&tmWstt, wstt_full, sm + OB_WSTT, 0, g * N48);
+      load_wst(0);
+      if (total_it > 1) load_wst(1);
+    }
+    for (int it = 0; it < total_it; ++it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bi = it & 1, wi = it & (WS_RING - 1), tb = d.tl & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      mbar_wait(&im_full[bi], n & 1u);
+      mbar_wait(&c_empty[bi], (n & 1u) ^ 1u);
+      tc_fence_after();
+      // conv UMMA (plain TF32 in the backward): Y[bi] = im2col . (wt/51)^T
+      const uint32_t ik = s0 + OB_IMK + (uint32_t)bi * KB_A, bc = s0 + OB_BC;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), umma_smem_desc(ik + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
+      if (BS) tc_commit(&im_empty[bi]);                  // B2: the dwt UMMA of this iteration still reads the MN-major copy
+      if (d.ci == 0) mbar_wait(&dyt_full[tb], (uint32_t)(d.tl >> 1) & 1u);
+      mbar_wait(&wst_full[wi], (uint32_t)(it / WS_RING) & 1u);
+      if (it == 0) mbar_wait(wstt_full, 0);
+      tc_fence_after();
+      // dA1[(s,p), k] = sum_j dY2[(s,p), j] * Ws[j, k, c]
+      const uint32_t dk = s0 + OB_DYK + (uint32_t)tb * KB_A, wk = s0 + OB_WST + (uint32_t)wi * KB_48;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t ao = kk < 4 ? dk + (uint32_t)kk * 32u : s0 + OB_TAIL + (uint32_t)tb * 32u;
+        const uint32_t bo = kk < 4 ? wk + (uint32_t)kk * 32u : s0 + OB_WSTT + (uint32_t)d.ci * 32u;
+        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
+      }
+      tc_commit(&wst_empty[wi]);
+      tc_commit(&c_full[bi]);
+      if (!BS && d.ci == gc - 1) tc_commit(&dyt_empty[tb]);   // B2: nothing reads the dY2 tile after its last dA1 UMMA
+      if (it + 2 < total_it) load_wst(it + 2);
+      if (it > 0) stage2(it - 1);
+    }
+    if (total_it > 0) stage2(total_it - 1);
+    tc_commit(final_full);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == CTRL_WARP) tmem_dealloc(tmem_base, 512);
+}
+
+// tsconv.4.weight [j][k][c] -> Ws_c^T as the B operand of the dA1 UMMA (rows k, reduction index j), TF32, zero padded:
+//   main [c][48 rows k][32 floats j 0..31]   and   tails [g][48 rows k][8*ci + (j-32)] for the 4 channels of group g
+__global__ void pack_wst_tc_kernel(const float* __restrict__ ws, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (int)WST_MAIN_FLOATS) {
+    const int j = idx & 31, k = (idx >> 5) % N48, c = idx / (N48 * 32);
+    out[idx] = k < N_FILT ? tf32_rn(ws[(j * N_FILT + k) * N_CH + c]) : 0.f;
+  } else if (idx < (int)(WST_MAIN_FLOATS + WST_TAIL_FLOATS)) {
+    const int t = idx - (int)WST_MAIN_FLOATS;
+    const int col = t & 31, k = (t >> 5) % N48, gg = t / (N48 * 32);
+    const int ci = col >> 3, j = 32 + (col & 7), c = gg * GC + ci;
+    out[idx] = (k < N_FILT && c < N_CH) ? tf32_rn(ws[(j * N_FILT + k) * N_CH + c]) : 0.f;
+  }
+}
+
+int sm_count() {
+  static int sms_by_dev[64] = {0};
+  const int dev = current_device();
+  if (sms_by_dev[dev] == 0) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms_by_dev[dev] = n > 0 ? n : 148;
+  }
+  return sms_by_dev[dev];
+}
+
 }  // namespace
 
 int conv_tc_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("EEGB200_CONV_TC");
-    on = (e && e[0] == '1') ? 1 : 0;        // experimental: off unless asked for
+    on = (e && e[0] == '0') ? 0 : 1;        // default on; EEGB200_CONV_TC=0 selects the round-1 unfused kernels (A/B switch)
   }
   return on;
 }
-size_t conv_tc_ws_floats() { return (size_t)N_CH * N48 * 64; }
+size_t conv_tc_ws_floats() { return (size_t)FWD_PACK_FLOATS + WST_MAIN_FLOATS + WST_TAIL_FLOATS; }
 
 // BatchNorm1 batch statistics of the temporal conv output without materialising it (kernel F1)
 int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s) {
   ProfScope _ps("conv_tc_stats", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * 63 * 1000.0);
   static PerDeviceOnce once;
-  if (once.first()) {
+  if (once.first())
     EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-  }
-  ConvTcParams p{x3, wt, bt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B};
+  const int n_tiles = cdiv(B, TILE_S);
+  ConvTcParams p{x3, wt, bt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, n_tiles};
   CUtensorMap dummy;
   memset(&dummy, 0, sizeof(dummy));
-  conv_tc_fwd_kernel<MODE_STATS><<<cdiv(B, TILE_S), CTC_THREADS, CTC_SMEM, s>>>(dummy, p);
+  const int grid = min(sm_count(), n_tiles * F_PARTS);
+  conv_tc_fwd_kernel<MODE_STATS><<<grid, F_THREADS, CTC_SMEM, s>>>(dummy, p);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-// temporal conv + pool + BatchNorm1 + ELU + spatial conv in one kernel (kernel F2); y1 / a1 may be nullptr
+// temporal conv + pool + BatchNorm1 + ELU + spatial conv in one kernel (kernel F2); y1 / a1 (debug stores) may be nullptr
 int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
                   const float* beta, const float* ws, const float* bs, float* ws_packed, float* y1, float* a1, float* y2,
                   int B, cudaStream_t s) {
@@ -437,18 +1111,78 @@ int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float
   pack_ws_tc_kernel<<<cdiv(N_CH * N48 * 64, 256), 256, 0, s>>>(ws, ws_packed);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
+  EEG_CUDA_OK(cudaMemsetAsync(y2, 0, (size_t)B * N_POOL * N_FILT * sizeof(float), s));   // the items add their shares
   CUtensorMap tw;
   int d3 = 0;
   EEG_TRY(gemm_make_tmap(&tw, GemmOperand{ws_packed, 64, 0}, N_CH * N48, 64, N48, &d3));
   static PerDeviceOnce once;
-  if (once.first()) {
+  if (once.first())
     EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-  }
-  ConvTcParams p{x3, wt, bt, mean_rstd, gamma, beta, bs, y1, a1, y2, nullptr, B};
-  conv_tc_fwd_kernel<MODE_APPLY><<<cdiv(B, TILE_S), CTC_THREADS, CTC_SMEM, s>>>(tw, p);
+  const int n_tiles = cdiv(B, TILE_S);
+  ConvTcParams p{x3, wt, bt, mean_rstd, gamma, beta, bs, y1, a1, y2, nullptr, B, n_tiles};
+  const int grid = min(sm_count(), n_tiles * F_PARTS);
+  conv_tc_fwd_kernel<MODE_APPLY><<<grid, F_THREADS, CTC_SMEM, s>>>(tw, p);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+static int bwd_launch(int mode, const ConvBwdParams& p, float* wst_packed, const float* ws_to_pack, cudaStream_t s) {
+  if (ws_to_pack != nullptr) {
+    pack_wst_tc_kernel<<<cdiv((int)(WST_MAIN_FLOATS + WST_TAIL_FLOATS), 256), 256, 0, s>>>(ws_to_pack, wst_packed);
+    EEG_CUDA_OK(cudaGetLastError());
+    count_launch();
+  }
+  CUtensorMap tm, tt;
+  int d3 = 0;
+  EEG_TRY(gemm_make_tmap(&tm, GemmOperand{wst_packed, 32, 0}, N_CH * N48, 32, N48, &d3));
+  EEG_TRY(gemm_make_tmap(&tt, GemmOperand{wst_packed + WST_MAIN_FLOATS, 32, 0}, N_GROUPS * N48, 32, N48, &d3));
+  int slots = sm_count() / N_GROUPS;
+  if (slots > p.n_tiles) slots = p.n_tiles;
+  if (slots < 1) slots = 1;
+  const int grid = N_GROUPS * slots;
+  if (mode == MODE_BSTATS) {
+    static PerDeviceOnce once;
+    if (once.first())
+      EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_bwd_kernel<MODE_BSTATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B1_SMEM));
+    conv_tc_bwd_kernel<MODE_BSTATS><<<grid, B1_THREADS, B1_SMEM, s>>>(tm, tt, p);
+  } else {
+    static PerDeviceOnce once;
+    if (once.first())
+      EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_bwd_kernel<MODE_BAPPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B2_SMEM));
+    conv_tc_bwd_kernel<MODE_BAPPLY><<<grid, B2_THREADS, B2_SMEM, s>>>(tm, tt, p);
+  }
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// B1: BatchNorm1-backward reductions (bsums +=, pre-zeroed by the caller) and the spatial conv weight gradient (dws +=)
+int conv_tc_bwd_stats(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                      const float* beta, const float* ws, const float* dy2, float* ws_packed, double* bsums, float* dws,
+                      int B, cudaStream_t s) {
+  ProfScope _ps("conv_tc_bwd_stats", s, (double)B * 36 * 63 * 40 * (50.0 + 80.0 + 80.0),
+                (double)B * (63 * 1000.0 + 36 * 160.0) + 63 * 1600 * 4.0);
+  ConvBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x3 = x3; p.wt = wt; p.bt = bt; p.mean_rstd = mean_rstd; p.gamma = gamma; p.beta = beta; p.dy2 = dy2;
+  p.bsums = bsums; p.dws = dws; p.B = B; p.n_tiles = cdiv(B, TILE_S); p.count = 1; p.gscale = 1.f;
+  return bwd_launch(MODE_BSTATS, p, ws_packed + FWD_PACK_FLOATS, ws, s);
+}
+
+// B2: BatchNorm1 backward apply + transposed temporal conv: dx3 (every row of the [B*64, 256] matrix is written), dwt, dbt,
+// dgamma, dbeta (+=).  Needs the packed weights of conv_tc_bwd_stats (same step) in ws_packed.
+int conv_tc_bwd_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                      const float* beta, const float* dy2, float* ws_packed, double* bsums, long long count, float gscale,
+                      float* dx3, float* dwt, float* dbt, float* dgamma, float* dbeta, int B, cudaStream_t s) {
+  ProfScope _ps("conv_tc_bwd_apply", s, (double)B * 36 * 63 * 40 * (50.0 + 80.0 + 50.0 + 50.0),
+                (double)B * (2 * 63 * 1000.0 + 36 * 160.0));
+  ConvBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.x3 = x3; p.wt = wt; p.bt = bt; p.mean_rstd = mean_rstd; p.gamma = gamma; p.beta = beta; p.dy2 = dy2;
+  p.bsums = bsums; p.dx3 = dx3; p.dwt = dwt; p.dbt = dbt; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.count = count; p.gscale = gscale; p.B = B; p.n_tiles = cdiv(B, TILE_S);
+  return bwd_launch(MODE_BAPPLY, p, ws_packed + FWD_PACK_FLOATS, nullptr, s);
 }
 
 }  // namespace eegb200

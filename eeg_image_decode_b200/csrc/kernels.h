@@ -97,13 +97,20 @@ int conv_temporal_bwd(const float* dz1, const float* y1, const float* x3, const 
                       const float* gamma, const double* bwd_sums, long long count, float* dx3, float* dwt, float* dbt,
                       float* dgamma, float* dbeta, int B, float gscale, cudaStream_t s);
 
-// ---- conv_tc.cu (EXPERIMENTAL, EEGB200_CONV_TC=1): temporal conv + pool + BatchNorm1 + ELU + spatial conv on tcgen05 ----
-int conv_tc_enabled();
-size_t conv_tc_ws_floats();     // packed spatial weights [63][48][64]
+// ---- conv_tc.cu: the conv stack on tcgen05, forward (F1 / F2) and backward (B1 / B2); y1 / a1 / d a1 stay on chip ----
+int conv_tc_enabled();          // default on, EEGB200_CONV_TC=0 selects the unfused round-1 kernels
+size_t conv_tc_ws_floats();     // packed spatial weights: forward [63][48][64] + backward [63][48][32] + tails [16][48][32]
 int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s);
 int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
                   const float* beta, const float* ws, const float* bs, float* ws_packed, float* y1, float* a1, float* y2,
                   int B, cudaStream_t s);
+int conv_tc_bwd_stats(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                      const float* beta, const float* ws, const float* dy2, float* ws_packed, double* bsums, float* dws,
+                      int B, cudaStream_t s);
+int conv_tc_bwd_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                      const float* beta, const float* dy2, float* ws_packed, double* bsums, long long count, float gscale,
+                      float* dx3, float* dwt, float* dbt, float* dgamma, float* dbeta, int B, cudaStream_t s);
+int debug_stores();             // eegb200_set_debug_stores: keep y1 / a1 in the workspace for the stage checks
 
 // ---- loss.cu ----
 struct InfoNceArgs {

@@ -47,6 +47,53 @@ def _adam_hparams(optimizer):
     return dict(lr=float(g["lr"]), betas=tuple(g["betas"]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
 
 
+def fused_optimizer_ok(model: ATMS, optimizer) -> bool:
+    """The fused AdamW kernel implements exactly torch.optim.AdamW with ONE parameter group that covers every trainable
+    parameter of the hot path and default flags.  Anything else (several groups, amsgrad / maximize, frozen or
+    missing parameters, another optimizer class) keeps the caller's semantics through optimizer.step()."""
+    if optimizer is None:
+        return True
+    if type(optimizer).__name__ not in ("AdamW", "FusedAdamW") or len(optimizer.param_groups) != 1:
+        return False
+    g = optimizer.param_groups[0]
+    if g.get("amsgrad", False) or g.get("maximize", False) or g.get("differentiable", False):
+        return False
+    if not all(isinstance(g.get(k), (int, float)) for k in ("lr", "eps", "weight_decay")):
+        return False          # tensor learning rates (capturable mode) are not baked into the kernel arguments
+    covered = {id(p) for p in g["params"]}
+    named = dict(model.named_parameters())
+    return all(id(named[n]) in covered and named[n].requires_grad for n in model._hot_order())
+
+
+def adopt_optimizer(model: ATMS, optimizer) -> None:
+    """Tie the flat moment arenas to ``optimizer``: a NEW optimizer object starts from zero moments (it must not inherit
+    another one's), and state that did not come from the arenas -- ``optimizer.load_state_dict(checkpoint)``, steps taken
+    through ``optimizer.step()`` -- is imported (exp_avg, exp_avg_sq, step) so that resuming continues where the
+    checkpoint stopped instead of silently restarting the moments and the bias correction."""
+    if optimizer is None:
+        return
+    if model._adam_m is None:
+        model._adam_m = torch.zeros_like(model.flat_grads)
+        model._adam_v = torch.zeros_like(model.flat_grads)
+    if getattr(model, "_adam_owner", None) != id(optimizer):
+        model._adam_m.zero_()
+        model._adam_v.zero_()
+        model._adam_steps = {k: 0 for k in model._adam_steps}
+        model._adam_owner = id(optimizer)
+    named = dict(model.named_parameters())
+    for n in model._hot_order():
+        p = named[n]
+        st = optimizer.state.get(p)
+        if not st or "exp_avg" not in st:
+            continue
+        o = model._offs[n]
+        if st["exp_avg"].data_ptr() == model._adam_m[o:].data_ptr():
+            continue                                   # already a view of the arena (publish_optimizer_state)
+        model._adam_m[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1).to(model._adam_m.device, torch.float32))
+        model._adam_v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1).to(model._adam_v.device, torch.float32))
+        model._adam_steps[model.adam_segment_of(n)] = int(float(st["step"]))
+
+
 def fused_adamw_step(model: ATMS, optimizer=None, use_shared: bool = False, device_steps=None, subjects=None) -> None:
     """torch.optim.AdamW semantics on model.flat_params / model.flat_grads.  Parameters that received no gradient
     this step (the unused half of {subject table, shared token}; in the joint-subject model the value embeddings of
@@ -102,7 +149,9 @@ class StepEngine:
         self.variant = variant
         self.nce = _InfoNCE()
         self.world, self.rank = _world()
-        self.fused = optimizer is None or type(optimizer).__name__ in ("AdamW", "FusedAdamW")
+        self.fused = fused_optimizer_ok(model, optimizer)
+        if self.fused:
+            adopt_optimizer(model, optimizer)
 
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
@@ -190,7 +239,8 @@ class StepEngine:
         named = dict(self.model.named_parameters())
         live = {seg[0] for seg in self.model.adam_segments(use_shared, subjects)}
         for n in self.model._hot_order():
-            named[n].grad = self.model.grad_view(n) if self.model.adam_segment_of(n) in live else None
+            on = self.model.adam_segment_of(n) in live and named[n].requires_grad
+            named[n].grad = self.model.grad_view(n) if on else None
         self.optimizer.step()
 
 
@@ -364,7 +414,9 @@ def _cached_graphed_step(model: ATMS, optimizer, alpha, variant, use_shared, kno
     gallery shape -- and the gallery itself is copied into the graph's static buffer.  Without this every epoch paid two
     eager steps plus a re-capture (~9 ms, 12 % of a 20-step epoch at B = 1024)."""
     world, _ = _world()
-    fused = optimizer is None or type(optimizer).__name__ in ("AdamW", "FusedAdamW")
+    fused = fused_optimizer_ok(model, optimizer)
+    if fused:
+        adopt_optimizer(model, optimizer)                 # imports a freshly loaded optimizer.state_dict() before stepping
     hp = _adam_hparams(optimizer) if fused else None      # foreign optimisers step eagerly: nothing of theirs is baked in
     hp_key = (hp["lr"], tuple(hp["betas"]), hp["eps"], hp["weight_decay"]) if hp else None
     key = (id(optimizer), type(optimizer).__name__, variant, float(alpha), bool(use_shared), known_subject,

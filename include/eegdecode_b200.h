@@ -31,6 +31,9 @@ long long eegb200_launch_count(void);
 /* 0 = tcgen05 TF32 tensor-core GEMMs (product path), 1 = exact-fp32 SIMT verification GEMM (tests only) */
 int eegb200_set_gemm_backend(int backend);
 int eegb200_get_gemm_backend(void);
+/* 1: the fused conv-stack kernels also store their on-chip intermediates (y1, a1: 363 KB per sample each) into the
+ * workspace so that eegb200_atms_ws_tensor("y1" / "a1") can be compared stage by stage (tests only; default 0) */
+int eegb200_set_debug_stores(int on);
 /* per-kernel CUDA-event profiler (bench.py roofline leg): enable, run steps, then fetch a JSON report
  * {"kernel name": {"ms": total, "n": launches, "flops": algorithmic, "bytes": algorithmic}} */
 int eegb200_prof_enable(int on);

@@ -65,6 +65,7 @@ def tok(t, B):   # [B*64, 250(ld256)] workspace view -> (B,64,250)
 @pytest.mark.parametrize("backend", [1, 0])
 def test_forward_eval_stages(lib, backend):
     lib.set_gemm_backend(backend)
+    lib.lib().eegb200_set_debug_stores(1)       # the fused conv stack keeps y1 / a1 on chip unless asked to store them
     try:
         B = 6
         sd = recipe.make_state_dict()
@@ -99,6 +100,7 @@ def test_forward_eval_stages(lib, backend):
         assert m.ws_tensor("h0").reshape(B * 64, -1).shape[1] == 256
     finally:
         lib.set_gemm_backend(0)
+        lib.lib().eegb200_set_debug_stores(0)
 
 
 def test_forward_matches_reference_golden(lib):

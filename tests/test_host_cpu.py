@@ -179,3 +179,59 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert got[cname] == ctypes.sizeof(st), cname
         for fname, _ in st._fields_:
             assert got[f"{cname}.{fname}"] == getattr(st, fname).offset, f"{cname}.{fname}"
+
+
+def test_fused_adamw_is_used_only_for_plain_single_group_adamw():
+    """the fused kernel must not silently replace other optimizer semantics"""
+    from eeg_image_decode_b200.atms import ATMS
+    from eeg_image_decode_b200.train import fused_optimizer_ok
+    m = ATMS()
+    assert fused_optimizer_ok(m, None)
+    assert fused_optimizer_ok(m, torch.optim.AdamW(m.parameters(), lr=3e-4))
+    assert not fused_optimizer_ok(m, torch.optim.SGD(m.parameters(), lr=1e-2))
+    assert not fused_optimizer_ok(m, torch.optim.AdamW(m.parameters(), lr=3e-4, amsgrad=True))
+    assert not fused_optimizer_ok(m, torch.optim.AdamW(m.parameters(), lr=3e-4, maximize=True))
+    ps = list(m.parameters())
+    assert not fused_optimizer_ok(m, torch.optim.AdamW([{"params": ps[:10]}, {"params": ps[10:], "lr": 1e-5}]))
+    assert not fused_optimizer_ok(m, torch.optim.AdamW(ps[:-3], lr=3e-4))            # hot parameters missing from the group
+    m.proj_eeg[0].weight.requires_grad_(False)
+    assert not fused_optimizer_ok(m, torch.optim.AdamW(m.parameters(), lr=3e-4))     # a frozen hot parameter
+
+
+def test_optimizer_state_is_imported_and_tied_to_the_optimizer_object():
+    """resuming from optimizer.load_state_dict() continues the moments / bias-correction step; a new optimizer object
+    starts from zero; .float() / .to() keep the moments"""
+    from eeg_image_decode_b200.atms import ATMS
+    from eeg_image_decode_b200.train import adopt_optimizer, publish_optimizer_state
+    m = ATMS()
+    named = dict(m.named_parameters())
+    hot = m._hot_order()
+    # a "checkpoint": a stock AdamW that has taken 3 steps on the same parameters
+    donor = torch.optim.AdamW(m.parameters(), lr=0.0)
+    for _ in range(3):
+        for n in hot:
+            named[n].grad = torch.full_like(named[n], 0.5)
+        donor.step()
+    ckpt = donor.state_dict()
+    opt = torch.optim.AdamW(m.parameters(), lr=3e-4)
+    adopt_optimizer(m, opt)
+    assert m._adam_steps["main"] == 0 and float(m._adam_m.abs().sum()) == 0.0
+    opt.load_state_dict(ckpt)
+    adopt_optimizer(m, opt)
+    w = "proj_eeg.0.weight"
+    o = m._offs[w]
+    assert m._adam_steps["main"] == 3 and m._adam_steps["table"] == 3
+    assert torch.allclose(m._adam_m[o:o + 8], donor.state[named[w]]["exp_avg"].reshape(-1)[:8])
+    assert torch.allclose(m._adam_v[o:o + 8], donor.state[named[w]]["exp_avg_sq"].reshape(-1)[:8])
+    # published views alias the arenas: adopting again is a no-op
+    publish_optimizer_state(m, opt)
+    assert opt.state[named[w]]["exp_avg"].data_ptr() == m._adam_m[o:].data_ptr()
+    before = m._adam_m.clone()
+    adopt_optimizer(m, opt)
+    assert torch.equal(before, m._adam_m) and m._adam_steps["main"] == 3
+    # .float() rebuilds the arenas: the moments and step counters survive
+    m.float()
+    assert torch.equal(before, m._adam_m) and m._adam_steps["main"] == 3
+    # a different optimizer object does not inherit them
+    adopt_optimizer(m, torch.optim.AdamW(m.parameters(), lr=3e-4))
+    assert m._adam_steps["main"] == 0 and float(m._adam_m.abs().sum()) == 0.0
