@@ -295,6 +295,18 @@ def mse(eeg, tgt, n_total_rows: int, weight: float, grad_out: float, loss=None, 
                                  ptr(loss_term), ptr(d_eeg), stream_ptr()), "mse")
 
 
+def l2norm_forward(x, y, norms) -> None:
+    with on_device(x):
+        check(lib().eegb200_l2norm_forward(ptr(x), ptr(y), ptr(norms), int(x.shape[0]), int(x.shape[1]), stream_ptr()),
+              "l2norm_forward")
+
+
+def l2norm_backward(y, norms, dy, dx) -> None:
+    with on_device(y):
+        check(lib().eegb200_l2norm_backward(ptr(y), ptr(norms), ptr(dy), ptr(dx), int(y.shape[0]), int(y.shape[1]),
+                                            stream_ptr()), "l2norm_backward")
+
+
 def dropout_mask(seed: int, site: int, p: float, rows: int, cols: int, ld: int, device="cuda"):
     import torch
     out = torch.empty(rows, cols, device=device, dtype=torch.float32)

@@ -123,11 +123,16 @@ class _Fn(_Holder):
 
 # ------------------------------------------------------------------------------------------------
 class ATMS(nn.Module):
-    """``ATMS(num_channels=63, sequence_length=250, num_subjects=2, num_features=64, num_latents=1024, num_blocks=1)``"""
+    """``ATMS(num_channels=63, sequence_length=250, num_subjects=2, num_features=64, num_latents=1024, num_blocks=1)``
+
+    ``normalize`` (keyword only, default False = the reference, which feeds the un-normalised LayerNorm output to the
+    logits, ATMS_retrieval.py:182-191): L2-normalise the returned embedding (forward and backward), the CLIP-style
+    variant BASELINE.json's north_star describes."""
 
     def __init__(self, num_channels=63, sequence_length=250, num_subjects=2, num_features=64, num_latents=1024,
-                 num_blocks=1, *, _joint_train=False):
+                 num_blocks=1, *, normalize=False, _joint_train=False):
         super().__init__()
+        self.normalize = bool(normalize)
         if num_channels != 63 or sequence_length != 250 or num_latents != 1024:
             raise ValueError("the sm_100a kernels are specialised for the reference geometry: 63 channels x 250 samples -> 1024")
         # per-subject value embeddings (the model of Retrieval/ATMS_retrieval_joint_train.py; see joint.py)
@@ -366,8 +371,15 @@ class ATMS(nn.Module):
         user_out = out
         if out is None or perm is not None:
             out = torch.empty(x.shape[0], 1024, device=x.device, dtype=torch.float32)
-        io = self._make_io(x, subject_ids, train, seed, out, groups)
+        raw = out
+        if self.normalize:      # the kernels write the LayerNorm output here; `out` receives its L2-normalised rows
+            raw = torch.empty_like(out)
+        io = self._make_io(x, subject_ids, train, seed, raw, groups)
         _lib.atms_forward(io, phases, x.device)
+        if self.normalize and (phases & _lib.PHASE_C):
+            self._norms = torch.empty(out.shape[0], device=out.device, dtype=torch.float32)
+            _lib.l2norm_forward(raw, out, self._norms)
+            self._norm_y = out
         if train and (phases & _lib.PHASE_C):
             for bn in (self.enc_eeg[0].tsconv[2], self.enc_eeg[0].tsconv[5]):
                 bn.num_batches_tracked.add_(1)
@@ -387,6 +399,10 @@ class ATMS(nn.Module):
         G = self._pointers()[1]
         if d_out is not None:
             d_out = d_out.contiguous() if perm is None else d_out.index_select(0, perm)
+            if self.normalize:
+                d_raw = torch.empty_like(d_out)
+                _lib.l2norm_backward(self._norm_y, self._norms, d_out.float(), d_raw)
+                d_out = d_raw
         _lib.atms_backward(io, d_out, ctypes.cast(G, ctypes.POINTER(ctypes.c_void_p)), phases, self.flat_params.device)
 
     def zero_flat_grads(self) -> None:

@@ -219,6 +219,15 @@ int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_to
   return mse_loss(eeg, tgt, B, D, n_total_rows, weight, grad_out, loss, loss_term, d_eeg, (cudaStream_t)stream);
 }
 
+int eegb200_l2norm_forward(const float* x, float* y, float* norms, int rows, int D, void* stream) {
+  EEG_REQUIRE(x && y && norms && rows > 0 && D > 0 && (D & 3) == 0, "l2norm_forward: bad arguments");
+  return l2norm_fwd(x, y, norms, rows, D, (cudaStream_t)stream);
+}
+int eegb200_l2norm_backward(const float* y, const float* norms, const float* dy, float* dx, int rows, int D, void* stream) {
+  EEG_REQUIRE(y && norms && dy && dx && rows > 0 && D > 0 && (D & 3) == 0, "l2norm_backward: bad arguments");
+  return l2norm_bwd(y, norms, dy, dx, rows, D, (cudaStream_t)stream);
+}
+
 int eegb200_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, void* stream) {
   EEG_REQUIRE(p && g && m && v && n > 0, "adamw: bad arguments");

@@ -7,9 +7,7 @@
 //   a1         = ELU(BN1(y))
 //   y2[b,p,j]  = sum_{c,k} a1[b,c,p,k] Ws[j,k,c] + bs[j]             "spatial MMA": K = (c,k), accumulated over channels
 //
-// A 128-row UMMA tile = 3 samples x 36 pooled positions (108 valid rows).  Four kernels, all warp-specialised
-// (builder warps: token rows -> pooled sums -> im2col operand in swizzled shared memory; one control thread: TMA of the
-// per-channel spatial weights + every tcgen05.mma; epilogue warps: thread = TMEM lane = tile row):
+// A 128-row UMMA tile = 3 samples x 36 pooled positions (108 valid rows).  Four kernels, all warp-specialised:
 //
 //   F1 conv_tc_stats      conv MMA (3xTF32) -> per-filter sum / sum of squares (BatchNorm1 batch statistics)
 //   F2 conv_tc_apply      conv MMA -> BN1 + ELU in registers -> A operand of the spatial MMA -> Y2 (red.add per item)
@@ -18,11 +16,20 @@
 //   B2 conv_tc_bwd_apply  same recomputation -> dy = A*dz + B*y + C (folded BatchNorm backward) -> G = dy . wt (UMMA)
 //                         scattered into the pooled positions, prefix-summed into d x3; dwt += dy^T . im2col (UMMA)
 //
-// F1 / F2 work items are (tile, 21 channels), B1 / B2 CTAs own a group of 4 channels and stride over the tiles, so that
-// the dWs / dwt accumulators stay in TMEM for the whole kernel.
+// Roles inside a CTA (one CTA per SM).  Every per-iteration resource is double buffered and the work of iteration `it`
+// belongs to group it & 1, so two iterations are always in flight:
+//   builders  2 groups x 4 warps   token rows (prefetched two iterations ahead) -> pooled sums -> im2col operand in
+//                                  swizzled shared memory (+ the dY2 tile in the backward kernels)
+//   epilogue  2 groups x 8 warps   thread = TMEM lane = tile row, two column halves; all the per-element math
+//   scatter   4 warps (B2 only)    G -> pooled positions -> prefix sums -> d x3 rows
+//   control   2 threads            A: first-stage UMMAs (conv, dA1); B: TMA + second-stage UMMAs (spatial / dWs / G, dwt)
+//
+// F1 / F2 work items are (tile, 21 channels) spread over all SMs; B1 / B2 CTAs own a group of 4 channels and stride
+// over the tiles, so that the dWs / dwt accumulators stay in TMEM for the whole kernel.
 #include "kernels.h"
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 namespace eegb200 {
 
@@ -39,6 +46,9 @@ constexpr int WS_RING = 4;
 constexpr int F_PARTS = 3, F_LEN = 21;            // forward work item = (tile, 21 of the 63 channels)
 constexpr int GC = 4, N_GROUPS = 16;              // backward: channel groups of 4 (the last one has 3)
 constexpr uint32_t PS_LD = 208, CSX_LD = 264;
+constexpr uint32_t SCAN_BYTES = (3 * PS_LD + 3 * CSX_LD) * 4;   // pooled sums [3][208] + scan scratch [3][264] floats
+constexpr int N_BUILD_WARPS = 8, N_EPI_WARPS = 16;
+constexpr int EPI_WARP0 = N_BUILD_WARPS, EPI_THREAD0 = EPI_WARP0 * 32;
 
 // ------------------------------------------------------------------------------------------------ small helpers
 // NOTE: the values of the *_nw loads may only be used after tmem_ld_wait()
@@ -53,6 +63,15 @@ __device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, float* v) {
       : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, float* v) {
   uint32_t r[4];
@@ -78,17 +97,22 @@ __device__ __forceinline__ uint32_t mn_off(int m, int k) {
 __device__ __forceinline__ float tf32_fast(float x) {     // cvt.rna for finite values: add half an ulp of tf32, truncate
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
-__device__ __forceinline__ float elu_fast(float z) {
-  const float e = __expf(z) - 1.f;
-  const float p = z * fmaf(z, fmaf(z, fmaf(z, 1.f / 24.f, 1.f / 6.f), 0.5f), 1.f);
-  const float neg = z > -0.0625f ? p : e;
-  return z > 0.f ? z : neg;
+__device__ __forceinline__ float tf32_trunc(float x) {    // what tcgen05.mma kind::tf32 reads from an fp32 operand
+  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
+// ELU(z).  exp(z) - 1 loses RELATIVE accuracy near 0 but its absolute error (6e-8) is far below the TF32 rounding of the
+// value that follows (2.4e-4 relative) and the O(1) terms it is summed with.
+__device__ __forceinline__ float elu_quick(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // filter index of register slot i (0..19) of an epilogue thread of column half h: {16h .. 16h+15} + {32+4h .. 32+4h+3}
-// (two naturally aligned tcgen05.ld: .x16 at column 16h, .x4 at column 32+4h)
+// (naturally aligned tcgen05.ld: .x16 / 2 x .x8 at column 16h, .x4 at column 32+4h)
 __device__ __forceinline__ int kidx(int h, int i) { return i < 16 ? 16 * h + i : 32 + 4 * h + (i - 16); }
 
 // box-51 pooled sums of one token row (8 floats per lane): cs[k] = sum of the first k samples, ps[u] = cs[u+51]-cs[u]
@@ -119,18 +143,19 @@ __device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int l
 // =================================================================================================================
 // forward
 // =================================================================================================================
-constexpr int F_THREADS = 13 * 32;                // 4 builder, 8 epilogue, 1 control warp
+constexpr int F_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 2) * 32;          // 832
+constexpr int F_CTRL_A = N_BUILD_WARPS + N_EPI_WARPS, F_CTRL_B = F_CTRL_A + 1;
 constexpr uint32_t OFF_IM = 0;                              // [2 buf][hi, lo] x 16 KB
 constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights hi, lo: 2 x 6 KB
 constexpr uint32_t OFF_A1 = OFF_BC + 2 * KB_48;             // [2 buf][2 k-blocks] x 16 KB
 constexpr uint32_t OFF_WS = OFF_A1 + 4 * KB_A;              // [4 ring][2 k-blocks] x 6 KB
-constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // pooled sums [3][208] + scan scratch [3][264] floats
-constexpr uint32_t OFF_TAB = OFF_PS + (3 * PS_LD + 3 * CSX_LD) * 4;      // BN scale / shift / bias tables [3][48] floats
-constexpr uint32_t OFF_RED = OFF_TAB + 3 * 48 * 4;                        // statistics reduction [2][40] floats
-constexpr uint32_t OFF_BAR = (OFF_RED + 80 * 4 + 7) & ~7u;                // mbarriers
+constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // scan scratch of the two builder groups
+constexpr uint32_t OFF_TAB = OFF_PS + 2 * SCAN_BYTES;       // BN scale / folded shift / conv bias tables [3][48] floats
+constexpr uint32_t OFF_RED = OFF_TAB + 3 * 48 * 4;          // statistics reduction [2][40] floats
+constexpr uint32_t OFF_BAR = (OFF_RED + 80 * 4 + 7) & ~7u;  // mbarriers
 constexpr int N_BARS = 6 * 2 + 2 * WS_RING + 2 * 2;
 constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
-constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;                        // + alignment slack
+constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;         // + alignment slack
 static_assert(OFF_BC % 1024 == 0 && OFF_A1 % 1024 == 0 && OFF_WS % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 static_assert(CTC_SMEM <= 227 * 1024, "conv forward kernel exceeds the shared memory of an SM");
 
@@ -171,21 +196,19 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
-  float* ps_all = reinterpret_cast<float*>(sm + OFF_PS);
-  float* cs_all = ps_all + 3 * PS_LD;
-  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);          // [0]: scale, [1]: shift, [2]: conv bias
+  float* tab = reinterpret_cast<float*>(sm + OFF_TAB);          // [0]: scale, [1]: shift (+ bias*scale), [2]: conv bias
   float* red = reinterpret_cast<float*>(sm + OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BAR);
-  uint64_t* tile_full = bars;            // [2] builders -> control
+  uint64_t* tile_full = bars;            // [2] builders -> control A
   uint64_t* tile_empty = bars + 2;       // [2] conv UMMAs done -> builders
   uint64_t* c1_full = bars + 4;          // [2] conv UMMAs done -> epilogue
-  uint64_t* c1_empty = bars + 6;         // [2] epilogue read TMEM -> control        (8 arrivals)
-  uint64_t* a1_full = bars + 8;          // [2] epilogue wrote the A1 slice -> control (8 arrivals)
+  uint64_t* c1_empty = bars + 6;         // [2] epilogue read TMEM -> control A      (8 arrivals)
+  uint64_t* a1_full = bars + 8;          // [2] epilogue wrote the A1 slice -> control B (8 arrivals)
   uint64_t* a1_empty = bars + 10;        // [2] spatial UMMAs done -> epilogue
-  uint64_t* ws_full = bars + 12;         // [4] TMA -> control
-  uint64_t* ws_empty = bars + 12 + WS_RING;   // [4] spatial UMMAs done -> control (TMA refill)
+  uint64_t* ws_full = bars + 12;         // [4] TMA -> control B
+  uint64_t* ws_empty = bars + 12 + WS_RING;   // [4] spatial UMMAs done -> control B (TMA refill)
   uint64_t* y2_full = bars + 12 + 2 * WS_RING;       // [2] last spatial UMMA of an item -> epilogue
-  uint64_t* y2_empty = y2_full + 2;                  // [2] epilogue drained Y2 -> control (8 arrivals)
+  uint64_t* y2_empty = y2_full + 2;                  // [2] epilogue drained Y2 -> control B (8 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,7 +244,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
   for (int i = threadIdx.x; i < N48 * 32; i += F_THREADS) {
     const int k = i >> 5, t = i & 31;
     const float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
-    const float hi = tf32_fast(w), lo = tf32_fast(w - hi);
+    const float hi = tf32_fast(w), lo = w - hi;
     const uint32_t off = sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u;
     *reinterpret_cast<float*>(sm + OFF_BC + off) = hi;
     *reinterpret_cast<float*>(sm + OFF_BC + KB_48 + off) = lo;
@@ -229,16 +252,17 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
   if (threadIdx.x < N48) {
     const int k = threadIdx.x;
     float sc = 0.f, sh = 0.f;
+    const float bt = k < N_FILT ? p.bt[k] : 0.f;
     if (MODE == MODE_APPLY && k < N_FILT) {
       sc = p.mean_rstd[N_FILT + k] * p.gamma[k];
-      sh = p.beta[k] - p.mean_rstd[k] * sc;
+      sh = p.beta[k] - p.mean_rstd[k] * sc + bt * sc;     // z = sc * (y_raw + bt) + (beta - mean*sc)
     }
     tab[k] = sc;
     tab[48 + k] = sh;
-    tab[96 + k] = k < N_FILT ? p.bt[k] : 0.f;
+    tab[96 + k] = bt;
   }
   if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
-  if (warp == 12) {
+  if (warp == F_CTRL_A) {
     tmem_alloc(tmem_slot, 256);          // C1[0]: cols 0..47, C1[1]: 64..111, Y2[0]: 128..175, Y2[1]: 192..239
     tmem_relinquish();
   }
@@ -248,68 +272,73 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // =============================== builders ===============================
-    const int r = threadIdx.x;                         // tile row 0..127
+  if (warp < N_BUILD_WARPS) {
+    // =============================== builders (group gb owns the iterations it & 1 == gb) ===============================
+    const int gb = warp >> 2, rq = warp & 3;
+    const int r = rq * 32 + lane;                      // tile row 0..127
     const int s_row = r / N_POOL, p_row = r % N_POOL;
+    float* ps_all = reinterpret_cast<float*>(sm + OFF_PS + (uint32_t)gb * SCAN_BYTES);
+    float* cs_all = ps_all + 3 * PS_LD;
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-    auto fetch = [&](int it) {                          // token row of (sample `warp` of the tile, channel) for iteration it
-      if (it < total_it && warp < TILE_S) {
+    auto fetch = [&](int it) {                          // token row of (sample rq of the tile, channel) for iteration it
+      if (it < total_it && rq < TILE_S) {
         const FwdIt d = fwd_decode(it, p.B);
-        if (warp < d.ns) {
-          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + warp) * N_TOK + d.c) * D_PAD + 8 * lane;
+        if (rq < d.ns) {
+          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + rq) * N_TOK + d.c) * D_PAD + 8 * lane;
           xa = __ldg(reinterpret_cast<const float4*>(xrow));
           xb = __ldg(reinterpret_cast<const float4*>(xrow + 4));
         }
       }
     };
-    fetch(0);
-    for (int it = 0; it < total_it; ++it) {
+    fetch(gb);
+    for (int it = gb; it < total_it; it += 2) {
       const FwdIt d = fwd_decode(it, p.B);
-      const int bi = it & 1;
+      const int bi = gb;
       const uint32_t n = (uint32_t)(it >> 1);
       const int rows_valid = d.ns * N_POOL;
       const float4 x0 = xa, x1 = xb;
-      fetch(it + 1);                                    // the next row travels while this one is processed
-      if (warp < d.ns) pool_row(x0, x1, lane, cs_all + warp * CSX_LD, ps_all + warp * PS_LD);
-      named_bar_sync(1, 128);
+      fetch(it + 2);                                    // the group's next row travels while this one is processed
+      if (rq < d.ns) pool_row(x0, x1, lane, cs_all + rq * CSX_LD, ps_all + rq * PS_LD);
+      named_bar_sync(1 + gb, 128);
       mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of iteration it-2 have consumed this buffer
       {
+        // kind::tf32 reads the top 19 bits of an fp32 operand: hi is the raw value, lo = a - trunc(a) is exact
         const float* src = ps_all + s_row * PS_LD + 5 * p_row;
         uint8_t* hi_t = sm + OFF_IM + (uint32_t)bi * 2 * KB_A;
         uint8_t* lo_t = hi_t + KB_A;
         const bool valid = r < rows_valid;
 #pragma unroll
         for (int ch = 0; ch < 7; ++ch) {                  // chunk 6 = tap 24 + zeros; chunk 7 stays zero
-          float a[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a[q] = (valid && (ch * 4 + q) < K_TEMP) ? src[ch * 4 + q] : 0.f;
-          float4 h, l;
-          h.x = tf32_fast(a[0]); h.y = tf32_fast(a[1]); h.z = tf32_fast(a[2]); h.w = tf32_fast(a[3]);
-          l.x = tf32_fast(a[0] - h.x); l.y = tf32_fast(a[1] - h.y); l.z = tf32_fast(a[2] - h.z); l.w = tf32_fast(a[3] - h.w);
+          float4 h;
+          h.x = (valid && (ch * 4 + 0) < K_TEMP) ? src[ch * 4 + 0] : 0.f;
+          h.y = (valid && (ch * 4 + 1) < K_TEMP) ? src[ch * 4 + 1] : 0.f;
+          h.z = (valid && (ch * 4 + 2) < K_TEMP) ? src[ch * 4 + 2] : 0.f;
+          h.w = (valid && (ch * 4 + 3) < K_TEMP) ? src[ch * 4 + 3] : 0.f;
+          const float4 l = make_float4(h.x - tf32_trunc(h.x), h.y - tf32_trunc(h.y), h.z - tf32_trunc(h.z), h.w - tf32_trunc(h.w));
           const uint32_t off = sw128_off(r, ch);
           *reinterpret_cast<float4*>(hi_t + off) = h;
           *reinterpret_cast<float4*>(lo_t + off) = l;
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) mbar_arrive(&tile_full[bi]);
+      named_bar_sync(1 + gb, 128);
+      if (rq == 0 && lane == 0) mbar_arrive(&tile_full[bi]);
     }
-  } else if (warp < 12) {
-    // =============================== epilogue ===============================
+  } else if (warp < F_CTRL_A) {
+    // =============================== epilogue (group ge owns the iterations it & 1 == ge) ===============================
+    const int ge = (warp - EPI_WARP0) >> 3;
+    const int h = ((warp - EPI_WARP0) >> 2) & 1;         // column half
     const int q = warp & 3;                              // TMEM lane quarter (== warp % 4)
-    const int h = (warp - 4) >> 2;                       // column half
     const int r = q * 32 + lane;                         // tile row
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float s1[20], s2[20];
-    if (MODE == MODE_STATS) {
+    float s1[MODE == MODE_STATS ? 20 : 1], s2[MODE == MODE_STATS ? 20 : 1];
+    if constexpr (MODE == MODE_STATS) {
 #pragma unroll
       for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
     }
-    for (int it = 0; it < total_it; ++it) {
+    for (int it = ge; it < total_it; it += 2) {
       const FwdIt d = fwd_decode(it, p.B);
-      const int bi = it & 1;
+      const int bi = ge;
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
       const size_t grow = (size_t)d.tile * TILE_ROWS + r;         // global (b, p) row
@@ -322,24 +351,29 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&c1_empty[bi]);         // the accumulator may be overwritten by iteration it+2
-#pragma unroll
-      for (int i = 0; i < 20; ++i) y[i] += tab[96 + kidx(h, i)];
-      if (MODE == MODE_STATS) {
+      if constexpr (MODE == MODE_STATS) {
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 20; ++i) { s1[i] += y[i]; s2[i] = fmaf(y[i], y[i], s2[i]); }
+          for (int i = 0; i < 20; ++i) {
+            const float v = y[i] + tab[96 + kidx(h, i)];
+            s1[i] += v;
+            s2[i] = fmaf(v, v, s2[i]);
+          }
         }
       } else {
         if (valid && p.y1 != nullptr) {
           float* dst = p.y1 + grow * K_SPAT + d.c * N_FILT;
 #pragma unroll
-          for (int j = 0; j < 5; ++j)
-            *reinterpret_cast<float4*>(dst + kidx(h, 4 * j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          for (int j = 0; j < 5; ++j) {
+            const int k = kidx(h, 4 * j);
+            *reinterpret_cast<float4*>(dst + k) = make_float4(y[4 * j] + tab[96 + k], y[4 * j + 1] + tab[97 + k],
+                                                              y[4 * j + 2] + tab[98 + k], y[4 * j + 3] + tab[99 + k]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 20; ++i) {
           const int k = kidx(h, i);
-          y[i] = valid ? tf32_fast(elu_fast(fmaf(y[i], tab[k], tab[48 + k]))) : 0.f;
+          y[i] = valid ? tf32_fast(elu_quick(fmaf(y[i], tab[k], tab[48 + k]))) : 0.f;
         }
         if (valid && p.a1 != nullptr) {
           float* dst = p.a1 + grow * K_SPAT + d.c * N_FILT;
@@ -382,52 +416,21 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
         }
       }
     }
-    if (MODE == MODE_STATS) {
+    if constexpr (MODE == MODE_STATS) {
       // per-filter sums over the 32 rows of this warp, then shared + one double atomic per filter per CTA
 #pragma unroll
       for (int i = 0; i < 20; ++i) {
         const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
         if (lane == 0) { atomicAdd(&red[kidx(h, i)], a); atomicAdd(&red[N_FILT + kidx(h, i)], b); }
       }
-      named_bar_sync(2, 256);
-      const int k = threadIdx.x - 128;
+      named_bar_sync(3, N_EPI_WARPS * 32);
+      const int k = threadIdx.x - EPI_THREAD0;
       if (k < 2 * N_FILT) atomicAdd(&p.sums[k], (double)red[k]);
     }
-  } else if (lane == 0) {
-    // =============================== control: TMA + UMMA issue ===============================
+  } else if (warp == F_CTRL_A && lane == 0) {
+    // =============================== control A: conv UMMAs ===============================
     constexpr uint32_t idesc = umma_idesc_tf32(128, N48, 0, 0);
-    const uint32_t im = smem_u32(sm + OFF_IM), bc = smem_u32(sm + OFF_BC), a1s = smem_u32(sm + OFF_A1), wss = smem_u32(sm + OFF_WS);
-    auto load_ws = [&](int it) {
-      const FwdIt d = fwd_decode(it, p.B);
-      const int wi = it & (WS_RING - 1);
-      const uint32_t n = (uint32_t)(it / WS_RING);
-      mbar_wait(&ws_empty[wi], (n & 1u) ^ 1u);
-      mbar_arrive_expect_tx(&ws_full[wi], 2 * KB_48);
-      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48, 0, d.c * N48);
-      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48 + KB_48, 32, d.c * N48);
-    };
-    auto spatial = [&](int it) {
-      const FwdIt d = fwd_decode(it, p.B);
-      const int bi = it & 1, wi = it & (WS_RING - 1), ib = d.item_local & 1;
-      if (d.l == 0) mbar_wait(&y2_empty[ib], ((uint32_t)(d.item_local >> 1) & 1u) ^ 1u);   // Y2[ib] drained (item - 2)
-      mbar_wait(&a1_full[bi], (uint32_t)(it >> 1) & 1u);
-      mbar_wait(&ws_full[wi], (uint32_t)(it / WS_RING) & 1u);
-      tc_fence_after();
-      const uint32_t a = a1s + (uint32_t)bi * 2 * KB_A, w = wss + (uint32_t)wi * 2 * KB_48;
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk) {                   // K = 40: four 8-steps of k-block 0 and the first of k-block 1
-        const uint32_t ao = kk < 4 ? (uint32_t)kk * 32u : KB_A, wo = kk < 4 ? (uint32_t)kk * 32u : KB_48;
-        tc_mma_tf32(tmem_base + 128u + (uint32_t)(ib * 64), umma_smem_desc(a + ao, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(w + wo, 16, 1024, UMMA_LAYOUT_SW128), idesc, (d.l > 0 || kk > 0) ? 1u : 0u);
-      }
-      tc_commit(&a1_empty[bi]);
-      tc_commit(&ws_empty[wi]);
-      if (d.l == F_LEN - 1) tc_commit(&y2_full[ib]);
-    };
-    if (MODE == MODE_APPLY) {
-      if (total_it > 0) load_ws(0);
-      if (total_it > 1) load_ws(1);
-    }
+    const uint32_t im = smem_u32(sm + OFF_IM), bc = smem_u32(sm + OFF_BC);
     for (int it = 0; it < total_it; ++it) {
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
@@ -451,17 +454,45 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
                     umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
       tc_commit(&tile_empty[bi]);
       tc_commit(&c1_full[bi]);
-      if (MODE == MODE_APPLY) {
-        if (it + 2 < total_it) load_ws(it + 2);
-        if (it > 0) spatial(it - 1);                     // one iteration behind: its epilogue ran while these MMAs were issued
-      }
     }
-    if (MODE == MODE_APPLY && total_it > 0) spatial(total_it - 1);
+  } else if (MODE == MODE_APPLY && warp == F_CTRL_B && lane == 0) {
+    // =============================== control B: weight TMA + spatial UMMAs ===============================
+    constexpr uint32_t idesc = umma_idesc_tf32(128, N48, 0, 0);
+    const uint32_t a1s = smem_u32(sm + OFF_A1), wss = smem_u32(sm + OFF_WS);
+    auto load_ws = [&](int it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int wi = it & (WS_RING - 1);
+      const uint32_t n = (uint32_t)(it / WS_RING);
+      mbar_wait(&ws_empty[wi], (n & 1u) ^ 1u);
+      mbar_arrive_expect_tx(&ws_full[wi], 2 * KB_48);
+      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48, 0, d.c * N48);
+      tma_load_2d(&tmWs, &ws_full[wi], sm + OFF_WS + (uint32_t)wi * 2 * KB_48 + KB_48, 32, d.c * N48);
+    };
+    for (int it = 0; it < 3 && it < total_it; ++it) load_ws(it);
+    for (int it = 0; it < total_it; ++it) {
+      const FwdIt d = fwd_decode(it, p.B);
+      const int bi = it & 1, wi = it & (WS_RING - 1), ib = d.item_local & 1;
+      if (d.l == 0) mbar_wait(&y2_empty[ib], ((uint32_t)(d.item_local >> 1) & 1u) ^ 1u);   // Y2[ib] drained (item - 2)
+      mbar_wait(&a1_full[bi], (uint32_t)(it >> 1) & 1u);
+      mbar_wait(&ws_full[wi], (uint32_t)(it / WS_RING) & 1u);
+      tc_fence_after();
+      const uint32_t a = a1s + (uint32_t)bi * 2 * KB_A, w = wss + (uint32_t)wi * 2 * KB_48;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {                   // K = 40: four 8-steps of k-block 0 and the first of k-block 1
+        const uint32_t ao = kk < 4 ? (uint32_t)kk * 32u : KB_A, wo = kk < 4 ? (uint32_t)kk * 32u : KB_48;
+        tc_mma_tf32(tmem_base + 128u + (uint32_t)(ib * 64), umma_smem_desc(a + ao, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(w + wo, 16, 1024, UMMA_LAYOUT_SW128), idesc, (d.l > 0 || kk > 0) ? 1u : 0u);
+      }
+      tc_commit(&a1_empty[bi]);
+      tc_commit(&ws_empty[wi]);
+      if (d.l == F_LEN - 1) tc_commit(&y2_full[ib]);
+      if (it + 3 < total_it) load_ws(it + 3);            // its ring slot was released by the UMMAs of iteration it-1
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, 256);
+  if (warp == F_CTRL_A) tmem_dealloc(tmem_base, 256);
 }
 
 // tsconv.4.weight [j][k][c] -> [c][48 rows j][64 floats k], TF32-rounded, zero padded: B operand of the spatial UMMA
@@ -476,45 +507,56 @@ __global__ void pack_ws_tc_kernel(const float* __restrict__ ws, float* __restric
 // backward
 // =================================================================================================================
 enum { MODE_BSTATS = 0, MODE_BAPPLY = 1 };
-constexpr int B1_THREADS = 13 * 32;               // 4 builder, 8 epilogue, 1 control warp
-constexpr int B2_THREADS = 17 * 32;               // + 4 scatter warps
+constexpr int B1_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 2) * 32;         // 832
+constexpr int B2_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 4 + 2) * 32;     // 960: + 4 scatter warps
+constexpr int SCAT_WARP0 = N_BUILD_WARPS + N_EPI_WARPS;
 constexpr uint32_t FWD_PACK_FLOATS = N_CH * N48 * 64;        // pack_ws_tc_kernel output
-constexpr uint32_t WST_MAIN_FLOATS = N_CH * N48 * 32;        // [c][48 rows k][32 floats j 0..31]
-constexpr uint32_t WST_TAIL_FLOATS = N_GROUPS * N48 * 32;    // [g][48 rows k][8 ci + (j - 32)]
+constexpr uint32_t WST_MAIN_FLOATS = N_GROUPS * GC * N48 * 32;   // [c (64 slots)][48 rows k][32 floats j 0..31]
+constexpr uint32_t WST_TAIL_FLOATS = N_GROUPS * N48 * 32;        // [g][48 rows k][8 ci + (j - 32)]
 // shared-memory map (common part)
-constexpr uint32_t OB_IMK = 0;                               // [2] x 16 KB   im2col, K-major (TF32 hi part only)
+constexpr uint32_t OB_IMK = 0;                               // [2] x 16 KB   im2col, K-major (TF32)
 constexpr uint32_t OB_BC = OB_IMK + 2 * KB_A;                // 6 KB          conv weights / 51, K-major
 constexpr uint32_t OB_DYK = OB_BC + KB_48;                   // [2] x 16 KB   dY2 tile columns 0..31, K-major
 constexpr uint32_t OB_TAIL = OB_DYK + 2 * KB_A;              // 16 KB         shared tail k-block, one 8-column k-step each:
                                                              //   kk = 0, 1: dY2 columns 32..39 of tile buffer 0, 1; kk = 2: dy tail
-constexpr uint32_t OB_WST = OB_TAIL + KB_A;                  // [4] x 6 KB    ring: Ws_c^T rows k, columns j 0..31
-constexpr uint32_t OB_WSTT = OB_WST + WS_RING * KB_48;       // 6 KB          the group's Ws^T tails (j 32..39), k-step ci
+constexpr uint32_t OB_WST = OB_TAIL + KB_A;                  // [4] x 6 KB    Ws_c^T of the group's channels: rows k, columns j 0..31
+constexpr uint32_t OB_WSTT = OB_WST + GC * KB_48;            // 6 KB          their tails (j 32..39), k-step ci
 constexpr uint32_t OB_MODE = OB_WSTT + KB_48;                // mode-specific tiles from here
 static_assert(OB_BC % 1024 == 0 && OB_DYK % 1024 == 0 && OB_TAIL % 1024 == 0 && OB_WST % 1024 == 0 &&
               OB_WSTT % 1024 == 0 && OB_MODE % 1024 == 0, "swizzled tiles need 1024-byte alignment");
-// B1: dY2 MN-major [2][2 slabs], a1 MN-major [2 slabs]
-constexpr uint32_t O1_DYM = OB_MODE;                         // [2] x 32 KB
-constexpr uint32_t O1_A1M = O1_DYM + 4 * SLAB;               // 32 KB  (the M = 128 A operand of the dWs UMMA reads two
-                                                             //   slabs past DYM[tb]: they must stay inside the allocation)
-constexpr uint32_t O1_MISC = O1_A1M + 2 * SLAB;
+// B1: dY2 MN-major [2 slabs] (single buffered), a1 MN-major [2][2 slabs]
+constexpr uint32_t O1_DYM = OB_MODE;                         // 32 KB  (the M = 128 A operand of the dWs UMMA reads two
+constexpr uint32_t O1_A1M = O1_DYM + 2 * SLAB;               // [2] x 32 KB   slabs past DYM: A1M[0], inside the allocation)
+constexpr uint32_t O1_MISC = O1_A1M + 4 * SLAB;
 // B2: dy MN-major [2 slabs], im2col MN-major [2][1 slab], dy K-major main, wt^T
 constexpr uint32_t O2_DYM = OB_MODE;                         // 32 KB (+ 2 don't-care slabs = the IMM tiles behind it)
 constexpr uint32_t O2_IMM = O2_DYM + 2 * SLAB;               // [2] x 16 KB
 constexpr uint32_t O2_DYK2 = O2_IMM + 2 * SLAB;              // 16 KB
 constexpr uint32_t O2_WTT = O2_DYK2 + KB_A;                  // 8 KB: [32 rows t][32 floats k 0..31] + tail block (k 32..39)
 constexpr uint32_t O2_MISC = O2_WTT + 2 * KB_32;
-// misc area: ps / cs (builders), dps / csd (scatter warps), tables [5][48], red [80], barriers, tmem slot
+// misc area: scan scratch of the two builder groups, (B2) dps / csd of the scatter warps, tables [5][48], red [80],
+// barriers, tmem slot
 constexpr uint32_t M_PS = 0;
-constexpr uint32_t M_DPS = M_PS + (3 * PS_LD + 3 * CSX_LD) * 4;
-constexpr uint32_t M_TAB = M_DPS + (3 * PS_LD + 3 * CSX_LD) * 4;
-constexpr uint32_t M_RED = M_TAB + 5 * 48 * 4;
-constexpr uint32_t M_BAR = (M_RED + 80 * 4 + 7) & ~7u;
-constexpr int NB_BARS = 6 * 2 + 2 * WS_RING + 1 + 4 * 2 + 1;
-constexpr uint32_t M_TMEM = M_BAR + NB_BARS * 8;
-constexpr uint32_t M_END = M_TMEM + 16;
-constexpr uint32_t B1_SMEM = O1_MISC + M_END + 1024;
-constexpr uint32_t B2_SMEM = O2_MISC + M_END + 1024;
+constexpr uint32_t M_DPS = M_PS + 2 * SCAN_BYTES;
+constexpr int NB_BARS = 8 * 2 + 1 + 2 + 2 * 2 + 2;
+template <int MODE> struct BwdMisc {
+  static constexpr uint32_t TAB = M_DPS + (MODE == MODE_BAPPLY ? SCAN_BYTES : 0u);
+  static constexpr uint32_t RED = TAB + 5 * 48 * 4;
+  static constexpr uint32_t BAR = (RED + 80 * 4 + 7) & ~7u;
+  static constexpr uint32_t TMEM = BAR + NB_BARS * 8;
+  static constexpr uint32_t END = TMEM + 16;
+};
+constexpr uint32_t B1_SMEM = O1_MISC + BwdMisc<MODE_BSTATS>::END + 1024;
+constexpr uint32_t B2_SMEM = O2_MISC + BwdMisc<MODE_BAPPLY>::END + 1024;
 static_assert(B1_SMEM <= 227 * 1024 && B2_SMEM <= 227 * 1024, "conv backward kernels exceed the shared memory of an SM");
+
+// optional cycle trace of CTA 0 (EEGB200_CONV_TRACE=<dir>): trace[(role * TRACE_IT + it) * 8 + event] = clock64()
+constexpr int TRACE_IT = 96, TRACE_ROLES = 8;
+#define CONV_TRACE(role, it, ev)                                                                      \
+  do {                                                                                                \
+    if (p.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_IT)                                     \
+      p.trace[((role) * TRACE_IT + (it)) * 8 + (ev)] = clock64();                                     \
+  } while (0)
 
 struct ConvBwdParams {
   const float* x3;          // [B*64, 256]
@@ -535,6 +577,7 @@ struct ConvBwdParams {
   float gscale;             // 1 / world size for the parameters whose gradient every rank computes in full
   int B;
   int n_tiles;
+  long long* trace;         // nullptr unless tracing
 };
 
 struct BwdIt { int tl, ci, c, tile, ns; };
@@ -553,34 +596,33 @@ __global__ void __launch_bounds__(MODE == MODE_BSTATS ? B1_THREADS : B2_THREADS,
 conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_constant__ CUtensorMap tmWstt, const ConvBwdParams p) {
   constexpr bool BS = MODE == MODE_BSTATS;
   constexpr int NTHREADS = BS ? B1_THREADS : B2_THREADS;
-  constexpr int CTRL_WARP = BS ? 12 : 16;
+  constexpr int CTRL_A = BS ? SCAT_WARP0 : SCAT_WARP0 + 4, CTRL_B = CTRL_A + 1;
   constexpr uint32_t O_MISC = BS ? O1_MISC : O2_MISC;
+  using MM = BwdMisc<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* misc = sm + O_MISC;
-  float* ps_all = reinterpret_cast<float*>(misc + M_PS);
-  float* cs_all = ps_all + 3 * PS_LD;
-  float* dps_all = reinterpret_cast<float*>(misc + M_DPS);
-  float* csd_all = dps_all + 3 * PS_LD;
-  float* tab = reinterpret_cast<float*>(misc + M_TAB);       // [0] bt, [1] sc, [2] sh, [3] p1, [4] p2 (see the epilogue)
-  float* red = reinterpret_cast<float*>(misc + M_RED);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + M_BAR);
-  uint64_t* im_full = bars;              // [2] builders -> control
-  uint64_t* im_empty = bars + 2;         // [2] last UMMA reading the im2col buffer -> builders
-  uint64_t* dyt_full = bars + 4;         // [2] builders wrote the dY2 tile -> control
-  uint64_t* dyt_empty = bars + 6;        // [2] last UMMA reading the dY2 tile -> builders
+  float* tab = reinterpret_cast<float*>(misc + MM::TAB);      // [0] bt, [1] sc, [2] sh, [3] p1, [4] p2 (see the epilogue)
+  float* red = reinterpret_cast<float*>(misc + MM::RED);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + MM::BAR);
+  uint64_t* im_full = bars;              // [2] builders -> control A
+  uint64_t* im_empty = bars + 2;         // [2] last UMMA reading the im2col buffer -> builders (B2: both control threads)
+  uint64_t* dyk_full = bars + 4;         // [2] builders wrote the K-major dY2 tile -> control A
+  uint64_t* dyk_empty = bars + 6;        // [2] last dA1 UMMA of the tile -> builders
   uint64_t* c_full = bars + 8;           // [2] conv + dA1 UMMAs done -> epilogue
-  uint64_t* c_empty = bars + 10;         // [2] epilogue read TMEM -> control (8 arrivals)
-  uint64_t* wst_full = bars + 12;        // [4]
-  uint64_t* wst_empty = bars + 12 + WS_RING;     // [4]
-  uint64_t* wstt_full = bars + 12 + 2 * WS_RING; // [1]
-  uint64_t* op_full = wstt_full + 1;     // [0 used] epilogue wrote a1 (B1) / dy (B2) -> control (8 arrivals)
-  uint64_t* op_empty = op_full + 2;      // [0 used] UMMAs reading it done -> epilogue
-  uint64_t* gg_full = op_empty + 2;      // [2] G UMMAs done -> scatter warps (B2)
-  uint64_t* gg_empty = gg_full + 2;      // [2] scatter warps read TMEM -> control (4 arrivals)
-  uint64_t* final_full = gg_empty + 2;   // everything issued by the control thread has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + M_TMEM);
+  uint64_t* c_empty = bars + 10;         // [2] epilogue read TMEM -> control A (8 arrivals)
+  uint64_t* op_full = bars + 12;         // [2] epilogue wrote a1 (B1: own buffer per group) / dy (B2: [0] only) -> control B
+  uint64_t* op_empty = bars + 14;        // [2] second-stage UMMAs reading it done -> epilogue.  B1: a1 buffer [bi] is free again;
+                                         //     B2 (ONE dy buffer): [g] = the UMMAs of the iteration before one of group g completed
+  uint64_t* wst_full = bars + 16;        // [1] the group's packed weights have landed (TMA, once)
+  uint64_t* dym_full = bars + 17;        // B1: builders wrote the MN-major dY2 tile -> control B
+  uint64_t* dym_empty = bars + 18;       // B1: last dWs UMMA of the tile -> builders
+  uint64_t* gg_full = bars + 19;         // [2] B2: G UMMAs done -> scatter warps
+  uint64_t* gg_empty = bars + 21;        // [2] B2: scatter warps read TMEM -> control B (4 arrivals)
+  uint64_t* final_a = bars + 23;         // everything issued by control A has completed
+  uint64_t* final_b = bars + 24;         // ... by control B
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + MM::TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x % N_GROUPS, slot = blockIdx.x / N_GROUPS, n_slots = gridDim.x / N_GROUPS;
@@ -592,28 +634,27 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&im_full[i], 1);
-      mbar_init(&im_empty[i], 1);
-      mbar_init(&dyt_full[i], 1);
-      mbar_init(&dyt_empty[i], 1);
+      mbar_init(&im_empty[i], BS ? 1 : 2);
+      mbar_init(&dyk_full[i], 1);
+      mbar_init(&dyk_empty[i], 1);
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], 8);
-      mbar_init(&gg_full[i], 1);
-      mbar_init(&gg_empty[i], 4);
       mbar_init(&op_full[i], 8);
       mbar_init(&op_empty[i], 1);
+      mbar_init(&gg_full[i], 1);
+      mbar_init(&gg_empty[i], 4);
     }
-    for (int i = 0; i < WS_RING; ++i) {
-      mbar_init(&wst_full[i], 1);
-      mbar_init(&wst_empty[i], 1);
-    }
-    mbar_init(wstt_full, 1);
-    mbar_init(final_full, 1);
+    mbar_init(wst_full, 1);
+    mbar_init(dym_full, 1);
+    mbar_init(dym_empty, 1);
+    mbar_init(final_a, 1);
+    mbar_init(final_b, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmWst);
     tma_prefetch_desc(&tmWstt);
   }
   // zero every operand tile and the scan scratch once: pad columns / rows that are never written must be finite zeros
-  for (uint32_t i = threadIdx.x * 16; i < O_MISC + M_TAB; i += NTHREADS * 16)
+  for (uint32_t i = threadIdx.x * 16; i < O_MISC + MM::TAB; i += NTHREADS * 16)
     *reinterpret_cast<float4*>(sm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   // conv weights / 51 (TF32) as the B operand of the conv UMMA: rows k < 40 (48), columns t < 25 (32)
@@ -658,7 +699,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     atomicAdd(&p.dgamma[threadIdx.x], p.gscale * (float)p.bsums[N_FILT + threadIdx.x]);
     atomicAdd(&p.dbeta[threadIdx.x], p.gscale * (float)p.bsums[threadIdx.x]);
   }
-  if (warp == CTRL_WARP) {
+  if (warp == CTRL_A) {
     tmem_alloc(tmem_slot, 512);   // Y[2]: 0, 64; DA[2]: 128, 192; B1: dWs[4] at 256 + 64 ci; B2: G[2] at 256, 288, dwt at 320
     tmem_relinquish();
   }
@@ -668,73 +709,64 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // =============================== builders ===============================
-    const int r = threadIdx.x;                         // tile row 0..127
+  if (warp < N_BUILD_WARPS) {
+    // =============================== builders (group gb owns the iterations it & 1 == gb) ===============================
+    const int gb = warp >> 2, rq = warp & 3;
+    const int r = rq * 32 + lane;                      // tile row 0..127
     const int s_row = r / N_POOL, p_row = r % N_POOL;
+    float* ps_all = reinterpret_cast<float*>(misc + M_PS + (uint32_t)gb * SCAN_BYTES);
+    float* cs_all = ps_all + 3 * PS_LD;
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-    float4 dyr[10];
     auto fetch_x = [&](int it) {
-      if (it < total_it && warp < TILE_S) {
+      if (it < total_it && rq < TILE_S) {
         const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-        if (warp < d.ns) {
-          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + warp) * N_TOK + d.c) * D_PAD + 8 * lane;
+        if (rq < d.ns) {
+          const float* xrow = p.x3 + ((size_t)(d.tile * TILE_S + rq) * N_TOK + d.c) * D_PAD + 8 * lane;
           xa = __ldg(reinterpret_cast<const float4*>(xrow));
           xb = __ldg(reinterpret_cast<const float4*>(xrow + 4));
         }
       }
     };
-    auto fetch_dy = [&](int tl) {                       // this thread's row of the dY2 tile of local tile tl
+    // dY2 rows go global -> shared with cp.async (no registers; dY2 is already TF32-rounded by its producer).  K-major
+    // tile of local tile tl into DYK[tl & 1] (+ its tail k-step): staged one tile ahead by the group that runs the
+    // previous tile's last iteration, completed (wait_group + proxy fence + arrive) at the end of that iteration.
+    auto stage_dyk = [&](int tl) {
+      const int tb = tl & 1;
+      const int tile = slot + tl * n_slots;
+      const int ns = min(TILE_S, p.B - tile * TILE_S);
+      mbar_wait(&dyk_empty[tb], ((uint32_t)(tl >> 1) & 1u) ^ 1u);       // last dA1 UMMA of local tile tl-2
+      uint8_t* dk = sm + OB_DYK + (uint32_t)tb * KB_A;
+      if (r < ns * N_POOL) {
+        const float* src = p.dy2 + ((size_t)tile * TILE_ROWS + r) * N_FILT;
 #pragma unroll
-      for (int j = 0; j < 10; ++j) dyr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tl < n_my_tiles) {
-        const int tile = slot + tl * n_slots;
-        const int ns = min(TILE_S, p.B - tile * TILE_S);
-        if (r < ns * N_POOL) {
-          const float4* src = reinterpret_cast<const float4*>(p.dy2 + ((size_t)tile * TILE_ROWS + r) * N_FILT);
+        for (int j = 0; j < 8; ++j) cp_async16(dk + sw128_off(r, j), src + 4 * j);
+        cp_async16(sm + OB_TAIL + sw128_off(r, 2 * tb), src + 32);
+        cp_async16(sm + OB_TAIL + sw128_off(r, 2 * tb + 1), src + 36);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 10; ++j) dyr[j] = __ldg(src + j);
-        }
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dk + sw128_off(r, j)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb + 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      cp_async_commit();
     };
-    fetch_x(0);
-    fetch_dy(0);
-    for (int it = 0; it < total_it; ++it) {
+    int pending_dyk = -1;                               // tile buffer whose cp.async group this group still has to complete
+    fetch_x(gb);
+    if (gb == 0 && total_it > 0) { stage_dyk(0); pending_dyk = 0; }
+    for (int it = gb; it < total_it; it += 2) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bi = it & 1;
+      const int bi = gb;
       const uint32_t n = (uint32_t)(it >> 1);
-      const int tb = d.tl & 1;
       const bool valid = r < d.ns * N_POOL;
       const float4 x0 = xa, x1 = xb;
-      fetch_x(it + 1);
-      if (warp < d.ns) pool_row(x0, x1, lane, cs_all + warp * CSX_LD, ps_all + warp * PS_LD);
-      if (d.ci == 0) {
-        // ---- dY2 rows of this (new) tile: K-major for the dA1 UMMA (+ MN-major for the dWs UMMA in B1) ----
-        mbar_wait(&dyt_empty[tb], ((uint32_t)(d.tl >> 1) & 1u) ^ 1u);
-        uint8_t* dk = sm + OB_DYK + (uint32_t)tb * KB_A;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          float4 v = dyr[j];
-          v.x = tf32_fast(v.x); v.y = tf32_fast(v.y); v.z = tf32_fast(v.z); v.w = tf32_fast(v.w);
-          dyr[j] = v;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dk + sw128_off(r, j)) = dyr[j];
-        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb)) = dyr[8];
-        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb + 1)) = dyr[9];
-        if (BS) {
-          uint8_t* dm = sm + O1_DYM + (uint32_t)tb * 2 * SLAB;
-#pragma unroll
-          for (int j8 = 0; j8 < 5; ++j8) {               // mn = j: 8 consecutive j per 32-byte chunk
-            const uint32_t off = mn_off(8 * j8, r);
-            *reinterpret_cast<float4*>(dm + off) = dyr[2 * j8];
-            *reinterpret_cast<float4*>(dm + off + 16) = dyr[2 * j8 + 1];
-          }
-        }
-        fetch_dy(d.tl + 1);                             // the next tile's row travels during this tile's iterations
-      }
-      named_bar_sync(1, 128);                             // pooled sums visible
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 0);
+      fetch_x(it + 2);
+      if (d.ci == gc - 1 && d.tl + 1 < n_my_tiles) { stage_dyk(d.tl + 1); pending_dyk = (d.tl + 1) & 1; }
+      if (rq < d.ns) pool_row(x0, x1, lane, cs_all + rq * CSX_LD, ps_all + rq * PS_LD);
+      named_bar_sync(1 + gb, 128);                        // pooled sums visible
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 1);
       mbar_wait(&im_empty[bi], (n & 1u) ^ 1u);
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 2);
       {
         const float* src = ps_all + s_row * PS_LD + 5 * p_row;
         float a[28];
@@ -758,17 +790,51 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           }
         }
       }
+      if (pending_dyk >= 0) cp_async_wait_all();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) {
-        if (d.ci == 0) mbar_arrive(&dyt_full[tb]);
+      named_bar_sync(1 + gb, 128);
+      if (rq == 0 && lane == 0) {
+        if (pending_dyk >= 0) mbar_arrive(&dyk_full[pending_dyk]);
         mbar_arrive(&im_full[bi]);
+        CONV_TRACE(gb, it, 3);
+      }
+      pending_dyk = -1;
+      if (BS && gb == 0 && d.ci < 2) {
+        // ---- MN-major copy of this tile's dY2 rows for the dWs UMMA (single buffered): the last dWs UMMA of the previous
+        //      tile must be done; the rows are L2-hot (the K-major staging read them one tile earlier).  ALWAYS group 0, at
+        //      its first iteration inside the tile (ci 0, or 1 when the tile starts on an odd iteration): parity waits are
+        //      only sound when one agent walks the phases in order (tools/conv_tc_protocol_sim.py) ----
+        mbar_wait(dym_empty, ((uint32_t)d.tl & 1u) ^ 1u);
+        if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 4);
+        uint8_t* dm = sm + O1_DYM;
+        if (valid) {
+          const float* src = p.dy2 + ((size_t)d.tile * TILE_ROWS + r) * N_FILT;
+#pragma unroll
+          for (int j8 = 0; j8 < 5; ++j8) {               // mn = j: 8 consecutive j per 32-byte chunk
+            const uint32_t off = mn_off(8 * j8, r);
+            cp_async16(dm + off, src + 8 * j8);
+            cp_async16(dm + off + 16, src + 8 * j8 + 4);
+          }
+        } else {
+#pragma unroll
+          for (int j8 = 0; j8 < 5; ++j8) {
+            const uint32_t off = mn_off(8 * j8, r);
+            *reinterpret_cast<float4*>(dm + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dm + off + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        fence_proxy_async_smem();
+        named_bar_sync(1 + gb, 128);
+        if (rq == 0 && lane == 0) { mbar_arrive(dym_full); CONV_TRACE(gb, it, 5); }
       }
     }
-  } else if (warp < 12) {
-    // =============================== epilogue ===============================
+  } else if (warp < SCAT_WARP0) {
+    // =============================== epilogue (group ge owns the iterations it & 1 == ge) ===============================
+    const int ge = (warp - EPI_WARP0) >> 3;
+    const int h = ((warp - EPI_WARP0) >> 2) & 1;
     const int q = warp & 3;
-    const int h = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float s1[BS ? 20 : 1], s2[BS ? 20 : 1];
@@ -776,64 +842,108 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
 #pragma unroll
       for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
     }
-    for (int it = 0; it < total_it; ++it) {
+    for (int it = ge; it < total_it; it += 2) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bi = it & 1;
+      const int bi = ge;
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
+      const bool tr = q == 0 && h == 0 && lane == 0;
+      if (tr) CONV_TRACE(2 + ge, it, 0);
       mbar_wait(&c_full[bi], n & 1u);
       tc_fence_after();
-      float y[20], da[20];
-      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
-      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
-      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 16 * h), da);
-      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 32 + 4 * h), da + 16);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&c_empty[bi]);
-      float o[20];
+      if (tr) CONV_TRACE(2 + ge, it, 1);
+      if constexpr (BS) {
+        // a1 goes to the group's own MN-major buffer (its dWs UMMAs of iteration it-2 are long done); the 20 columns are
+        // processed in chunks of 8 / 8 / 4 to keep the 40 running sums in registers
+        mbar_wait(&op_empty[bi], (n & 1u) ^ 1u);
+        if (tr) CONV_TRACE(2 + ge, it, 2);
+        uint8_t* mt = sm + O1_A1M + (uint32_t)bi * 2 * SLAB;
 #pragma unroll
-      for (int i = 0; i < 20; ++i) {
-        const int k = kidx(h, i);
-        const float yv = y[i] + tab[k];
-        const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
-        const float dz = da[i] * (z > 0.f ? 1.f : __expf(z));          // ELU'(z)
-        if constexpr (BS) {
-          const float yh = fmaf(yv, tab[144 + k], tab[192 + k]);
-          if (valid) { s1[i] += dz; s2[i] = fmaf(dz, yh, s2[i]); }
-          o[i] = valid ? tf32_fast(elu_fast(z)) : 0.f;                  // a1
-        } else {
-          o[i] = valid ? tf32_fast(fmaf(tab[48 + k], dz, fmaf(tab[144 + k], yv, tab[192 + k]))) : 0.f;   // dy
+        for (int ch = 0; ch < 3; ++ch) {
+          float y[8], da[8];
+          const uint32_t col = ch < 2 ? (uint32_t)(16 * h + 8 * ch) : (uint32_t)(32 + 4 * h);
+          if (ch < 2) {
+            tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(bi * 64) + col, y);
+            tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64) + col, da);
+          } else {
+            tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64) + col, y);
+            tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64) + col, da);
+          }
+          tmem_ld_wait();
+          const int nc = ch < 2 ? 8 : 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nc) {
+              const int k = (int)col + i;
+              const float yv = y[i] + tab[k];
+              const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
+              const float e = __expf(z);
+              const float dz = da[i] * (z > 0.f ? 1.f : e);              // ELU'(z)
+              const float yh = fmaf(yv, tab[144 + k], tab[192 + k]);
+              if (valid) { s1[8 * ch + i] += dz; s2[8 * ch + i] = fmaf(dz, yh, s2[8 * ch + i]); }
+              y[i] = valid ? tf32_fast(z > 0.f ? z : e - 1.f) : 0.f;      // a1
+            }
+          }
+          const uint32_t off = mn_off((int)col, r);                      // MN-major: mn = filter k, k-row = tile row r
+          *reinterpret_cast<float4*>(mt + off) = make_float4(y[0], y[1], y[2], y[3]);
+          if (ch < 2) *reinterpret_cast<float4*>(mt + off + 16) = make_float4(y[4], y[5], y[6], y[7]);
         }
-      }
-      // ---- operand tiles of the second-stage UMMAs (single buffered: those of iteration it-1 must have completed) ----
-      mbar_wait(&op_empty[0], ((uint32_t)it & 1u) ^ 1u);
-      {
-        uint8_t* mt = sm + (BS ? O1_A1M : O2_DYM);                     // MN-major: mn = filter k, k-row = tile row r
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&c_empty[bi]);
+          mbar_arrive(&op_full[bi]);
+        }
+        if (tr) CONV_TRACE(2 + ge, it, 3);
+      } else {
+        float y[20], da[20];
+        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
+        tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
+        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 16 * h), da);
+        tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 32 + 4 * h), da + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_empty[bi]);
+#pragma unroll
+        for (int i = 0; i < 20; ++i) {
+          const int k = kidx(h, i);
+          const float yv = y[i] + tab[k];
+          const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
+          const float dz = da[i] * (z > 0.f ? 1.f : __expf(z));          // ELU'(z)
+          y[i] = valid ? tf32_fast(fmaf(tab[48 + k], dz, fmaf(tab[144 + k], yv, tab[192 + k]))) : 0.f;   // dy
+        }
+        // dy tiles are single buffered: the second-stage UMMAs of iteration it-1 (the other group's) must have completed.
+        // Each group waits on its OWN barrier, completed once per iteration of the other group: a shared barrier with
+        // per-iteration phases lets a group that is two phases ahead slip through the parity test
+        if (tr) CONV_TRACE(2 + ge, it, 4);
+        if (it > 0) mbar_wait(&op_empty[bi], ((uint32_t)((it - 1) >> 1)) & 1u);
+        if (tr) CONV_TRACE(2 + ge, it, 2);
+        uint8_t* mt = sm + O2_DYM;                                       // MN-major: mn = filter k, k-row = tile row r
         const uint32_t o0 = mn_off(16 * h, r), o1 = mn_off(16 * h + 8, r), o2 = mn_off(32 + 4 * h, r);
-        *reinterpret_cast<float4*>(mt + o0) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(mt + o0 + 16) = make_float4(o[4], o[5], o[6], o[7]);
-        *reinterpret_cast<float4*>(mt + o1) = make_float4(o[8], o[9], o[10], o[11]);
-        *reinterpret_cast<float4*>(mt + o1 + 16) = make_float4(o[12], o[13], o[14], o[15]);
-        *reinterpret_cast<float4*>(mt + o2) = make_float4(o[16], o[17], o[18], o[19]);
-        if (!BS) {
-          uint8_t* kt = sm + O2_DYK2;                                  // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
+        *reinterpret_cast<float4*>(mt + o0) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(mt + o0 + 16) = make_float4(y[4], y[5], y[6], y[7]);
+        *reinterpret_cast<float4*>(mt + o1) = make_float4(y[8], y[9], y[10], y[11]);
+        *reinterpret_cast<float4*>(mt + o1 + 16) = make_float4(y[12], y[13], y[14], y[15]);
+        *reinterpret_cast<float4*>(mt + o2) = make_float4(y[16], y[17], y[18], y[19]);
+        uint8_t* kt = sm + O2_DYK2;                                      // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(kt + sw128_off(r, 4 * h + j)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 4 + h)) = make_float4(o[16], o[17], o[18], o[19]);
-        }
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(kt + sw128_off(r, 4 * h + j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 4 + h)) = make_float4(y[16], y[17], y[18], y[19]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&op_full[0]);
+        if (tr) CONV_TRACE(2 + ge, it, 3);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&op_full[0]);
     }
     // ---- after the loop: the accumulators that lived in TMEM for the whole kernel ----
-    mbar_wait(final_full, 0);
+    mbar_wait(final_a, 0);
+    mbar_wait(final_b, 0);
     tc_fence_after();
     if constexpr (BS) {
-      if (total_it > 0 && q < 2) {                                     // TMEM lane = j (output filter of the spatial conv)
+      if (total_it > 0 && ge == 0 && q < 2) {                          // TMEM lane = j (output filter of the spatial conv)
         for (int ci = 0; ci < gc; ++ci) {
           float w[20];
           tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64 + 16 * h), w);
@@ -846,16 +956,18 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           }
         }
       }
+      // running sums: slot 8*ch + i of chunk ch holds filter (ch < 2 ? 16h + 8ch : 32 + 4h) + i
 #pragma unroll
       for (int i = 0; i < 20; ++i) {
+        const int k = i < 16 ? 16 * h + i : 32 + 4 * h + (i - 16);
         const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
-        if (lane == 0) { atomicAdd(&red[kidx(h, i)], a); atomicAdd(&red[N_FILT + kidx(h, i)], b); }
+        if (lane == 0) { atomicAdd(&red[k], a); atomicAdd(&red[N_FILT + k], b); }
       }
-      named_bar_sync(2, 256);
-      const int k = threadIdx.x - 128;
+      named_bar_sync(3, N_EPI_WARPS * 32);
+      const int k = threadIdx.x - EPI_THREAD0;
       if (k < 2 * N_FILT) atomicAdd(&p.bsums[k], (double)red[k]);
     } else {
-      if (total_it > 0 && q < 2) {                                     // TMEM lane = filter k, column = tap t (25: ones column)
+      if (total_it > 0 && ge == 0 && q < 2) {                          // TMEM lane = filter k, column = tap t (25: ones column)
         float w[16];
         tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(320 + 16 * h), w);
         tmem_ld_wait();
@@ -869,20 +981,24 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         }
       }
     }
-  } else if (!BS && warp < 16) {
+  } else if (!BS && warp < SCAT_WARP0 + 4) {
     // =============================== scatter warps (B2): G -> pooled positions -> d x3 ===============================
     const int q = warp & 3;
-    const int sw = warp - 12;
+    const int sw = warp - SCAT_WARP0;
     const int r = q * 32 + lane;
     const int s_row = r / N_POOL, p_row = r % N_POOL;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* dps_all = reinterpret_cast<float*>(misc + M_DPS);
+    float* csd_all = dps_all + 3 * PS_LD;
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
+      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 0);
       mbar_wait(&gg_full[bi], n & 1u);
       tc_fence_after();
+      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 1);
       float gv[32];
       tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32), gv);
       tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32 + 16), gv + 16);
@@ -895,7 +1011,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
 #pragma unroll
         for (int t = 0; t < K_TEMP; ++t) atomicAdd(dp + t, gv[t]);
       }
-      named_bar_sync(3, 128);
+      named_bar_sync(4, 128);
       if (sw < d.ns) {
         // d x3[v] = (1/51) * sum_{u = max(0, v-50)}^{min(v, 199)} dps[u]  via the prefix P: (P[hi+1] - P[lo]) / 51
         float* dp = dps_all + sw * PS_LD;
@@ -943,40 +1059,83 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           *reinterpret_cast<float4*>(dz + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      named_bar_sync(3, 128);
+      named_bar_sync(4, 128);
+      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 2);
     }
-  } else if (warp == CTRL_WARP && lane == 0) {
-    // =============================== control: TMA + UMMA issue ===============================
+  } else if (warp == CTRL_A && lane == 0) {
+    // =============================== control A: weight TMA (once), conv + dA1 UMMAs ===============================
     constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0);
+    const uint32_t s0 = smem_u32(sm);
+    if (total_it > 0) {
+      mbar_arrive_expect_tx(wst_full, GC * KB_48 + KB_48);
+      tma_load_2d(&tmWst, wst_full, sm + OB_WST, 0, g * GC * N48);           // [4 channels x 48 rows][32]
+      tma_load_2d(&tmWstt, wst_full, sm + OB_WSTT, 0, g * N48);
+    }
+    for (int it = 0; it < total_it; ++it) {
+      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
+      const int bi = it & 1, tb = d.tl & 1;
+      const uint32_t n = (uint32_t)(it >> 1);
+      CONV_TRACE(4, it, 0);
+      mbar_wait(&im_full[bi], n & 1u);
+      CONV_TRACE(4, it, 1);
+      mbar_wait(&c_empty[bi], (n & 1u) ^ 1u);
+      CONV_TRACE(4, it, 2);
+      tc_fence_after();
+      // conv UMMA (plain TF32 in the backward): Y[bi] = im2col . (wt/51)^T
+      const uint32_t ik = s0 + OB_IMK + (uint32_t)bi * KB_A, bc = s0 + OB_BC;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), umma_smem_desc(ik + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
+      tc_commit(&im_empty[bi]);                          // B2: control B adds the second arrival (MN-major copy, dwt UMMA)
+      if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);
+      if (it == 0) mbar_wait(wst_full, 0);
+      tc_fence_after();
+      // dA1[(s,p), k] = sum_j dY2[(s,p), j] * Ws[j, k, c]
+      const uint32_t dk = s0 + OB_DYK + (uint32_t)tb * KB_A, wk = s0 + OB_WST + (uint32_t)d.ci * KB_48;
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t ao = kk < 4 ? dk + (uint32_t)kk * 32u : s0 + OB_TAIL + (uint32_t)tb * 32u;
+        const uint32_t bo = kk < 4 ? wk + (uint32_t)kk * 32u : s0 + OB_WSTT + (uint32_t)d.ci * 32u;
+        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
+                    umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
+      }
+      tc_commit(&c_full[bi]);
+      CONV_TRACE(4, it, 3);
+      if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);     // nothing reads the K-major dY2 tile after its last dA1 UMMA
+    }
+    tc_commit(final_a);
+  } else if (warp == CTRL_B && lane == 0) {
+    // =============================== control B: second-stage UMMAs ===============================
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32, 0, 0);
     constexpr uint32_t idesc48_mn = umma_idesc_tf32(128, N48, 1, 1);
     constexpr uint32_t idesc32_mn = umma_idesc_tf32(128, 32, 1, 1);
     const uint32_t s0 = smem_u32(sm);
-    auto load_wst = [&](int it) {
+    for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int wi = it & (WS_RING - 1);
-      const uint32_t n = (uint32_t)(it / WS_RING);
-      mbar_wait(&wst_empty[wi], (n & 1u) ^ 1u);
-      mbar_arrive_expect_tx(&wst_full[wi], KB_48);
-      tma_load_2d(&tmWst, &wst_full[wi], sm + OB_WST + (uint32_t)wi * KB_48, 0, d.c * N48);
-    };
-    auto stage2 = [&](int it) {
-      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bj = it & 1, tb = d.tl & 1;
-      mbar_wait(&op_full[0], (uint32_t)it & 1u);
+      const int bj = it & 1;
+      CONV_TRACE(5, it, 0);
       if (BS) {
+        if (d.ci == 0) mbar_wait(dym_full, (uint32_t)d.tl & 1u);
+        CONV_TRACE(5, it, 1);
+        mbar_wait(&op_full[bj], (uint32_t)(it >> 1) & 1u);
+        CONV_TRACE(5, it, 2);
         tc_fence_after();
         // dWs_c[j, k] += sum_rows dY2[row, j] * a1[row, k]: both operands MN-major, K = the 128 tile rows
-        const uint32_t a = s0 + O1_DYM + (uint32_t)tb * 2 * SLAB, b = s0 + O1_A1M;
+        const uint32_t a = s0 + O1_DYM, b = s0 + O1_A1M + (uint32_t)bj * 2 * SLAB;
 #pragma unroll 4
         for (int kk = 0; kk < 16; ++kk)
           tc_mma_tf32(tmem_base + 256u + (uint32_t)(d.ci * 64), umma_smem_desc(a + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
                       umma_smem_desc(b + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc48_mn,
                       (d.tl > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&op_empty[0]);
-        if (d.ci == gc - 1) tc_commit(&dyt_empty[tb]);
+        tc_commit(&op_empty[bj]);
+        CONV_TRACE(5, it, 3);
+        if (d.ci == gc - 1) tc_commit(dym_empty);
       } else {
+        mbar_wait(&op_full[0], (uint32_t)it & 1u);
+        CONV_TRACE(5, it, 1);
         mbar_wait(&gg_empty[bj], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        CONV_TRACE(5, it, 2);
         tc_fence_after();
         // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
         const uint32_t a = s0 + O2_DYK2, b = s0 + O2_WTT;
@@ -995,65 +1154,26 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           tc_mma_tf32(tmem_base + 320u, umma_smem_desc(am + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
                       umma_smem_desc(bm + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc32_mn,
                       (it > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&op_empty[0]);
+        tc_commit(&op_empty[bj ^ 1]);                    // the next iteration's group may overwrite the dy tiles
         tc_commit(&im_empty[bj]);
+        CONV_TRACE(5, it, 3);
       }
-    };
-    if (total_it > 0) {
-      mbar_arrive_expect_tx(wstt_full, KB_48);
-      tma_load_2d(&tmWstt, wstt_full, sm + OB_WSTT, 0, g * N48);
-      load_wst(0);
-      if (total_it > 1) load_wst(1);
     }
-    for (int it = 0; it < total_it; ++it) {
-      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bi = it & 1, wi = it & (WS_RING - 1), tb = d.tl & 1;
-      const uint32_t n = (uint32_t)(it >> 1);
-      mbar_wait(&im_full[bi], n & 1u);
-      mbar_wait(&c_empty[bi], (n & 1u) ^ 1u);
-      tc_fence_after();
-      // conv UMMA (plain TF32 in the backward): Y[bi] = im2col . (wt/51)^T
-      const uint32_t ik = s0 + OB_IMK + (uint32_t)bi * KB_A, bc = s0 + OB_BC;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), umma_smem_desc(ik + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
-      if (BS) tc_commit(&im_empty[bi]);                  // B2: the dwt UMMA of this iteration still reads the MN-major copy
-      if (d.ci == 0) mbar_wait(&dyt_full[tb], (uint32_t)(d.tl >> 1) & 1u);
-      mbar_wait(&wst_full[wi], (uint32_t)(it / WS_RING) & 1u);
-      if (it == 0) mbar_wait(wstt_full, 0);
-      tc_fence_after();
-      // dA1[(s,p), k] = sum_j dY2[(s,p), j] * Ws[j, k, c]
-      const uint32_t dk = s0 + OB_DYK + (uint32_t)tb * KB_A, wk = s0 + OB_WST + (uint32_t)wi * KB_48;
-#pragma unroll
-      for (int kk = 0; kk < 5; ++kk) {
-        const uint32_t ao = kk < 4 ? dk + (uint32_t)kk * 32u : s0 + OB_TAIL + (uint32_t)tb * 32u;
-        const uint32_t bo = kk < 4 ? wk + (uint32_t)kk * 32u : s0 + OB_WSTT + (uint32_t)d.ci * 32u;
-        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
-      }
-      tc_commit(&wst_empty[wi]);
-      tc_commit(&c_full[bi]);
-      if (!BS && d.ci == gc - 1) tc_commit(&dyt_empty[tb]);   // B2: nothing reads the dY2 tile after its last dA1 UMMA
-      if (it + 2 < total_it) load_wst(it + 2);
-      if (it > 0) stage2(it - 1);
-    }
-    if (total_it > 0) stage2(total_it - 1);
-    tc_commit(final_full);
+    tc_commit(final_b);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == CTRL_WARP) tmem_dealloc(tmem_base, 512);
+  if (warp == CTRL_A) tmem_dealloc(tmem_base, 512);
 }
 
 // tsconv.4.weight [j][k][c] -> Ws_c^T as the B operand of the dA1 UMMA (rows k, reduction index j), TF32, zero padded:
-//   main [c][48 rows k][32 floats j 0..31]   and   tails [g][48 rows k][8*ci + (j-32)] for the 4 channels of group g
+//   main [c (64 slots)][48 rows k][32 floats j 0..31]   and   tails [g][48 rows k][8*ci + (j-32)] for the channels of group g
 __global__ void pack_wst_tc_kernel(const float* __restrict__ ws, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < (int)WST_MAIN_FLOATS) {
     const int j = idx & 31, k = (idx >> 5) % N48, c = idx / (N48 * 32);
-    out[idx] = k < N_FILT ? tf32_rn(ws[(j * N_FILT + k) * N_CH + c]) : 0.f;
+    out[idx] = (k < N_FILT && c < N_CH) ? tf32_rn(ws[(j * N_FILT + k) * N_CH + c]) : 0.f;
   } else if (idx < (int)(WST_MAIN_FLOATS + WST_TAIL_FLOATS)) {
     const int t = idx - (int)WST_MAIN_FLOATS;
     const int col = t & 31, k = (t >> 5) % N48, gg = t / (N48 * 32);
@@ -1127,7 +1247,31 @@ int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float
   return 0;
 }
 
-static int bwd_launch(int mode, const ConvBwdParams& p, float* wst_packed, const float* ws_to_pack, cudaStream_t s) {
+// EEGB200_CONV_TRACE=<dir>: CTA 0 of the backward kernels records clock64() at every handshake; dumped after the launch
+static int trace_dump(const char* name, long long* dev, cudaStream_t s) {
+  const char* dir = getenv("EEGB200_CONV_TRACE");
+  if (!dir || !dev) return 0;
+  const size_t n = (size_t)TRACE_ROLES * TRACE_IT * 8;
+  std::vector<long long> host(n);
+  EEG_CUDA_OK(cudaStreamSynchronize(s));
+  EEG_CUDA_OK(cudaMemcpy(host.data(), dev, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  char path[512];
+  snprintf(path, sizeof(path), "%s/conv_trace_%s.bin", dir, name);
+  FILE* f = fopen(path, "wb");
+  if (f) { fwrite(host.data(), sizeof(long long), n, f); fclose(f); }
+  return 0;
+}
+static long long* trace_buffer(cudaStream_t s) {
+  if (!getenv("EEGB200_CONV_TRACE")) return nullptr;
+  static long long* buf = nullptr;
+  if (!buf && cudaMalloc(&buf, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(buf, 0, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long), s);
+  return buf;
+}
+
+static int bwd_launch(int mode, const ConvBwdParams& p_in, float* wst_packed, const float* ws_to_pack, cudaStream_t s) {
+  ConvBwdParams p = p_in;
+  p.trace = trace_buffer(s);
   if (ws_to_pack != nullptr) {
     pack_wst_tc_kernel<<<cdiv((int)(WST_MAIN_FLOATS + WST_TAIL_FLOATS), 256), 256, 0, s>>>(ws_to_pack, wst_packed);
     EEG_CUDA_OK(cudaGetLastError());
@@ -1135,7 +1279,7 @@ static int bwd_launch(int mode, const ConvBwdParams& p, float* wst_packed, const
   }
   CUtensorMap tm, tt;
   int d3 = 0;
-  EEG_TRY(gemm_make_tmap(&tm, GemmOperand{wst_packed, 32, 0}, N_CH * N48, 32, N48, &d3));
+  EEG_TRY(gemm_make_tmap(&tm, GemmOperand{wst_packed, 32, 0}, N_GROUPS * GC * N48, 32, GC * N48, &d3));
   EEG_TRY(gemm_make_tmap(&tt, GemmOperand{wst_packed + WST_MAIN_FLOATS, 32, 0}, N_GROUPS * N48, 32, N48, &d3));
   int slots = sm_count() / N_GROUPS;
   if (slots > p.n_tiles) slots = p.n_tiles;
@@ -1154,6 +1298,7 @@ static int bwd_launch(int mode, const ConvBwdParams& p, float* wst_packed, const
   }
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
+  if (p.trace) EEG_TRY(trace_dump(mode == MODE_BSTATS ? "bwd_stats" : "bwd_apply", p.trace, s));
   return 0;
 }
 

@@ -59,6 +59,8 @@ int dropout_mask(DropoutCfg cfg, int rows, int cols, int ld, float* out, cudaStr
 int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, cudaStream_t s);
 int dropout_apply_colsum(const float* src, float* dst, int rows, int ld, DropoutCfg cfg, int round_tf, float* colsum_out,
                          int cs_cols, int row_mod, int row_skip, cudaStream_t s);
+int l2norm_fwd(const float* x, float* y, float* norms, int rows, int D, cudaStream_t s);
+int l2norm_bwd(const float* y, const float* norms, const float* dy, float* dx, int rows, int D, cudaStream_t s);
 int pad_copy(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, int rows_dst, int round_tf,
              float scale, cudaStream_t s);
 

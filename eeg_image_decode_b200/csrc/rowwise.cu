@@ -676,4 +676,63 @@ int dropout_apply(const float* src, float* dst, int rows, int ld, DropoutCfg cfg
   count_launch();
   return 0;
 }
+// ------------------------------------------------------------------------------------------------
+// optional L2 normalisation of the embedding (north_star wording; the reference does NOT normalise the EEG embedding,
+// ATMS_retrieval.py:182-191, so ATMS(normalize=False) is the default): y = x / max(|x|, eps), one warp per row
+// backward: dx = (dy - y * (y . dy)) / max(|x|, eps)
+// ------------------------------------------------------------------------------------------------
+__global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norms, int rows,
+                                  int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  float s = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = xr[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float nrm = fmaxf(sqrtf(warp_sum(s)), eps);
+  const float inv = 1.f / nrm;
+  if (lane == 0) norms[row] = nrm;
+  float4* yr = reinterpret_cast<float4*>(y + (size_t)row * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = xr[i];
+    yr[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+}
+__global__ void l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ norms,
+                                  const float* __restrict__ dy, float* __restrict__ dx, int rows, int D) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* yr = reinterpret_cast<const float4*>(y + (size_t)row * D);
+  const float4* gr = reinterpret_cast<const float4*>(dy + (size_t)row * D);
+  float s = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 a = yr[i], g = gr[i];
+    s += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+  }
+  const float dot = warp_sum(s), inv = 1.f / norms[row];
+  float4* dr = reinterpret_cast<float4*>(dx + (size_t)row * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 a = yr[i], g = gr[i];
+    dr[i] = make_float4((g.x - a.x * dot) * inv, (g.y - a.y * dot) * inv, (g.z - a.z * dot) * inv, (g.w - a.w * dot) * inv);
+  }
+}
+int l2norm_fwd(const float* x, float* y, float* norms, int rows, int D, cudaStream_t s) {
+  ProfScope _ps("l2norm_fwd", s, 0.0, (double)rows * D * 8.0);
+  EEG_REQUIRE((D & 3) == 0, "l2norm: D %d must be a multiple of 4", D);
+  l2norm_fwd_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(x, y, norms, rows, D, 1e-12f);   // F.normalize eps
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+int l2norm_bwd(const float* y, const float* norms, const float* dy, float* dx, int rows, int D, cudaStream_t s) {
+  ProfScope _ps("l2norm_bwd", s, 0.0, (double)rows * D * 12.0);
+  EEG_REQUIRE((D & 3) == 0, "l2norm: D %d must be a multiple of 4", D);
+  l2norm_bwd_kernel<<<cdiv(rows * 32, 256), 256, 0, s>>>(y, norms, dy, dx, rows, D);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace eegb200

@@ -556,10 +556,73 @@ def evaluate_model(sub, eeg_model, dataloader, device, text_features_all, img_fe
                            variant="retrieval", alpha=0.99)
 
 
+EVAL_CHUNK = 1024       # trials per eval-mode forward launch chain
+
+
+def _drain(dataloader):
+    """the loader's batches as lists (EEG, labels, text features, image features); nothing is computed yet"""
+    eeg, labels, txt, img = [], [], [], []
+    for (eeg_data, lab, _text, text_features, _img, img_features) in dataloader:
+        eeg.append(eeg_data)
+        labels.append(lab)
+        txt.append(text_features)
+        img.append(img_features)
+    return eeg, labels, txt, img
+
+
+def _encode_batches(eeg_model, eeg_list, device, subject_id, known_subject):
+    """Eval-mode embeddings of every trial of a drained loader, EVAL_CHUNK trials per forward instead of one forward
+    per loader batch (the reference's test loader has batch size 1: 200 B=1 forwards per evaluate_model call,
+    ATMS_retrieval.py:264-279).  Eval-mode BatchNorm uses the running statistics, so a trial's embedding does not depend
+    on which other trials share its launch."""
+    n = sum(int(e.size(0)) for e in eeg_list)
+    feats = torch.empty(n, 1024, device=device, dtype=torch.float32)
+    sid = subject_id if subject_id is not None else -1
+    i0, cur, cur_n = 0, [], 0
+
+    def flush():
+        nonlocal i0, cur, cur_n
+        if not cur:
+            return
+        x = cur[0].to(device) if len(cur) == 1 else torch.cat([e.to(device) for e in cur], dim=0)
+        ids = torch.full((cur_n,), sid, dtype=torch.long, device=device)
+        eeg_model.encode(x, ids, train=False, known_subject=known_subject, out=feats[i0:i0 + cur_n])
+        i0, cur, cur_n = i0 + cur_n, [], 0
+
+    for e in eeg_list:
+        if cur_n + int(e.size(0)) > EVAL_CHUNK:
+            flush()
+        cur.append(e)
+        cur_n += int(e.size(0))
+    flush()
+    return feats
+
+
+def _eval_losses(eng, feats, sizes, img_list, txt_list, device):
+    """sum over the loader's batches of the per-batch loss (the reference averages per-batch losses, :282-293)"""
+    total = torch.zeros(3, device=device)
+    if all(b == 1 for b in sizes):
+        # batch size 1 (the reference's test loader): ClipLoss is exactly 0 -- cross entropy of a 1x1 logit matrix
+        # (models/loss.py:137-140); only the MSE term of the reconstruction variant remains, summed by one kernel
+        if eng.variant == "reconstruction":
+            img = torch.cat([t.to(device).float() for t in img_list], dim=0).contiguous()
+            _lib.mse(feats, img, 1, eng.alpha * 10.0, 1.0, loss=total[0:1], loss_term=total[2:3], d_eeg=None)
+        return total
+    off = 0
+    for b, img, txt in zip(sizes, img_list, txt_list):
+        loss, _, _ = eng.loss_and_grad(feats[off:off + b], img.to(device).float().contiguous(),
+                                       txt.to(device).float().contiguous() if txt is not None else None, need_grad=False)
+        total += loss
+        off += b
+    return total
+
+
 def _evaluate_epoch(sub, eeg_model, dataloader, device, text_features_all, img_features_all, k, config, *, variant, alpha):
     """shared by the retrieval script (loss alpha*ClipLoss(img) + (1-alpha)*ClipLoss(txt), ATMS_retrieval.py:290-293) and
     the reconstruction script (alpha*10*MSE + (1-alpha)*10*ClipLoss(img), ATMS_reconstruction.py:283-286); the k-way
-    scoring below is identical in both (:295-357 / :290-349)"""
+    scoring below is identical in both (:295-357 / :290-349).
+    The reference's loop (one B=1 forward, one loss, k-way scoring per loader batch) is run as: drain the loader, draw the
+    candidate sets (same ``random.sample`` calls in the same order), ONE batched forward, ONE scoring launch."""
     eeg_model.eval()
     device = torch.device(device)
     if device.type != "cuda":
@@ -572,57 +635,48 @@ def _evaluate_epoch(sub, eeg_model, dataloader, device, text_features_all, img_f
     all_labels = set(range(n_cls))
     eng = StepEngine(eeg_model, None, alpha, variant)
     eng.world, eng.rank = 1, 0          # evaluation is per process (the reference evaluates on one device), no collectives
-    total_loss = torch.zeros(3, device=device)
-    correct = 0
-    top5_correct_count = 0
-    total = 0
-    n_batches = 0
     subject_id = extract_id_from_string(sub)
     known_subject = None
     if eeg_model.joint_train:
         if subject_id is None or not 0 <= subject_id < N_SUBJECT_ROWS:
             raise KeyError(str(subject_id))
         known_subject = subject_id
-    pend = []
+    eeg_list, label_batches, txt_list, img_list = _drain(dataloader)
+    if not eeg_list:
+        raise RuntimeError("evaluate_model: empty dataloader")
+    sizes = [int(e.size(0)) for e in eeg_list]
+    # host side: the reference's per-sample candidate draw (:297-300).  For every k other than 200 it draws a second list
+    # AFTER the candidate features were gathered (:323-325 and :340-341); the scores still belong to the first list and
+    # the true label is last in both, so the second draw only advances the RNG
+    label_list, sel_rows = [], []
+    for lab in label_batches:
+        for label in lab.tolist():
+            possible_classes = list(all_labels - {label})
+            selected_classes = random.sample(possible_classes, k - 1) + [label]
+            if k in (2, 4, 10, 50, 100):
+                random.sample(possible_classes, k - 1)
+            sel_rows.append(selected_classes)
+            label_list.append(label)
     with torch.no_grad():
-        for batch_idx, (eeg_data, labels, text, text_features, img, img_features) in enumerate(dataloader):
-            eeg_data = eeg_data.to(device)
-            text_features = text_features.to(device).float()
-            img_features = img_features.to(device).float()
-            batch_size = eeg_data.size(0)
-            subject_ids = torch.full((batch_size,), subject_id if subject_id is not None else -1, dtype=torch.long, device=device)
-            eeg_features = eeg_model.encode(eeg_data, subject_ids, train=False, known_subject=known_subject)
-            loss, _, _ = eng.loss_and_grad(eeg_features, img_features.contiguous(), text_features.contiguous(), need_grad=False)
-            total_loss += loss
-            n_batches += 1
-            # host side: the reference's per-sample candidate draw (:297-300).  For every k other than 200 it draws a
-            # second list AFTER the candidate features were gathered (:323-325 and :340-341); the scores still belong to
-            # the first list and the true label is last in both, so the second draw only advances the RNG
-            label_list = labels.tolist()
-            sel_rows = []
-            for label in label_list:
-                possible_classes = list(all_labels - {label})
-                selected_classes = random.sample(possible_classes, k - 1) + [label]
-                if k in (2, 4, 10, 50, 100):
-                    random.sample(possible_classes, k - 1)
-                sel_rows.append(selected_classes)
-            pend.append((eeg_features, torch.tensor(sel_rows, dtype=torch.int32), label_list))
-        for eeg_features, sel, label_list in pend:
-            r = _lib.retrieval(eeg_features, img_features_all, eeg_model.logit_scale.detach(), sel=sel,
-                               want_top5=(k >= 50))
-            top1 = r["top1"].tolist()
-            top5 = r["top5"].tolist() if k >= 50 else None
-            sel_l = sel.tolist()
-            for i, label in enumerate(label_list):
-                if sel_l[i][top1[i]] == label:
-                    correct += 1
-                if top5 is not None and label in [sel_l[i][j] for j in top5[i] if j >= 0]:
-                    top5_correct_count += 1
-                total += 1
-    average_loss = float(total_loss[0].item()) / max(n_batches, 1)
-    accuracy = correct / total
-    top5_acc = top5_correct_count / total
-    return average_loss, accuracy, top5_acc
+        feats = _encode_batches(eeg_model, eeg_list, device, subject_id, known_subject)
+        total_loss = _eval_losses(eng, feats, sizes, img_list, txt_list if variant == "retrieval" else [None] * len(sizes), device)
+        sel = torch.tensor(sel_rows, dtype=torch.int32)
+        r = _lib.retrieval(feats, img_features_all, eeg_model.logit_scale.detach(), sel=sel, want_top5=(k >= 50))
+    top1 = r["top1"].tolist()
+    top5 = r["top5"].tolist() if k >= 50 else None
+    correct = top5_correct_count = 0
+    for i, label in enumerate(label_list):
+        t1 = top1[i]
+        if not 0 <= t1 < k:
+            raise RuntimeError(f"evaluate_model: invalid argmax {t1} for trial {i} (non-finite scores? logit_scale = "
+                               f"{float(eeg_model.logit_scale)})")
+        if sel_rows[i][t1] == label:
+            correct += 1
+        if top5 is not None and label in [sel_rows[i][j] for j in top5[i] if 0 <= j < k]:
+            top5_correct_count += 1
+    total = len(label_list)
+    average_loss = float(total_loss[0].item()) / len(sizes)
+    return average_loss, correct / total, top5_correct_count / total
 
 
 def main_train_loop(sub, current_time, eeg_model, train_dataloader, test_dataloader, optimizer, device,

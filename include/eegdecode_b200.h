@@ -195,6 +195,13 @@ int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
 int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_total_rows, float weight, float grad_out,
                 float* loss, float* loss_term, float* d_eeg, void* stream);
 
+/* Optional L2 normalisation of the EEG embedding before the logits (BASELINE.json north_star wording).  The reference
+ * does NOT normalise (ATMS.forward, Retrieval/ATMS_retrieval.py:182-191): ATMS(normalize=False) is the default and the
+ * parity path.  y = x / max(|x|_2, 1e-12) row-wise (torch.nn.functional.normalize), norms[row] = the denominator;
+ * backward dx = (dy - y (y . dy)) / norm.  x, y, dy, dx: [rows, D] fp32, D % 4 == 0, 16-byte aligned. */
+int eegb200_l2norm_forward(const float* x, float* y, float* norms, int rows, int D, void* stream);
+int eegb200_l2norm_backward(const float* y, const float* norms, const float* dy, float* dx, int rows, int D, void* stream);
+
 /* scores = logit_scale * eeg @ gallery^T into logits_ws [Q, ld >= G rounded up to 4]; optional argmax
  * count against labels (train accuracy, ATMS_retrieval.py:241-250), top-1 / top-5 indices
  * (evaluate_model, :306-320).  `sel` (int32 [Q,k] or NULL) restricts each query to its own candidate

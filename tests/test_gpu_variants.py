@@ -290,7 +290,7 @@ def test_reconstruction_loops_and_feature_export(lib, tmp_path):
     saved = torch.load(os.path.join(str(tmp_path), "ATM_S_eeg_features_sub-08.pt"))
     assert torch.equal(saved, ft)
     direct = m.encode(teeg.cuda(), torch.full((10,), 8).cuda(), train=False)
-    assert rows_rel(ft, direct) < 1e-5
+    assert rows_rel(ft, direct) < 1e-4       # batch 5 vs 10: the (tile, part) partial sums of Y2 are red.add-ed in a different order
     want = O.reconstruction_loss(ft[:5], timg_all[tlabels][:5], m.logit_scale.detach().cpu(), 0.9)
     want2 = O.reconstruction_loss(ft[5:], timg_all[tlabels][5:], m.logit_scale.detach().cpu(), 0.9)
     assert abs(l2 - 0.5 * (want.item() + want2.item())) < 3e-3 * abs(l2)

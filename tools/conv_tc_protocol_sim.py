@@ -1,210 +1,292 @@
-"""Protocol simulator for csrc/conv_tc.cu (the warp-specialised fused conv forward, not yet run on a GPU): the mbarrier
-waits / arrivals / tcgen05.commit completions / TMA completions of one CTA are replayed with randomised timing, with
-every shared-memory tile and TMEM accumulator tracked as a resource, so that
-
-  * a parity or ordering mistake shows up as a deadlock (no agent can make progress), and
-  * a missing dependency shows up as a hazard (a buffer overwritten while the async proxy may still read it, or read
-    before it was produced).
-
-The agent programs below restate the kernel's control flow line by line (same barrier names, same parity expressions);
-keep them in sync with the kernel.   python tools/conv_tc_protocol_sim.py [--mode stats|apply] [--trials N]
-"""
-import argparse
+"""Protocol replay of the mbarrier handshakes of csrc/conv_tc.cu (the backward kernels B1 / B2) on the CPU: every role is
+a coroutine issuing the same wait / arrive / commit sequence as the CUDA code, barriers implement the mbarrier phase /
+parity / arrival-count rules (a wait on parity P succeeds iff the phase of parity P has completed and the waiter is at
+most one phase behind), tcgen05.commit arrives after a random delay.  Finds deadlocks and parity mistakes before a GPU
+run.     python tools/conv_tc_protocol_sim.py"""
 import random
-
-N_CH = 63
-WS_RING = 4
+import sys
 
 
-class MBar:
+class Bar:
     def __init__(self, name, count):
         self.name, self.count, self.pending, self.phase = name, count, count, 0
 
     def arrive(self):
         self.pending -= 1
-        assert self.pending >= 0, f"{self.name}: too many arrivals"
+        assert self.pending >= 0, f"{self.name}: too many arrivals in phase {self.phase}"
         if self.pending == 0:
+            self.phase += 1
             self.pending = self.count
-            self.phase ^= 1
 
-    def passed(self, parity):
-        # mbarrier.try_wait.parity succeeds when the phase with that parity has completed
-        return self.phase != parity
+    def test(self, parity):            # mbarrier.try_wait.parity
+        return (self.phase & 1) != parity
 
 
-class Sim:
-    def __init__(self, mode, rng):
-        self.mode, self.rng = mode, rng
-        B = {}
-        for nm, cnt in (("tile_full", 1), ("tile_empty", 1), ("c1_full", 1), ("c1_empty", 4), ("a1_full", 4), ("a1_empty", 1)):
-            B[nm] = [MBar(f"{nm}[{i}]", cnt) for i in range(2)]
-        B["ws_full"] = [MBar(f"ws_full[{i}]", 1) for i in range(WS_RING)]
-        B["ws_empty"] = [MBar(f"ws_empty[{i}]", 1) for i in range(WS_RING)]
-        B["y2_full"] = [MBar("y2_full", 1)]
-        self.B = B
-        self.async_ops = []            # (remaining delay, callback)
-        # resource states: what each buffer currently holds / who may still be reading it
-        self.im = [None, None]         # channel whose im2col tile is in the buffer
-        self.im_reading = [0, 0]       # outstanding conv UMMAs reading it
-        self.c1 = [None, None]         # channel whose conv result is in the TMEM buffer
-        self.c1_writing = [0, 0]
-        self.a1 = [None, None]
-        self.a1_written = [0, 0]       # epilogue warps that have written their rows
-        self.a1_reading = [0, 0]
-        self.ws = [None] * WS_RING
-        self.ws_reading = [0] * WS_RING
-        self.y2_count = 0              # channels accumulated into Y2
-        self.done_epi = 0
+def run(mode, gc, n_tiles, seed, verbose=False):
+    rnd = random.Random(seed)
+    BS = mode == "B1"
+    total = n_tiles * gc
+    B = {}
+    for nm, cnt in (("im_full", 1), ("im_empty", 1 if BS else 2), ("dyk_full", 1), ("dyk_empty", 1), ("c_full", 1),
+                    ("c_empty", 8), ("op_full", 8), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4)):
+        B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
+    for nm in ("dym_full", "dym_empty", "final_a", "final_b"):
+        B[nm] = Bar(nm, 1)
+    delayed = []            # (time, barrier): tcgen05.commit arrivals
+    now = [0]
 
-    # ---- async engines ----
-    def commit(self, bars, on_done=None):
-        """tcgen05.commit: arrives on `bars` once every UMMA issued so far has completed"""
-        self.async_ops.append([self.rng.randint(1, 6), bars, on_done])
+    def commit(bar):
+        delayed.append((now[0] + rnd.randint(1, 40), bar))
 
-    def tma(self, bar, on_done):
-        self.async_ops.append([self.rng.randint(1, 8), [bar], on_done])
+    def dec(it):
+        tl = it // gc
+        return tl, it - tl * gc
 
-    def tick_async(self):
-        # UMMA / commits complete in issue order (the tensor pipe is in-order); TMA completions may be reordered
-        if not self.async_ops:
-            return False
-        self.async_ops[0][0] -= 1
+    def builder(gb, lanes=1):
+        # one coroutine stands for the 128 threads of the group (they move in lock step through the named barriers)
+        pending = -1
+        if gb == 0 and total > 0:
+            yield ("wait", B["dyk_empty"][0], 1)
+            pending = 0
+        for it in range(gb, total, 2):
+            tl, ci = dec(it)
+            bi, n = gb, it >> 1
+            if ci == gc - 1 and tl + 1 < n_tiles:
+                tb = (tl + 1) & 1
+                yield ("wait", B["dyk_empty"][tb], (((tl + 1) >> 1) & 1) ^ 1)
+                pending = tb
+            yield ("wait", B["im_empty"][bi], (n & 1) ^ 1)
+            if pending >= 0:
+                yield ("arrive", B["dyk_full"][pending])
+            yield ("arrive", B["im_full"][bi])
+            pending = -1
+            if BS and gb == 0 and ci < 2:
+                yield ("wait", B["dym_empty"], (tl & 1) ^ 1)
+                yield ("arrive", B["dym_full"])
+
+    def epilogue(ge, w):
+        for it in range(ge, total, 2):
+            bi, n = ge, it >> 1
+            yield ("wait", B["c_full"][bi], n & 1)
+            if BS:
+                yield ("wait", B["op_empty"][bi], (n & 1) ^ 1)
+                yield ("arrive", B["c_empty"][bi])
+                yield ("arrive", B["op_full"][bi])
+            else:
+                yield ("arrive", B["c_empty"][bi])
+                if it > 0:
+                    yield ("wait", B["op_empty"][bi], ((it - 1) >> 1) & 1)
+                yield ("arrive", B["op_full"][0])
+        yield ("wait", B["final_a"], 0)
+        yield ("wait", B["final_b"], 0)
+
+    def scatter(w):
+        for it in range(total):
+            bi, n = it & 1, it >> 1
+            yield ("wait", B["gg_full"][bi], n & 1)
+            yield ("arrive", B["gg_empty"][bi])
+
+    def ctrl_a():
+        for it in range(total):
+            tl, ci = dec(it)
+            bi, tb, n = it & 1, tl & 1, it >> 1
+            yield ("wait", B["im_full"][bi], n & 1)
+            yield ("wait", B["c_empty"][bi], (n & 1) ^ 1)
+            yield ("commit", B["im_empty"][bi])
+            if ci == 0:
+                yield ("wait", B["dyk_full"][tb], (tl >> 1) & 1)
+            yield ("commit", B["c_full"][bi])
+            if ci == gc - 1:
+                yield ("commit", B["dyk_empty"][tb])
+        yield ("commit", B["final_a"])
+
+    def ctrl_b():
+        for it in range(total):
+            tl, ci = dec(it)
+            bj = it & 1
+            if BS:
+                if ci == 0:
+                    yield ("wait", B["dym_full"], tl & 1)
+                yield ("wait", B["op_full"][bj], (it >> 1) & 1)
+                yield ("commit", B["op_empty"][bj])
+                if ci == gc - 1:
+                    yield ("commit", B["dym_empty"])
+            else:
+                yield ("wait", B["op_full"][0], it & 1)
+                yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
+                yield ("commit", B["gg_full"][bj])
+                yield ("commit", B["op_empty"][bj ^ 1])
+                yield ("commit", B["im_empty"][bj])
+        yield ("commit", B["final_b"])
+
+    roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a(), "ctrlB": ctrl_b()}
+    for ge in range(2):
+        for w in range(8):
+            roles[f"epi{ge}.{w}"] = epilogue(ge, w)
+    if not BS:
+        for w in range(4):
+            roles[f"scat{w}"] = scatter(w)
+    cur = {k: None for k in roles}
+    done = set()
+    while len(done) < len(roles):
         progressed = False
-        while self.async_ops and self.async_ops[0][0] <= 0:
-            _, bars, on_done = self.async_ops.pop(0)
-            if on_done:
-                on_done()
-            for b in bars:
-                b.arrive()
+        now[0] += 1
+        for t, bar in [d for d in delayed if d[0] <= now[0]]:
+            bar.arrive()
+            delayed.remove((t, bar))
             progressed = True
-        return progressed or bool(self.async_ops)
-
-    # ---- agents (generators yield a predicate to wait for) ----
-    def builders(self):
-        B = self.B
-        for c in range(N_CH):
-            bi, n = c & 1, c >> 1
-            yield lambda: True                                   # pooled sums (smem scratch private to the builders)
-            yield (lambda bi=bi, n=n: B["tile_empty"][bi].passed((n & 1) ^ 1))
-            assert self.im_reading[bi] == 0, f"builders overwrite im2col buffer {bi} (channel {c}) while UMMAs read channel {self.im[bi]}"
-            self.im[bi] = c
-            B["tile_full"][bi].arrive()
-
-    def epilogue(self, q):
-        B = self.B
-        for c in range(N_CH):
-            bi, n = c & 1, c >> 1
-            yield (lambda bi=bi, n=n: B["c1_full"][bi].passed(n & 1))
-            assert self.c1[bi] == c and self.c1_writing[bi] == 0, f"epilogue {q} reads C1[{bi}] for channel {c}, holds {self.c1[bi]}"
-            B["c1_empty"][bi].arrive()
-            if self.mode == "apply":
-                yield (lambda bi=bi, n=n: B["a1_empty"][bi].passed((n & 1) ^ 1))
-                assert self.a1_reading[bi] == 0, f"epilogue {q} overwrites A1[{bi}] (channel {c}) while spatial UMMAs read channel {self.a1[bi]}"
-                if self.a1_written[bi] == 0:
-                    self.a1[bi] = c
-                assert self.a1[bi] == c, f"A1[{bi}] mixes channels {self.a1[bi]} and {c}"
-                self.a1_written[bi] += 1
-                B["a1_full"][bi].arrive()
-        if self.mode == "apply":
-            yield lambda: B["y2_full"][0].passed(0)
-            assert self.y2_count == N_CH, f"Y2 read after {self.y2_count} channels"
-        self.done_epi += 1
-
-    def control(self):
-        B = self.B
-
-        def load_ws(c):
-            wi, n = c % WS_RING, c // WS_RING
-            yield (lambda: B["ws_empty"][wi].passed((n & 1) ^ 1))
-            assert self.ws_reading[wi] == 0, f"TMA overwrites Ws ring slot {wi} (channel {c}) while UMMAs read channel {self.ws[wi]}"
-
-            def landed(wi=wi, c=c):
-                self.ws[wi] = c
-            self.tma(B["ws_full"][wi], landed)
-
-        def spatial(c):
-            bi, wi = c & 1, c % WS_RING
-            yield (lambda: B["a1_full"][bi].passed((c >> 1) & 1))
-            yield (lambda: B["ws_full"][wi].passed((c // WS_RING) & 1))
-            assert self.a1[bi] == c and self.a1_written[bi] == 4, f"spatial({c}) reads A1[{bi}] = channel {self.a1[bi]}, {self.a1_written[bi]} warps"
-            assert self.ws[wi] == c, f"spatial({c}) reads Ws slot {wi} holding channel {self.ws[wi]}"
-            self.a1_reading[bi] += 1
-            self.ws_reading[wi] += 1
-
-            def done(bi=bi, wi=wi):
-                self.a1_reading[bi] -= 1
-                self.a1_written[bi] = 0
-                self.ws_reading[wi] -= 1
-                self.y2_count += 1
-            self.commit([B["a1_empty"][bi], B["ws_empty"][wi]], done)
-
-        if self.mode == "apply":
-            yield from load_ws(0)
-            yield from load_ws(1)
-        for c in range(N_CH):
-            bi, n = c & 1, c >> 1
-            yield (lambda bi=bi, n=n: B["tile_full"][bi].passed(n & 1))
-            yield (lambda bi=bi, n=n: B["c1_empty"][bi].passed((n & 1) ^ 1))
-            assert self.im[bi] == c, f"conv({c}) reads im2col buffer {bi} holding channel {self.im[bi]}"
-            self.im_reading[bi] += 1
-            self.c1_writing[bi] += 1
-
-            def done(bi=bi, c=c):
-                self.im_reading[bi] -= 1
-                self.c1_writing[bi] -= 1
-                self.c1[bi] = c
-            self.commit([B["tile_empty"][bi], B["c1_full"][bi]], done)
-            if self.mode == "apply":
-                if c + 2 < N_CH:
-                    yield from load_ws(c + 2)
-                if c > 0:
-                    yield from spatial(c - 1)
-        if self.mode == "apply":
-            yield from spatial(N_CH - 1)
-            self.commit([B["y2_full"][0]])
-
-    def run(self):
-        agents = [("builders", self.builders())] + [(f"epilogue{q}", self.epilogue(q)) for q in range(4)] + \
-                 [("control", self.control())]
-        waiting = {}
-        for name, g in agents:
-            waiting[name] = (g, next(g))
-        steps = 0
-        while waiting:
-            steps += 1
-            assert steps < 2_000_000, "livelock"
-            ready = [n for n, (g, pred) in waiting.items() if pred()]
-            if not ready:
-                if not self.tick_async():
-                    states = {n: "blocked" for n in waiting}
-                    raise RuntimeError(f"DEADLOCK with agents {states}")
-                continue
-            if self.rng.random() < 0.3:
-                self.tick_async()
-            name = self.rng.choice(ready)
-            g, _ = waiting[name]
-            try:
-                waiting[name] = (g, next(g))
-            except StopIteration:
-                del waiting[name]
-        while self.tick_async():
-            pass
-        assert self.done_epi == 4
-        if self.mode == "apply":
-            assert self.y2_count == N_CH
+        names = [k for k in roles if k not in done]
+        rnd.shuffle(names)
+        for k in names:
+            for _ in range(rnd.randint(1, 3)):
+                if cur[k] is None:
+                    try:
+                        cur[k] = next(roles[k])
+                    except StopIteration:
+                        done.add(k)
+                        progressed = True
+                        break
+                op = cur[k]
+                if op[0] == "wait":
+                    if not op[1].test(op[2]):
+                        break
+                elif op[0] == "arrive":
+                    op[1].arrive()
+                else:
+                    commit(op[1])
+                cur[k] = None
+                progressed = True
+        if not progressed and not delayed:
+            stuck = {k: (cur[k][1].name, cur[k][2], "phase", cur[k][1].phase) for k in roles if k not in done and cur[k]}
+            return False, stuck
+    return True, None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="both")
-    ap.add_argument("--trials", type=int, default=200)
-    args = ap.parse_args()
-    modes = ["stats", "apply"] if args.mode == "both" else [args.mode]
-    for mode in modes:
-        for t in range(args.trials):
-            Sim(mode, random.Random(t)).run()
-        print(f"{mode}: {args.trials} randomised schedules, no deadlock, no hazard")
+def run_fwd(n_items, seed, F_LEN=21, RING=4):
+    """forward kernel F2 (conv_tc_fwd_kernel<MODE_APPLY>): same engine, roles of the forward protocol"""
+    rnd = random.Random(seed)
+    total = n_items * F_LEN
+    B = {}
+    for nm, cnt in (("tile_full", 1), ("tile_empty", 1), ("c1_full", 1), ("c1_empty", 8), ("a1_full", 8), ("a1_empty", 1),
+                    ("y2_full", 1), ("y2_empty", 8)):
+        B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
+    B["ws_full"] = [Bar(f"ws_full[{i}]", 1) for i in range(RING)]
+    B["ws_empty"] = [Bar(f"ws_empty[{i}]", 1) for i in range(RING)]
+    delayed, now = [], [0]
+
+    def commit(bar):
+        delayed.append((now[0] + rnd.randint(1, 40), bar))
+
+    def builder(gb):
+        for it in range(gb, total, 2):
+            yield ("wait", B["tile_empty"][gb], ((it >> 1) & 1) ^ 1)
+            yield ("arrive", B["tile_full"][gb])
+
+    def epilogue(ge, w):
+        for it in range(ge, total, 2):
+            n, item, l = it >> 1, it // F_LEN, it % F_LEN
+            yield ("wait", B["c1_full"][ge], n & 1)
+            yield ("arrive", B["c1_empty"][ge])
+            yield ("wait", B["a1_empty"][ge], (n & 1) ^ 1)
+            yield ("arrive", B["a1_full"][ge])
+            if l == F_LEN - 1:
+                ib = item & 1
+                yield ("wait", B["y2_full"][ib], (item >> 1) & 1)
+                yield ("arrive", B["y2_empty"][ib])
+
+    def ctrl_a():
+        for it in range(total):
+            bi, n = it & 1, it >> 1
+            yield ("wait", B["tile_full"][bi], n & 1)
+            yield ("wait", B["c1_empty"][bi], (n & 1) ^ 1)
+            yield ("commit", B["tile_empty"][bi])
+            yield ("commit", B["c1_full"][bi])
+
+    def ctrl_b():
+        def load(it):
+            wi, n = it % RING, it // RING
+            yield ("wait", B["ws_empty"][wi], (n & 1) ^ 1)
+            yield ("commit", B["ws_full"][wi])          # TMA completion = delayed arrival
+        for it in range(min(3, total)):
+            yield from load(it)
+        for it in range(total):
+            bi, wi, item, l = it & 1, it % RING, it // F_LEN, it % F_LEN
+            ib = item & 1
+            if l == 0:
+                yield ("wait", B["y2_empty"][ib], ((item >> 1) & 1) ^ 1)
+            yield ("wait", B["a1_full"][bi], (it >> 1) & 1)
+            yield ("wait", B["ws_full"][wi], (it // RING) & 1)
+            yield ("commit", B["a1_empty"][bi])
+            yield ("commit", B["ws_empty"][wi])
+            if l == F_LEN - 1:
+                yield ("commit", B["y2_full"][ib])
+            if it + 3 < total:
+                yield from load(it + 3)
+
+    roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a(), "ctrlB": ctrl_b()}
+    for ge in range(2):
+        for w in range(8):
+            roles[f"epi{ge}.{w}"] = epilogue(ge, w)
+    return _drive(roles, delayed, now, commit, rnd)
+
+
+def _drive(roles, delayed, now, commit, rnd):
+    cur = {k: None for k in roles}
+    done = set()
+    while len(done) < len(roles):
+        progressed = False
+        now[0] += 1
+        for t, bar in [d for d in delayed if d[0] <= now[0]]:
+            bar.arrive()
+            delayed.remove((t, bar))
+            progressed = True
+        names = [k for k in roles if k not in done]
+        rnd.shuffle(names)
+        for k in names:
+            for _ in range(rnd.randint(1, 3)):
+                if cur[k] is None:
+                    try:
+                        cur[k] = next(roles[k])
+                    except StopIteration:
+                        done.add(k)
+                        progressed = True
+                        break
+                op = cur[k]
+                if op[0] == "wait":
+                    if not op[1].test(op[2]):
+                        break
+                elif op[0] == "arrive":
+                    op[1].arrive()
+                else:
+                    commit(op[1])
+                cur[k] = None
+                progressed = True
+        if not progressed and not delayed:
+            return False, {k: (cur[k][1].name, cur[k][2], "phase", cur[k][1].phase) for k in roles if k not in done and cur[k]}
+    return True, None
 
 
 if __name__ == "__main__":
-    main()
+    bad = 0
+    for mode in ("B1", "B2"):
+        for gc in (4, 3):
+            for n_tiles in (1, 2, 3, 4, 7, 12, 38):
+                for seed in range(60):
+                    ok, stuck = run(mode, gc, n_tiles, seed)
+                    if not ok:
+                        bad += 1
+                        print(f"DEADLOCK mode={mode} gc={gc} tiles={n_tiles} seed={seed}")
+                        for k, v in sorted(stuck.items()):
+                            print("   ", k, v)
+                        break
+    for n_items in (1, 2, 3, 7):
+        for seed in range(40):
+            ok, stuck = run_fwd(n_items, seed)
+            if not ok:
+                bad += 1
+                print(f"DEADLOCK forward items={n_items} seed={seed}")
+                for k, v in sorted(stuck.items()):
+                    print("   ", k, v)
+                break
+    print("protocol sim:", "FAIL" if bad else "PASS")
+    sys.exit(1 if bad else 0)
