@@ -213,7 +213,7 @@ int eegb200_retrieval(const float* eeg, const float* gallery, int Q, int G, int 
 
 int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_total_rows, float weight, float grad_out,
                 float* loss, float* loss_term, float* d_eeg, void* stream) {
-  EEG_REQUIRE(eeg && tgt && B > 0 && D > 0 && (D & 3) == 0 && n_total_rows >= B, "mse: bad arguments");
+  EEG_REQUIRE(eeg && tgt && B > 0 && D > 0 && (D & 3) == 0 && n_total_rows > 0, "mse: bad arguments");
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   EEG_REQUIRE(al(eeg) && al(tgt) && al(d_eeg), "mse: pointers must be 16-byte aligned");
   return mse_loss(eeg, tgt, B, D, n_total_rows, weight, grad_out, loss, loss_term, d_eeg, (cudaStream_t)stream);

@@ -178,23 +178,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef EEGB200_TRYWAIT_HINT_NS
+#define EEGB200_TRYWAIT_HINT_NS 128u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // the suspend-time hint (ns) lets the hardware park the warp until the phase completes or the hint expires instead of
+  // returning at once: far fewer polling instructions compete with the working warps for issue slots
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(EEGB200_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a mis-programmed TMA/MMA would otherwise hang the GPU; after ~2^28 polls we trap so
-// the launch fails with an error instead.
+// Bounded wait: a mis-programmed TMA/MMA would otherwise hang the GPU; after 2^25 polls (seconds) we trap so the launch fails with an error instead.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
+    if (++spins > (1u << 25)) {
       printf("eegb200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
       __trap();

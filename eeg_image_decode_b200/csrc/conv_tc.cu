@@ -45,7 +45,7 @@ constexpr int N48 = 48;
 constexpr int WS_RING = 4;
 constexpr int F_PARTS = 3, F_LEN = 21;            // forward work item = (tile, 21 of the 63 channels)
 constexpr int GC = 4, N_GROUPS = 16;              // backward: channel groups of 4 (the last one has 3)
-constexpr uint32_t PS_LD = 208, CSX_LD = 264;
+constexpr uint32_t PS_LD = 208, CSX_LD = 296;        // CSX_LD >= csi(256) + 1 = 289
 constexpr uint32_t SCAN_BYTES = (3 * PS_LD + 3 * CSX_LD) * 4;   // pooled sums [3][208] + scan scratch [3][264] floats
 constexpr int N_BUILD_WARPS = 8, N_EPI_WARPS = 16;
 constexpr int EPI_WARP0 = N_BUILD_WARPS, EPI_THREAD0 = EPI_WARP0 * 32;
@@ -82,6 +82,12 @@ __device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld2_nw(uint32_t taddr, float* v) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a K-major SWIZZLE_128B k-block
@@ -93,6 +99,15 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
 __device__ __forceinline__ uint32_t mn_off(int m, int k) {
   return (uint32_t)(m >> 5) * SLAB + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
          (uint32_t)((((m & 31) >> 3) ^ (k & 3)) << 5) + (uint32_t)(m & 7) * 4u;
+}
+// one 32-byte chunk (8 consecutive mn elements m0 .. m0+7, m0 % 8 == 0) of k-row r.  Lanes whose (r >> 2) & 1 is set store
+// the two halves in the opposite order: within one st.shared.v4 the 8 lanes of a quarter-warp then hit 32 distinct banks
+// (same order: lanes r and r+4 share a bank -> 2-way conflict on every store)
+__device__ __forceinline__ void mn_store8(uint8_t* tile, int m0, int r, float4 a, float4 b) {
+  const uint32_t off = mn_off(m0, r);
+  const bool sw = ((r >> 2) & 1) != 0;
+  *reinterpret_cast<float4*>(tile + off + (sw ? 16u : 0u)) = sw ? b : a;
+  *reinterpret_cast<float4*>(tile + off + (sw ? 0u : 16u)) = sw ? a : b;
 }
 __device__ __forceinline__ float tf32_fast(float x) {     // cvt.rna for finite values: add half an ulp of tf32, truncate
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -111,11 +126,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-// filter index of register slot i (0..19) of an epilogue thread of column half h: {16h .. 16h+15} + {32+4h .. 32+4h+3}
-// (naturally aligned tcgen05.ld: .x16 / 2 x .x8 at column 16h, .x4 at column 32+4h)
-__device__ __forceinline__ int kidx(int h, int i) { return i < 16 ? 16 * h + i : 32 + 4 * h + (i - 16); }
+// The 16 epilogue warps tile the [128 rows x 40 filters] accumulator as 4 lane quarters (q = warp % 4, a TMEM rule) x 4
+// column quarters cq: filters {8cq .. 8cq+7} and {32+2cq, 33+2cq} -- two naturally aligned tcgen05.ld (.x8 at column 8cq,
+// .x2 at column 32+2cq), whole 32-byte chunks of the MN-major layout and whole 16-byte chunks of the K-major layout.
+// kq(cq, i): filter index of register slot i (0..9)
+__device__ __forceinline__ int kq(int cq, int i) { return i < 8 ? 8 * cq + i : 32 + 2 * cq + (i - 8); }
+__device__ __forceinline__ void tmem_ld10_nw(uint32_t taddr_col0, int cq, float* v) {
+  tmem_ld8_nw(taddr_col0 + (uint32_t)(8 * cq), v);
+  tmem_ld2_nw(taddr_col0 + (uint32_t)(32 + 2 * cq), v + 8);
+}
+// shared-memory matrix descriptors with the constant fields folded in; stepping through a tile is an add on the
+// 16-byte-granular start-address field (no carry: every tile lives below 256 KB)
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024, UMMA_LAYOUT_SW128); }
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_desc(addr, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B); }
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// box-51 pooled sums of one token row (8 floats per lane): cs[k] = sum of the first k samples, ps[u] = cs[u+51]-cs[u]
+// box-51 pooled sums of one token row (8 floats per lane): C[k] = sum of the first k samples, ps[u] = C[u+51] - C[u].
+// C[k] lives at cs[k + (k >> 3)]: the per-lane stride-8 stores would otherwise hit 4 banks (8-way conflicts)
+__device__ __forceinline__ int csi(int k) { return k + (k >> 3); }
 __device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int lane, float* cs, float* ps) {
   float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
@@ -128,15 +156,15 @@ __device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int l
     if (lane >= o) inc += nb;
   }
   const float excl = inc - tot;
-  cs[8 * lane] = excl;
+  cs[9 * lane] = excl;                                 // csi(8*lane + i) = 9*lane + i for i < 8
 #pragma unroll
-  for (int i = 0; i < 7; ++i) cs[8 * lane + 1 + i] = v[i] + excl;
-  if (lane == 31) cs[256] = inc;
+  for (int i = 0; i < 7; ++i) cs[9 * lane + 1 + i] = v[i] + excl;
+  if (lane == 31) cs[csi(256)] = inc;
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < 7; ++q) {
     const int u = lane + 32 * q;
-    if (u < N_PSUM) ps[u] = cs[u + K_POOL] - cs[u];
+    if (u < N_PSUM) ps[u] = cs[csi(u + K_POOL)] - cs[csi(u)];
   }
 }
 
@@ -146,7 +174,7 @@ __device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int l
 constexpr int F_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 2) * 32;          // 832
 constexpr int F_CTRL_A = N_BUILD_WARPS + N_EPI_WARPS, F_CTRL_B = F_CTRL_A + 1;
 constexpr uint32_t OFF_IM = 0;                              // [2 buf][hi, lo] x 16 KB
-constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights hi, lo: 2 x 6 KB
+constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights [w_hi (48 rows) | w_lo (48 rows)] x 32: 12 KB, one N = 96 operand
 constexpr uint32_t OFF_A1 = OFF_BC + 2 * KB_48;             // [2 buf][2 k-blocks] x 16 KB
 constexpr uint32_t OFF_WS = OFF_A1 + 4 * KB_A;              // [4 ring][2 k-blocks] x 6 KB
 constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // scan scratch of the two builder groups
@@ -222,11 +250,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       mbar_init(&tile_full[i], 1);
       mbar_init(&tile_empty[i], 1);
       mbar_init(&c1_full[i], 1);
-      mbar_init(&c1_empty[i], 8);
-      mbar_init(&a1_full[i], 8);
+      mbar_init(&c1_empty[i], N_EPI_WARPS);
+      mbar_init(&a1_full[i], N_EPI_WARPS);
       mbar_init(&a1_empty[i], 1);
       mbar_init(&y2_full[i], 1);
-      mbar_init(&y2_empty[i], 8);
+      mbar_init(&y2_empty[i], N_EPI_WARPS);
     }
     for (int i = 0; i < WS_RING; ++i) {
       mbar_init(&ws_full[i], 1);
@@ -263,7 +291,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
   }
   if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
   if (warp == F_CTRL_A) {
-    tmem_alloc(tmem_slot, 256);          // C1[0]: cols 0..47, C1[1]: 64..111, Y2[0]: 128..175, Y2[1]: 192..239
+    tmem_alloc(tmem_slot, 512);          // C1[0]: cols 0..95, C1[1]: 128..223 (a.w_hi | a.w_lo), Y2[0]: 256..303, Y2[1]: 320..367
     tmem_relinquish();
   }
   fence_proxy_async_smem();
@@ -302,22 +330,24 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       named_bar_sync(1 + gb, 128);
       mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of iteration it-2 have consumed this buffer
       {
-        // kind::tf32 reads the top 19 bits of an fp32 operand: hi is the raw value, lo = a - trunc(a) is exact
+        // hi = RN-rounded TF32 part (the BatchNorm statistics average over 2.3 M products: the rounding must be unbiased,
+        // truncation shifts the variance by 7e-4), lo = a - hi exactly (kind::tf32 reads its top 19 bits).  The statistics
+        // pass only needs hi: a_hi.(w_hi + w_lo) has zero-mean errors of 2^-12 that average out (1e-5 on mean and variance)
         const float* src = ps_all + s_row * PS_LD + 5 * p_row;
         uint8_t* hi_t = sm + OFF_IM + (uint32_t)bi * 2 * KB_A;
         uint8_t* lo_t = hi_t + KB_A;
         const bool valid = r < rows_valid;
 #pragma unroll
         for (int ch = 0; ch < 7; ++ch) {                  // chunk 6 = tap 24 + zeros; chunk 7 stays zero
-          float4 h;
-          h.x = (valid && (ch * 4 + 0) < K_TEMP) ? src[ch * 4 + 0] : 0.f;
-          h.y = (valid && (ch * 4 + 1) < K_TEMP) ? src[ch * 4 + 1] : 0.f;
-          h.z = (valid && (ch * 4 + 2) < K_TEMP) ? src[ch * 4 + 2] : 0.f;
-          h.w = (valid && (ch * 4 + 3) < K_TEMP) ? src[ch * 4 + 3] : 0.f;
-          const float4 l = make_float4(h.x - tf32_trunc(h.x), h.y - tf32_trunc(h.y), h.z - tf32_trunc(h.z), h.w - tf32_trunc(h.w));
+          float4 a, h;
+          a.x = (valid && (ch * 4 + 0) < K_TEMP) ? src[ch * 4 + 0] : 0.f;
+          a.y = (valid && (ch * 4 + 1) < K_TEMP) ? src[ch * 4 + 1] : 0.f;
+          a.z = (valid && (ch * 4 + 2) < K_TEMP) ? src[ch * 4 + 2] : 0.f;
+          a.w = (valid && (ch * 4 + 3) < K_TEMP) ? src[ch * 4 + 3] : 0.f;
+          h = make_float4(tf32_fast(a.x), tf32_fast(a.y), tf32_fast(a.z), tf32_fast(a.w));
           const uint32_t off = sw128_off(r, ch);
           *reinterpret_cast<float4*>(hi_t + off) = h;
-          *reinterpret_cast<float4*>(lo_t + off) = l;
+          if (MODE == MODE_APPLY) *reinterpret_cast<float4*>(lo_t + off) = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
         }
       }
       fence_proxy_async_smem();
@@ -325,37 +355,41 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       if (rq == 0 && lane == 0) mbar_arrive(&tile_full[bi]);
     }
   } else if (warp < F_CTRL_A) {
-    // =============================== epilogue (group ge owns the iterations it & 1 == ge) ===============================
-    const int ge = (warp - EPI_WARP0) >> 3;
-    const int h = ((warp - EPI_WARP0) >> 2) & 1;         // column half
+    // =============================== epilogue: 16 warps = 4 lane quarters x 4 column quarters ===============================
     const int q = warp & 3;                              // TMEM lane quarter (== warp % 4)
+    const int cq = (warp - EPI_WARP0) >> 2;              // column quarter
     const int r = q * 32 + lane;                         // tile row
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float s1[MODE == MODE_STATS ? 20 : 1], s2[MODE == MODE_STATS ? 20 : 1];
+    float s1[MODE == MODE_STATS ? 10 : 1], s2[MODE == MODE_STATS ? 10 : 1];
+    float c_sc[10], c_sh[10];                            // per-filter constants of this thread's 10 columns:
+#pragma unroll                                           //   APPLY: z = c_sc * y_raw + c_sh;  STATS: c_sh = conv bias
+    for (int i = 0; i < 10; ++i) { c_sc[i] = tab[kq(cq, i)]; c_sh[i] = MODE == MODE_STATS ? tab[96 + kq(cq, i)] : tab[48 + kq(cq, i)]; }
     if constexpr (MODE == MODE_STATS) {
 #pragma unroll
-      for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < 10; ++i) s1[i] = s2[i] = 0.f;
     }
-    for (int it = ge; it < total_it; it += 2) {
+    for (int it = 0; it < total_it; ++it) {
       const FwdIt d = fwd_decode(it, p.B);
-      const int bi = ge;
+      const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
       const size_t grow = (size_t)d.tile * TILE_ROWS + r;         // global (b, p) row
       mbar_wait(&c1_full[bi], n & 1u);
       tc_fence_after();
-      float y[20];
-      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
-      tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
+      float y[10], y2[10];
+      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 128), cq, y);          // a . w_hi (+ a_lo . w_hi in F2)
+      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 128 + N48), cq, y2);   // a_hi . w_lo
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&c1_empty[bi]);         // the accumulator may be overwritten by iteration it+2
+#pragma unroll
+      for (int i = 0; i < 10; ++i) y[i] += y2[i];
       if constexpr (MODE == MODE_STATS) {
         if (valid) {
 #pragma unroll
-          for (int i = 0; i < 20; ++i) {
-            const float v = y[i] + tab[96 + kidx(h, i)];
+          for (int i = 0; i < 10; ++i) {
+            const float v = y[i] + c_sh[i];
             s1[i] += v;
             s2[i] = fmaf(v, v, s2[i]);
           }
@@ -363,31 +397,25 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       } else {
         if (valid && p.y1 != nullptr) {
           float* dst = p.y1 + grow * K_SPAT + d.c * N_FILT;
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int k = kidx(h, 4 * j);
-            *reinterpret_cast<float4*>(dst + k) = make_float4(y[4 * j] + tab[96 + k], y[4 * j + 1] + tab[97 + k],
-                                                              y[4 * j + 2] + tab[98 + k], y[4 * j + 3] + tab[99 + k]);
-          }
+          const float* bt = tab + 96;
+          *reinterpret_cast<float4*>(dst + 8 * cq) = make_float4(y[0] + bt[8 * cq], y[1] + bt[8 * cq + 1], y[2] + bt[8 * cq + 2], y[3] + bt[8 * cq + 3]);
+          *reinterpret_cast<float4*>(dst + 8 * cq + 4) = make_float4(y[4] + bt[8 * cq + 4], y[5] + bt[8 * cq + 5], y[6] + bt[8 * cq + 6], y[7] + bt[8 * cq + 7]);
+          *reinterpret_cast<float2*>(dst + 32 + 2 * cq) = make_float2(y[8] + bt[32 + 2 * cq], y[9] + bt[33 + 2 * cq]);
         }
 #pragma unroll
-        for (int i = 0; i < 20; ++i) {
-          const int k = kidx(h, i);
-          y[i] = valid ? tf32_fast(elu_quick(fmaf(y[i], tab[k], tab[48 + k]))) : 0.f;
-        }
+        for (int i = 0; i < 10; ++i) y[i] = valid ? tf32_fast(elu_quick(fmaf(y[i], c_sc[i], c_sh[i]))) : 0.f;
         if (valid && p.a1 != nullptr) {
           float* dst = p.a1 + grow * K_SPAT + d.c * N_FILT;
-#pragma unroll
-          for (int j = 0; j < 5; ++j)
-            *reinterpret_cast<float4*>(dst + kidx(h, 4 * j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          *reinterpret_cast<float4*>(dst + 8 * cq) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(dst + 8 * cq + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          *reinterpret_cast<float2*>(dst + 32 + 2 * cq) = make_float2(y[8], y[9]);
         }
         // K slice of the spatial A operand: k 0..31 -> k-block 0 (chunk k/4), k 32..39 -> chunks 0, 1 of k-block 1
         mbar_wait(&a1_empty[bi], (n & 1u) ^ 1u);         // spatial UMMAs of iteration it-2 are done with this buffer
         uint8_t* a1t = sm + OFF_A1 + (uint32_t)bi * 2 * KB_A;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(a1t + sw128_off(r, 4 * h + j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        *reinterpret_cast<float4*>(a1t + KB_A + sw128_off(r, h)) = make_float4(y[16], y[17], y[18], y[19]);
+        *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq)) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq + 1)) = make_float4(y[4], y[5], y[6], y[7]);
+        *reinterpret_cast<float2*>(a1t + KB_A + sw128_off(r, cq >> 1) + (uint32_t)(cq & 1) * 8u) = make_float2(y[8], y[9]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1_full[bi]);
@@ -396,22 +424,21 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
           const int ib = d.item_local & 1;
           mbar_wait(&y2_full[ib], (uint32_t)(d.item_local >> 1) & 1u);
           tc_fence_after();
-          float o[20];
-          tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + ib * 64 + 16 * h), o);
-          tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + ib * 64 + 32 + 4 * h), o + 16);
+          float o[10];
+          tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(256 + ib * 64), cq, o);
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&y2_empty[ib]);
           if (valid) {
             float* dst = p.y2 + grow * N_FILT;
+            if (d.part == 0) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              const int k = kidx(h, 4 * j);
-              float4 v = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              if (d.part == 0) { v.x += p.bs[k]; v.y += p.bs[k + 1]; v.z += p.bs[k + 2]; v.w += p.bs[k + 3]; }
-              red_add_v4(dst + k, v.x, v.y, v.z, v.w);
+              for (int i = 0; i < 10; ++i) o[i] += p.bs[kq(cq, i)];
             }
+            red_add_v4(dst + 8 * cq, o[0], o[1], o[2], o[3]);
+            red_add_v4(dst + 8 * cq + 4, o[4], o[5], o[6], o[7]);
+            red_add_v2(dst + 32 + 2 * cq, o[8], o[9]);
           }
         }
       }
@@ -419,9 +446,9 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     if constexpr (MODE == MODE_STATS) {
       // per-filter sums over the 32 rows of this warp, then shared + one double atomic per filter per CTA
 #pragma unroll
-      for (int i = 0; i < 20; ++i) {
+      for (int i = 0; i < 10; ++i) {
         const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
-        if (lane == 0) { atomicAdd(&red[kidx(h, i)], a); atomicAdd(&red[N_FILT + kidx(h, i)], b); }
+        if (lane == 0) { atomicAdd(&red[kq(cq, i)], a); atomicAdd(&red[N_FILT + kq(cq, i)], b); }
       }
       named_bar_sync(3, N_EPI_WARPS * 32);
       const int k = threadIdx.x - EPI_THREAD0;
@@ -429,36 +456,39 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     }
   } else if (warp == F_CTRL_A && lane == 0) {
     // =============================== control A: conv UMMAs ===============================
-    constexpr uint32_t idesc = umma_idesc_tf32(128, N48, 0, 0);
-    const uint32_t im = smem_u32(sm + OFF_IM), bc = smem_u32(sm + OFF_BC);
+    constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0), idesc96 = umma_idesc_tf32(128, 2 * N48, 0, 0);
+    const uint64_t d_bc = desc_k(smem_u32(sm + OFF_BC));       // rows 0..47: w_hi, rows 48..95: w_lo
+    uint64_t d_hi[2], d_lo[2];
+    for (int b = 0; b < 2; ++b) {
+      d_hi[b] = desc_k(smem_u32(sm + OFF_IM + (uint32_t)b * 2 * KB_A));
+      d_lo[b] = desc_k(smem_u32(sm + OFF_IM + (uint32_t)b * 2 * KB_A + KB_A));
+    }
     for (int it = 0; it < total_it; ++it) {
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
       mbar_wait(&tile_full[bi], n & 1u);
       mbar_wait(&c1_empty[bi], (n & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t hi = im + (uint32_t)bi * 2 * KB_A, lo = hi + KB_A;
-      const uint32_t dcol = tmem_base + (uint32_t)(bi * 64);
-      // 3xTF32: lo.hi + hi.lo + hi.hi (small terms first)
+      const uint32_t dcol = tmem_base + (uint32_t)(bi * 128);
+      // a_hi . [w_hi | w_lo] as ONE N = 96 UMMA chain (the 16 KB a_hi tile is read once), then in F2 a_lo . w_hi on
+      // top of the first 48 columns: the classic 3xTF32 sum, assembled by the epilogue (columns k and 48 + k)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(dcol, umma_smem_desc(lo + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, kk > 0 ? 1u : 0u);
+        tc_mma_tf32(dcol, desc_adv(d_hi[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc96, kk > 0 ? 1u : 0u);
+      if (MODE == MODE_APPLY) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(dcol, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + KB_48 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(dcol, umma_smem_desc(hi + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc, 1u);
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_tf32(dcol, desc_adv(d_lo[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc48, 1u);
+      }
       tc_commit(&tile_empty[bi]);
       tc_commit(&c1_full[bi]);
     }
   } else if (MODE == MODE_APPLY && warp == F_CTRL_B && lane == 0) {
     // =============================== control B: weight TMA + spatial UMMAs ===============================
     constexpr uint32_t idesc = umma_idesc_tf32(128, N48, 0, 0);
-    const uint32_t a1s = smem_u32(sm + OFF_A1), wss = smem_u32(sm + OFF_WS);
+    uint64_t d_a1[2], d_ws[WS_RING];
+    for (int b = 0; b < 2; ++b) d_a1[b] = desc_k(smem_u32(sm + OFF_A1 + (uint32_t)b * 2 * KB_A));
+    for (int b = 0; b < WS_RING; ++b) d_ws[b] = desc_k(smem_u32(sm + OFF_WS + (uint32_t)b * 2 * KB_48));
     auto load_ws = [&](int it) {
       const FwdIt d = fwd_decode(it, p.B);
       const int wi = it & (WS_RING - 1);
@@ -476,12 +506,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       mbar_wait(&a1_full[bi], (uint32_t)(it >> 1) & 1u);
       mbar_wait(&ws_full[wi], (uint32_t)(it / WS_RING) & 1u);
       tc_fence_after();
-      const uint32_t a = a1s + (uint32_t)bi * 2 * KB_A, w = wss + (uint32_t)wi * 2 * KB_48;
+      const uint32_t dcol = tmem_base + 256u + (uint32_t)(ib * 64);
 #pragma unroll
       for (int kk = 0; kk < 5; ++kk) {                   // K = 40: four 8-steps of k-block 0 and the first of k-block 1
         const uint32_t ao = kk < 4 ? (uint32_t)kk * 32u : KB_A, wo = kk < 4 ? (uint32_t)kk * 32u : KB_48;
-        tc_mma_tf32(tmem_base + 128u + (uint32_t)(ib * 64), umma_smem_desc(a + ao, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(w + wo, 16, 1024, UMMA_LAYOUT_SW128), idesc, (d.l > 0 || kk > 0) ? 1u : 0u);
+        tc_mma_tf32(dcol, desc_adv(d_a1[bi], ao), desc_adv(d_ws[wi], wo), idesc, (d.l > 0 || kk > 0) ? 1u : 0u);
       }
       tc_commit(&a1_empty[bi]);
       tc_commit(&ws_empty[wi]);
@@ -492,7 +521,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == F_CTRL_A) tmem_dealloc(tmem_base, 256);
+  if (warp == F_CTRL_A) tmem_dealloc(tmem_base, 512);
 }
 
 // tsconv.4.weight [j][k][c] -> [c][48 rows j][64 floats k], TF32-rounded, zero padded: B operand of the spatial UMMA
@@ -638,8 +667,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_init(&dyk_full[i], 1);
       mbar_init(&dyk_empty[i], 1);
       mbar_init(&c_full[i], 1);
-      mbar_init(&c_empty[i], 8);
-      mbar_init(&op_full[i], 8);
+      mbar_init(&c_empty[i], N_EPI_WARPS);
+      mbar_init(&op_full[i], N_EPI_WARPS);
       mbar_init(&op_empty[i], 1);
       mbar_init(&gg_full[i], 1);
       mbar_init(&gg_empty[i], 4);
@@ -690,6 +719,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         p1 = -sc * rs * m2;                          // Bc
         p2 = sc * (mu * rs * m2 - m1);               // Cc
       }
+      // the epilogue works on the raw accumulator y_raw = y - bt: fold the conv bias into the additive constants
+      sh += sc * bt;
+      p2 += p1 * bt;
     }
     tab[k] = bt; tab[48 + k] = sc; tab[96 + k] = sh; tab[144 + k] = p1; tab[192 + k] = p2;
   }
@@ -782,12 +814,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           a[25] = valid ? 1.f : 0.f;
           uint8_t* mt = sm + O2_IMM + (uint32_t)bi * SLAB;
 #pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            const uint32_t off = mn_off(8 * j8, r);
-            *reinterpret_cast<float4*>(mt + off) = make_float4(a[8 * j8], a[8 * j8 + 1], a[8 * j8 + 2], a[8 * j8 + 3]);
-            *reinterpret_cast<float4*>(mt + off + 16) =
-                j8 < 3 ? make_float4(a[8 * j8 + 4], a[8 * j8 + 5], a[8 * j8 + 6], a[8 * j8 + 7]) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j8 = 0; j8 < 4; ++j8)
+            mn_store8(mt, 8 * j8, r, make_float4(a[8 * j8], a[8 * j8 + 1], a[8 * j8 + 2], a[8 * j8 + 3]),
+                      j8 < 3 ? make_float4(a[8 * j8 + 4], a[8 * j8 + 5], a[8 * j8 + 6], a[8 * j8 + 7]) : make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
       if (pending_dyk >= 0) cp_async_wait_all();
@@ -807,176 +836,130 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         mbar_wait(dym_empty, ((uint32_t)d.tl & 1u) ^ 1u);
         if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 4);
         uint8_t* dm = sm + O1_DYM;
-        if (valid) {
-          const float* src = p.dy2 + ((size_t)d.tile * TILE_ROWS + r) * N_FILT;
+        {
+          // this thread's row of the K-major tile staged one tile earlier (zeros for rows past the batch), re-laid MN-major
+          const int tbm = d.tl & 1;
+          mbar_wait(&dyk_full[tbm], (uint32_t)(d.tl >> 1) & 1u);      // acquire: the other group may have staged this tile
+          const uint8_t* dk = sm + OB_DYK + (uint32_t)tbm * KB_A;
+          float4 v[10];
 #pragma unroll
-          for (int j8 = 0; j8 < 5; ++j8) {               // mn = j: 8 consecutive j per 32-byte chunk
-            const uint32_t off = mn_off(8 * j8, r);
-            cp_async16(dm + off, src + 8 * j8);
-            cp_async16(dm + off + 16, src + 8 * j8 + 4);
-          }
-        } else {
+          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(dk + sw128_off(r, j));
+          v[8] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm));
+          v[9] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm + 1));
 #pragma unroll
-          for (int j8 = 0; j8 < 5; ++j8) {
-            const uint32_t off = mn_off(8 * j8, r);
-            *reinterpret_cast<float4*>(dm + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(dm + off + 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int j8 = 0; j8 < 5; ++j8) mn_store8(dm, 8 * j8, r, v[2 * j8], v[2 * j8 + 1]);   // mn = j, 8 per 32-byte chunk
         }
-        cp_async_commit();
-        cp_async_wait_all();
         fence_proxy_async_smem();
         named_bar_sync(1 + gb, 128);
         if (rq == 0 && lane == 0) { mbar_arrive(dym_full); CONV_TRACE(gb, it, 5); }
       }
     }
   } else if (warp < SCAT_WARP0) {
-    // =============================== epilogue (group ge owns the iterations it & 1 == ge) ===============================
-    const int ge = (warp - EPI_WARP0) >> 3;
-    const int h = ((warp - EPI_WARP0) >> 2) & 1;
+    // =============================== epilogue: 16 warps = 4 lane quarters x 4 column quarters ===============================
     const int q = warp & 3;
+    const int cq = (warp - EPI_WARP0) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float s1[BS ? 20 : 1], s2[BS ? 20 : 1];
+    const bool tr = q == 0 && cq == 0 && lane == 0;
+    float s1[BS ? 10 : 1], s2[BS ? 10 : 1];
+    float c_sc[10], c_sh[10];      // z = c_sc * y_raw + c_sh for this thread's 10 columns (conv bias folded in); the two
+                                   // BatchNorm-backward constants per column come from shared memory (register budget)
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { c_sc[i] = tab[48 + kq(cq, i)]; c_sh[i] = tab[96 + kq(cq, i)]; }
     if constexpr (BS) {
 #pragma unroll
-      for (int i = 0; i < 20; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < 10; ++i) s1[i] = s2[i] = 0.f;
     }
-    for (int it = ge; it < total_it; it += 2) {
+    for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bi = ge;
+      const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
-      const bool tr = q == 0 && h == 0 && lane == 0;
-      if (tr) CONV_TRACE(2 + ge, it, 0);
+      if (tr) CONV_TRACE(2, it, 0);
       mbar_wait(&c_full[bi], n & 1u);
       tc_fence_after();
-      if (tr) CONV_TRACE(2 + ge, it, 1);
-      if constexpr (BS) {
-        // a1 goes to the group's own MN-major buffer (its dWs UMMAs of iteration it-2 are long done); the 20 columns are
-        // processed in chunks of 8 / 8 / 4 to keep the 40 running sums in registers
-        mbar_wait(&op_empty[bi], (n & 1u) ^ 1u);
-        if (tr) CONV_TRACE(2 + ge, it, 2);
-        uint8_t* mt = sm + O1_A1M + (uint32_t)bi * 2 * SLAB;
+      if (tr) CONV_TRACE(2, it, 1);
+      float y[10], da[10];
+      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 64), cq, y);
+      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64), cq, da);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&c_empty[bi]);          // Y / dA1 of this buffer may be overwritten by iteration it+2
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          float y[8], da[8];
-          const uint32_t col = ch < 2 ? (uint32_t)(16 * h + 8 * ch) : (uint32_t)(32 + 4 * h);
-          if (ch < 2) {
-            tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(bi * 64) + col, y);
-            tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64) + col, da);
-          } else {
-            tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64) + col, y);
-            tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64) + col, da);
-          }
-          tmem_ld_wait();
-          const int nc = ch < 2 ? 8 : 4;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < nc) {
-              const int k = (int)col + i;
-              const float yv = y[i] + tab[k];
-              const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
-              const float e = __expf(z);
-              const float dz = da[i] * (z > 0.f ? 1.f : e);              // ELU'(z)
-              const float yh = fmaf(yv, tab[144 + k], tab[192 + k]);
-              if (valid) { s1[8 * ch + i] += dz; s2[8 * ch + i] = fmaf(dz, yh, s2[8 * ch + i]); }
-              y[i] = valid ? tf32_fast(z > 0.f ? z : e - 1.f) : 0.f;      // a1
-            }
-          }
-          const uint32_t off = mn_off((int)col, r);                      // MN-major: mn = filter k, k-row = tile row r
-          *reinterpret_cast<float4*>(mt + off) = make_float4(y[0], y[1], y[2], y[3]);
-          if (ch < 2) *reinterpret_cast<float4*>(mt + off + 16) = make_float4(y[4], y[5], y[6], y[7]);
+      for (int i = 0; i < 10; ++i) {
+        const int k = kq(cq, i);
+        const float z = fmaf(y[i], c_sc[i], c_sh[i]);
+        const float e = __expf(z);
+        const float dz = da[i] * (z > 0.f ? 1.f : e);                  // ELU'(z)
+        const float lin = fmaf(y[i], tab[144 + k], tab[192 + k]);      // B1: yhat;  B2: Bc*y + Cc
+        if constexpr (BS) {
+          if (valid) { s1[i] += dz; s2[i] = fmaf(dz, lin, s2[i]); }
+          y[i] = valid ? tf32_fast(z > 0.f ? z : e - 1.f) : 0.f;        // a1
+        } else {
+          y[i] = valid ? tf32_fast(fmaf(c_sc[i], dz, lin)) : 0.f;       // dy = A*dz + Bc*y + Cc
         }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&c_empty[bi]);
-          mbar_arrive(&op_full[bi]);
-        }
-        if (tr) CONV_TRACE(2 + ge, it, 3);
-      } else {
-        float y[20], da[20];
-        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 16 * h), y);
-        tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(bi * 64 + 32 + 4 * h), y + 16);
-        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 16 * h), da);
-        tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64 + 32 + 4 * h), da + 16);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c_empty[bi]);
-#pragma unroll
-        for (int i = 0; i < 20; ++i) {
-          const int k = kidx(h, i);
-          const float yv = y[i] + tab[k];
-          const float z = fmaf(yv, tab[48 + k], tab[96 + k]);
-          const float dz = da[i] * (z > 0.f ? 1.f : __expf(z));          // ELU'(z)
-          y[i] = valid ? tf32_fast(fmaf(tab[48 + k], dz, fmaf(tab[144 + k], yv, tab[192 + k]))) : 0.f;   // dy
-        }
-        // dy tiles are single buffered: the second-stage UMMAs of iteration it-1 (the other group's) must have completed.
-        // Each group waits on its OWN barrier, completed once per iteration of the other group: a shared barrier with
-        // per-iteration phases lets a group that is two phases ahead slip through the parity test
-        if (tr) CONV_TRACE(2 + ge, it, 4);
-        if (it > 0) mbar_wait(&op_empty[bi], ((uint32_t)((it - 1) >> 1)) & 1u);
-        if (tr) CONV_TRACE(2 + ge, it, 2);
-        uint8_t* mt = sm + O2_DYM;                                       // MN-major: mn = filter k, k-row = tile row r
-        const uint32_t o0 = mn_off(16 * h, r), o1 = mn_off(16 * h + 8, r), o2 = mn_off(32 + 4 * h, r);
-        *reinterpret_cast<float4*>(mt + o0) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(mt + o0 + 16) = make_float4(y[4], y[5], y[6], y[7]);
-        *reinterpret_cast<float4*>(mt + o1) = make_float4(y[8], y[9], y[10], y[11]);
-        *reinterpret_cast<float4*>(mt + o1 + 16) = make_float4(y[12], y[13], y[14], y[15]);
-        *reinterpret_cast<float4*>(mt + o2) = make_float4(y[16], y[17], y[18], y[19]);
-        uint8_t* kt = sm + O2_DYK2;                                      // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<float4*>(kt + sw128_off(r, 4 * h + j)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 4 + h)) = make_float4(y[16], y[17], y[18], y[19]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&op_full[0]);
-        if (tr) CONV_TRACE(2 + ge, it, 3);
       }
+      if (tr) CONV_TRACE(2, it, 4);
+      // operand tiles of the second-stage UMMAs.  B1: a1, double buffered (its dWs UMMAs of iteration it-2 must be done);
+      // B2: dy, ONE buffer (the G / dwt UMMAs of iteration it-1 must be done)
+      const int ob = BS ? bi : 0;
+      mbar_wait(&op_empty[ob], ((BS ? n : (uint32_t)it) & 1u) ^ 1u);
+      if (tr) CONV_TRACE(2, it, 2);
+      {
+        uint8_t* mt = sm + (BS ? O1_A1M + (uint32_t)bi * 2 * SLAB : O2_DYM);   // MN-major: mn = filter k, k-row = tile row r
+        mn_store8(mt, 8 * cq, r, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]));
+        *reinterpret_cast<float2*>(mt + mn_off(32 + 2 * cq, r)) = make_float2(y[8], y[9]);
+        if constexpr (!BS) {
+          uint8_t* kt = sm + O2_DYK2;                                    // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
+          *reinterpret_cast<float4*>(kt + sw128_off(r, 2 * cq)) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(kt + sw128_off(r, 2 * cq + 1)) = make_float4(y[4], y[5], y[6], y[7]);
+          *reinterpret_cast<float2*>(sm + OB_TAIL + sw128_off(r, 4 + (cq >> 1)) + (uint32_t)(cq & 1) * 8u) = make_float2(y[8], y[9]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&op_full[ob]);
+      if (tr) CONV_TRACE(2, it, 3);
     }
     // ---- after the loop: the accumulators that lived in TMEM for the whole kernel ----
     mbar_wait(final_a, 0);
     mbar_wait(final_b, 0);
     tc_fence_after();
     if constexpr (BS) {
-      if (total_it > 0 && ge == 0 && q < 2) {                          // TMEM lane = j (output filter of the spatial conv)
+      const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
+      if (total_it > 0 && q < 3) {                                     // accumulator row = j (output filter of the spatial conv)
         for (int ci = 0; ci < gc; ++ci) {
-          float w[20];
-          tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64 + 16 * h), w);
-          tmem_ld4_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64 + 32 + 4 * h), w + 16);
+          float w[10];
+          tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64), cq, w);
           tmem_ld_wait();
           const int c = g * GC + ci;
-          if (r < N_FILT) {
+          if (lane < 16 && row64 < N_FILT) {
 #pragma unroll
-            for (int i = 0; i < 20; ++i) atomicAdd(&p.dws[((size_t)r * N_FILT + kidx(h, i)) * N_CH + c], w[i]);
+            for (int i = 0; i < 10; ++i) atomicAdd(&p.dws[((size_t)row64 * N_FILT + kq(cq, i)) * N_CH + c], w[i]);
           }
         }
       }
-      // running sums: slot 8*ch + i of chunk ch holds filter (ch < 2 ? 16h + 8ch : 32 + 4h) + i
 #pragma unroll
-      for (int i = 0; i < 20; ++i) {
-        const int k = i < 16 ? 16 * h + i : 32 + 4 * h + (i - 16);
+      for (int i = 0; i < 10; ++i) {
         const float a = warp_sum(s1[i]), b = warp_sum(s2[i]);
-        if (lane == 0) { atomicAdd(&red[k], a); atomicAdd(&red[N_FILT + k], b); }
+        if (lane == 0) { atomicAdd(&red[kq(cq, i)], a); atomicAdd(&red[N_FILT + kq(cq, i)], b); }
       }
       named_bar_sync(3, N_EPI_WARPS * 32);
       const int k = threadIdx.x - EPI_THREAD0;
       if (k < 2 * N_FILT) atomicAdd(&p.bsums[k], (double)red[k]);
     } else {
-      if (total_it > 0 && ge == 0 && q < 2) {                          // TMEM lane = filter k, column = tap t (25: ones column)
-        float w[16];
-        tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(320 + 16 * h), w);
+      const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
+      if (total_it > 0 && q < 3) {                                     // accumulator row = filter k, column = tap t (25: ones column)
+        float w[8];
+        tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(320 + 8 * cq), w);
         tmem_ld_wait();
-        if (r < N_FILT) {
+        if (lane < 16 && row64 < N_FILT) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int t = 16 * h + i;
-            if (t < K_TEMP) atomicAdd(&p.dwt[r * K_TEMP + t], w[i] * (1.f / K_POOL));
-            else if (t == K_TEMP) atomicAdd(&p.dbt[r], w[i]);
+          for (int i = 0; i < 8; ++i) {
+            const int t = 8 * cq + i;
+            if (t < K_TEMP) atomicAdd(&p.dwt[row64 * K_TEMP + t], w[i] * (1.f / K_POOL));
+            else if (t == K_TEMP) atomicAdd(&p.dbt[row64], w[i]);
           }
         }
       }
@@ -1006,26 +989,32 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&gg_empty[bi]);
-      if (valid) {
-        float* dp = dps_all + s_row * PS_LD + 5 * p_row;      // dps[u] += G[(s,p), t] at u = 5p + t
+      // dps[5p + t] += G[(s,p), t], t = 5a + e: in round a every row p touches the 5 positions 5(p+a) .. 5(p+a)+4, which
+      // are distinct across the rows of a sample -> plain read-modify-write, no atomics (shared atomics cost ~3200 cycles
+      // per iteration here); rounds are separated by the warps' barrier
+      float* dp = dps_all + s_row * PS_LD + 5 * p_row;
 #pragma unroll
-        for (int t = 0; t < K_TEMP; ++t) atomicAdd(dp + t, gv[t]);
+      for (int a = 0; a < 5; ++a) {
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < 5; ++e) dp[5 * a + e] += gv[5 * a + e];
+        }
+        named_bar_sync(4, 128);
       }
-      named_bar_sync(4, 128);
       if (sw < d.ns) {
         // d x3[v] = (1/51) * sum_{u = max(0, v-50)}^{min(v, 199)} dps[u]  via the prefix P: (P[hi+1] - P[lo]) / 51
-        float* dp = dps_all + sw * PS_LD;
+        float* dpr = dps_all + sw * PS_LD;
         float* cs = csd_all + sw * CSX_LD;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
         if (lane < 25) {
-          const float4 a = *reinterpret_cast<const float4*>(dp + 8 * lane), b = *reinterpret_cast<const float4*>(dp + 8 * lane + 4);
+          const float4 a = *reinterpret_cast<const float4*>(dpr + 8 * lane), b = *reinterpret_cast<const float4*>(dpr + 8 * lane + 4);
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
           for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
-          *reinterpret_cast<float4*>(dp + 8 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);     // ready for the next iteration
-          *reinterpret_cast<float4*>(dp + 8 * lane + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dpr + 8 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);    // ready for the next iteration
+          *reinterpret_cast<float4*>(dpr + 8 * lane + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float tot = v[7];
         float inc = tot;
@@ -1038,7 +1027,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         if (lane == 0) cs[0] = 0.f;
         if (lane < 25) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cs[8 * lane + 1 + i] = v[i] + excl;         // P[u+1] = sum of dps[0..u]
+          for (int i = 0; i < 8; ++i) cs[csi(8 * lane + 1 + i)] = v[i] + excl;    // P[u+1] = sum of dps[0..u]
         }
         __syncwarp();
         float o8[8];
@@ -1047,7 +1036,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           const int t = 8 * lane + i;
           const int hi = t < N_PSUM - 1 ? t : N_PSUM - 1;
           const int lo = t - (K_POOL - 1) > 0 ? t - (K_POOL - 1) : 0;
-          o8[i] = t < N_T ? (cs[hi + 1] - cs[lo]) * (1.f / K_POOL) : 0.f;
+          o8[i] = t < N_T ? (cs[csi(hi + 1)] - cs[csi(lo)]) * (1.f / K_POOL) : 0.f;
         }
         float* dxr = p.dx3 + ((size_t)(d.tile * TILE_S + sw) * N_TOK + d.c) * D_PAD + 8 * lane;
         *reinterpret_cast<float4*>(dxr) = make_float4(o8[0], o8[1], o8[2], o8[3]);
@@ -1059,13 +1048,16 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           *reinterpret_cast<float4*>(dz + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      named_bar_sync(4, 128);
+      named_bar_sync(4, 128);                            // the zeroed dps rows are visible before the next round 0
       if (sw == 0 && lane == 0) CONV_TRACE(6, it, 2);
     }
   } else if (warp == CTRL_A && lane == 0) {
     // =============================== control A: weight TMA (once), conv + dA1 UMMAs ===============================
     constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0);
     const uint32_t s0 = smem_u32(sm);
+    const uint64_t d_bc = desc_k(s0 + OB_BC), d_tail = desc_k(s0 + OB_TAIL), d_wst = desc_k(s0 + OB_WST), d_wstt = desc_k(s0 + OB_WSTT);
+    uint64_t d_im[2], d_dyk[2];
+    for (int b = 0; b < 2; ++b) { d_im[b] = desc_k(s0 + OB_IMK + (uint32_t)b * KB_A); d_dyk[b] = desc_k(s0 + OB_DYK + (uint32_t)b * KB_A); }
     if (total_it > 0) {
       mbar_arrive_expect_tx(wst_full, GC * KB_48 + KB_48);
       tma_load_2d(&tmWst, wst_full, sm + OB_WST, 0, g * GC * N48);           // [4 channels x 48 rows][32]
@@ -1082,24 +1074,19 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       CONV_TRACE(4, it, 2);
       tc_fence_after();
       // conv UMMA (plain TF32 in the backward): Y[bi] = im2col . (wt/51)^T
-      const uint32_t ik = s0 + OB_IMK + (uint32_t)bi * KB_A, bc = s0 + OB_BC;
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), umma_smem_desc(ik + kk * 32, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bc + kk * 32, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
+        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), desc_adv(d_im[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc48, kk > 0 ? 1u : 0u);
       tc_commit(&im_empty[bi]);                          // B2: control B adds the second arrival (MN-major copy, dwt UMMA)
       if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);
       if (it == 0) mbar_wait(wst_full, 0);
       tc_fence_after();
       // dA1[(s,p), k] = sum_j dY2[(s,p), j] * Ws[j, k, c]
-      const uint32_t dk = s0 + OB_DYK + (uint32_t)tb * KB_A, wk = s0 + OB_WST + (uint32_t)d.ci * KB_48;
+      const uint64_t d_w = desc_adv(d_wst, (uint32_t)d.ci * KB_48);
 #pragma unroll
-      for (int kk = 0; kk < 5; ++kk) {
-        const uint32_t ao = kk < 4 ? dk + (uint32_t)kk * 32u : s0 + OB_TAIL + (uint32_t)tb * 32u;
-        const uint32_t bo = kk < 4 ? wk + (uint32_t)kk * 32u : s0 + OB_WSTT + (uint32_t)d.ci * 32u;
-        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
-                    umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc48, kk > 0 ? 1u : 0u);
-      }
+      for (int kk = 0; kk < 4; ++kk)
+        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), desc_adv(d_dyk[tb], kk * 32), desc_adv(d_w, kk * 32), idesc48, kk > 0 ? 1u : 0u);
+      tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), desc_adv(d_tail, (uint32_t)tb * 32u), desc_adv(d_wstt, (uint32_t)d.ci * 32u), idesc48, 1u);
       tc_commit(&c_full[bi]);
       CONV_TRACE(4, it, 3);
       if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);     // nothing reads the K-major dY2 tile after its last dA1 UMMA
@@ -1108,9 +1095,15 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   } else if (warp == CTRL_B && lane == 0) {
     // =============================== control B: second-stage UMMAs ===============================
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32, 0, 0);
-    constexpr uint32_t idesc48_mn = umma_idesc_tf32(128, N48, 1, 1);
-    constexpr uint32_t idesc32_mn = umma_idesc_tf32(128, 32, 1, 1);
+    // the weight-gradient UMMAs have only 40 useful output rows: M = 64 halves the A-operand traffic (2 slabs instead of 4).
+    // An M = 64 accumulator keeps row i in TMEM lane 32*(i/16) + i%16 (tools/gpu_m64_probe.py)
+    constexpr uint32_t idesc48_mn = umma_idesc_tf32(64, N48, 1, 1);
+    constexpr uint32_t idesc32_mn = umma_idesc_tf32(64, 32, 1, 1);
     const uint32_t s0 = smem_u32(sm);
+    const uint64_t d_dym1 = desc_mn(s0 + O1_DYM), d_a1m0 = desc_mn(s0 + O1_A1M), d_a1m1 = desc_mn(s0 + O1_A1M + 2 * SLAB);
+    const uint64_t d_dyk2 = desc_k(s0 + O2_DYK2), d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + O2_WTT + KB_32);
+    const uint64_t d_tail2 = desc_k(s0 + OB_TAIL + 2u * 32u), d_dym2 = desc_mn(s0 + O2_DYM);
+    const uint64_t d_imm0 = desc_mn(s0 + O2_IMM), d_imm1 = desc_mn(s0 + O2_IMM + SLAB);
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bj = it & 1;
@@ -1122,12 +1115,12 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         CONV_TRACE(5, it, 2);
         tc_fence_after();
         // dWs_c[j, k] += sum_rows dY2[row, j] * a1[row, k]: both operands MN-major, K = the 128 tile rows
-        const uint32_t a = s0 + O1_DYM, b = s0 + O1_A1M + (uint32_t)bj * 2 * SLAB;
-#pragma unroll 4
+        const uint64_t db = bj ? d_a1m1 : d_a1m0;
+        const uint32_t dcol = tmem_base + 256u + (uint32_t)(d.ci * 64);
+        const uint32_t acc0 = d.tl > 0 ? 1u : 0u;
+#pragma unroll
         for (int kk = 0; kk < 16; ++kk)
-          tc_mma_tf32(tmem_base + 256u + (uint32_t)(d.ci * 64), umma_smem_desc(a + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
-                      umma_smem_desc(b + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc48_mn,
-                      (d.tl > 0 || kk > 0) ? 1u : 0u);
+          tc_mma_tf32(dcol, desc_adv(d_dym1, kk * 1024), desc_adv(db, kk * 1024), idesc48_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[bj]);
         CONV_TRACE(5, it, 3);
         if (d.ci == gc - 1) tc_commit(dym_empty);
@@ -1138,23 +1131,19 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         CONV_TRACE(5, it, 2);
         tc_fence_after();
         // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
-        const uint32_t a = s0 + O2_DYK2, b = s0 + O2_WTT;
+        const uint32_t gcol = tmem_base + 256u + (uint32_t)(bj * 32);
 #pragma unroll
-        for (int kk = 0; kk < 5; ++kk) {
-          const uint32_t ao = kk < 4 ? a + (uint32_t)kk * 32u : s0 + OB_TAIL + 2u * 32u;
-          const uint32_t bo = kk < 4 ? b + (uint32_t)kk * 32u : b + KB_32;
-          tc_mma_tf32(tmem_base + 256u + (uint32_t)(bj * 32), umma_smem_desc(ao, 16, 1024, UMMA_LAYOUT_SW128),
-                      umma_smem_desc(bo, 16, 1024, UMMA_LAYOUT_SW128), idesc32, kk > 0 ? 1u : 0u);
-        }
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_tf32(gcol, desc_adv(d_dyk2, kk * 32), desc_adv(d_wtt, kk * 32), idesc32, kk > 0 ? 1u : 0u);
+        tc_mma_tf32(gcol, d_tail2, d_wttt, idesc32, 1u);
         tc_commit(&gg_full[bj]);
         // dwt[k, t] += sum_rows dy[row, k] * im2col[row, t]  (column 25 of the im2col operand is the ones column)
-        const uint32_t am = s0 + O2_DYM, bm = s0 + O2_IMM + (uint32_t)bj * SLAB;
-#pragma unroll 4
+        const uint64_t dbm = bj ? d_imm1 : d_imm0;
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
         for (int kk = 0; kk < 16; ++kk)
-          tc_mma_tf32(tmem_base + 320u, umma_smem_desc(am + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B),
-                      umma_smem_desc(bm + kk * 1024, SLAB, 512, UMMA_LAYOUT_SW128_BASE32B), idesc32_mn,
-                      (it > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&op_empty[bj ^ 1]);                    // the next iteration's group may overwrite the dy tiles
+          tc_mma_tf32(tmem_base + 320u, desc_adv(d_dym2, kk * 1024), desc_adv(dbm, kk * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
+        tc_commit(&op_empty[0]);
         tc_commit(&im_empty[bj]);
         CONV_TRACE(5, it, 3);
       }

@@ -28,6 +28,110 @@ __global__ void tma_tile_dump_kernel(const __grid_constant__ CUtensorMap tm, int
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) out[i] = reinterpret_cast<float*>(tile)[i];
 }
 
+
+// Which TMEM lanes hold the rows of an M = 64 accumulator (cta_group::1)?  One UMMA with A[r][0] = r + 1 (K-major, 64
+// rows), B[0][0] = 1 writes D[r][0] = r + 1; every lane's column 0 is dumped (untouched lanes keep the -1 they were
+// pre-filled with through an M = 128 UMMA with a -1 operand).   tools/gpu_m64_probe.py
+__global__ void umma_m64_probe_kernel(float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* A = sm;                       // [128 rows][32 floats] K-major SWIZZLE_128B
+  uint8_t* Bm = sm + 16384;              // [8 rows][32 floats]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 16384 + 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  for (int i = threadIdx.x; i < (16384 + 1024) / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
+  __syncthreads();
+  const int r = threadIdx.x;
+  // element (r, 0): chunk 0 of row r
+  *reinterpret_cast<float*>(A + (r >> 3) * 1024 + (r & 7) * 128 + ((0 ^ (r & 7)) << 4)) = -1.f;     // pass 1: all 128 rows = -1
+  if (r == 0) *reinterpret_cast<float*>(Bm) = 1.f;
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(slot, 32); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    tc_mma_tf32(tmem, umma_smem_desc(smem_u32(A), 16, 1024, UMMA_LAYOUT_SW128), umma_smem_desc(smem_u32(Bm), 16, 1024, UMMA_LAYOUT_SW128),
+                umma_idesc_tf32(128, 8, 0, 0), 0u);
+    tc_commit(&bar[0]);
+  }
+  mbar_wait(&bar[0], 0);
+  tc_fence_after();
+  __syncthreads();
+  if (r < 64) *reinterpret_cast<float*>(A + (r >> 3) * 1024 + (r & 7) * 128 + ((0 ^ (r & 7)) << 4)) = (float)(r + 1);   // pass 2
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    tc_mma_tf32(tmem, umma_smem_desc(smem_u32(A), 16, 1024, UMMA_LAYOUT_SW128), umma_smem_desc(smem_u32(Bm), 16, 1024, UMMA_LAYOUT_SW128),
+                umma_idesc_tf32(64, 8, 0, 0), 0u);
+    tc_commit(&bar[1]);
+  }
+  mbar_wait(&bar[1], 0);
+  tc_fence_after();
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16)) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  out[threadIdx.x] = __uint_as_float(v);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 32);
+}
+
+
+// Cycles per tcgen05.mma (kind::tf32, K = 8) for the small shapes of the fused conv kernels: a chain of `n` UMMAs issued
+// back to back by one thread into one accumulator, operands resident in shared memory, nothing else running on the SM.
+// out[0] = cycles from the first issue to the commit arrival, out[1] = cycles spent issuing.   tools/gpu_mma_cost.py
+__global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int k_steps, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 160 * 1024);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm + 64 * 1024);
+    const uint32_t idesc = umma_idesc_tf32(M, N, mn_major, mn_major);
+    // descriptors of the 4 k-steps precomputed: the loop body is 4 x (tcgen05.mma) and nothing else
+    uint64_t ad[4], bd[4];
+    for (int kk = 0; kk < 4; ++kk) {
+      ad[kk] = mn_major ? umma_smem_desc(a0 + kk * 1024, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                        : umma_smem_desc(a0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+      bd[kk] = mn_major ? umma_smem_desc(b0 + kk * 1024, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
+                        : umma_smem_desc(b0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+    }
+    const long long t0 = clock64();
+    tc_mma_tf32(tmem, ad[0], bd[0], idesc, 0u);
+    for (int i = 1; i < n / 4; ++i) {
+      tc_mma_tf32(tmem, ad[0], bd[0], idesc, 1u);
+      tc_mma_tf32(tmem, ad[1], bd[1], idesc, 1u);
+      tc_mma_tf32(tmem, ad[2], bd[2], idesc, 1u);
+      tc_mma_tf32(tmem, ad[3], bd[3], idesc, 1u);
+    }
+    (void)k_steps;
+    const long long t1 = clock64();
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0;
+    out[1] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace eegb200
 
 using namespace eegb200;
@@ -44,6 +148,28 @@ extern "C" int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, fl
     EEG_CUDA_OK(cudaFuncSetAttribute(tma_tile_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 64 + 1024));
   }
   tma_tile_dump_kernel<<<1, 128, 16384 + 64 + 1024, (cudaStream_t)stream>>>(tm, d3, out);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int eegb200_debug_umma_m64(float* out128, void* stream) {
+  EEG_REQUIRE(out128 != nullptr, "debug_umma_m64: null output");
+  static PerDeviceOnce once;
+  if (once.first())
+    EEG_CUDA_OK(cudaFuncSetAttribute(umma_m64_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 1024 + 64 + 1024));
+  umma_m64_probe_kernel<<<1, 128, 16384 + 1024 + 64 + 1024, (cudaStream_t)stream>>>(out128);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int k_steps, long long* out2, void* stream) {
+  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && k_steps > 0 && k_steps <= 16, "debug_umma_cost: bad arguments");
+  static PerDeviceOnce once;
+  if (once.first())
+    EEG_CUDA_OK(cudaFuncSetAttribute(umma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 64 + 1024));
+  umma_cost_kernel<<<1, 128, 160 * 1024 + 64 + 1024, (cudaStream_t)stream>>>(M, N, mn_major, n, k_steps, out2);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -191,7 +191,8 @@ int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
  * this rank's B rows contribute
  *     *loss, *loss_term += weight * sum_{b,d} (eeg-tgt)^2 / (n_total_rows*D)          (either may be NULL)
  *     d_eeg[b,d]        += weight * grad_out * 2 (eeg-tgt)[b,d] / (n_total_rows*D)     (NULL: loss only)
- * so it composes with eegb200_infonce, whose phase B writes loss[0] and d_eeg first. */
+ * so it composes with eegb200_infonce, whose phase B writes loss[0] and d_eeg first.  n_total_rows = b with B = n*b rows
+ * gives the SUM of the n per-batch means of batches of b rows (evaluate_model averages per-batch losses). */
 int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_total_rows, float weight, float grad_out,
                 float* loss, float* loss_term, float* d_eeg, void* stream);
 
@@ -222,6 +223,10 @@ int eegb200_adamw_step_dev(float* p, const float* g, float* m, float* v, long lo
  * [128 rows x 32 k] k-block of a GEMM operand, K-major (src[row*ld + k], SWIZZLE_128B) or MN-major (src[k*ld + row],
  * SWIZZLE_128B_ATOM_32B).  Used to validate the layouts thread-written UMMA operands must follow. */
 int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, float* out, void* stream);
+/* debug: out128[lane] = column 0 of TMEM lane `lane` after an M = 64 UMMA wrote D[r][0] = r + 1 (lanes it did not touch: -1) */
+int eegb200_debug_umma_m64(float* out128, void* stream);
+/* debug: cycles of a chain of n tcgen05.mma (kind::tf32, K = 8) of shape M x N: out2[0] = issue..completion, out2[1] = issue */
+int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int k_steps, long long* out2, void* stream);
 
 #ifdef __cplusplus
 }

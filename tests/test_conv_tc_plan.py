@@ -18,12 +18,19 @@ def test_conv_tc_plan_ragged_last_tile():
 
 
 def test_conv_tc_kernel_protocol_has_no_deadlock_or_hazard():
-    """mbarrier / commit / TMA protocol of csrc/conv_tc.cu replayed with randomised timing (tools/conv_tc_protocol_sim.py)"""
-    import random
+    """mbarrier / commit / TMA protocol of the four csrc/conv_tc.cu kernels replayed with randomised timing
+    (tools/conv_tc_protocol_sim.py): every role issues the same wait / arrive / commit sequence as the CUDA code"""
     import conv_tc_protocol_sim as S
-    for mode in ("stats", "apply"):
-        for seed in range(40):
-            S.Sim(mode, random.Random(seed)).run()
+    for mode in ("B1", "B2"):
+        for gc in (4, 3):
+            for n_tiles in (1, 2, 3, 7):
+                for seed in range(8):
+                    ok, stuck = S.run(mode, gc, n_tiles, seed)
+                    assert ok, (mode, gc, n_tiles, seed, stuck)
+    for n_items in (1, 3):
+        for seed in range(8):
+            ok, stuck = S.run_fwd(n_items, seed)
+            assert ok, (n_items, seed, stuck)
 
 
 def test_attention_block_diagonal_plan_matches_autograd():

@@ -330,3 +330,34 @@ def test_model_on_second_device_with_other_current_device(lib):
     assert rows_rel(res[1][1], res[0][1]) < 2e-4
     assert abs(res[1][0][0].item() - res[0][0][0].item()) < 1e-3 * abs(res[0][0][0].item())
     assert rel_l2(res[1][2], res[0][2]) < 5e-3
+
+
+def test_normalize_option_matches_l2_normalised_reference(lib):
+    """ATMS(normalize=True): the embedding is F.normalize(reference embedding); its backward is the exact Jacobian
+    (checked by pushing the analytically transformed gradient through a normalize=False twin)"""
+    from eeg_image_decode_b200.atms import ATMS
+    B = 16
+    x = recipe.make_eeg(B, seed=77)
+    sid = torch.full((B,), 8)
+    ref = O.atms_forward(recipe.make_state_dict(), x, sid, train=True, dtype=torch.float64)["out"]
+    twins = []
+    for norm in (True, False):
+        m = ATMS(normalize=norm)
+        m.load_state_dict(recipe.make_state_dict())
+        m = m.cuda().train()
+        m.dropout_p = [0.0] * 8
+        twins.append(m)
+    out = twins[0].encode(x.cuda(), sid.cuda(), train=True, seed=1)
+    want = torch.nn.functional.normalize(ref, dim=-1)
+    assert rows_rel(out, want) < 1e-3
+    assert (out.norm(dim=1) - 1).abs().max().item() < 1e-5
+    d = torch.randn(B, 1024, generator=torch.Generator().manual_seed(1))
+    twins[0].zero_flat_grads()
+    twins[0].backprop(d.cuda())
+    raw = twins[1].encode(x.cuda(), sid.cuda(), train=True, seed=1)
+    y = torch.nn.functional.normalize(raw.double(), dim=-1)
+    d_raw = ((d.double().cuda() - y * (y * d.double().cuda()).sum(1, keepdim=True)) / raw.double().norm(dim=1, keepdim=True)).float()
+    twins[1].zero_flat_grads()
+    twins[1].backprop(d_raw)
+    for k in ("proj_eeg.2.weight", "proj_eeg.0.weight", "enc_eeg.0.tsconv.4.weight", "encoder.enc_embedding.value_embedding.weight"):
+        assert rel_l2(twins[0].grad_view(k), twins[1].grad_view(k)) < 5e-3, k

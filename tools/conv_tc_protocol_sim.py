@@ -28,7 +28,7 @@ def run(mode, gc, n_tiles, seed, verbose=False):
     total = n_tiles * gc
     B = {}
     for nm, cnt in (("im_full", 1), ("im_empty", 1 if BS else 2), ("dyk_full", 1), ("dyk_empty", 1), ("c_full", 1),
-                    ("c_empty", 8), ("op_full", 8), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4)):
+                    ("c_empty", 16), ("op_full", 16), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4)):
         B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
     for nm in ("dym_full", "dym_empty", "final_a", "final_b"):
         B[nm] = Bar(nm, 1)
@@ -62,20 +62,19 @@ def run(mode, gc, n_tiles, seed, verbose=False):
             pending = -1
             if BS and gb == 0 and ci < 2:
                 yield ("wait", B["dym_empty"], (tl & 1) ^ 1)
+                yield ("wait", B["dyk_full"][tl & 1], (tl >> 1) & 1)
                 yield ("arrive", B["dym_full"])
 
     def epilogue(ge, w):
-        for it in range(ge, total, 2):
-            bi, n = ge, it >> 1
+        for it in range(total):
+            bi, n = it & 1, it >> 1
             yield ("wait", B["c_full"][bi], n & 1)
+            yield ("arrive", B["c_empty"][bi])
             if BS:
                 yield ("wait", B["op_empty"][bi], (n & 1) ^ 1)
-                yield ("arrive", B["c_empty"][bi])
                 yield ("arrive", B["op_full"][bi])
             else:
-                yield ("arrive", B["c_empty"][bi])
-                if it > 0:
-                    yield ("wait", B["op_empty"][bi], ((it - 1) >> 1) & 1)
+                yield ("wait", B["op_empty"][0], (it & 1) ^ 1)
                 yield ("arrive", B["op_full"][0])
         yield ("wait", B["final_a"], 0)
         yield ("wait", B["final_b"], 0)
@@ -115,7 +114,7 @@ def run(mode, gc, n_tiles, seed, verbose=False):
                 yield ("wait", B["op_full"][0], it & 1)
                 yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
                 yield ("commit", B["gg_full"][bj])
-                yield ("commit", B["op_empty"][bj ^ 1])
+                yield ("commit", B["op_empty"][0])
                 yield ("commit", B["im_empty"][bj])
         yield ("commit", B["final_b"])
 
@@ -167,8 +166,8 @@ def run_fwd(n_items, seed, F_LEN=21, RING=4):
     rnd = random.Random(seed)
     total = n_items * F_LEN
     B = {}
-    for nm, cnt in (("tile_full", 1), ("tile_empty", 1), ("c1_full", 1), ("c1_empty", 8), ("a1_full", 8), ("a1_empty", 1),
-                    ("y2_full", 1), ("y2_empty", 8)):
+    for nm, cnt in (("tile_full", 1), ("tile_empty", 1), ("c1_full", 1), ("c1_empty", 16), ("a1_full", 16), ("a1_empty", 1),
+                    ("y2_full", 1), ("y2_empty", 16)):
         B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
     B["ws_full"] = [Bar(f"ws_full[{i}]", 1) for i in range(RING)]
     B["ws_empty"] = [Bar(f"ws_empty[{i}]", 1) for i in range(RING)]
@@ -183,12 +182,12 @@ def run_fwd(n_items, seed, F_LEN=21, RING=4):
             yield ("arrive", B["tile_full"][gb])
 
     def epilogue(ge, w):
-        for it in range(ge, total, 2):
-            n, item, l = it >> 1, it // F_LEN, it % F_LEN
-            yield ("wait", B["c1_full"][ge], n & 1)
-            yield ("arrive", B["c1_empty"][ge])
-            yield ("wait", B["a1_empty"][ge], (n & 1) ^ 1)
-            yield ("arrive", B["a1_full"][ge])
+        for it in range(total):
+            bi, n, item, l = it & 1, it >> 1, it // F_LEN, it % F_LEN
+            yield ("wait", B["c1_full"][bi], n & 1)
+            yield ("arrive", B["c1_empty"][bi])
+            yield ("wait", B["a1_empty"][bi], (n & 1) ^ 1)
+            yield ("arrive", B["a1_full"][bi])
             if l == F_LEN - 1:
                 ib = item & 1
                 yield ("wait", B["y2_full"][ib], (item >> 1) & 1)
