@@ -274,6 +274,9 @@ class ATMS(nn.Module):
 
     def workspace(self, B: int) -> torch.Tensor:
         ws = self._ws.get(B)
+        # the size depends on the library state (fused conv path vs. verification backend / debug stage stores)
+        if ws is not None and ws.numel() < _lib.atms_workspace_bytes(B) and B not in self._ws_pinned:
+            ws = None
         if ws is None:
             ws = torch.empty(_lib.atms_workspace_bytes(B), dtype=torch.uint8, device=self.flat_params.device)
             # keep only the latest batch size resident, plus the ones a live CUDA graph was captured on

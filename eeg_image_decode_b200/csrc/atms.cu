@@ -43,8 +43,13 @@ struct Carver {
   }
 };
 
+// The (b,p) x (c,k) conv intermediates Y1 / A1 / dA1 (363 KB per sample each) only exist for the unfused round-1 kernels,
+// the exact-fp32 verification backend and the debug stage stores; the fused tcgen05 path keeps them on chip.
+static bool need_conv_intermediates() { return !(tf32_rounding() && conv_tc_enabled()) || debug_stores() != 0; }
+
 static size_t carve(void* base, int B, Ws* w) {
   Carver c{reinterpret_cast<uint8_t*>(base)};
+  const size_t conv_rows = need_conv_intermediates() ? (size_t)B * N_POOL : 0;
   const size_t M = (size_t)B * N_TOK;          // token rows
   const size_t R = (size_t)B * N_POOL;         // (b, j) rows of the conv stack
   Ws t;
@@ -74,8 +79,8 @@ static size_t carve(void* base, int B, Ws* w) {
   t.st1 = c.take<float>(M * 2);
   t.st2 = c.take<float>(M * 2);
   t.stf = c.take<float>(M * 2);
-  t.Y1 = c.take<float>(R * K_SPAT);
-  t.A1 = c.take<float>(R * K_SPAT);
+  t.Y1 = c.take<float>(conv_rows * K_SPAT);
+  t.A1 = c.take<float>(conv_rows * K_SPAT);
   t.Y2 = c.take<float>(R * N_FILT);
   t.feat = c.take<float>((size_t)B * D_FEAT);
   t.Z1 = c.take<float>((size_t)B * D_OUT);
@@ -95,7 +100,7 @@ static size_t carve(void* base, int B, Ws* w) {
   t.dfeat = c.take<float>((size_t)B * D_FEAT);
   t.dz2 = c.take<float>(R * N_FILT);
   t.dY2 = c.take<float>(R * N_FILT);
-  t.dA1 = c.take<float>(R * K_SPAT);
+  t.dA1 = c.take<float>(conv_rows * K_SPAT);
   t.dX3 = c.take<float>(M * 256);
   t.dR2 = c.take<float>(M * 256);
   t.T1 = c.take<float>(M * 256);
@@ -816,6 +821,10 @@ int eegb200_atms_ws_tensor(void* workspace, int B, const char* name, void** ptr,
       {"dqkv", w.dQKV, M, 768, 768},  {"dr1", w.dR1, M, 256, 256},     {"dr2", w.dR2, M, 256, 256},
       {"da1", w.dA1, R, K_SPAT, K_SPAT}, {"dy2", w.dY2, R, N_FILT, N_FILT},
   };
+  if ((strcmp(name, "y1") == 0 || strcmp(name, "a1") == 0 || strcmp(name, "da1") == 0) && !need_conv_intermediates()) {
+    set_error("ws_tensor: '%s' stays on chip in the fused conv path; call eegb200_set_debug_stores(1) before the forward", name);
+    return 2;
+  }
   for (const NamedTensor& e : t)
     if (strcmp(e.name, name) == 0) {
       *ptr = e.ptr; *rows = e.rows; *cols = e.cols; *ld = e.ld;

@@ -84,52 +84,75 @@ __global__ void umma_m64_probe_kernel(float* __restrict__ out) {
 
 
 // Cycles per tcgen05.mma (kind::tf32, K = 8) for the small shapes of the fused conv kernels: a chain of `n` UMMAs issued
-// back to back by one thread into one accumulator, operands resident in shared memory, nothing else running on the SM.
+// back to back by one thread into one accumulator, operands resident in shared memory.  `bg` adds background activity on
+// the same SM: 1 = 8 warps streaming st.shared.v4, 2 = a SECOND thread (another warp) issuing its own UMMA chain,
+// 4 = 4 warps looping tcgen05.ld on the accumulator (bits may be combined).
 // out[0] = cycles from the first issue to the commit arrival, out[1] = cycles spent issuing.   tools/gpu_mma_cost.py
-__global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int k_steps, long long* __restrict__ out) {
+__global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int bg, long long* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 160 * 1024);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+  volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
-  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  if (threadIdx.x < 32) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); *stop = 0; }
+  if (threadIdx.x < 32) { tmem_alloc(slot, 512); tmem_relinquish(); }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
-  if (threadIdx.x == 0) {
-    const uint32_t a0 = smem_u32(sm), b0 = smem_u32(sm + 64 * 1024);
-    const uint32_t idesc = umma_idesc_tf32(M, N, mn_major, mn_major);
-    // descriptors of the 4 k-steps precomputed: the loop body is 4 x (tcgen05.mma) and nothing else
-    uint64_t ad[4], bd[4];
-    for (int kk = 0; kk < 4; ++kk) {
-      ad[kk] = mn_major ? umma_smem_desc(a0 + kk * 1024, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
-                        : umma_smem_desc(a0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
-      bd[kk] = mn_major ? umma_smem_desc(b0 + kk * 1024, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B)
-                        : umma_smem_desc(b0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 || (warp == 1 && (bg & 2))) {
+    if (lane == 0) {
+      const uint32_t a0 = smem_u32(sm) + warp * 32768, b0 = smem_u32(sm + 64 * 1024) + warp * 32768;
+      const uint32_t idesc = umma_idesc_tf32(M, N, mn_major, mn_major);
+      uint64_t ad[4], bd[4];
+      for (int kk = 0; kk < 4; ++kk) {
+        ad[kk] = mn_major ? umma_smem_desc(a0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
+                          : umma_smem_desc(a0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        bd[kk] = mn_major ? umma_smem_desc(b0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
+                          : umma_smem_desc(b0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+      }
+      const uint32_t d = tmem + warp * 256;
+      const long long t0 = clock64();
+      tc_mma_tf32(d, ad[0], bd[0], idesc, 0u);
+      for (int i = 1; i < n / 4; ++i) {
+        tc_mma_tf32(d, ad[0], bd[0], idesc, 1u);
+        tc_mma_tf32(d, ad[1], bd[1], idesc, 1u);
+        tc_mma_tf32(d, ad[2], bd[2], idesc, 1u);
+        tc_mma_tf32(d, ad[3], bd[3], idesc, 1u);
+      }
+      const long long t1 = clock64();
+      tc_commit(&bar[warp]);
+      mbar_wait(&bar[warp], 0);
+      const long long t2 = clock64();
+      if (warp == 0) { out[0] = t2 - t0; out[1] = t1 - t0; *stop = 1; }
     }
-    const long long t0 = clock64();
-    tc_mma_tf32(tmem, ad[0], bd[0], idesc, 0u);
-    for (int i = 1; i < n / 4; ++i) {
-      tc_mma_tf32(tmem, ad[0], bd[0], idesc, 1u);
-      tc_mma_tf32(tmem, ad[1], bd[1], idesc, 1u);
-      tc_mma_tf32(tmem, ad[2], bd[2], idesc, 1u);
-      tc_mma_tf32(tmem, ad[3], bd[3], idesc, 1u);
+  } else if (warp >= 4 && warp < 12 && (bg & 1)) {
+    // background shared-memory stores (conflict-free 512 B per instruction) into a region nobody reads
+    float4* dst = reinterpret_cast<float4*>(sm + 128 * 1024) + (warp - 4) * 32 + lane;
+    int it = 0;
+    while (!*stop && it < (1 << 22)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[(j & 3) * 256] = make_float4((float)it, 0.f, 0.f, 0.f);
+      ++it;
     }
-    (void)k_steps;
-    const long long t1 = clock64();
-    tc_commit(bar);
-    mbar_wait(bar, 0);
-    const long long t2 = clock64();
-    out[0] = t2 - t0;
-    out[1] = t1 - t0;
+  } else if (warp >= 12 && warp < 16 && (bg & 4)) {
+    int it = 0;
+    float acc = 0.f;
+    while (!*stop && it < (1 << 22)) {
+      float v[16];
+      tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128u, v);     // columns the MMAs do not write
+      acc += v[0];
+      ++it;
+    }
+    if (acc == 12345.f) out[1] = 0;
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace eegb200
@@ -164,12 +187,13 @@ extern "C" int eegb200_debug_umma_m64(float* out128, void* stream) {
   return 0;
 }
 
-extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int k_steps, long long* out2, void* stream) {
-  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && k_steps > 0 && k_steps <= 16, "debug_umma_cost: bad arguments");
+extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int bg, long long* out2, void* stream) {
+  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && bg >= 0 && bg < 8 && (!mn_major || N <= 128),
+              "debug_umma_cost: bad arguments");
   static PerDeviceOnce once;
   if (once.first())
     EEG_CUDA_OK(cudaFuncSetAttribute(umma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 64 + 1024));
-  umma_cost_kernel<<<1, 128, 160 * 1024 + 64 + 1024, (cudaStream_t)stream>>>(M, N, mn_major, n, k_steps, out2);
+  umma_cost_kernel<<<1, 512, 160 * 1024 + 64 + 1024, (cudaStream_t)stream>>>(M, N, mn_major, n, bg, out2);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

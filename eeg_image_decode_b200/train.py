@@ -156,14 +156,37 @@ class StepEngine:
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
 
-    def loss_and_grad(self, feats, img_feat, txt_feat, need_grad=True):
+    def gather_async(self, img_feat, txt_feat):
+        """start the all-gather of the (input) target blocks; it overlaps the encoder forward.  Returns what
+        loss_and_grad(gathered=...) consumes."""
+        W = self.world
+        if W == 1:
+            return None
+        out = []
+        for t in (img_feat, txt_feat if self.variant == "retrieval" else None):
+            if t is None:
+                out.append((None, None))
+                continue
+            t = t.contiguous()
+            buf = torch.empty(W * t.shape[0], t.shape[1], device=t.device, dtype=t.dtype)
+            out.append((buf, torch.distributed.all_gather_into_tensor(buf, t, async_op=True)))
+        return out
+
+    def loss_and_grad(self, feats, img_feat, txt_feat, need_grad=True, gathered=None):
         """this rank's share of the step loss ([3] device tensor: total, ClipLoss(img), second term) and d loss / d feats,
-        d loss / d logit_scale.  Targets are the LOCAL rows; the global-batch gather happens here."""
+        d loss / d logit_scale.  Targets are the LOCAL rows; the global-batch gather happens here (or was started by
+        gather_async)."""
         m, W = self.model, self.world
-        img_all = gather_targets(img_feat, W)
+        if gathered is not None:
+            for _, h in gathered:
+                if h is not None:
+                    h.wait()
+            img_all = gathered[0][0]
+        else:
+            img_all = gather_targets(img_feat, W)
         row0 = self.rank * feats.shape[0]
         if self.variant == "retrieval":
-            txt_all = gather_targets(txt_feat, W)
+            txt_all = gathered[1][0] if gathered is not None else gather_targets(txt_feat, W)
             return fused_contrastive(self.nce, feats, img_all, txt_all, m.logit_scale.detach(), self.alpha,
                                      row_offset=row0, need_grad=need_grad, world_size=W)
         w_clip, w_mse = (1.0 - self.alpha) * 10.0, self.alpha * 10.0
@@ -182,7 +205,9 @@ class StepEngine:
         W = self.world
         m.zero_flat_grads()
         seed = m.next_seed() if seed is None else seed
+        gathered = None
         if W > 1:
+            gathered = self.gather_async(img_feat, txt_feat)   # inputs only: travels while the encoder runs
             seed ^= (self.rank + 1) * 0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF     # decorrelate the ranks' dropout masks
             # SyncBN: all-reduce the batch statistics between the forward phases
             m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A, known_subject=known_subject)
@@ -198,15 +223,23 @@ class StepEngine:
             feats = m.encode(eeg, subject_ids, train=True, seed=seed, known_subject=known_subject)
         if after_forward is not None:
             after_forward(feats)
-        loss, d_e, d_s = self.loss_and_grad(feats, img_feat, txt_feat)
+        loss, d_e, d_s = self.loss_and_grad(feats, img_feat, txt_feat, gathered=gathered)
         m.grad_view("logit_scale").add_(d_s)
         if W > 1:
             m.backprop(d_e, phases=_lib.PHASE_A)
+            # Gradient all-reduce in two buckets.  After phase A the projector, the conv head and logit_scale are final:
+            # that contiguous tail of the arena is 2.6 M of the 3.2 M parameters (10 MB) and its all-reduce (NCCL's own
+            # stream) hides behind phases B and C; only the encoder / conv part (2.5 MB) is exposed at the end.
+            o_tail = m._offs["enc_eeg.0.projection.0.weight"]
+            o_tab = m._offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]
+            h_tail = torch.distributed.all_reduce(m.flat_grads[o_tail:o_tab], async_op=True)
             self._allreduce(m.ws_tensor("bn2_bwd_sums"))
             self._phase(_lib.PHASE_B, fwd=False, batch_scale=W)
             self._allreduce(m.ws_tensor("bn1_bwd_sums"))
             self._phase(_lib.PHASE_C, fwd=False, batch_scale=W)
-            self._allreduce(m.flat_grads)
+            self._allreduce(m.flat_grads[:o_tail])
+            self._allreduce(m.flat_grads[o_tab:])
+            h_tail.wait()
         else:
             m.backprop(d_e)
         subjects = m._last_subjects          # joint-subject model: whose value embeddings got a gradient

@@ -226,7 +226,7 @@ int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, float* out, v
 /* debug: out128[lane] = column 0 of TMEM lane `lane` after an M = 64 UMMA wrote D[r][0] = r + 1 (lanes it did not touch: -1) */
 int eegb200_debug_umma_m64(float* out128, void* stream);
 /* debug: cycles of a chain of n tcgen05.mma (kind::tf32, K = 8) of shape M x N: out2[0] = issue..completion, out2[1] = issue */
-int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int k_steps, long long* out2, void* stream);
+int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int background, long long* out2, void* stream);
 
 #ifdef __cplusplus
 }

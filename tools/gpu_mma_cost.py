@@ -1,4 +1,5 @@
-"""Cycles per tcgen05.mma (kind::tf32, K = 8) for small shapes, chained into one accumulator (csrc/debug_probe.cu).
+"""Cycles per tcgen05.mma (kind::tf32, K = 8) for small shapes, chained into one accumulator, alone and with background
+activity on the same SM (shared-memory stores / a second issuing thread / tcgen05.ld traffic): csrc/debug_probe.cu.
     python tools/gpu_mma_cost.py"""
 import ctypes
 import os
@@ -12,13 +13,14 @@ from eeg_image_decode_b200 import _lib  # noqa: E402
 L = _lib.lib()
 L.eegb200_debug_umma_cost.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-print("M   N    major  k_steps   cycles/MMA (complete)  cycles/MMA (issue)   floor M*N/256... (N/2 at M=128)")
+BG = {0: "alone", 1: "+smem stores", 2: "+2nd issuer", 4: "+tcgen05.ld", 7: "+all three"}
+print("M    N  major  background       cycles/MMA (complete)  (issue)   floor N/2")
 for mn in (0, 1):
     for M in (128, 64):
-        for N in (32, 48, 96, 160, 192, 256):
-            for ks in (4,):
+        for N in (32, 48, 96, 128):
+            for bg in (0, 1, 2, 4, 7):
                 for rep in range(2):
-                    _lib.check(L.eegb200_debug_umma_cost(M, N, mn, 256, ks, _lib.ptr(out), _lib.stream_ptr()), "umma_cost")
+                    _lib.check(L.eegb200_debug_umma_cost(M, N, mn, 512, bg, _lib.ptr(out), _lib.stream_ptr()), "umma_cost")
                     torch.cuda.synchronize()
                 a, b = out.tolist()
-                print(f"{M:3d} {N:4d}   {'MN' if mn else 'K '}    {ks:3d}       {a / 256:8.1f}               {b / 256:8.1f}          {N / 2:6.0f}")
+                print(f"{M:3d} {N:4d}   {'MN' if mn else 'K '}   {BG[bg]:14s}   {a / 512:8.1f}            {b / 512:8.1f}    {N / 2:6.0f}")
