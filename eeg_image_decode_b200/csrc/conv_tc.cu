@@ -187,6 +187,14 @@ constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;         // + alignment slack
 static_assert(OFF_BC % 1024 == 0 && OFF_A1 % 1024 == 0 && OFF_WS % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 static_assert(CTC_SMEM <= 227 * 1024, "conv forward kernel exceeds the shared memory of an SM");
 
+// optional cycle trace of CTA 0 (EEGB200_CONV_TRACE=<dir>): trace[(role * TRACE_IT + it) * 8 + event] = clock64()
+constexpr int TRACE_IT = 96, TRACE_ROLES = 8;
+#define CONV_TRACE(role, it, ev)                                                                      \
+  do {                                                                                                \
+    if (p.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_IT)                                     \
+      p.trace[((role) * TRACE_IT + (it)) * 8 + (ev)] = clock64();                                     \
+  } while (0)
+
 enum { MODE_STATS = 0, MODE_APPLY = 1 };
 
 struct ConvTcParams {
@@ -203,6 +211,7 @@ struct ConvTcParams {
   double* sums;             // [2][40]   (MODE_STATS)
   int B;
   int n_tiles;
+  long long* trace;         // nullptr unless tracing
 };
 
 struct FwdIt { int tile, c, l, item_local, part, ns; };
@@ -325,10 +334,13 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       const uint32_t n = (uint32_t)(it >> 1);
       const int rows_valid = d.ns * N_POOL;
       const float4 x0 = xa, x1 = xb;
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 0);
       fetch(it + 2);                                    // the group's next row travels while this one is processed
       if (rq < d.ns) pool_row(x0, x1, lane, cs_all + rq * CSX_LD, ps_all + rq * PS_LD);
       named_bar_sync(1 + gb, 128);
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 1);
       mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of iteration it-2 have consumed this buffer
+      if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 2);
       {
         // hi = RN-rounded TF32 part (the BatchNorm statistics average over 2.3 M products: the rounding must be unbiased,
         // truncation shifts the variance by 7e-4), lo = a - hi exactly (kind::tf32 reads its top 19 bits).  The statistics
@@ -352,7 +364,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + gb, 128);
-      if (rq == 0 && lane == 0) mbar_arrive(&tile_full[bi]);
+      if (rq == 0 && lane == 0) { mbar_arrive(&tile_full[bi]); CONV_TRACE(gb, it, 3); }
     }
   } else if (warp < F_CTRL_A) {
     // =============================== epilogue: 16 warps = 4 lane quarters x 4 column quarters ===============================
@@ -374,8 +386,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       const uint32_t n = (uint32_t)(it >> 1);
       const bool valid = r < d.ns * N_POOL;
       const size_t grow = (size_t)d.tile * TILE_ROWS + r;         // global (b, p) row
+      const bool tr = q == 0 && cq == 0 && lane == 0;
+      if (tr) CONV_TRACE(2, it, 0);
       mbar_wait(&c1_full[bi], n & 1u);
       tc_fence_after();
+      if (tr) CONV_TRACE(2, it, 1);
       float y[10], y2[10];
       tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 128), cq, y);          // a . w_hi (+ a_lo . w_hi in F2)
       tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 128 + N48), cq, y2);   // a_hi . w_lo
@@ -411,7 +426,9 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
           *reinterpret_cast<float2*>(dst + 32 + 2 * cq) = make_float2(y[8], y[9]);
         }
         // K slice of the spatial A operand: k 0..31 -> k-block 0 (chunk k/4), k 32..39 -> chunks 0, 1 of k-block 1
+        if (tr) CONV_TRACE(2, it, 4);
         mbar_wait(&a1_empty[bi], (n & 1u) ^ 1u);         // spatial UMMAs of iteration it-2 are done with this buffer
+        if (tr) CONV_TRACE(2, it, 2);
         uint8_t* a1t = sm + OFF_A1 + (uint32_t)bi * 2 * KB_A;
         *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq)) = make_float4(y[0], y[1], y[2], y[3]);
         *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq + 1)) = make_float4(y[4], y[5], y[6], y[7]);
@@ -419,6 +436,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1_full[bi]);
+        if (tr) CONV_TRACE(2, it, 3);
         if (d.l == F_LEN - 1) {
           // ---- last channel of the item: y2 share = accumulated spatial product (+ bias once per tile) ----
           const int ib = d.item_local & 1;
@@ -466,8 +484,11 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     for (int it = 0; it < total_it; ++it) {
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
+      CONV_TRACE(4, it, 0);
       mbar_wait(&tile_full[bi], n & 1u);
+      CONV_TRACE(4, it, 1);
       mbar_wait(&c1_empty[bi], (n & 1u) ^ 1u);
+      CONV_TRACE(4, it, 2);
       tc_fence_after();
       const uint32_t dcol = tmem_base + (uint32_t)(bi * 128);
       // a_hi . [w_hi | w_lo] as ONE N = 96 UMMA chain (the 16 KB a_hi tile is read once), then in F2 a_lo . w_hi on
@@ -482,6 +503,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       }
       tc_commit(&tile_empty[bi]);
       tc_commit(&c1_full[bi]);
+      CONV_TRACE(4, it, 3);
     }
   } else if (MODE == MODE_APPLY && warp == F_CTRL_B && lane == 0) {
     // =============================== control B: weight TMA + spatial UMMAs ===============================
@@ -502,9 +524,12 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     for (int it = 0; it < total_it; ++it) {
       const FwdIt d = fwd_decode(it, p.B);
       const int bi = it & 1, wi = it & (WS_RING - 1), ib = d.item_local & 1;
+      CONV_TRACE(5, it, 0);
       if (d.l == 0) mbar_wait(&y2_empty[ib], ((uint32_t)(d.item_local >> 1) & 1u) ^ 1u);   // Y2[ib] drained (item - 2)
       mbar_wait(&a1_full[bi], (uint32_t)(it >> 1) & 1u);
+      CONV_TRACE(5, it, 1);
       mbar_wait(&ws_full[wi], (uint32_t)(it / WS_RING) & 1u);
+      CONV_TRACE(5, it, 2);
       tc_fence_after();
       const uint32_t dcol = tmem_base + 256u + (uint32_t)(ib * 64);
 #pragma unroll
@@ -515,6 +540,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       tc_commit(&a1_empty[bi]);
       tc_commit(&ws_empty[wi]);
       if (d.l == F_LEN - 1) tc_commit(&y2_full[ib]);
+      CONV_TRACE(5, it, 3);
       if (it + 3 < total_it) load_ws(it + 3);            // its ring slot was released by the UMMAs of iteration it-1
     }
   }
@@ -578,14 +604,6 @@ template <int MODE> struct BwdMisc {
 constexpr uint32_t B1_SMEM = O1_MISC + BwdMisc<MODE_BSTATS>::END + 1024;
 constexpr uint32_t B2_SMEM = O2_MISC + BwdMisc<MODE_BAPPLY>::END + 1024;
 static_assert(B1_SMEM <= 227 * 1024 && B2_SMEM <= 227 * 1024, "conv backward kernels exceed the shared memory of an SM");
-
-// optional cycle trace of CTA 0 (EEGB200_CONV_TRACE=<dir>): trace[(role * TRACE_IT + it) * 8 + event] = clock64()
-constexpr int TRACE_IT = 96, TRACE_ROLES = 8;
-#define CONV_TRACE(role, it, ev)                                                                      \
-  do {                                                                                                \
-    if (p.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_IT)                                     \
-      p.trace[((role) * TRACE_IT + (it)) * 8 + (ev)] = clock64();                                     \
-  } while (0)
 
 struct ConvBwdParams {
   const float* x3;          // [B*64, 256]
@@ -1194,48 +1212,6 @@ int conv_tc_enabled() {
 }
 size_t conv_tc_ws_floats() { return (size_t)FWD_PACK_FLOATS + WST_MAIN_FLOATS + WST_TAIL_FLOATS; }
 
-// BatchNorm1 batch statistics of the temporal conv output without materialising it (kernel F1)
-int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s) {
-  ProfScope _ps("conv_tc_stats", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * 63 * 1000.0);
-  static PerDeviceOnce once;
-  if (once.first())
-    EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-  const int n_tiles = cdiv(B, TILE_S);
-  ConvTcParams p{x3, wt, bt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, n_tiles};
-  CUtensorMap dummy;
-  memset(&dummy, 0, sizeof(dummy));
-  const int grid = min(sm_count(), n_tiles * F_PARTS);
-  conv_tc_fwd_kernel<MODE_STATS><<<grid, F_THREADS, CTC_SMEM, s>>>(dummy, p);
-  EEG_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
-// temporal conv + pool + BatchNorm1 + ELU + spatial conv in one kernel (kernel F2); y1 / a1 (debug stores) may be nullptr
-int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
-                  const float* beta, const float* ws, const float* bs, float* ws_packed, float* y1, float* a1, float* y2,
-                  int B, cudaStream_t s) {
-  ProfScope _ps("conv_tc_apply", s, (double)B * 36 * (63 * 40 * 50.0 + 2520 * 80.0),
-                (double)B * (63 * 1000.0 + 36 * 160.0 + ((y1 ? 1 : 0) + (a1 ? 1 : 0)) * 36 * 2520 * 4.0));
-  pack_ws_tc_kernel<<<cdiv(N_CH * N48 * 64, 256), 256, 0, s>>>(ws, ws_packed);
-  EEG_CUDA_OK(cudaGetLastError());
-  count_launch();
-  EEG_CUDA_OK(cudaMemsetAsync(y2, 0, (size_t)B * N_POOL * N_FILT * sizeof(float), s));   // the items add their shares
-  CUtensorMap tw;
-  int d3 = 0;
-  EEG_TRY(gemm_make_tmap(&tw, GemmOperand{ws_packed, 64, 0}, N_CH * N48, 64, N48, &d3));
-  static PerDeviceOnce once;
-  if (once.first())
-    EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
-  const int n_tiles = cdiv(B, TILE_S);
-  ConvTcParams p{x3, wt, bt, mean_rstd, gamma, beta, bs, y1, a1, y2, nullptr, B, n_tiles};
-  const int grid = min(sm_count(), n_tiles * F_PARTS);
-  conv_tc_fwd_kernel<MODE_APPLY><<<grid, F_THREADS, CTC_SMEM, s>>>(tw, p);
-  EEG_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 // EEGB200_CONV_TRACE=<dir>: CTA 0 of the backward kernels records clock64() at every handshake; dumped after the launch
 static int trace_dump(const char* name, long long* dev, cudaStream_t s) {
   const char* dir = getenv("EEGB200_CONV_TRACE");
@@ -1256,6 +1232,50 @@ static long long* trace_buffer(cudaStream_t s) {
   if (!buf && cudaMalloc(&buf, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
   cudaMemsetAsync(buf, 0, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long), s);
   return buf;
+}
+
+// BatchNorm1 batch statistics of the temporal conv output without materialising it (kernel F1)
+int conv_tc_stats(const float* x3, const float* wt, const float* bt, double* sums, int B, cudaStream_t s) {
+  ProfScope _ps("conv_tc_stats", s, (double)B * 63 * 36 * 40 * 50.0, (double)B * 63 * 1000.0);
+  static PerDeviceOnce once;
+  if (once.first())
+    EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
+  const int n_tiles = cdiv(B, TILE_S);
+  ConvTcParams p{x3, wt, bt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, B, n_tiles, trace_buffer(s)};
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  const int grid = min(sm_count(), n_tiles * F_PARTS);
+  conv_tc_fwd_kernel<MODE_STATS><<<grid, F_THREADS, CTC_SMEM, s>>>(dummy, p);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  if (p.trace) EEG_TRY(trace_dump("fwd_stats", p.trace, s));
+  return 0;
+}
+
+// temporal conv + pool + BatchNorm1 + ELU + spatial conv in one kernel (kernel F2); y1 / a1 (debug stores) may be nullptr
+int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float* mean_rstd, const float* gamma,
+                  const float* beta, const float* ws, const float* bs, float* ws_packed, float* y1, float* a1, float* y2,
+                  int B, cudaStream_t s) {
+  ProfScope _ps("conv_tc_apply", s, (double)B * 36 * (63 * 40 * 50.0 + 2520 * 80.0),
+                (double)B * (63 * 1000.0 + 36 * 160.0 + ((y1 ? 1 : 0) + (a1 ? 1 : 0)) * 36 * 2520 * 4.0));
+  pack_ws_tc_kernel<<<cdiv(N_CH * N48 * 64, 256), 256, 0, s>>>(ws, ws_packed);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  EEG_CUDA_OK(cudaMemsetAsync(y2, 0, (size_t)B * N_POOL * N_FILT * sizeof(float), s));   // the items add their shares
+  CUtensorMap tw;
+  int d3 = 0;
+  EEG_TRY(gemm_make_tmap(&tw, GemmOperand{ws_packed, 64, 0}, N_CH * N48, 64, N48, &d3));
+  static PerDeviceOnce once;
+  if (once.first())
+    EEG_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<MODE_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CTC_SMEM));
+  const int n_tiles = cdiv(B, TILE_S);
+  ConvTcParams p{x3, wt, bt, mean_rstd, gamma, beta, bs, y1, a1, y2, nullptr, B, n_tiles, trace_buffer(s)};
+  const int grid = min(sm_count(), n_tiles * F_PARTS);
+  conv_tc_fwd_kernel<MODE_APPLY><<<grid, F_THREADS, CTC_SMEM, s>>>(tw, p);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  if (p.trace) EEG_TRY(trace_dump("fwd_apply", p.trace, s));
+  return 0;
 }
 
 static int bwd_launch(int mode, const ConvBwdParams& p_in, float* wst_packed, const float* ws_to_pack, cudaStream_t s) {

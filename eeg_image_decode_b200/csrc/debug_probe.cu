@@ -123,6 +123,7 @@ __global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int bg, long
         tc_mma_tf32(d, ad[1], bd[1], idesc, 1u);
         tc_mma_tf32(d, ad[2], bd[2], idesc, 1u);
         tc_mma_tf32(d, ad[3], bd[3], idesc, 1u);
+        if (bg & 8) tc_commit(&bar[1 - warp]);         // a tcgen05.commit after every 4 UMMAs (nobody waits on it)
       }
       const long long t1 = clock64();
       tc_commit(&bar[warp]);
@@ -137,6 +138,13 @@ __global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int bg, long
     while (!*stop && it < (1 << 22)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) dst[(j & 3) * 256] = make_float4((float)it, 0.f, 0.f, 0.f);
+      ++it;
+    }
+  } else if (warp >= 4 && warp < 16 && (bg & 16)) {
+    // background mbarrier polling: 12 warps spin on a barrier phase that never completes (what waiting roles do)
+    int it = 0;
+    while (!*stop && it < (1 << 22)) {
+      (void)mbar_try_wait(&bar[1], 0);
       ++it;
     }
   } else if (warp >= 12 && warp < 16 && (bg & 4)) {
@@ -188,7 +196,7 @@ extern "C" int eegb200_debug_umma_m64(float* out128, void* stream) {
 }
 
 extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int bg, long long* out2, void* stream) {
-  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && bg >= 0 && bg < 8 && (!mn_major || N <= 128),
+  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && bg >= 0 && bg < 32 && (!mn_major || N <= 128),
               "debug_umma_cost: bad arguments");
   static PerDeviceOnce once;
   if (once.first())

@@ -15,7 +15,7 @@ EV = {
 
 
 def main(d):
-    for kern in ("bwd_stats", "bwd_apply"):
+    for kern in ("fwd_stats", "fwd_apply", "bwd_stats", "bwd_apply"):
         try:
             raw = open(f"{d}/conv_trace_{kern}.bin", "rb").read()
         except FileNotFoundError:

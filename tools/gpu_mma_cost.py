@@ -13,12 +13,12 @@ from eeg_image_decode_b200 import _lib  # noqa: E402
 L = _lib.lib()
 L.eegb200_debug_umma_cost.argtypes = [ctypes.c_int] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-BG = {0: "alone", 1: "+smem stores", 2: "+2nd issuer", 4: "+tcgen05.ld", 7: "+all three"}
+BG = {0: "alone", 1: "+smem stores", 2: "+2nd issuer", 4: "+tcgen05.ld", 7: "+all three", 8: "+commit/4 MMAs", 16: "+12 warps polling", 17: "+polling+stores"}
 print("M    N  major  background       cycles/MMA (complete)  (issue)   floor N/2")
-for mn in (0, 1):
+for mn in (0,):
     for M in (128, 64):
-        for N in (32, 48, 96, 128):
-            for bg in (0, 1, 2, 4, 7):
+        for N in (48, 96):
+            for bg in (0, 16, 17):
                 for rep in range(2):
                     _lib.check(L.eegb200_debug_umma_cost(M, N, mn, 512, bg, _lib.ptr(out), _lib.stream_ptr()), "umma_cost")
                     torch.cuda.synchronize()
