@@ -18,6 +18,8 @@ LIB = os.path.join(LIBDIR, "libeegdecode_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+if os.environ.get("EEGB200_BUILD_TRACE", "0") not in ("", "0"):
+    FLAGS.append("-DEEGB200_CONV_TRACE_BUILD")      # clock64() handshake trace inside csrc/conv_tc.cu (tools/conv_trace_report.py)
 
 
 def _sources():

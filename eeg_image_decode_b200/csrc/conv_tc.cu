@@ -46,7 +46,8 @@ constexpr int WS_RING = 4;
 constexpr int F_PARTS = 3, F_LEN = 21;            // forward work item = (tile, 21 of the 63 channels)
 constexpr int GC = 4, N_GROUPS = 16;              // backward: channel groups of 4 (the last one has 3)
 constexpr uint32_t PS_LD = 208, CSX_LD = 296;        // CSX_LD >= csi(256) + 1 = 289
-constexpr uint32_t SCAN_BYTES = (3 * PS_LD + 3 * CSX_LD) * 4;   // pooled sums [3][208] + scan scratch [3][264] floats
+constexpr uint32_t POOL_BYTES = 3 * PS_LD * 4;                  // pooled sums [3][208] floats of one builder group
+constexpr uint32_t SCAN_BYTES = (3 * PS_LD + 3 * CSX_LD) * 4;   // B2 scatter warps: d pooled sums [3][208] + prefix scratch [3][296]
 constexpr int N_BUILD_WARPS = 8, N_EPI_WARPS = 16;
 constexpr int EPI_WARP0 = N_BUILD_WARPS, EPI_THREAD0 = EPI_WARP0 * 32;
 
@@ -139,12 +140,19 @@ __device__ __forceinline__ void tmem_ld10_nw(uint32_t taddr_col0, int cq, float*
 // 16-byte-granular start-address field (no carry: every tile lives below 256 KB)
 __device__ __forceinline__ uint64_t desc_k(uint32_t addr) { return umma_smem_desc(addr, 16, 1024, UMMA_LAYOUT_SW128); }
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_desc(addr, 128 * 128, 512, UMMA_LAYOUT_SW128_BASE32B); }
+// MN-major operand whose second 32-wide slab lives `slab_stride` bytes after the first (the leading-dimension byte offset)
+__device__ __forceinline__ uint64_t desc_mn_split(uint32_t addr, uint32_t slab_stride) {
+  return umma_smem_desc(addr, slab_stride, 512, UMMA_LAYOUT_SW128_BASE32B);
+}
 __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// box-51 pooled sums of one token row (8 floats per lane): C[k] = sum of the first k samples, ps[u] = C[u+51] - C[u].
-// C[k] lives at cs[k + (k >> 3)]: the per-lane stride-8 stores would otherwise hit 4 banks (8-way conflicts)
+// padded index of the B2 scatter warps' prefix array: per-lane stride-8 stores would otherwise hit 4 banks (8-way conflicts)
 __device__ __forceinline__ int csi(int k) { return k + (k >> 3); }
-__device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int lane, float* cs, float* ps) {
+// box-51 pooled sums of one token row (8 samples per lane), entirely in registers: I[k] = inclusive prefix sum of the
+// row, ps[u] = I[u+50] - I[u-1].  For u = 8*lane + i the upper term sits 50 = 6*8 + 2 samples ahead: slot i+2 of lane+6
+// (i < 6) or slot i-6 of lane+7; the lower term is the lane's own slot i-1 (its exclusive prefix for i = 0).  Lanes
+// 0..24 hold the 200 pooled sums and store them as two float4.
+__device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int lane, float* ps) {
   float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
   for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
@@ -156,15 +164,17 @@ __device__ __forceinline__ void pool_row(const float4 x0, const float4 x1, int l
     if (lane >= o) inc += nb;
   }
   const float excl = inc - tot;
-  cs[9 * lane] = excl;                                 // csi(8*lane + i) = 9*lane + i for i < 8
 #pragma unroll
-  for (int i = 0; i < 7; ++i) cs[9 * lane + 1 + i] = v[i] + excl;
-  if (lane == 31) cs[csi(256)] = inc;
-  __syncwarp();
+  for (int i = 0; i < 8; ++i) v[i] += excl;
+  float o8[8];
 #pragma unroll
-  for (int q = 0; q < 7; ++q) {
-    const int u = lane + 32 * q;
-    if (u < N_PSUM) ps[u] = cs[csi(u + K_POOL)] - cs[csi(u)];
+  for (int i = 0; i < 8; ++i) {
+    const float up = i < 6 ? __shfl_down_sync(0xffffffffu, v[i + 2], 6) : __shfl_down_sync(0xffffffffu, v[i - 6], 7);
+    o8[i] = up - (i == 0 ? excl : v[i - 1]);
+  }
+  if (lane < N_PSUM / 8) {
+    *reinterpret_cast<float4*>(ps + 8 * lane) = make_float4(o8[0], o8[1], o8[2], o8[3]);
+    *reinterpret_cast<float4*>(ps + 8 * lane + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
   }
 }
 
@@ -177,8 +187,8 @@ constexpr uint32_t OFF_IM = 0;                              // [2 buf][hi, lo] x
 constexpr uint32_t OFF_BC = OFF_IM + 4 * KB_A;              // conv weights [w_hi (48 rows) | w_lo (48 rows)] x 32: 12 KB, one N = 96 operand
 constexpr uint32_t OFF_A1 = OFF_BC + 2 * KB_48;             // [2 buf][2 k-blocks] x 16 KB
 constexpr uint32_t OFF_WS = OFF_A1 + 4 * KB_A;              // [4 ring][2 k-blocks] x 6 KB
-constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // scan scratch of the two builder groups
-constexpr uint32_t OFF_TAB = OFF_PS + 2 * SCAN_BYTES;       // BN scale / folded shift / conv bias tables [3][48] floats
+constexpr uint32_t OFF_PS = OFF_WS + WS_RING * 2 * KB_48;   // pooled sums of the two builder groups
+constexpr uint32_t OFF_TAB = OFF_PS + 2 * POOL_BYTES;       // BN scale / folded shift / conv bias tables [3][48] floats
 constexpr uint32_t OFF_RED = OFF_TAB + 3 * 48 * 4;          // statistics reduction [2][40] floats
 constexpr uint32_t OFF_BAR = (OFF_RED + 80 * 4 + 7) & ~7u;  // mbarriers
 constexpr int N_BARS = 6 * 2 + 2 * WS_RING + 2 * 2;
@@ -187,13 +197,19 @@ constexpr uint32_t CTC_SMEM = OFF_TMEM + 16 + 1024;         // + alignment slack
 static_assert(OFF_BC % 1024 == 0 && OFF_A1 % 1024 == 0 && OFF_WS % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 static_assert(CTC_SMEM <= 227 * 1024, "conv forward kernel exceeds the shared memory of an SM");
 
-// optional cycle trace of CTA 0 (EEGB200_CONV_TRACE=<dir>): trace[(role * TRACE_IT + it) * 8 + event] = clock64()
+// optional cycle trace of CTA 0: trace[(role * TRACE_IT + it) * 8 + event] = clock64().  Compiled in only when the library
+// is built with EEGB200_BUILD_TRACE=1 (-DEEGB200_CONV_TRACE_BUILD; the checks cost ~10 % of the epilogue's instructions);
+// at run time EEGB200_CONV_TRACE=<dir> then switches it on and names the dump directory (tools/conv_trace_report.py)
 constexpr int TRACE_IT = 96, TRACE_ROLES = 8;
+#ifdef EEGB200_CONV_TRACE_BUILD
 #define CONV_TRACE(role, it, ev)                                                                      \
   do {                                                                                                \
     if (p.trace != nullptr && blockIdx.x == 0 && (it) < TRACE_IT)                                     \
       p.trace[((role) * TRACE_IT + (it)) * 8 + (ev)] = clock64();                                     \
   } while (0)
+#else
+#define CONV_TRACE(role, it, ev) do { } while (0)
+#endif
 
 enum { MODE_STATS = 0, MODE_APPLY = 1 };
 
@@ -314,8 +330,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     const int gb = warp >> 2, rq = warp & 3;
     const int r = rq * 32 + lane;                      // tile row 0..127
     const int s_row = r / N_POOL, p_row = r % N_POOL;
-    float* ps_all = reinterpret_cast<float*>(sm + OFF_PS + (uint32_t)gb * SCAN_BYTES);
-    float* cs_all = ps_all + 3 * PS_LD;
+    float* ps_all = reinterpret_cast<float*>(sm + OFF_PS + (uint32_t)gb * POOL_BYTES);
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
     auto fetch = [&](int it) {                          // token row of (sample rq of the tile, channel) for iteration it
       if (it < total_it && rq < TILE_S) {
@@ -336,7 +351,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
       const float4 x0 = xa, x1 = xb;
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 0);
       fetch(it + 2);                                    // the group's next row travels while this one is processed
-      if (rq < d.ns) pool_row(x0, x1, lane, cs_all + rq * CSX_LD, ps_all + rq * PS_LD);
+      if (rq < d.ns) pool_row(x0, x1, lane, ps_all + rq * PS_LD);
       named_bar_sync(1 + gb, 128);
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 1);
       mbar_wait(&tile_empty[bi], (n & 1u) ^ 1u);          // conv UMMAs of iteration it-2 have consumed this buffer
@@ -570,30 +585,40 @@ constexpr uint32_t WST_MAIN_FLOATS = N_GROUPS * GC * N48 * 32;   // [c (64 slots
 constexpr uint32_t WST_TAIL_FLOATS = N_GROUPS * N48 * 32;        // [g][48 rows k][8 ci + (j - 32)]
 // shared-memory map (common part)
 constexpr uint32_t OB_IMK = 0;                               // [2] x 16 KB   im2col, K-major (TF32)
-constexpr uint32_t OB_BC = OB_IMK + 2 * KB_A;                // 6 KB          conv weights / 51, K-major
-constexpr uint32_t OB_DYK = OB_BC + KB_48;                   // [2] x 16 KB   dY2 tile columns 0..31, K-major
+constexpr uint32_t OB_DYK = OB_IMK + 2 * KB_A;               // [2] x 16 KB   dY2 tile columns 0..31, K-major
 constexpr uint32_t OB_TAIL = OB_DYK + 2 * KB_A;              // 16 KB         shared tail k-block, one 8-column k-step each:
                                                              //   kk = 0, 1: dY2 columns 32..39 of tile buffer 0, 1; kk = 2: dy tail
+                                                             //   (B2); kk = 3, rows 0..31: wt^T columns 32..39 (B2)
 constexpr uint32_t OB_WST = OB_TAIL + KB_A;                  // [4] x 6 KB    Ws_c^T of the group's channels: rows k, columns j 0..31
 constexpr uint32_t OB_WSTT = OB_WST + GC * KB_48;            // 6 KB          their tails (j 32..39), k-step ci
 constexpr uint32_t OB_MODE = OB_WSTT + KB_48;                // mode-specific tiles from here
-static_assert(OB_BC % 1024 == 0 && OB_DYK % 1024 == 0 && OB_TAIL % 1024 == 0 && OB_WST % 1024 == 0 &&
+static_assert(OB_DYK % 1024 == 0 && OB_TAIL % 1024 == 0 && OB_WST % 1024 == 0 &&
               OB_WSTT % 1024 == 0 && OB_MODE % 1024 == 0, "swizzled tiles need 1024-byte alignment");
-// B1: dY2 MN-major [2 slabs] (single buffered), a1 MN-major [2][2 slabs]
-constexpr uint32_t O1_DYM = OB_MODE;                         // 32 KB  (the M = 128 A operand of the dWs UMMA reads two
-constexpr uint32_t O1_A1M = O1_DYM + 2 * SLAB;               // [2] x 32 KB   slabs past DYM: A1M[0], inside the allocation)
-constexpr uint32_t O1_MISC = O1_A1M + 4 * SLAB;
+// B1: the two MN-major operands of the dWs UMMA, both double buffered.  Each has 40 useful mn columns = one full slab
+// (0..31) + 8 columns of a second slab, and a slab spends only one 32-byte chunk per 128-byte row on 8 columns -- so the
+// second slabs are SHARED: tail slab T[x] holds dY2 columns 32..39 of DYM[x] in chunk 0 (mn 0..7) and a1 columns 32..39
+// of A1M[x] in chunk 1 (mn 8..15).  What an operand reads from the other's chunk only reaches accumulator rows (A: j
+// 40..47) or columns (B: 32..39) nobody reads; the a1 tail therefore lands in accumulator columns 40..47.
+// Both modes start with the conv weights, K-major, ONE operand with the BatchNorm affine maps folded in (setup code):
+// rows 0..47 -> z; rows 48..95 -> B1: yhat, B2: hi part of Bc*y + Cc; B2 only, rows 96..143 -> its lo part
+constexpr uint32_t O1_BC = OB_MODE;                          // 12 KB
+constexpr uint32_t O1_DYM = O1_BC + 2 * KB_48;               // [2] x 16 KB  dY2 columns 0..31
+constexpr uint32_t O1_A1M = O1_DYM + 2 * SLAB;               // [2] x 16 KB  a1 columns 0..31
+constexpr uint32_t O1_TAILS = O1_A1M + 2 * SLAB;             // [2] x 16 KB  shared tail slabs
+constexpr uint32_t O1_MISC = O1_TAILS + 2 * SLAB;
 // B2: dy MN-major [2 slabs], im2col MN-major [2][1 slab], dy K-major main, wt^T
-constexpr uint32_t O2_DYM = OB_MODE;                         // 32 KB (+ 2 don't-care slabs = the IMM tiles behind it)
+constexpr uint32_t O2_BC = OB_MODE;                          // 18 KB
+constexpr uint32_t O2_DYM = O2_BC + 3 * KB_48;               // 32 KB (+ 2 don't-care slabs = the IMM tiles behind it)
 constexpr uint32_t O2_IMM = O2_DYM + 2 * SLAB;               // [2] x 16 KB
 constexpr uint32_t O2_DYK2 = O2_IMM + 2 * SLAB;              // 16 KB
-constexpr uint32_t O2_WTT = O2_DYK2 + KB_A;                  // 8 KB: [32 rows t][32 floats k 0..31] + tail block (k 32..39)
-constexpr uint32_t O2_MISC = O2_WTT + 2 * KB_32;
+constexpr uint32_t O2_WTT = O2_DYK2 + KB_A;                  // 4 KB: wt^T [32 rows t][32 floats k 0..31]; k 32..39 live in OB_TAIL
+constexpr uint32_t O2_MISC = O2_WTT + KB_32;
+static_assert(O1_DYM % 1024 == 0 && O2_DYM % 1024 == 0 && O2_WTT % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 // misc area: scan scratch of the two builder groups, (B2) dps / csd of the scatter warps, tables [5][48], red [80],
 // barriers, tmem slot
 constexpr uint32_t M_PS = 0;
-constexpr uint32_t M_DPS = M_PS + 2 * SCAN_BYTES;
-constexpr int NB_BARS = 8 * 2 + 1 + 2 + 2 * 2 + 2;
+constexpr uint32_t M_DPS = M_PS + 2 * POOL_BYTES;
+constexpr int NB_BARS = 8 * 2 + 1 + 2 * 2 + 2 * 2 + 2;
 template <int MODE> struct BwdMisc {
   static constexpr uint32_t TAB = M_DPS + (MODE == MODE_BAPPLY ? SCAN_BYTES : 0u);
   static constexpr uint32_t RED = TAB + 5 * 48 * 4;
@@ -630,7 +655,7 @@ struct ConvBwdParams {
 struct BwdIt { int tl, ci, c, tile, ns; };
 __device__ __forceinline__ BwdIt bwd_decode(int it, int gc, int g, int slot, int n_slots, int B) {
   BwdIt d;
-  d.tl = it / gc;
+  d.tl = gc == GC ? it >> 2 : it / 3;               // gc is 4, or 3 for the last channel group
   d.ci = it - d.tl * gc;
   d.c = g * GC + d.ci;
   d.tile = slot + d.tl * n_slots;
@@ -645,6 +670,11 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   constexpr int NTHREADS = BS ? B1_THREADS : B2_THREADS;
   constexpr int CTRL_A = BS ? SCAT_WARP0 : SCAT_WARP0 + 4, CTRL_B = CTRL_A + 1;
   constexpr uint32_t O_MISC = BS ? O1_MISC : O2_MISC;
+  constexpr uint32_t O_BC = BS ? O1_BC : O2_BC;
+  // TMEM columns.  Y[2] = the folded conv product (B1: z | yhat = 96 columns, B2: z | lin_hi | lin_lo = 144), DA[2] = dA1
+  // (48), then B1: dWs[ci] (48 each);  B2: G[2] (32 each), dwt (32)
+  constexpr uint32_t Y_COLS = BS ? 96u : 144u, T_DA = 2 * Y_COLS, T_ACC = T_DA + 96u, T_DWT = T_ACC + 64u;
+  static_assert(BS ? T_ACC + 4 * 48 <= 512 : T_DWT + 32 <= 512, "TMEM columns");
   using MM = BwdMisc<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -663,12 +693,12 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   uint64_t* op_empty = bars + 14;        // [2] second-stage UMMAs reading it done -> epilogue.  B1: a1 buffer [bi] is free again;
                                          //     B2 (ONE dy buffer): [g] = the UMMAs of the iteration before one of group g completed
   uint64_t* wst_full = bars + 16;        // [1] the group's packed weights have landed (TMA, once)
-  uint64_t* dym_full = bars + 17;        // B1: builders wrote the MN-major dY2 tile -> control B
-  uint64_t* dym_empty = bars + 18;       // B1: last dWs UMMA of the tile -> builders
-  uint64_t* gg_full = bars + 19;         // [2] B2: G UMMAs done -> scatter warps
-  uint64_t* gg_empty = bars + 21;        // [2] B2: scatter warps read TMEM -> control B (4 arrivals)
-  uint64_t* final_a = bars + 23;         // everything issued by control A has completed
-  uint64_t* final_b = bars + 24;         // ... by control B
+  uint64_t* dym_full = bars + 17;        // [2] B1: builders wrote the MN-major dY2 tile (buffer tl & 1) -> control B
+  uint64_t* dym_empty = bars + 19;       // [2] B1: last dWs UMMA of the tile -> builders
+  uint64_t* gg_full = bars + 21;         // [2] B2: G UMMAs done -> scatter warps
+  uint64_t* gg_empty = bars + 23;        // [2] B2: scatter warps read TMEM -> control B (4 arrivals)
+  uint64_t* final_a = bars + 25;         // everything issued by control A has completed
+  uint64_t* final_b = bars + 26;         // ... by control B
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + MM::TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -690,10 +720,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_init(&op_empty[i], 1);
       mbar_init(&gg_full[i], 1);
       mbar_init(&gg_empty[i], 4);
+      mbar_init(&dym_full[i], 1);
+      mbar_init(&dym_empty[i], 1);
     }
     mbar_init(wst_full, 1);
-    mbar_init(dym_full, 1);
-    mbar_init(dym_empty, 1);
     mbar_init(final_a, 1);
     mbar_init(final_b, 1);
     mbar_fence_init();
@@ -703,23 +733,6 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   // zero every operand tile and the scan scratch once: pad columns / rows that are never written must be finite zeros
   for (uint32_t i = threadIdx.x * 16; i < O_MISC + MM::TAB; i += NTHREADS * 16)
     *reinterpret_cast<float4*>(sm + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  // conv weights / 51 (TF32) as the B operand of the conv UMMA: rows k < 40 (48), columns t < 25 (32)
-  for (int i = threadIdx.x; i < N48 * 32; i += NTHREADS) {
-    const int k = i >> 5, t = i & 31;
-    const float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
-    *reinterpret_cast<float*>(sm + OB_BC + sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u) = tf32_fast(w);
-  }
-  if (!BS) {
-    // wt^T (unscaled) as the B operand of the G UMMA: rows t < 25 (32), columns k: 0..31 main block, 32..39 tail block
-    for (int i = threadIdx.x; i < 32 * N_FILT; i += NTHREADS) {
-      const int t = i / N_FILT, k = i - t * N_FILT;
-      const float w = t < K_TEMP ? tf32_fast(p.wt[k * K_TEMP + t]) : 0.f;
-      const uint32_t blk = k < 32 ? 0u : KB_32;
-      const int kc = k & 31;
-      *reinterpret_cast<float*>(sm + O2_WTT + blk + sw128_off(t, kc >> 2) + (uint32_t)(kc & 3) * 4u) = w;
-    }
-  }
   if (threadIdx.x < N48) {
     const int k = threadIdx.x;
     float bt = 0.f, sc = 0.f, sh = 0.f, p1 = 0.f, p2 = 0.f;
@@ -737,11 +750,45 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         p1 = -sc * rs * m2;                          // Bc
         p2 = sc * (mu * rs * m2 - m1);               // Cc
       }
-      // the epilogue works on the raw accumulator y_raw = y - bt: fold the conv bias into the additive constants
+      // the UMMA delivers y_raw = y - bt: fold the conv bias into the additive constants
       sh += sc * bt;
       p2 += p1 * bt;
     }
     tab[k] = bt; tab[48 + k] = sc; tab[96 + k] = sh; tab[144 + k] = p1; tab[192 + k] = p2;
+  }
+  __syncthreads();
+  // B operand of the conv UMMA, N = 96, with both affine maps of the epilogue folded in: the im2col rows carry two ones
+  // columns (t = 25, 26, zero for rows past the batch), so
+  //   rows k      : [sc_k * wt[k,:] / 51 | hi(sh_k) | lo(sh_k)]   ->  accumulator column k      = z = sc*y + sh
+  //   rows 48 + k : [p1_k * wt[k,:] / 51 | hi(p2_k) | lo(p2_k)]   ->  accumulator column 48 + k = yhat (B1) / Bc*y + Cc (B2)
+  //   rows 96 + k : B2 only, the TF32 remainder of p1_k * wt[k,:] / 51: dy = A*dz + Bc*y + Cc sums to zero over the batch
+  //                 by cancellation (that IS the conv-bias gradient) and feeds dwt, so Bc*y keeps fp32-level accuracy
+  // (constants as a TF32 hi + lo pair: exact to 2^-22).  The epilogue reads both straight from TMEM: no per-column
+  // constants, no FMAs, and rows past the batch come out as exact zeros (no masks).
+  for (int i = threadIdx.x; i < (BS ? 2 : 3) * N48 * 32; i += NTHREADS) {
+    const int blk = i / (N48 * 32), k = (i >> 5) % N48, t = i & 31;
+    const float mul = tab[(blk ? 144 : 48) + k], add = tab[(blk ? 192 : 96) + k];
+    float w = 0.f;
+    if (k < N_FILT) {
+      if (t < K_TEMP) {
+        const float full = mul * p.wt[k * K_TEMP + t] * (1.f / K_POOL);
+        w = blk < 2 ? tf32_fast(full) : tf32_fast(full - tf32_fast(full));      // B2 block 2: the lo part of Bc * wt / 51
+      } else if (blk < 2) {
+        if (t == K_TEMP) w = tf32_fast(add);
+        else if (t == K_TEMP + 1) w = tf32_fast(add - tf32_fast(add));
+      }
+    }
+    *reinterpret_cast<float*>(sm + O_BC + (uint32_t)blk * KB_48 + sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u) = w;
+  }
+  if (!BS) {
+    // wt^T (unscaled) as the B operand of the G UMMA: rows t < 25 (32), columns k: 0..31 main block, 32..39 tail block
+    for (int i = threadIdx.x; i < 32 * N_FILT; i += NTHREADS) {
+      const int t = i / N_FILT, k = i - t * N_FILT;
+      const float w = t < K_TEMP ? tf32_fast(p.wt[k * K_TEMP + t]) : 0.f;
+      const int kc = k & 31;
+      uint8_t* dst = k < 32 ? sm + O2_WTT + sw128_off(t, kc >> 2) : sm + OB_TAIL + sw128_off(t, 6 + (kc >> 2));
+      *reinterpret_cast<float*>(dst + (uint32_t)(kc & 3) * 4u) = w;
+    }
   }
   if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
   if (!BS && blockIdx.x == 0 && threadIdx.x < N_FILT) {
@@ -750,7 +797,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     atomicAdd(&p.dbeta[threadIdx.x], p.gscale * (float)p.bsums[threadIdx.x]);
   }
   if (warp == CTRL_A) {
-    tmem_alloc(tmem_slot, 512);   // Y[2]: 0, 64; DA[2]: 128, 192; B1: dWs[4] at 256 + 64 ci; B2: G[2] at 256, 288, dwt at 320
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   fence_proxy_async_smem();
@@ -764,8 +811,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     const int gb = warp >> 2, rq = warp & 3;
     const int r = rq * 32 + lane;                      // tile row 0..127
     const int s_row = r / N_POOL, p_row = r % N_POOL;
-    float* ps_all = reinterpret_cast<float*>(misc + M_PS + (uint32_t)gb * SCAN_BYTES);
-    float* cs_all = ps_all + 3 * PS_LD;
+    float* ps_all = reinterpret_cast<float*>(misc + M_PS + (uint32_t)gb * POOL_BYTES);
     float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
     auto fetch_x = [&](int it) {
       if (it < total_it && rq < TILE_S) {
@@ -812,7 +858,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 0);
       fetch_x(it + 2);
       if (d.ci == gc - 1 && d.tl + 1 < n_my_tiles) { stage_dyk(d.tl + 1); pending_dyk = (d.tl + 1) & 1; }
-      if (rq < d.ns) pool_row(x0, x1, lane, cs_all + rq * CSX_LD, ps_all + rq * PS_LD);
+      if (rq < d.ns) pool_row(x0, x1, lane, ps_all + rq * PS_LD);
       named_bar_sync(1 + gb, 128);                        // pooled sums visible
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 1);
       mbar_wait(&im_empty[bi], (n & 1u) ^ 1u);
@@ -822,14 +868,14 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         float a[28];
 #pragma unroll
         for (int t = 0; t < 28; ++t) a[t] = (valid && t < K_TEMP) ? tf32_fast(src[t]) : 0.f;
+        a[K_TEMP] = a[K_TEMP + 1] = valid ? 1.f : 0.f;   // the ones columns that carry the folded affine constants
         uint8_t* kt = sm + OB_IMK + (uint32_t)bi * KB_A;
 #pragma unroll
         for (int ch = 0; ch < 7; ++ch)
           *reinterpret_cast<float4*>(kt + sw128_off(r, ch)) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
         if (!BS) {
           // the same row as k-row r of the MN-major operand (mn = tap t); column 25 = 1 for valid rows: the dwt UMMA
-          // then also delivers sum_rows dy (the conv bias gradient) in output column 25
-          a[25] = valid ? 1.f : 0.f;
+          // then also delivers sum_rows dy (the conv bias gradient) in output column 25 (and again in 26, unread)
           uint8_t* mt = sm + O2_IMM + (uint32_t)bi * SLAB;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8)
@@ -847,16 +893,17 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       }
       pending_dyk = -1;
       if (BS && gb == 0 && d.ci < 2) {
-        // ---- MN-major copy of this tile's dY2 rows for the dWs UMMA (single buffered): the last dWs UMMA of the previous
-        //      tile must be done; the rows are L2-hot (the K-major staging read them one tile earlier).  ALWAYS group 0, at
-        //      its first iteration inside the tile (ci 0, or 1 when the tile starts on an odd iteration): parity waits are
-        //      only sound when one agent walks the phases in order (tools/conv_tc_protocol_sim.py) ----
-        mbar_wait(dym_empty, ((uint32_t)d.tl & 1u) ^ 1u);
+        // ---- MN-major copy of this tile's dY2 rows for the dWs UMMA, double buffered like the K-major tile it is copied
+        //      from (a single buffer drained the whole pipeline once per tile: its last reader is the LAST UMMA of the
+        //      previous tile): the last dWs UMMA of tile tl-2 must be done.  ALWAYS group 0, at its first iteration inside
+        //      the tile (ci 0, or 1 when the tile starts on an odd iteration): parity waits are only sound when one agent
+        //      walks the phases in order (tools/conv_tc_protocol_sim.py) ----
+        const int tbm = d.tl & 1;
+        mbar_wait(&dym_empty[tbm], ((uint32_t)(d.tl >> 1) & 1u) ^ 1u);
         if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 4);
-        uint8_t* dm = sm + O1_DYM;
+        uint8_t* dm = sm + O1_DYM + (uint32_t)tbm * SLAB;
         {
           // this thread's row of the K-major tile staged one tile earlier (zeros for rows past the batch), re-laid MN-major
-          const int tbm = d.tl & 1;
           mbar_wait(&dyk_full[tbm], (uint32_t)(d.tl >> 1) & 1u);      // acquire: the other group may have staged this tile
           const uint8_t* dk = sm + OB_DYK + (uint32_t)tbm * KB_A;
           float4 v[10];
@@ -865,11 +912,12 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           v[8] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm));
           v[9] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm + 1));
 #pragma unroll
-          for (int j8 = 0; j8 < 5; ++j8) mn_store8(dm, 8 * j8, r, v[2 * j8], v[2 * j8 + 1]);   // mn = j, 8 per 32-byte chunk
+          for (int j8 = 0; j8 < 4; ++j8) mn_store8(dm, 8 * j8, r, v[2 * j8], v[2 * j8 + 1]);   // mn = j, 8 per 32-byte chunk
+          mn_store8(sm + O1_TAILS + (uint32_t)tbm * SLAB, 0, r, v[8], v[9]);                   // j 32..39: chunk 0 of T[tbm]
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + gb, 128);
-        if (rq == 0 && lane == 0) { mbar_arrive(dym_full); CONV_TRACE(gb, it, 5); }
+        if (rq == 0 && lane == 0) { mbar_arrive(&dym_full[tbm]); CONV_TRACE(gb, it, 5); }
       }
     }
   } else if (warp < SCAT_WARP0) {
@@ -880,42 +928,51 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool tr = q == 0 && cq == 0 && lane == 0;
     float s1[BS ? 10 : 1], s2[BS ? 10 : 1];
-    float c_sc[10], c_sh[10];      // z = c_sc * y_raw + c_sh for this thread's 10 columns (conv bias folded in); the two
-                                   // BatchNorm-backward constants per column come from shared memory (register budget)
-#pragma unroll
-    for (int i = 0; i < 10; ++i) { c_sc[i] = tab[48 + kq(cq, i)]; c_sh[i] = tab[96 + kq(cq, i)]; }
+    float c_sc[BS ? 1 : 10];       // B2: the A of dy = A*dz + (Bc*y + Cc); everything else arrives folded into the UMMA
     if constexpr (BS) {
 #pragma unroll
       for (int i = 0; i < 10; ++i) s1[i] = s2[i] = 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) c_sc[i] = tab[48 + kq(cq, i)];
     }
+    // operand-tile offsets of this thread's row: loop invariant
+    const uint32_t o_mn8 = mn_off(8 * cq, r);                       // 32-byte chunk of mn 8cq..8cq+7, k-row r
+    const bool swp = ((r >> 2) & 1) != 0;                            // see mn_store8
+    const uint32_t o_mn_lo = o_mn8 + (swp ? 16u : 0u), o_mn_hi = o_mn8 + (swp ? 0u : 16u);
+    const uint32_t o_tail = BS ? mn_off(8 + 2 * cq, r) : mn_off(32 + 2 * cq, r);
+    const uint32_t o_k0 = sw128_off(r, 2 * cq), o_k1 = sw128_off(r, 2 * cq + 1);
+    const uint32_t o_kt = sw128_off(r, 4 + (cq >> 1)) + (uint32_t)(cq & 1) * 8u;
     for (int it = 0; it < total_it; ++it) {
-      const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
-      const bool valid = r < d.ns * N_POOL;
       if (tr) CONV_TRACE(2, it, 0);
       mbar_wait(&c_full[bi], n & 1u);
       tc_fence_after();
       if (tr) CONV_TRACE(2, it, 1);
-      float y[10], da[10];
-      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(bi * 64), cq, y);
-      tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(128 + bi * 64), cq, da);
+      float z[10], lin[10], da[10], lin_lo[BS ? 1 : 10];
+      const uint32_t ycol = tmem_base + lane_addr + (uint32_t)bi * Y_COLS;
+      tmem_ld10_nw(ycol, cq, z);                                                   // z = sc*y + sh
+      tmem_ld10_nw(ycol + N48, cq, lin);                                           // B1: yhat;  B2: Bc*y + Cc (hi)
+      if constexpr (!BS) tmem_ld10_nw(ycol + 2 * N48, cq, lin_lo);
+      tmem_ld10_nw(tmem_base + lane_addr + T_DA + (uint32_t)(bi * 48), cq, da);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&c_empty[bi]);          // Y / dA1 of this buffer may be overwritten by iteration it+2
+      // rows past the batch need no mask: their im2col row (ones columns included) and their dY2 row are zero, so
+      // z = lin = dA1 = 0 and everything below evaluates to exact zeros
 #pragma unroll
       for (int i = 0; i < 10; ++i) {
-        const int k = kq(cq, i);
-        const float z = fmaf(y[i], c_sc[i], c_sh[i]);
-        const float e = __expf(z);
-        const float dz = da[i] * (z > 0.f ? 1.f : e);                  // ELU'(z)
-        const float lin = fmaf(y[i], tab[144 + k], tab[192 + k]);      // B1: yhat;  B2: Bc*y + Cc
+        const float e = __expf(z[i]);
+        const bool pos = z[i] > 0.f;
+        const float dz = da[i] * (pos ? 1.f : e);                         // ELU'(z)
         if constexpr (BS) {
-          if (valid) { s1[i] += dz; s2[i] = fmaf(dz, lin, s2[i]); }
-          y[i] = valid ? tf32_fast(z > 0.f ? z : e - 1.f) : 0.f;        // a1
+          s1[i] += dz;
+          s2[i] = fmaf(dz, lin[i], s2[i]);
+          z[i] = tf32_fast(pos ? z[i] : e - 1.f);                          // a1
         } else {
-          y[i] = valid ? tf32_fast(fmaf(c_sc[i], dz, lin)) : 0.f;       // dy = A*dz + Bc*y + Cc
+          z[i] = tf32_fast(fmaf(c_sc[i], dz, lin[i] + lin_lo[i]));         // dy = A*dz + Bc*y + Cc
         }
       }
       if (tr) CONV_TRACE(2, it, 4);
@@ -925,14 +982,18 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_wait(&op_empty[ob], ((BS ? n : (uint32_t)it) & 1u) ^ 1u);
       if (tr) CONV_TRACE(2, it, 2);
       {
-        uint8_t* mt = sm + (BS ? O1_A1M + (uint32_t)bi * 2 * SLAB : O2_DYM);   // MN-major: mn = filter k, k-row = tile row r
-        mn_store8(mt, 8 * cq, r, make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]));
-        *reinterpret_cast<float2*>(mt + mn_off(32 + 2 * cq, r)) = make_float2(y[8], y[9]);
-        if constexpr (!BS) {
+        const float4 v0 = make_float4(z[0], z[1], z[2], z[3]), v1 = make_float4(z[4], z[5], z[6], z[7]);
+        uint8_t* mt = sm + (BS ? O1_A1M + (uint32_t)bi * SLAB : O2_DYM);       // MN-major: mn = filter k, k-row = tile row r
+        *reinterpret_cast<float4*>(mt + o_mn_lo) = swp ? v1 : v0;
+        *reinterpret_cast<float4*>(mt + o_mn_hi) = swp ? v0 : v1;
+        if constexpr (BS) {    // filters 32..39 -> mn 8..15 (chunk 1) of the shared tail slab T[bi]
+          *reinterpret_cast<float2*>(sm + O1_TAILS + (uint32_t)bi * SLAB + o_tail) = make_float2(z[8], z[9]);
+        } else {
+          *reinterpret_cast<float2*>(mt + o_tail) = make_float2(z[8], z[9]);
           uint8_t* kt = sm + O2_DYK2;                                    // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
-          *reinterpret_cast<float4*>(kt + sw128_off(r, 2 * cq)) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(kt + sw128_off(r, 2 * cq + 1)) = make_float4(y[4], y[5], y[6], y[7]);
-          *reinterpret_cast<float2*>(sm + OB_TAIL + sw128_off(r, 4 + (cq >> 1)) + (uint32_t)(cq & 1) * 8u) = make_float2(y[8], y[9]);
+          *reinterpret_cast<float4*>(kt + o_k0) = v0;
+          *reinterpret_cast<float4*>(kt + o_k1) = v1;
+          *reinterpret_cast<float2*>(sm + OB_TAIL + o_kt) = make_float2(z[8], z[9]);
         }
       }
       fence_proxy_async_smem();
@@ -948,8 +1009,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
       if (total_it > 0 && q < 3) {                                     // accumulator row = j (output filter of the spatial conv)
         for (int ci = 0; ci < gc; ++ci) {
-          float w[10];
-          tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(256 + ci * 64), cq, w);
+          float w[10];                 // accumulator columns: k 0..31 in place, k 32..39 at 40..47 (shared tail slabs)
+          tmem_ld8_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(ci * 48 + 8 * cq), w);
+          tmem_ld2_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(ci * 48 + 40 + 2 * cq), w + 8);
           tmem_ld_wait();
           const int c = g * GC + ci;
           if (lane < 16 && row64 < N_FILT) {
@@ -970,7 +1032,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
       if (total_it > 0 && q < 3) {                                     // accumulator row = filter k, column = tap t (25: ones column)
         float w[8];
-        tmem_ld8_nw(tmem_base + lane_addr + (uint32_t)(320 + 8 * cq), w);
+        tmem_ld8_nw(tmem_base + lane_addr + T_DWT + (uint32_t)(8 * cq), w);
         tmem_ld_wait();
         if (lane < 16 && row64 < N_FILT) {
 #pragma unroll
@@ -1001,8 +1063,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       tc_fence_after();
       if (sw == 0 && lane == 0) CONV_TRACE(6, it, 1);
       float gv[32];
-      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32), gv);
-      tmem_ld16_nw(tmem_base + lane_addr + (uint32_t)(256 + bi * 32 + 16), gv + 16);
+      tmem_ld16_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(bi * 32), gv);
+      tmem_ld16_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(bi * 32 + 16), gv + 16);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -1071,9 +1133,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     }
   } else if (warp == CTRL_A && lane == 0) {
     // =============================== control A: weight TMA (once), conv + dA1 UMMAs ===============================
-    constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0);
+    constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0), idesc_conv = umma_idesc_tf32(128, (int)Y_COLS, 0, 0);
     const uint32_t s0 = smem_u32(sm);
-    const uint64_t d_bc = desc_k(s0 + OB_BC), d_tail = desc_k(s0 + OB_TAIL), d_wst = desc_k(s0 + OB_WST), d_wstt = desc_k(s0 + OB_WSTT);
+    const uint64_t d_bc = desc_k(s0 + O_BC), d_tail = desc_k(s0 + OB_TAIL), d_wst = desc_k(s0 + OB_WST), d_wstt = desc_k(s0 + OB_WSTT);
     uint64_t d_im[2], d_dyk[2];
     for (int b = 0; b < 2; ++b) { d_im[b] = desc_k(s0 + OB_IMK + (uint32_t)b * KB_A); d_dyk[b] = desc_k(s0 + OB_DYK + (uint32_t)b * KB_A); }
     if (total_it > 0) {
@@ -1091,10 +1153,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_wait(&c_empty[bi], (n & 1u) ^ 1u);
       CONV_TRACE(4, it, 2);
       tc_fence_after();
-      // conv UMMA (plain TF32 in the backward): Y[bi] = im2col . (wt/51)^T
+      // conv UMMA (plain TF32 in the backward), both affine maps folded in: Y[bi] = [im2col | 1 | 1] . [z rows | lin rows]^T
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(tmem_base + (uint32_t)(bi * 64), desc_adv(d_im[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc48, kk > 0 ? 1u : 0u);
+        tc_mma_tf32(tmem_base + (uint32_t)bi * Y_COLS, desc_adv(d_im[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc_conv, kk > 0 ? 1u : 0u);
       tc_commit(&im_empty[bi]);                          // B2: control B adds the second arrival (MN-major copy, dwt UMMA)
       if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);
       if (it == 0) mbar_wait(wst_full, 0);
@@ -1103,8 +1165,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       const uint64_t d_w = desc_adv(d_wst, (uint32_t)d.ci * KB_48);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), desc_adv(d_dyk[tb], kk * 32), desc_adv(d_w, kk * 32), idesc48, kk > 0 ? 1u : 0u);
-      tc_mma_tf32(tmem_base + 128u + (uint32_t)(bi * 64), desc_adv(d_tail, (uint32_t)tb * 32u), desc_adv(d_wstt, (uint32_t)d.ci * 32u), idesc48, 1u);
+        tc_mma_tf32(tmem_base + T_DA + (uint32_t)(bi * 48), desc_adv(d_dyk[tb], kk * 32), desc_adv(d_w, kk * 32), idesc48, kk > 0 ? 1u : 0u);
+      tc_mma_tf32(tmem_base + T_DA + (uint32_t)(bi * 48), desc_adv(d_tail, (uint32_t)tb * 32u), desc_adv(d_wstt, (uint32_t)d.ci * 32u), idesc48, 1u);
       tc_commit(&c_full[bi]);
       CONV_TRACE(4, it, 3);
       if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);     // nothing reads the K-major dY2 tile after its last dA1 UMMA
@@ -1118,8 +1180,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     constexpr uint32_t idesc48_mn = umma_idesc_tf32(64, N48, 1, 1);
     constexpr uint32_t idesc32_mn = umma_idesc_tf32(64, 32, 1, 1);
     const uint32_t s0 = smem_u32(sm);
-    const uint64_t d_dym1 = desc_mn(s0 + O1_DYM), d_a1m0 = desc_mn(s0 + O1_A1M), d_a1m1 = desc_mn(s0 + O1_A1M + 2 * SLAB);
-    const uint64_t d_dyk2 = desc_k(s0 + O2_DYK2), d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + O2_WTT + KB_32);
+    // B1 operands: first slab + shared tail slab T[x] (x = the operand's own buffer index)
+    const uint64_t d_dym1[2] = {desc_mn_split(s0 + O1_DYM, O1_TAILS - O1_DYM), desc_mn_split(s0 + O1_DYM + SLAB, O1_TAILS - O1_DYM)};
+    const uint64_t d_a1m0 = desc_mn_split(s0 + O1_A1M, O1_TAILS - O1_A1M), d_a1m1 = desc_mn_split(s0 + O1_A1M + SLAB, O1_TAILS - O1_A1M);
+    const uint64_t d_dyk2 = desc_k(s0 + O2_DYK2), d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + OB_TAIL + 3u * 32u);
     const uint64_t d_tail2 = desc_k(s0 + OB_TAIL + 2u * 32u), d_dym2 = desc_mn(s0 + O2_DYM);
     const uint64_t d_imm0 = desc_mn(s0 + O2_IMM), d_imm1 = desc_mn(s0 + O2_IMM + SLAB);
     for (int it = 0; it < total_it; ++it) {
@@ -1127,21 +1191,22 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       const int bj = it & 1;
       CONV_TRACE(5, it, 0);
       if (BS) {
-        if (d.ci == 0) mbar_wait(dym_full, (uint32_t)d.tl & 1u);
+        const int tb = d.tl & 1;
+        if (d.ci == 0) mbar_wait(&dym_full[tb], (uint32_t)(d.tl >> 1) & 1u);
         CONV_TRACE(5, it, 1);
         mbar_wait(&op_full[bj], (uint32_t)(it >> 1) & 1u);
         CONV_TRACE(5, it, 2);
         tc_fence_after();
         // dWs_c[j, k] += sum_rows dY2[row, j] * a1[row, k]: both operands MN-major, K = the 128 tile rows
         const uint64_t db = bj ? d_a1m1 : d_a1m0;
-        const uint32_t dcol = tmem_base + 256u + (uint32_t)(d.ci * 64);
+        const uint32_t dcol = tmem_base + T_ACC + (uint32_t)(d.ci * 48);
         const uint32_t acc0 = d.tl > 0 ? 1u : 0u;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk)
-          tc_mma_tf32(dcol, desc_adv(d_dym1, kk * 1024), desc_adv(db, kk * 1024), idesc48_mn, kk > 0 ? 1u : acc0);
+          tc_mma_tf32(dcol, desc_adv(d_dym1[tb], kk * 1024), desc_adv(db, kk * 1024), idesc48_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[bj]);
         CONV_TRACE(5, it, 3);
-        if (d.ci == gc - 1) tc_commit(dym_empty);
+        if (d.ci == gc - 1) tc_commit(&dym_empty[tb]);
       } else {
         mbar_wait(&op_full[0], (uint32_t)it & 1u);
         CONV_TRACE(5, it, 1);
@@ -1149,7 +1214,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         CONV_TRACE(5, it, 2);
         tc_fence_after();
         // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
-        const uint32_t gcol = tmem_base + 256u + (uint32_t)(bj * 32);
+        const uint32_t gcol = tmem_base + T_ACC + (uint32_t)(bj * 32);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           tc_mma_tf32(gcol, desc_adv(d_dyk2, kk * 32), desc_adv(d_wtt, kk * 32), idesc32, kk > 0 ? 1u : 0u);
@@ -1160,7 +1225,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk)
-          tc_mma_tf32(tmem_base + 320u, desc_adv(d_dym2, kk * 1024), desc_adv(dbm, kk * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
+          tc_mma_tf32(tmem_base + T_DWT, desc_adv(d_dym2, kk * 1024), desc_adv(dbm, kk * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[0]);
         tc_commit(&im_empty[bj]);
         CONV_TRACE(5, it, 3);
@@ -1228,6 +1293,11 @@ static int trace_dump(const char* name, long long* dev, cudaStream_t s) {
 }
 static long long* trace_buffer(cudaStream_t s) {
   if (!getenv("EEGB200_CONV_TRACE")) return nullptr;
+#ifndef EEGB200_CONV_TRACE_BUILD
+  static bool told = false;
+  if (!told) { fprintf(stderr, "eegb200: EEGB200_CONV_TRACE needs a library built with EEGB200_BUILD_TRACE=1\n"); told = true; }
+  return nullptr;
+#endif
   static long long* buf = nullptr;
   if (!buf && cudaMalloc(&buf, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long)) != cudaSuccess) return nullptr;
   cudaMemsetAsync(buf, 0, (size_t)TRACE_ROLES * TRACE_IT * 8 * sizeof(long long), s);

@@ -107,22 +107,37 @@ __global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int bg, long
   if (warp == 0 || (warp == 1 && (bg & 2))) {
     if (lane == 0) {
       const uint32_t a0 = smem_u32(sm) + warp * 32768, b0 = smem_u32(sm + 64 * 1024) + warp * 32768;
-      const uint32_t idesc = umma_idesc_tf32(M, N, mn_major, mn_major);
-      uint64_t ad[4], bd[4];
+      // bit 64: the SECOND issuer runs the other shape (M = 128, N = 48, K-major) instead of the primary's
+      const bool other = warp == 1 && (bg & 64);
+      const int mnm = other ? 0 : mn_major;
+      const uint32_t idesc = other ? umma_idesc_tf32(128, 48, 0, 0) : umma_idesc_tf32(M, N, mn_major, mn_major);
+      const uint32_t idesc_alt = umma_idesc_tf32(128, 48, 0, 0);
+      uint64_t ad[4], bd[4], ad2[4], bd2[4];
       for (int kk = 0; kk < 4; ++kk) {
-        ad[kk] = mn_major ? umma_smem_desc(a0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
-                          : umma_smem_desc(a0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
-        bd[kk] = mn_major ? umma_smem_desc(b0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
-                          : umma_smem_desc(b0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        ad[kk] = mnm ? umma_smem_desc(a0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
+                     : umma_smem_desc(a0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        bd[kk] = mnm ? umma_smem_desc(b0 + kk * 1024, 4096, 512, UMMA_LAYOUT_SW128_BASE32B)
+                     : umma_smem_desc(b0 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        ad2[kk] = umma_smem_desc(a0 + 16384 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        bd2[kk] = umma_smem_desc(b0 + 16384 + kk * 32, 16, 1024, UMMA_LAYOUT_SW128);
       }
       const uint32_t d = tmem + warp * 256;
       const long long t0 = clock64();
       tc_mma_tf32(d, ad[0], bd[0], idesc, 0u);
+      tc_mma_tf32(d + 128, ad2[0], bd2[0], idesc_alt, 0u);
       for (int i = 1; i < n / 4; ++i) {
-        tc_mma_tf32(d, ad[0], bd[0], idesc, 1u);
-        tc_mma_tf32(d, ad[1], bd[1], idesc, 1u);
-        tc_mma_tf32(d, ad[2], bd[2], idesc, 1u);
-        tc_mma_tf32(d, ad[3], bd[3], idesc, 1u);
+        if ((bg & 32) && (i & 1)) {
+          // bit 32: every other block of 4 UMMAs has the other shape (M = 128, N = 48, K-major) and its own accumulator
+          tc_mma_tf32(d + 128, ad2[0], bd2[0], idesc_alt, 1u);
+          tc_mma_tf32(d + 128, ad2[1], bd2[1], idesc_alt, 1u);
+          tc_mma_tf32(d + 128, ad2[2], bd2[2], idesc_alt, 1u);
+          tc_mma_tf32(d + 128, ad2[3], bd2[3], idesc_alt, 1u);
+        } else {
+          tc_mma_tf32(d, ad[0], bd[0], idesc, 1u);
+          tc_mma_tf32(d, ad[1], bd[1], idesc, 1u);
+          tc_mma_tf32(d, ad[2], bd[2], idesc, 1u);
+          tc_mma_tf32(d, ad[3], bd[3], idesc, 1u);
+        }
         if (bg & 8) tc_commit(&bar[1 - warp]);         // a tcgen05.commit after every 4 UMMAs (nobody waits on it)
       }
       const long long t1 = clock64();
@@ -138,6 +153,29 @@ __global__ void umma_cost_kernel(int M, int N, int mn_major, int n, int bg, long
     while (!*stop && it < (1 << 22)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) dst[(j & 3) * 256] = make_float4((float)it, 0.f, 0.f, 0.f);
+      ++it;
+    }
+  } else if (warp >= 4 && warp < 16 && (bg & 128)) {
+    // background shared-memory LOADS and stores, 12 warps, scalar and partly bank-conflicted (what builders / scatter do)
+    float* base = reinterpret_cast<float*>(sm + 128 * 1024) + (warp - 4) * 640;
+    int it = 0;
+    float acc = 0.f;
+    while (!*stop && it < (1 << 22)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += base[5 * lane + j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) base[(8 * lane + j) & 511] = acc;
+      ++it;
+    }
+    if (acc == 12345.f) out[1] = 0;
+  } else if (warp >= 4 && warp < 16 && (bg & 256)) {
+    // background generic-proxy stores each followed by fence.proxy.async (what every operand-writing thread does)
+    float4* dst = reinterpret_cast<float4*>(sm + 128 * 1024) + (warp - 4) * 32 + lane;
+    int it = 0;
+    while (!*stop && it < (1 << 22)) {
+      dst[(it & 3) * 512] = make_float4((float)it, 0.f, 0.f, 0.f);
+      fence_proxy_async_smem();
+      if (bg & 512) __nanosleep(200);       // ~ one fence per warp per few hundred cycles instead of back to back
       ++it;
     }
   } else if (warp >= 4 && warp < 16 && (bg & 16)) {
@@ -196,7 +234,7 @@ extern "C" int eegb200_debug_umma_m64(float* out128, void* stream) {
 }
 
 extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int bg, long long* out2, void* stream) {
-  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && bg >= 0 && bg < 32 && (!mn_major || N <= 128),
+  EEG_REQUIRE(out2 && (M == 64 || M == 128) && N >= 8 && N <= 256 && n > 0 && bg >= 0 && bg < 1024 && (!mn_major || N <= 128),
               "debug_umma_cost: bad arguments");
   static PerDeviceOnce once;
   if (once.first())

@@ -28,9 +28,10 @@ def run(mode, gc, n_tiles, seed, verbose=False):
     total = n_tiles * gc
     B = {}
     for nm, cnt in (("im_full", 1), ("im_empty", 1 if BS else 2), ("dyk_full", 1), ("dyk_empty", 1), ("c_full", 1),
-                    ("c_empty", 16), ("op_full", 16), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4)):
+                    ("c_empty", 16), ("op_full", 16), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4),
+                    ("dym_full", 1), ("dym_empty", 1)):
         B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
-    for nm in ("dym_full", "dym_empty", "final_a", "final_b"):
+    for nm in ("final_a", "final_b"):
         B[nm] = Bar(nm, 1)
     delayed = []            # (time, barrier): tcgen05.commit arrivals
     now = [0]
@@ -61,9 +62,9 @@ def run(mode, gc, n_tiles, seed, verbose=False):
             yield ("arrive", B["im_full"][bi])
             pending = -1
             if BS and gb == 0 and ci < 2:
-                yield ("wait", B["dym_empty"], (tl & 1) ^ 1)
+                yield ("wait", B["dym_empty"][tl & 1], ((tl >> 1) & 1) ^ 1)
                 yield ("wait", B["dyk_full"][tl & 1], (tl >> 1) & 1)
-                yield ("arrive", B["dym_full"])
+                yield ("arrive", B["dym_full"][tl & 1])
 
     def epilogue(ge, w):
         for it in range(total):
@@ -105,11 +106,11 @@ def run(mode, gc, n_tiles, seed, verbose=False):
             bj = it & 1
             if BS:
                 if ci == 0:
-                    yield ("wait", B["dym_full"], tl & 1)
+                    yield ("wait", B["dym_full"][tl & 1], (tl >> 1) & 1)
                 yield ("wait", B["op_full"][bj], (it >> 1) & 1)
                 yield ("commit", B["op_empty"][bj])
                 if ci == gc - 1:
-                    yield ("commit", B["dym_empty"])
+                    yield ("commit", B["dym_empty"][tl & 1])
             else:
                 yield ("wait", B["op_full"][0], it & 1)
                 yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
