@@ -45,9 +45,9 @@ constexpr int N48 = 48;
 constexpr int WS_RING = 4;
 constexpr int F_PARTS = 3, F_LEN = 21;            // forward work item = (tile, 21 of the 63 channels)
 constexpr int GC = 4, N_GROUPS = 16;              // backward: channel groups of 4 (the last one has 3)
-constexpr uint32_t PS_LD = 208, CSX_LD = 296;        // CSX_LD >= csi(256) + 1 = 289
+constexpr uint32_t PS_LD = 208;
 constexpr uint32_t POOL_BYTES = 3 * PS_LD * 4;                  // pooled sums [3][208] floats of one builder group
-constexpr uint32_t SCAN_BYTES = (3 * PS_LD + 3 * CSX_LD) * 4;   // B2 scatter warps: d pooled sums [3][208] + prefix scratch [3][296]
+constexpr uint32_t SCAN_BYTES = (2 * 3 * PS_LD + 4 * 4 * 20) * 4;   // B2 scatter warps: d pooled sums [2 buf][3][208] + halo [4][4][20]
 constexpr int N_BUILD_WARPS = 8, N_EPI_WARPS = 16;
 constexpr int EPI_WARP0 = N_BUILD_WARPS, EPI_THREAD0 = EPI_WARP0 * 32;
 
@@ -118,7 +118,13 @@ __device__ __forceinline__ float tf32_trunc(float x) {    // what tcgen05.mma ki
 }
 // ELU(z).  exp(z) - 1 loses RELATIVE accuracy near 0 but its absolute error (6e-8) is far below the TF32 rounding of the
 // value that follows (2.4e-4 relative) and the O(1) terms it is summed with.
-__device__ __forceinline__ float elu_quick(float z) { return z > 0.f ? z : __expf(z) - 1.f; }
+// exp via ex2.approx.ftz (2 instructions; __expf adds a denormal-range rescale the ELU does not need: e^z - 1 = -1 there)
+__device__ __forceinline__ float exp_quick(float z) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float elu_quick(float z) { return z > 0.f ? z : exp_quick(z) - 1.f; }
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
@@ -146,8 +152,6 @@ __device__ __forceinline__ uint64_t desc_mn_split(uint32_t addr, uint32_t slab_s
 }
 __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
-// padded index of the B2 scatter warps' prefix array: per-lane stride-8 stores would otherwise hit 4 banks (8-way conflicts)
-__device__ __forceinline__ int csi(int k) { return k + (k >> 3); }
 // box-51 pooled sums of one token row (8 samples per lane), entirely in registers: I[k] = inclusive prefix sum of the
 // row, ps[u] = I[u+50] - I[u-1].  For u = 8*lane + i the upper term sits 50 = 6*8 + 2 samples ahead: slot i+2 of lane+6
 // (i < 6) or slot i-6 of lane+7; the lower term is the lane's own slot i-1 (its exclusive prefix for i = 0).  Lanes
@@ -293,15 +297,6 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     *reinterpret_cast<float4*>(sm + OFF_IM + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(sm + OFF_A1 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // conv weights / 51 as the B operand, hi and lo parts: rows k < 40 (48 with padding), columns t < 25 (32)
-  for (int i = threadIdx.x; i < N48 * 32; i += F_THREADS) {
-    const int k = i >> 5, t = i & 31;
-    const float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
-    const float hi = tf32_fast(w), lo = w - hi;
-    const uint32_t off = sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u;
-    *reinterpret_cast<float*>(sm + OFF_BC + off) = hi;
-    *reinterpret_cast<float*>(sm + OFF_BC + KB_48 + off) = lo;
-  }
   if (threadIdx.x < N48) {
     const int k = threadIdx.x;
     float sc = 0.f, sh = 0.f;
@@ -313,6 +308,24 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     tab[k] = sc;
     tab[48 + k] = sh;
     tab[96 + k] = bt;
+  }
+  __syncthreads();
+  // conv weights / 51 as the B operand, hi and lo parts: rows k < 40 (48 with padding), columns t < 25 (32).  F2 folds the
+  // BatchNorm affine map in: rows scaled by sc_k, and the shift sh_k as a TF32 hi + lo pair in columns 25, 26, which meet
+  // the two ones columns of the im2col hi tile -- the accumulator holds z = sc*y + sh, zero for rows past the batch
+  for (int i = threadIdx.x; i < N48 * 32; i += F_THREADS) {
+    const int k = i >> 5, t = i & 31;
+    float w = (k < N_FILT && t < K_TEMP) ? p.wt[k * K_TEMP + t] * (1.f / K_POOL) : 0.f;
+    if (MODE == MODE_APPLY) w *= tab[k];
+    float hi = tf32_fast(w), lo = w - hi;
+    if (MODE == MODE_APPLY && k < N_FILT && (t == K_TEMP || t == K_TEMP + 1)) {
+      const float c = tab[48 + k], ch = tf32_fast(c);
+      hi = t == K_TEMP ? ch : tf32_fast(c - ch);
+      lo = 0.f;
+    }
+    const uint32_t off = sw128_off(k, t >> 2) + (uint32_t)(t & 3) * 4u;
+    *reinterpret_cast<float*>(sm + OFF_BC + off) = hi;
+    *reinterpret_cast<float*>(sm + OFF_BC + KB_48 + off) = lo;
   }
   if (threadIdx.x < 80) red[threadIdx.x] = 0.f;
   if (warp == F_CTRL_A) {
@@ -371,6 +384,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
           a.y = (valid && (ch * 4 + 1) < K_TEMP) ? src[ch * 4 + 1] : 0.f;
           a.z = (valid && (ch * 4 + 2) < K_TEMP) ? src[ch * 4 + 2] : 0.f;
           a.w = (valid && (ch * 4 + 3) < K_TEMP) ? src[ch * 4 + 3] : 0.f;
+          if (ch == 6) a.y = a.z = valid ? 1.f : 0.f;   // taps 25, 26: the ones columns (F2: folded BatchNorm shift)
           h = make_float4(tf32_fast(a.x), tf32_fast(a.y), tf32_fast(a.z), tf32_fast(a.w));
           const uint32_t off = sw128_off(r, ch);
           *reinterpret_cast<float4*>(hi_t + off) = h;
@@ -388,20 +402,18 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
     const int r = q * 32 + lane;                         // tile row
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float s1[MODE == MODE_STATS ? 10 : 1], s2[MODE == MODE_STATS ? 10 : 1];
-    float c_sc[10], c_sh[10];                            // per-filter constants of this thread's 10 columns:
-#pragma unroll                                           //   APPLY: z = c_sc * y_raw + c_sh;  STATS: c_sh = conv bias
-    for (int i = 0; i < 10; ++i) { c_sc[i] = tab[kq(cq, i)]; c_sh[i] = MODE == MODE_STATS ? tab[96 + kq(cq, i)] : tab[48 + kq(cq, i)]; }
+    float c_bt[MODE == MODE_STATS ? 10 : 1];             // F1: conv bias of this thread's 10 columns (F2: folded into the UMMA)
     if constexpr (MODE == MODE_STATS) {
 #pragma unroll
-      for (int i = 0; i < 10; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < 10; ++i) { s1[i] = s2[i] = 0.f; c_bt[i] = tab[96 + kq(cq, i)]; }
     }
+    const bool tr = q == 0 && cq == 0 && lane == 0;
+    const uint32_t o_a0 = sw128_off(r, 2 * cq), o_a1 = sw128_off(r, 2 * cq + 1);      // A1 slice offsets of this row
+    const uint32_t o_at = KB_A + sw128_off(r, cq >> 1) + (uint32_t)(cq & 1) * 8u;
+    int l = 0, item_local = 0;                           // channel inside the item, item index of this CTA (see fwd_decode)
     for (int it = 0; it < total_it; ++it) {
-      const FwdIt d = fwd_decode(it, p.B);
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
-      const bool valid = r < d.ns * N_POOL;
-      const size_t grow = (size_t)d.tile * TILE_ROWS + r;         // global (b, p) row
-      const bool tr = q == 0 && cq == 0 && lane == 0;
       if (tr) CONV_TRACE(2, it, 0);
       mbar_wait(&c1_full[bi], n & 1u);
       tc_fence_after();
@@ -416,46 +428,49 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
 #pragma unroll
       for (int i = 0; i < 10; ++i) y[i] += y2[i];
       if constexpr (MODE == MODE_STATS) {
-        if (valid) {
+        const FwdIt d = fwd_decode(it, p.B);
+        if (r < d.ns * N_POOL) {
 #pragma unroll
           for (int i = 0; i < 10; ++i) {
-            const float v = y[i] + c_sh[i];
+            const float v = y[i] + c_bt[i];
             s1[i] += v;
             s2[i] = fmaf(v, v, s2[i]);
           }
         }
       } else {
-        if (valid && p.y1 != nullptr) {
-          float* dst = p.y1 + grow * K_SPAT + d.c * N_FILT;
-          const float* bt = tab + 96;
-          *reinterpret_cast<float4*>(dst + 8 * cq) = make_float4(y[0] + bt[8 * cq], y[1] + bt[8 * cq + 1], y[2] + bt[8 * cq + 2], y[3] + bt[8 * cq + 3]);
-          *reinterpret_cast<float4*>(dst + 8 * cq + 4) = make_float4(y[4] + bt[8 * cq + 4], y[5] + bt[8 * cq + 5], y[6] + bt[8 * cq + 6], y[7] + bt[8 * cq + 7]);
-          *reinterpret_cast<float2*>(dst + 32 + 2 * cq) = make_float2(y[8] + bt[32 + 2 * cq], y[9] + bt[33 + 2 * cq]);
+        // y = z = sc * conv + sh (folded); rows past the batch are exact zeros and ELU(0) = 0: no masks
+        if (p.y1 != nullptr || p.a1 != nullptr) {
+          // debug stores for the stage checks: y1 recovered from z (exact enough for a 1e-3 check unless gamma ~ 0)
+          const FwdIt d = fwd_decode(it, p.B);
+          if (r < d.ns * N_POOL) {
+            const size_t o = ((size_t)d.tile * TILE_ROWS + r) * K_SPAT + d.c * N_FILT;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+              const int k = kq(cq, i);
+              if (p.y1 != nullptr) p.y1[o + k] = (y[i] - tab[48 + k]) / tab[k] + tab[96 + k];
+              if (p.a1 != nullptr) p.a1[o + k] = tf32_fast(elu_quick(y[i]));
+            }
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 10; ++i) y[i] = valid ? tf32_fast(elu_quick(fmaf(y[i], c_sc[i], c_sh[i]))) : 0.f;
-        if (valid && p.a1 != nullptr) {
-          float* dst = p.a1 + grow * K_SPAT + d.c * N_FILT;
-          *reinterpret_cast<float4*>(dst + 8 * cq) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(dst + 8 * cq + 4) = make_float4(y[4], y[5], y[6], y[7]);
-          *reinterpret_cast<float2*>(dst + 32 + 2 * cq) = make_float2(y[8], y[9]);
-        }
+        for (int i = 0; i < 10; ++i) y[i] = tf32_fast(elu_quick(y[i]));
         // K slice of the spatial A operand: k 0..31 -> k-block 0 (chunk k/4), k 32..39 -> chunks 0, 1 of k-block 1
         if (tr) CONV_TRACE(2, it, 4);
         mbar_wait(&a1_empty[bi], (n & 1u) ^ 1u);         // spatial UMMAs of iteration it-2 are done with this buffer
         if (tr) CONV_TRACE(2, it, 2);
         uint8_t* a1t = sm + OFF_A1 + (uint32_t)bi * 2 * KB_A;
-        *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq)) = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(a1t + sw128_off(r, 2 * cq + 1)) = make_float4(y[4], y[5], y[6], y[7]);
-        *reinterpret_cast<float2*>(a1t + KB_A + sw128_off(r, cq >> 1) + (uint32_t)(cq & 1) * 8u) = make_float2(y[8], y[9]);
+        *reinterpret_cast<float4*>(a1t + o_a0) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(a1t + o_a1) = make_float4(y[4], y[5], y[6], y[7]);
+        *reinterpret_cast<float2*>(a1t + o_at) = make_float2(y[8], y[9]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a1_full[bi]);
         if (tr) CONV_TRACE(2, it, 3);
-        if (d.l == F_LEN - 1) {
+        if (l == F_LEN - 1) {
           // ---- last channel of the item: y2 share = accumulated spatial product (+ bias once per tile) ----
-          const int ib = d.item_local & 1;
-          mbar_wait(&y2_full[ib], (uint32_t)(d.item_local >> 1) & 1u);
+          const FwdIt d = fwd_decode(it, p.B);
+          const int ib = item_local & 1;
+          mbar_wait(&y2_full[ib], (uint32_t)(item_local >> 1) & 1u);
           tc_fence_after();
           float o[10];
           tmem_ld10_nw(tmem_base + lane_addr + (uint32_t)(256 + ib * 64), cq, o);
@@ -463,8 +478,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&y2_empty[ib]);
-          if (valid) {
-            float* dst = p.y2 + grow * N_FILT;
+          if (r < d.ns * N_POOL) {
+            float* dst = p.y2 + ((size_t)d.tile * TILE_ROWS + r) * N_FILT;
             if (d.part == 0) {
 #pragma unroll
               for (int i = 0; i < 10; ++i) o[i] += p.bs[kq(cq, i)];
@@ -473,6 +488,10 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmWs, const ConvTcParams 
             red_add_v4(dst + 8 * cq + 4, o[4], o[5], o[6], o[7]);
             red_add_v2(dst + 32 + 2 * cq, o[8], o[9]);
           }
+          l = 0;
+          ++item_local;
+        } else {
+          ++l;
         }
       }
     }
@@ -964,7 +983,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       // z = lin = dA1 = 0 and everything below evaluates to exact zeros
 #pragma unroll
       for (int i = 0; i < 10; ++i) {
-        const float e = __expf(z[i]);
+        const float e = exp_quick(z[i]);
         const bool pos = z[i] > 0.f;
         const float dz = da[i] * (pos ? 1.f : e);                         // ELU'(z)
         if constexpr (BS) {
@@ -1046,22 +1065,25 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     }
   } else if (!BS && warp < SCAT_WARP0 + 4) {
     // =============================== scatter warps (B2): G -> pooled positions -> d x3 ===============================
-    const int q = warp & 3;
-    const int sw = warp - SCAT_WARP0;
+    // d pooled sums dps[5p' + e] = sum_{a=0..4} G[(s, p'-a), 5a + e]: row p' gathers its five 5-tap groups from the rows
+    // p', p'-1 .. p'-4 -- warp shuffles, plus a 4-row halo through shared memory at the warp boundaries.  Tile rows are
+    // the samples back to back (36 rows each), so what rows p < 4 collect from the rows BEFORE their sample is exactly the
+    // block p' = 36 + p (positions 180..199) of the previous sample ("prev"; rows 36*ns .. 36*ns+3 hold zeros themselves
+    // and only complete the last sample).  Every position is written exactly once: no read-modify-write, no zeroing.
+    const int q = warp & 3;                              // TMEM lane quarter == sample row handled in the second stage
     const int r = q * 32 + lane;
     const int s_row = r / N_POOL, p_row = r % N_POOL;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float* dps_all = reinterpret_cast<float*>(misc + M_DPS);
-    float* csd_all = dps_all + 3 * PS_LD;
+    float* halo = dps_all + 2 * 3 * PS_LD;               // [warp][row 28..31][gv 5..24]
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
-      const bool valid = r < d.ns * N_POOL;
-      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 0);
+      if (q == 0 && lane == 0) CONV_TRACE(6, it, 0);
       mbar_wait(&gg_full[bi], n & 1u);
       tc_fence_after();
-      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 1);
+      if (q == 0 && lane == 0) CONV_TRACE(6, it, 1);
       float gv[32];
       tmem_ld16_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(bi * 32), gv);
       tmem_ld16_nw(tmem_base + lane_addr + T_ACC + (uint32_t)(bi * 32 + 16), gv + 16);
@@ -1069,33 +1091,50 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&gg_empty[bi]);
-      // dps[5p + t] += G[(s,p), t], t = 5a + e: in round a every row p touches the 5 positions 5(p+a) .. 5(p+a)+4, which
-      // are distinct across the rows of a sample -> plain read-modify-write, no atomics (shared atomics cost ~3200 cycles
-      // per iteration here); rounds are separated by the warps' barrier
-      float* dp = dps_all + s_row * PS_LD + 5 * p_row;
+      if (lane >= 28) {
+        float4* h = reinterpret_cast<float4*>(halo + (q * 4 + lane - 28) * 20);
 #pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        if (valid) {
-#pragma unroll
-          for (int e = 0; e < 5; ++e) dp[5 * a + e] += gv[5 * a + e];
-        }
-        named_bar_sync(4, 128);
+        for (int j = 0; j < 5; ++j) h[j] = make_float4(gv[5 + 4 * j], gv[6 + 4 * j], gv[7 + 4 * j], gv[8 + 4 * j]);
       }
-      if (sw < d.ns) {
-        // d x3[v] = (1/51) * sum_{u = max(0, v-50)}^{min(v, 199)} dps[u]  via the prefix P: (P[hi+1] - P[lo]) / 51
-        float* dpr = dps_all + sw * PS_LD;
-        float* cs = csd_all + sw * CSX_LD;
+      named_bar_sync(4, 128);
+      float own[5], prev[5];
+#pragma unroll
+      for (int e = 0; e < 5; ++e) { own[e] = gv[e]; prev[e] = 0.f; }
+#pragma unroll
+      for (int a = 1; a < 5; ++a) {
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+          float t = __shfl_up_sync(0xffffffffu, gv[5 * a + e], a);
+          if (lane < a) t = q > 0 ? halo[((q - 1) * 4 + 4 + lane - a) * 20 + 5 * a - 5 + e] : 0.f;
+          if (a <= p_row) own[e] += t; else prev[e] += t;
+        }
+      }
+      float* dbuf = dps_all + bi * 3 * PS_LD;
+      if (s_row < TILE_S) {
+        float* dp = dbuf + s_row * PS_LD + 5 * p_row;
+#pragma unroll
+        for (int e = 0; e < 5; ++e) dp[e] = own[e];
+      }
+      if (s_row > 0 && p_row < 4) {
+        float* dp = dbuf + (s_row - 1) * PS_LD + 5 * (N_POOL + p_row);
+#pragma unroll
+        for (int e = 0; e < 5; ++e) dp[e] = prev[e];
+      }
+      named_bar_sync(4, 128);
+      if (q == 0 && lane == 0) CONV_TRACE(6, it, 3);
+      if (q < d.ns) {
+        // d x3[v] = (1/51) * sum_{u = max(0, v-50)}^{min(v, 199)} dps[u] = (I[min(v,199)] - I[v-51]) / 51 with the inclusive
+        // prefix I in registers (lanes >= 25 hold zeros, so I is flat past 199); I[v-51] sits 6 or 7 lanes down
+        const float* dpr = dbuf + q * PS_LD;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        if (lane < 25) {
+        if (lane < N_PSUM / 8) {
           const float4 a = *reinterpret_cast<const float4*>(dpr + 8 * lane), b = *reinterpret_cast<const float4*>(dpr + 8 * lane + 4);
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-#pragma unroll
-          for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
-          *reinterpret_cast<float4*>(dpr + 8 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);    // ready for the next iteration
-          *reinterpret_cast<float4*>(dpr + 8 * lane + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int i = 1; i < 8; ++i) v[i] += v[i - 1];
         const float tot = v[7];
         float inc = tot;
 #pragma unroll
@@ -1104,21 +1143,16 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           if (lane >= o) inc += nb;
         }
         const float excl = inc - tot;
-        if (lane == 0) cs[0] = 0.f;
-        if (lane < 25) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cs[csi(8 * lane + 1 + i)] = v[i] + excl;    // P[u+1] = sum of dps[0..u]
-        }
-        __syncwarp();
+        for (int i = 0; i < 8; ++i) v[i] += excl;
         float o8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int t = 8 * lane + i;
-          const int hi = t < N_PSUM - 1 ? t : N_PSUM - 1;
-          const int lo = t - (K_POOL - 1) > 0 ? t - (K_POOL - 1) : 0;
-          o8[i] = t < N_T ? (cs[csi(hi + 1)] - cs[csi(lo)]) * (1.f / K_POOL) : 0.f;
+          const float lo = i < 3 ? __shfl_up_sync(0xffffffffu, v[i + 5], 7) : __shfl_up_sync(0xffffffffu, v[i - 3], 6);
+          o8[i] = t < N_T ? (v[i] - (t >= K_POOL ? lo : 0.f)) * (1.f / K_POOL) : 0.f;
         }
-        float* dxr = p.dx3 + ((size_t)(d.tile * TILE_S + sw) * N_TOK + d.c) * D_PAD + 8 * lane;
+        float* dxr = p.dx3 + ((size_t)(d.tile * TILE_S + q) * N_TOK + d.c) * D_PAD + 8 * lane;
         *reinterpret_cast<float4*>(dxr) = make_float4(o8[0], o8[1], o8[2], o8[3]);
         *reinterpret_cast<float4*>(dxr + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
         if (d.c == N_CH - 1) {
@@ -1128,8 +1162,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           *reinterpret_cast<float4*>(dz + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      named_bar_sync(4, 128);                            // the zeroed dps rows are visible before the next round 0
-      if (sw == 0 && lane == 0) CONV_TRACE(6, it, 2);
+      if (q == 0 && lane == 0) CONV_TRACE(6, it, 2);
     }
   } else if (warp == CTRL_A && lane == 0) {
     // =============================== control A: weight TMA (once), conv + dA1 UMMAs ===============================
