@@ -82,6 +82,56 @@ __global__ void umma_m64_probe_kernel(float* __restrict__ out) {
   if (threadIdx.x < 32) tmem_dealloc(tmem, 32);
 }
 
+// Generic operand-layout probe: one UMMA chain D[128][N] = A . B^T (kind::tf32) over shared-memory IMAGES prepared on the
+// host (a_img: 32 KB, b_img: 32 KB, copied verbatim), with every descriptor field given by the caller:
+// cfg = {a_layout, a_lbo, a_sbo, a_kadv, a_major, b_layout, b_lbo, b_sbo, b_kadv, b_major, N, nk}.  Used to check which
+// (major, swizzle) combinations the tensor core accepts for a tile that two different UMMAs want to read
+// (tools/gpu_dual_layout_probe.py).  out: [128][N] accumulator rows.
+struct UmmaProbeCfg { int v[12]; };
+__global__ void umma_generic_probe_kernel(const float* __restrict__ a_img, const float* __restrict__ b_img, UmmaProbeCfg c,
+                                          float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* A = sm;
+  uint8_t* Bm = sm + 32768;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  for (int i = threadIdx.x; i < 8192; i += blockDim.x) {
+    reinterpret_cast<float*>(A)[i] = a_img[i];
+    reinterpret_cast<float*>(Bm)[i] = b_img[i];
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(slot, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const int N = c.v[10], nk = c.v[11];
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, N, c.v[4], c.v[9]);
+    for (int kk = 0; kk < nk; ++kk) {
+      const uint64_t da = umma_smem_desc(smem_u32(A) + (uint32_t)(kk * c.v[3]), (uint32_t)c.v[1], (uint32_t)c.v[2], (uint32_t)c.v[0]);
+      const uint64_t db = umma_smem_desc(smem_u32(Bm) + (uint32_t)(kk * c.v[8]), (uint32_t)c.v[6], (uint32_t)c.v[7], (uint32_t)c.v[5]);
+      tc_mma_tf32(tmem, da, db, idesc, kk > 0 ? 1u : 0u);
+    }
+    tc_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5;
+  for (int n = 0; n < N; ++n) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    out[threadIdx.x * N + n] = __uint_as_float(v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 256);
+}
+
 
 // Cycles per tcgen05.mma (kind::tf32, K = 8) for the small shapes of the fused conv kernels: a chain of `n` UMMAs issued
 // back to back by one thread into one accumulator, operands resident in shared memory.  `bg` adds background activity on
@@ -240,6 +290,20 @@ extern "C" int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int bg
   if (once.first())
     EEG_CUDA_OK(cudaFuncSetAttribute(umma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024 + 64 + 1024));
   umma_cost_kernel<<<1, 512, 160 * 1024 + 64 + 1024, (cudaStream_t)stream>>>(M, N, mn_major, n, bg, out2);
+  EEG_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int eegb200_debug_umma_generic(const float* a_img, const float* b_img, const int* cfg12, float* out, void* stream) {
+  EEG_REQUIRE(a_img && b_img && cfg12 && out, "debug_umma_generic: null argument");
+  UmmaProbeCfg c;
+  for (int i = 0; i < 12; ++i) c.v[i] = cfg12[i];
+  EEG_REQUIRE(c.v[10] >= 8 && c.v[10] <= 256 && c.v[10] % 8 == 0 && c.v[11] >= 1 && c.v[11] <= 64, "debug_umma_generic: bad N / nk");
+  static PerDeviceOnce once;
+  if (once.first())
+    EEG_CUDA_OK(cudaFuncSetAttribute(umma_generic_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 64 + 1024));
+  umma_generic_probe_kernel<<<1, 128, 65536 + 64 + 1024, (cudaStream_t)stream>>>(a_img, b_img, c, out);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -227,6 +227,10 @@ int eegb200_debug_tma_tile(const float* src, int ld, int mn_major, float* out, v
 int eegb200_debug_umma_m64(float* out128, void* stream);
 /* debug: cycles of a chain of n tcgen05.mma (kind::tf32, K = 8) of shape M x N: out2[0] = issue..completion, out2[1] = issue */
 int eegb200_debug_umma_cost(int M, int N, int mn_major, int n, int background, long long* out2, void* stream);
+/* debug: one UMMA chain D[128][N] = A . B^T over host-prepared shared-memory images (32 KB each) with caller-given
+ * descriptor fields cfg12 = {a_layout, a_lbo, a_sbo, a_kadv, a_major, b_layout, b_lbo, b_sbo, b_kadv, b_major, N, nk};
+ * out = [128][N].  tools/gpu_dual_layout_probe.py */
+int eegb200_debug_umma_generic(const float* a_img, const float* b_img, const int* cfg12, float* out, void* stream);
 
 #ifdef __cplusplus
 }
