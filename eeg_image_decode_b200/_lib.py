@@ -246,6 +246,19 @@ def infonce_workspace_bytes(B: int, N: int, D: int, nt: int) -> int:
     return int(_sig().eegb200_infonce_workspace_bytes(int(B), int(N), int(D), int(nt)))
 
 
+def infonce_target_offset(B: int, N: int, D: int, nt: int) -> int:
+    L = _sig()
+    L.eegb200_infonce_target_offset.restype = ctypes.c_size_t
+    L.eegb200_infonce_target_offset.argtypes = [ctypes.c_int] * 4
+    return int(L.eegb200_infonce_target_offset(int(B), int(N), int(D), int(nt)))
+
+
+def tf32_round(src, dst) -> None:
+    """dst = src rounded to TF32 (round to nearest; plain copy when EEGB200_TF32_ROUND=0), [rows, D] contiguous fp32"""
+    with on_device(src):
+        check(_sig().eegb200_tf32_round(ptr(src), ptr(dst), int(src.shape[0]), int(src.shape[1]), stream_ptr()), "tf32_round")
+
+
 def atms_forward(io: AtmsIO, phases: int, device) -> None:
     with on_device(device):
         check(_sig().eegb200_atms_forward(ctypes.byref(io), phases, stream_ptr()), "atms_forward")

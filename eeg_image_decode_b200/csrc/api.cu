@@ -102,6 +102,19 @@ size_t eegb200_infonce_workspace_bytes(int B, int N, int D, int n_targets) {
   return info_carve(nullptr, B, N, D, n_targets, nullptr);
 }
 
+size_t eegb200_infonce_target_offset(int B, int N, int D, int n_targets) {
+  if (B <= 0 || N <= 0 || D <= 0 || n_targets < 1 || n_targets > 2) return 0;
+  InfoWs w;
+  uint8_t* fake = reinterpret_cast<uint8_t*>(uintptr_t(1) << 20);      // any 256-aligned base: only the offset is used
+  info_carve(fake, B, N, D, n_targets, &w);
+  return (size_t)(reinterpret_cast<uint8_t*>(w.T_r) - fake);
+}
+
+int eegb200_tf32_round(const float* src, float* dst, int rows, int D, void* stream) {
+  EEG_REQUIRE(src && dst && rows > 0 && D > 0 && (D & 3) == 0, "tf32_round: bad arguments");
+  return pad_copy(src, D, rows, D, dst, D, rows, tf32_rounding(), 1.f, (cudaStream_t)stream);
+}
+
 int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream) {
   EEG_REQUIRE(io && io->eeg && io->tgt_img && io->logit_scale && io->workspace && io->col_stats, "infonce: null pointer");
   EEG_REQUIRE(io->B > 0 && io->N >= io->B && io->D > 0 && (io->D & 3) == 0, "infonce: bad shape B=%d N=%d D=%d", io->B,
@@ -119,8 +132,12 @@ int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream) 
 
   if (phase_mask & EEGB200_PHASE_A) {
     EEG_TRY(pad_copy(io->eeg, io->D, io->B, io->D, w.E_r, io->D, io->B, tf32_rounding(), 1.f, s));
-    EEG_TRY(pad_copy(io->tgt_img, io->D, io->N, io->D, w.T_r, io->D, io->N, tf32_rounding(), 1.f, s));
-    if (nt == 2) EEG_TRY(pad_copy(io->tgt_txt, io->D, io->N, io->D, w.T_r + (size_t)io->N * io->D, io->D, io->N, tf32_rounding(), 1.f, s));
+    // targets that already sit in the workspace's own slots (eegb200_infonce_target_offset: the data-parallel step
+    // all-gathers the ranks' eegb200_tf32_round-ed blocks straight into them) are used in place
+    if (io->tgt_img != w.T_r)
+      EEG_TRY(pad_copy(io->tgt_img, io->D, io->N, io->D, w.T_r, io->D, io->N, tf32_rounding(), 1.f, s));
+    if (nt == 2 && io->tgt_txt != w.T_r + (size_t)io->N * io->D)
+      EEG_TRY(pad_copy(io->tgt_txt, io->D, io->N, io->D, w.T_r + (size_t)io->N * io->D, io->D, io->N, tf32_rounding(), 1.f, s));
     GemmArgs g;
     g.M = io->B; g.N = w.ncol; g.K = io->D;
     g.A = {w.E_r, io->D, 0};

@@ -27,10 +27,37 @@ __global__ void infonce_row_lse_kernel(InfoNceArgs a, float* __restrict__ row_ls
     diag[w] = row[a.row_offset + i];
   }
 }
+// the same, one pass (online max / sum) over float4 loads: N % 4 == 0 and 16-byte aligned rows.  At the data-parallel
+// sizes (N = 8192 per target) the logits block is 67 MB and this kernel is bandwidth-bound
+__global__ void infonce_row_lse_vec_kernel(InfoNceArgs a, float* __restrict__ row_lse, float* __restrict__ diag) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= a.nt * a.B) return;
+  const int t = w / a.B, i = w % a.B;
+  const float* row = a.logits + (size_t)i * a.ld + (size_t)t * a.N;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  float mx = -INFINITY, s = 0.f;
+  for (int j = lane; j < a.N / 4; j += 32) {
+    const float4 v = row4[j];
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (m4 > mx) { s *= __expf(mx - m4); mx = m4; }
+    s += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  const float M = warp_max(mx);
+  s = warp_sum(mx > -INFINITY ? s * __expf(mx - M) : 0.f);
+  if (lane == 0) {
+    row_lse[w] = M + logf(s);
+    diag[w] = row[a.row_offset + i];
+  }
+}
+static bool info_vec_ok(const InfoNceArgs& a) {
+  return (a.N & 3) == 0 && (a.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(a.logits) & 15) == 0;
+}
 int infonce_row_lse(const InfoNceArgs& a, float* row_lse, float* diag, cudaStream_t s) {
   ProfScope _ps("infonce_row_lse", s, 0.0, (double)a.B * a.nt * a.N * 4.0);
   const int warps = a.nt * a.B;
-  infonce_row_lse_kernel<<<cdiv(warps * 32, 256), 256, 0, s>>>(a, row_lse, diag);
+  if (info_vec_ok(a)) infonce_row_lse_vec_kernel<<<cdiv(warps * 32, 128), 128, 0, s>>>(a, row_lse, diag);
+  else infonce_row_lse_kernel<<<cdiv(warps * 32, 256), 256, 0, s>>>(a, row_lse, diag);
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -67,6 +94,43 @@ __global__ void infonce_col_partial_kernel(InfoNceArgs a, int rows_per_chunk, fl
     part_sum[(size_t)blockIdx.y * ncol + c] = S;
   }
 }
+// the same with four columns per thread (float4 rows of 512 contiguous bytes per warp): block = 128 columns x 8 row lanes
+__global__ void infonce_col_partial_vec_kernel(InfoNceArgs a, int rows_per_chunk, float* __restrict__ part_max,
+                                               float* __restrict__ part_sum) {
+  __shared__ float4 sm[8][33], ss[8][33];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int ncol = a.nt * a.N;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(a.B, r0 + rows_per_chunk);
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < ncol) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 v4 = *reinterpret_cast<const float4*>(a.logits + (size_t)r * a.ld + c);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float nm = fmaxf(mx[q], v[q]);
+        s[q] = s[q] * __expf(mx[q] - nm) + __expf(v[q] - nm);      // exp(-inf - finite) = 0 on the first row
+        mx[q] = nm;
+      }
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = make_float4(mx[0], mx[1], mx[2], mx[3]);
+  ss[threadIdx.y][threadIdx.x] = make_float4(s[0], s[1], s[2], s[3]);
+  __syncthreads();
+  if (threadIdx.y < 4 && c < ncol) {                       // row lane q merges column c + q
+    const int q = threadIdx.y;
+    float M = -INFINITY;
+    for (int y = 0; y < 8; ++y) M = fmaxf(M, reinterpret_cast<const float*>(&sm[y][threadIdx.x])[q]);
+    float S = 0.f;
+    for (int y = 0; y < 8; ++y) {
+      const float m = reinterpret_cast<const float*>(&sm[y][threadIdx.x])[q];
+      if (m > -INFINITY) S += reinterpret_cast<const float*>(&ss[y][threadIdx.x])[q] * __expf(m - M);
+    }
+    part_max[(size_t)blockIdx.y * ncol + c + q] = M;
+    part_sum[(size_t)blockIdx.y * ncol + c + q] = S;
+  }
+}
 int infonce_col_chunks(int B) {
   int chunks = B / 64;
   if (chunks < 1) chunks = 1;
@@ -77,8 +141,13 @@ int infonce_col_partial(const InfoNceArgs& a, float* part_max, float* part_sum, 
   ProfScope _ps("infonce_col_partial", s, 0.0, (double)a.B * a.nt * a.N * 4.0);
   const int chunks = infonce_col_chunks(a.B);
   const int rpc = cdiv(a.B, chunks);
-  dim3 grid(cdiv(a.nt * a.N, 32), chunks);
-  infonce_col_partial_kernel<<<grid, dim3(32, 8), 0, s>>>(a, rpc, part_max, part_sum);
+  if (info_vec_ok(a)) {
+    dim3 grid(cdiv(a.nt * a.N, 128), chunks);
+    infonce_col_partial_vec_kernel<<<grid, dim3(32, 8), 0, s>>>(a, rpc, part_max, part_sum);
+  } else {
+    dim3 grid(cdiv(a.nt * a.N, 32), chunks);
+    infonce_col_partial_kernel<<<grid, dim3(32, 8), 0, s>>>(a, rpc, part_max, part_sum);
+  }
   EEG_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -174,9 +243,56 @@ __global__ void infonce_grad_kernel(InfoNceArgs a, float* __restrict__ L, const 
     atomicAdd(dscale, s / __ldg(scale_dev));
   }
 }
+// the same on a 2-D grid: blockIdx.x = 1024-column slab (float4 per thread), blockIdx.y strides over the rows -- no
+// per-element index division, 16-byte accesses
+__global__ void infonce_grad_vec_kernel(InfoNceArgs a, float* __restrict__ L, const float* __restrict__ row_lse,
+                                        const float* __restrict__ col_lse, float w_img, float w_txt,
+                                        const float* __restrict__ scale_dev, float* __restrict__ dscale, float gout, int rt) {
+  __shared__ float red[8];
+  const int ncol = a.nt * a.N;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  float ds = 0.f;
+  if (c < ncol) {
+    const int t = c >= a.N ? 1 : 0;                       // N % 4 == 0: a float4 never straddles the two targets
+    const int j0 = c - t * a.N;
+    const float w = (t ? w_txt : w_img) * gout / (2.f * a.N);
+    const float4 cl = *reinterpret_cast<const float4*>(col_lse + c);
+    for (int i = blockIdx.y; i < a.B; i += gridDim.y) {
+      float4* p = reinterpret_cast<float4*>(L + (size_t)i * a.ld + c);
+      const float4 l = *p;
+      const float rl = row_lse[t * a.B + i];
+      float g[4] = {__expf(l.x - rl) + __expf(l.x - cl.x), __expf(l.y - rl) + __expf(l.y - cl.y),
+                    __expf(l.z - rl) + __expf(l.z - cl.z), __expf(l.w - rl) + __expf(l.w - cl.w)};
+      const int dj = a.row_offset + i - j0;                // the diagonal element of this row, if inside the float4
+      if (dj >= 0 && dj < 4) g[dj] -= 2.f;
+      g[0] *= w; g[1] *= w; g[2] *= w; g[3] *= w;
+      ds = fmaf(g[0], l.x, fmaf(g[1], l.y, fmaf(g[2], l.z, fmaf(g[3], l.w, ds))));
+      *p = make_float4(tf32_if(g[0], rt), tf32_if(g[1], rt), tf32_if(g[2], rt), tf32_if(g[3], rt));
+    }
+  }
+  ds = warp_sum(ds);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ds;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[q];
+    atomicAdd(dscale, s / __ldg(scale_dev));
+  }
+}
 int infonce_grad(const InfoNceArgs& a, float* logits_inout, const float* row_lse, const float* col_lse, float w_img,
                  float w_txt, const float* logit_scale_dev, float* dscale, float grad_out_scale, cudaStream_t s) {
   ProfScope _ps("infonce_grad", s, 0.0, (double)a.B * a.nt * a.N * 8.0);
+  if (info_vec_ok(a) && (reinterpret_cast<uintptr_t>(col_lse) & 15) == 0) {
+    const int slabs = cdiv(a.nt * a.N, 1024);
+    int rows = 148 * 8 / slabs;                            // ~8 blocks of 256 threads per SM
+    if (rows < 1) rows = 1;
+    if (rows > a.B) rows = a.B;
+    infonce_grad_vec_kernel<<<dim3(slabs, rows), 256, 0, s>>>(a, logits_inout, row_lse, col_lse, w_img, w_txt, logit_scale_dev,
+                                                              dscale, grad_out_scale, tf32_rounding());
+    EEG_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const long long total = (long long)a.B * a.nt * a.N;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;

@@ -32,21 +32,32 @@ class _InfoNCE:
         # (e.g. the full-batch shape) while a ragged last batch runs eagerly with another
         self._ws_by_key = {}
 
+    def workspace(self, B, N, D, nt, device):
+        key = (B, N, D, nt, device)
+        ws = self._ws_by_key.get(key)
+        if ws is None:
+            if len(self._ws_by_key) >= 8 and not torch.cuda.is_current_stream_capturing():
+                self._ws_by_key.pop(next(k for k in self._ws_by_key if k != getattr(self, "_graph_key", None)))
+            ws = torch.empty(_lib.infonce_workspace_bytes(B, N, D, nt), dtype=torch.uint8, device=device)
+            self._ws_by_key[key] = ws
+        if torch.cuda.is_current_stream_capturing():
+            self._graph_key = key           # never evicted
+        return ws
+
+    def target_slots(self, B, N, D, nt, device):
+        """[nt, N, D] fp32 view of the operand the logits GEMM reads inside the workspace of this shape: targets gathered
+        (TF32-rounded) straight into it and passed to run() are used in place (eegb200_infonce_target_offset)"""
+        ws = self.workspace(B, N, D, nt, device)
+        off = _lib.infonce_target_offset(B, N, D, nt)
+        return ws[off:off + nt * N * D * 4].view(torch.float32).view(nt, N, D)
+
     def run(self, eeg, tgt_img, tgt_txt, logit_scale, w_img, w_txt, row_offset, need_grad, grad_out=1.0, group=None,
             world_size=1):
         """targets are the GLOBAL (already gathered) [N,D] matrices.  Returns (loss[3] device, d_eeg, d_scale)."""
         B, D = eeg.shape
         N = tgt_img.shape[0]
         nt = 2 if tgt_txt is not None else 1
-        key = (B, N, D, nt, eeg.device)
-        ws = self._ws_by_key.get(key)
-        if ws is None:
-            if len(self._ws_by_key) >= 8 and not torch.cuda.is_current_stream_capturing():
-                self._ws_by_key.pop(next(k for k in self._ws_by_key if k != getattr(self, "_graph_key", None)))
-            ws = torch.empty(_lib.infonce_workspace_bytes(B, N, D, nt), dtype=torch.uint8, device=eeg.device)
-            self._ws_by_key[key] = ws
-        if torch.cuda.is_current_stream_capturing():
-            self._graph_key = key           # never evicted
+        ws = self.workspace(B, N, D, nt, eeg.device)
         dev = eeg.device
         col_stats = torch.empty(2, nt * N, device=dev, dtype=torch.float32)
         loss = torch.zeros(3, device=dev, dtype=torch.float32)

@@ -156,20 +156,42 @@ class StepEngine:
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
 
+    def _allreduce_pair(self, a, b):
+        """two all-reduces as ONE NCCL group launch (the encoder part of the gradient arena and the subject table sit on
+        either side of the bucket that is already in flight)"""
+        cm = getattr(torch.distributed, "_coalescing_manager", None)
+        if cm is not None and a.is_cuda and not getattr(self, "_no_coalesce", False):
+            try:
+                with cm(device=a.device):
+                    torch.distributed.all_reduce(a)
+                    torch.distributed.all_reduce(b)
+                return
+            except Exception:            # older / different process-group back ends: fall back for good
+                if torch.cuda.is_current_stream_capturing():
+                    raise
+                self._no_coalesce = True
+        self._allreduce(a)
+        self._allreduce(b)
+
     def gather_async(self, img_feat, txt_feat):
         """start the all-gather of the (input) target blocks; it overlaps the encoder forward.  Returns what
         loss_and_grad(gathered=...) consumes."""
         W = self.world
         if W == 1:
             return None
+        # Each rank rounds its own block to TF32 (what the loss kernel would otherwise do to all W blocks) and the
+        # all-gather lands directly in the logits GEMM's operand inside the loss workspace: no copy of the 2 x N x D targets
+        B, D = img_feat.shape
+        nt = 2 if self.variant == "retrieval" else 1
+        slots = self.nce.target_slots(B, W * B, D, nt, img_feat.device)
         out = []
-        for t in (img_feat, txt_feat if self.variant == "retrieval" else None):
+        for i, t in enumerate((img_feat, txt_feat if nt == 2 else None)):
             if t is None:
                 out.append((None, None))
                 continue
-            t = t.contiguous()
-            buf = torch.empty(W * t.shape[0], t.shape[1], device=t.device, dtype=t.dtype)
-            out.append((buf, torch.distributed.all_gather_into_tensor(buf, t, async_op=True)))
+            r = torch.empty_like(t, memory_format=torch.contiguous_format)
+            _lib.tf32_round(t.contiguous(), r)
+            out.append((slots[i], torch.distributed.all_gather_into_tensor(slots[i], r, async_op=True)))
         return out
 
     def loss_and_grad(self, feats, img_feat, txt_feat, need_grad=True, gathered=None):
@@ -237,8 +259,7 @@ class StepEngine:
             self._phase(_lib.PHASE_B, fwd=False, batch_scale=W)
             self._allreduce(m.ws_tensor("bn1_bwd_sums"))
             self._phase(_lib.PHASE_C, fwd=False, batch_scale=W)
-            self._allreduce(m.flat_grads[:o_tail])
-            self._allreduce(m.flat_grads[o_tab:])
+            self._allreduce_pair(m.flat_grads[:o_tail], m.flat_grads[o_tab:])
             h_tail.wait()
         else:
             m.backprop(d_e)

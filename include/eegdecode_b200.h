@@ -184,6 +184,12 @@ typedef struct eegb200_infonce_io {
 } eegb200_infonce_io;
 size_t eegb200_infonce_workspace_bytes(int B, int N, int D, int n_targets);
 int eegb200_infonce(const eegb200_infonce_io* io, int phase_mask, void* stream);
+/* Zero-copy targets for the data-parallel step: byte offset, inside an eegb200_infonce workspace of this shape, of the
+ * [n_targets][N, D] operand the logits GEMM reads.  A caller may all-gather the ranks' target blocks straight into it
+ * (each block rounded first with eegb200_tf32_round: the tensor core truncates, the loss wants round-to-nearest) and pass
+ * those addresses as tgt_img / tgt_txt: eegb200_infonce then skips its own round-and-copy of the 2 x N x D targets. */
+size_t eegb200_infonce_target_offset(int B, int N, int D, int n_targets);
+int eegb200_tf32_round(const float* src, float* dst, int rows, int D, void* stream);
 
 /* Regression term of the reconstruction-training variant (replaces nn.MSELoss()(eeg_features, img_features),
  * Generation/ATMS_reconstruction.py:201, 227-228 and :264, 285-286; the step loss there is
