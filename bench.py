@@ -452,6 +452,7 @@ def bench_ours(args):
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "top_kernels": top, "final_loss": final_loss,
     }
     _emit(line)
+    eng.check_collectives()
     _leave(world, (gstep, eager, model))
 
 

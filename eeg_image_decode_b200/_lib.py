@@ -259,6 +259,19 @@ def tf32_round(src, dst) -> None:
         check(_sig().eegb200_tf32_round(ptr(src), ptr(dst), int(src.shape[0]), int(src.shape[1]), stream_ptr()), "tf32_round")
 
 
+def peer_sum_buffer_bytes() -> int:
+    L = lib()
+    L.eegb200_peer_sum_buffer_bytes.restype = ctypes.c_size_t
+    return int(L.eegb200_peer_sum_buffer_bytes())
+
+
+def peer_sum_f64(data, peer_ptr_array, rank: int, world: int, seq_dev, err_dev) -> None:
+    """in-place one-shot all-reduce of a small float64 tensor over peer memory (csrc/peer_sum.cu)"""
+    with on_device(data):
+        check(lib().eegb200_peer_sum_f64(ptr(data), int(data.numel()), peer_ptr_array, int(rank), int(world), ptr(seq_dev),
+                                         ptr(err_dev), stream_ptr()), "peer_sum_f64")
+
+
 def atms_forward(io: AtmsIO, phases: int, device) -> None:
     with on_device(device):
         check(_sig().eegb200_atms_forward(ctypes.byref(io), phases, stream_ptr()), "atms_forward")

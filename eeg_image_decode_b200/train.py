@@ -135,6 +135,60 @@ def publish_optimizer_state(model: ATMS, optimizer) -> None:
 # ------------------------------------------------------------------------------------------------
 # one contrastive step (forward, 2x InfoNCE, backward, optimiser), optionally data-parallel
 # ------------------------------------------------------------------------------------------------
+class _PeerSum:
+    """symmetric NVLink buffer + device-side sequence counter behind eegb200_peer_sum_f64 (one per process).
+    EEGB200_PEER_SYNCBN=0 keeps the SyncBatchNorm exchange on NCCL."""
+    _instance = None
+    _failed = False
+
+    @classmethod
+    def create(cls, device, rank, world):
+        import os
+        if cls._instance is not None or cls._failed:
+            return cls._instance
+        if (os.environ.get("EEGB200_PEER_SYNCBN", "1") == "0" or device.type != "cuda" or world > 16
+                or not torch.distributed.is_initialized() or torch.distributed.get_backend() != "nccl"):
+            cls._failed = True
+            return None
+        try:
+            import ctypes
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = _lib.peer_sum_buffer_bytes()
+            with torch.cuda.device(device):
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, torch.distributed.group.WORLD)
+                ptrs = [int(x) for x in hdl.buffer_ptrs]
+                if len(ptrs) != world or any(x == 0 for x in ptrs):
+                    raise RuntimeError("symmetric memory: peer pointers unavailable")
+                self = cls()
+                self.buf, self.hdl, self.rank, self.world = buf, hdl, rank, world
+                self.ptr_array = (ctypes.c_void_p * world)(*ptrs)
+                self.seq = torch.zeros(1, dtype=torch.int64, device=device)
+                self.err = torch.zeros(1, dtype=torch.int32, device=device)
+                torch.cuda.synchronize(device)
+            torch.distributed.barrier()          # every rank's buffer is zeroed before anyone pushes into it
+            ok = torch.ones(1, device=device)
+        except Exception as e:                    # no fabric / IPC support: fall back to NCCL on every rank alike
+            import warnings
+            warnings.warn(f"eeg_image_decode_b200: NVLink peer SyncBN exchange unavailable ({e!r}); using NCCL")
+            self, ok = None, torch.zeros(1, device=device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)      # all ranks or none
+        if ok.item() < 1:
+            cls._failed = True
+            return None
+        cls._instance = self
+        return self
+
+    def sum_(self, t):
+        _lib.peer_sum_f64(t, self.ptr_array, self.rank, self.world, self.seq, self.err)
+
+    def check(self):
+        """host-side check after a synchronisation point: did every exchange complete?"""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("eegb200_peer_sum_f64: a rank never arrived at a SyncBatchNorm exchange")
+
+
 class StepEngine:
     """``variant``: "retrieval" -- alpha*ClipLoss(img) + (1-alpha)*ClipLoss(txt), alpha = 0.99 (ATMS_retrieval.py:229-234);
     "reconstruction" -- alpha*10*MSE(eeg, img) + (1-alpha)*10*ClipLoss(img), alpha = 0.90
@@ -152,9 +206,25 @@ class StepEngine:
         self.fused = fused_optimizer_ok(model, optimizer)
         if self.fused:
             adopt_optimizer(model, optimizer)
+        self._peer = None
+        if self.world > 1:
+            self._peer = _PeerSum.create(model.flat_params.device, self.rank, self.world)
 
     def _allreduce(self, t):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+
+    def check_collectives(self):
+        """call at a host synchronisation point: raises if a peer-memory exchange gave up waiting for a rank"""
+        if self._peer is not None:
+            self._peer.check()
+
+    def _allreduce_stats(self, t):
+        """SyncBatchNorm sums (80 doubles): one-shot exchange over NVLink peer memory when available (csrc/peer_sum.cu),
+        else NCCL"""
+        if self._peer is not None and t.dtype == torch.float64 and t.numel() <= 256:
+            self._peer.sum_(t)
+        else:
+            self._allreduce(t)
 
     def _allreduce_pair(self, a, b):
         """two all-reduces as ONE NCCL group launch (the encoder part of the gradient arena and the subject table sit on
@@ -233,10 +303,10 @@ class StepEngine:
             seed ^= (self.rank + 1) * 0x9E3779B97F4A7C15 & 0x3FFFFFFFFFFFFFFF     # decorrelate the ranks' dropout masks
             # SyncBN: all-reduce the batch statistics between the forward phases
             m.encode(eeg, subject_ids, train=True, seed=seed, phases=_lib.PHASE_A, known_subject=known_subject)
-            self._allreduce(m.ws_tensor("bn1_sums"))
+            self._allreduce_stats(m.ws_tensor("bn1_sums"))
             out = m._last[3]
             self._phase(_lib.PHASE_B, fwd=True, batch_scale=W)
-            self._allreduce(m.ws_tensor("bn2_sums"))
+            self._allreduce_stats(m.ws_tensor("bn2_sums"))
             self._phase(_lib.PHASE_C, fwd=True, batch_scale=W)
             for bn in (m.enc_eeg[0].tsconv[2], m.enc_eeg[0].tsconv[5]):
                 bn.num_batches_tracked.add_(1)
@@ -255,9 +325,9 @@ class StepEngine:
             o_tail = m._offs["enc_eeg.0.projection.0.weight"]
             o_tab = m._offs[_lib.P_NAMES[_lib.P_SUBJ_TABLE]]
             h_tail = torch.distributed.all_reduce(m.flat_grads[o_tail:o_tab], async_op=True)
-            self._allreduce(m.ws_tensor("bn2_bwd_sums"))
+            self._allreduce_stats(m.ws_tensor("bn2_bwd_sums"))
             self._phase(_lib.PHASE_B, fwd=False, batch_scale=W)
-            self._allreduce(m.ws_tensor("bn1_bwd_sums"))
+            self._allreduce_stats(m.ws_tensor("bn1_bwd_sums"))
             self._phase(_lib.PHASE_C, fwd=False, batch_scale=W)
             self._allreduce_pair(m.flat_grads[:o_tail], m.flat_grads[o_tab:])
             h_tail.wait()
@@ -597,6 +667,7 @@ def _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_al
         raise RuntimeError("train_model: empty dataloader")
     if eng.world > 1:
         torch.distributed.all_reduce(loss_acc)
+        eng.check_collectives()
     publish_optimizer_state(eeg_model, optimizer if eng.fused else None)
     average_loss = float(loss_acc[0].item()) / n_batches
     accuracy = int(correct.item()) / total

@@ -202,6 +202,17 @@ int eegb200_tf32_round(const float* src, float* dst, int rows, int D, void* stre
 int eegb200_mse(const float* eeg, const float* tgt, int B, int D, long long n_total_rows, float weight, float grad_out,
                 float* loss, float* loss_term, float* d_eeg, void* stream);
 
+/* SyncBatchNorm statistics exchange of the data-parallel step without NCCL: one-shot all-reduce (sum, fp64, n <= 256) over
+ * NVLink peer memory.  peer_buffers[r] = rank r's symmetric buffer of eegb200_peer_sum_buffer_bytes() bytes as mapped in
+ * THIS process (zero-initialised once, e.g. torch.distributed._symmetric_memory.empty + rendezvous -> buffer_ptrs);
+ * seq_dev = this rank's call counter (device uint64, starts at 0, advanced by the kernel: CUDA-graph replayable);
+ * *error_flag_dev is set to 1 if a peer never arrived (the kernel gives up after a few seconds instead of hanging).
+ * Every rank must make the same sequence of calls.  data (local, device) is summed in place, identically on all ranks.
+ * Replaces torch.distributed.all_reduce on the 2 x 40 BatchNorm sums (train.py StepEngine). */
+size_t eegb200_peer_sum_buffer_bytes(void);
+int eegb200_peer_sum_f64(double* data, int n, const void* const* peer_buffers, int rank, int world,
+                         unsigned long long* seq_dev, int* error_flag_dev, void* stream);
+
 /* Optional L2 normalisation of the EEG embedding before the logits (BASELINE.json north_star wording).  The reference
  * does NOT normalise (ATMS.forward, Retrieval/ATMS_retrieval.py:182-191): ATMS(normalize=False) is the default and the
  * parity path.  y = x / max(|x|_2, 1e-12) row-wise (torch.nn.functional.normalize), norms[row] = the denominator;

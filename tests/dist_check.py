@@ -119,6 +119,7 @@ def main():
         print(f"graphed DP: captured={finals[True][2]} loss rel diff vs eager={gerr:.2e} -> {'PASS' if gok else 'FAIL'}", flush=True)
     ok = ok and gok
     torch.cuda.synchronize()
+    eng.check_collectives()          # the NVLink peer SyncBN exchange (csrc/peer_sum.cu) never gave up on a rank
     if rank == 0:
         print("DIST_CHECK " + ("PASS" if ok else "FAIL"), flush=True)
     # destroy_process_group() with captured collectives alive hung on this stack: drop the graphs, run the interpreter's
