@@ -150,6 +150,11 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr) { return umma_smem_de
 __device__ __forceinline__ uint64_t desc_mn_split(uint32_t addr, uint32_t slab_stride) {
   return umma_smem_desc(addr, slab_stride, 512, UMMA_LAYOUT_SW128_BASE32B);
 }
+// The SAME [128 k-rows][32 floats] slab read as a K-MAJOR operand (rows = the 128 k-rows, reduction index = the 32 mn
+// floats): the tensor core accepts SWIZZLE_128B_BASE32B for K-major tiles with LBO = 4096 (32 rows) and SBO = 512 (4 rows),
+// k-steps of 8 = +32 bytes (tools/gpu_dual_layout_probe.py, exact on random data).  One thread-written tile can therefore
+// feed both a product that contracts over its columns and one that contracts over its rows -- no second copy.
+__device__ __forceinline__ uint64_t desc_k_of_mn(uint32_t addr) { return umma_smem_desc(addr, 4096, 512, UMMA_LAYOUT_SW128_BASE32B); }
 __device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 // box-51 pooled sums of one token row (8 samples per lane), entirely in registers: I[k] = inclusive prefix sum of the
@@ -637,7 +642,7 @@ static_assert(O1_DYM % 1024 == 0 && O2_DYM % 1024 == 0 && O2_WTT % 1024 == 0, "s
 // barriers, tmem slot
 constexpr uint32_t M_PS = 0;
 constexpr uint32_t M_DPS = M_PS + 2 * POOL_BYTES;
-constexpr int NB_BARS = 8 * 2 + 1 + 2 * 2 + 2 * 2 + 2;
+constexpr int NB_BARS = 8 * 2 + 1 + 2 * 2 + 2 * 2 + 2 + 8;
 template <int MODE> struct BwdMisc {
   static constexpr uint32_t TAB = M_DPS + (MODE == MODE_BAPPLY ? SCAN_BYTES : 0u);
   static constexpr uint32_t RED = TAB + 5 * 48 * 4;
@@ -702,22 +707,27 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   float* tab = reinterpret_cast<float*>(misc + MM::TAB);      // [0] bt, [1] sc, [2] sh, [3] p1, [4] p2 (see the epilogue)
   float* red = reinterpret_cast<float*>(misc + MM::RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + MM::BAR);
-  uint64_t* im_full = bars;              // [2] builders -> control A
-  uint64_t* im_empty = bars + 2;         // [2] last UMMA reading the im2col buffer -> builders (B2: both control threads)
-  uint64_t* dyk_full = bars + 4;         // [2] builders wrote the K-major dY2 tile -> control A
-  uint64_t* dyk_empty = bars + 6;        // [2] last dA1 UMMA of the tile -> builders
+  uint64_t* im_full = bars;              // [2] builders -> control A                     (B2: a ring of 4, see im4_*)
+  uint64_t* im_empty = bars + 2;         // [2] last UMMA reading the im2col buffer -> builders
+  uint64_t* dyk_full = bars + 4;         // [2] builders staged the dY2 tile -> control A (B1: and control B, same tile)
+  uint64_t* dyk_empty = bars + 6;        // [2] last dA1 UMMA of the tile (B1: and its last dWs UMMA) -> builders
   uint64_t* c_full = bars + 8;           // [2] conv + dA1 UMMAs done -> epilogue
   uint64_t* c_empty = bars + 10;         // [2] epilogue read TMEM -> control A (8 arrivals)
   uint64_t* op_full = bars + 12;         // [2] epilogue wrote a1 (B1: own buffer per group) / dy (B2: [0] only) -> control B
   uint64_t* op_empty = bars + 14;        // [2] second-stage UMMAs reading it done -> epilogue.  B1: a1 buffer [bi] is free again;
                                          //     B2 (ONE dy buffer): [g] = the UMMAs of the iteration before one of group g completed
   uint64_t* wst_full = bars + 16;        // [1] the group's packed weights have landed (TMA, once)
-  uint64_t* dym_full = bars + 17;        // [2] B1: builders wrote the MN-major dY2 tile (buffer tl & 1) -> control B
-  uint64_t* dym_empty = bars + 19;       // [2] B1: last dWs UMMA of the tile -> builders
+  uint64_t* dym_full = bars + 17;        // [2] (unused since the dY2 tile is shared by both UMMAs)
+  uint64_t* dym_empty = bars + 19;       // [2] (unused)
   uint64_t* gg_full = bars + 21;         // [2] B2: G UMMAs done -> scatter warps
   uint64_t* gg_empty = bars + 23;        // [2] B2: scatter warps read TMEM -> control B (4 arrivals)
   uint64_t* final_a = bars + 25;         // everything issued by control A has completed
   uint64_t* final_b = bars + 26;         // ... by control B
+  // B2: ONE im2col tile per iteration (MN-major slab, read K-major by the conv UMMA and MN-major by the dwt UMMA, which
+  // is the LAST stage of the pipeline) in a ring of 4: the tile is held for the whole pipeline latency, two buffers
+  // throttled the kernel to latency / 2 per iteration
+  uint64_t* im4_full = bars + 27;        // [4] builders -> control A
+  uint64_t* im4_empty = bars + 31;       // [4] conv UMMAs (control A) + dwt UMMAs (control B) done -> builders
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + MM::TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -732,7 +742,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_init(&im_full[i], 1);
       mbar_init(&im_empty[i], BS ? 1 : 2);
       mbar_init(&dyk_full[i], 1);
-      mbar_init(&dyk_empty[i], 1);
+      mbar_init(&dyk_empty[i], BS ? 2 : 1);
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], N_EPI_WARPS);
       mbar_init(&op_full[i], N_EPI_WARPS);
@@ -741,6 +751,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_init(&gg_empty[i], 4);
       mbar_init(&dym_full[i], 1);
       mbar_init(&dym_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&im4_full[i], 1);
+      mbar_init(&im4_empty[i], 2);
     }
     mbar_init(wst_full, 1);
     mbar_init(final_a, 1);
@@ -850,18 +864,27 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       const int tile = slot + tl * n_slots;
       const int ns = min(TILE_S, p.B - tile * TILE_S);
       mbar_wait(&dyk_empty[tb], ((uint32_t)(tl >> 1) & 1u) ^ 1u);       // last dA1 UMMA of local tile tl-2
-      uint8_t* dk = sm + OB_DYK + (uint32_t)tb * KB_A;
+      // B2: K-major SWIZZLE_128B tile (+ tail k-step) for the dA1 UMMA.  B1: ONE MN-major slab (+ chunk 0 of the shared
+      // tail slab T[tb]) that the dA1 UMMA reads K-major and the dWs UMMA reads MN-major (desc_k_of_mn): 16-byte pieces
+      // 2c, 2c+1 of row r form its 32-byte chunk c, stored at chunk c ^ (r & 3)
+      uint8_t* dk = sm + (BS ? O1_DYM + (uint32_t)tb * SLAB : OB_DYK + (uint32_t)tb * KB_A);
+      uint8_t* dt = BS ? sm + O1_TAILS + (uint32_t)tb * SLAB + (uint32_t)r * 128u + (uint32_t)((r & 3) << 5)
+                       : sm + OB_TAIL + sw128_off(r, 2 * tb);
+      const uint32_t dt1 = BS ? 16u : (uint32_t)(sw128_off(r, 2 * tb + 1) - sw128_off(r, 2 * tb));
+      auto piece = [&](int j) -> uint32_t {
+        return BS ? (uint32_t)r * 128u + (uint32_t)(((j >> 1) ^ (r & 3)) << 5) + (uint32_t)(j & 1) * 16u : sw128_off(r, j);
+      };
       if (r < ns * N_POOL) {
         const float* src = p.dy2 + ((size_t)tile * TILE_ROWS + r) * N_FILT;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp_async16(dk + sw128_off(r, j), src + 4 * j);
-        cp_async16(sm + OB_TAIL + sw128_off(r, 2 * tb), src + 32);
-        cp_async16(sm + OB_TAIL + sw128_off(r, 2 * tb + 1), src + 36);
+        for (int j = 0; j < 8; ++j) cp_async16(dk + piece(j), src + 4 * j);
+        cp_async16(dt, src + 32);
+        cp_async16(dt + dt1, src + 36);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dk + sw128_off(r, j)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(sm + OB_TAIL + sw128_off(r, 2 * tb + 1)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dk + piece(j)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dt) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dt + dt1) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_commit();
     };
@@ -870,8 +893,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     if (gb == 0 && total_it > 0) { stage_dyk(0); pending_dyk = 0; }
     for (int it = gb; it < total_it; it += 2) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
-      const int bi = gb;
-      const uint32_t n = (uint32_t)(it >> 1);
+      const int bi = BS ? gb : (it & 3);                  // B1: K-major tile, 2 buffers;  B2: MN-major tile, ring of 4
+      const uint32_t n = BS ? (uint32_t)(it >> 1) : (uint32_t)(it >> 2);
       const bool valid = r < d.ns * N_POOL;
       const float4 x0 = xa, x1 = xb;
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 0);
@@ -880,7 +903,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       if (rq < d.ns) pool_row(x0, x1, lane, ps_all + rq * PS_LD);
       named_bar_sync(1 + gb, 128);                        // pooled sums visible
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 1);
-      mbar_wait(&im_empty[bi], (n & 1u) ^ 1u);
+      mbar_wait(BS ? &im_empty[bi] : &im4_empty[bi], (n & 1u) ^ 1u);
       if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 2);
       {
         const float* src = ps_all + s_row * PS_LD + 5 * p_row;
@@ -888,14 +911,15 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
 #pragma unroll
         for (int t = 0; t < 28; ++t) a[t] = (valid && t < K_TEMP) ? tf32_fast(src[t]) : 0.f;
         a[K_TEMP] = a[K_TEMP + 1] = valid ? 1.f : 0.f;   // the ones columns that carry the folded affine constants
-        uint8_t* kt = sm + OB_IMK + (uint32_t)bi * KB_A;
+        if (BS) {
+          uint8_t* kt = sm + OB_IMK + (uint32_t)bi * KB_A;
 #pragma unroll
-        for (int ch = 0; ch < 7; ++ch)
-          *reinterpret_cast<float4*>(kt + sw128_off(r, ch)) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
-        if (!BS) {
+          for (int ch = 0; ch < 7; ++ch)
+            *reinterpret_cast<float4*>(kt + sw128_off(r, ch)) = make_float4(a[4 * ch], a[4 * ch + 1], a[4 * ch + 2], a[4 * ch + 3]);
+        } else {
           // the same row as k-row r of the MN-major operand (mn = tap t); column 25 = 1 for valid rows: the dwt UMMA
           // then also delivers sum_rows dy (the conv bias gradient) in output column 25 (and again in 26, unread)
-          uint8_t* mt = sm + O2_IMM + (uint32_t)bi * SLAB;
+          uint8_t* mt = sm + (bi < 2 ? O2_IMM + (uint32_t)bi * SLAB : OB_IMK + (uint32_t)(bi - 2) * SLAB);
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8)
             mn_store8(mt, 8 * j8, r, make_float4(a[8 * j8], a[8 * j8 + 1], a[8 * j8 + 2], a[8 * j8 + 3]),
@@ -907,37 +931,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       named_bar_sync(1 + gb, 128);
       if (rq == 0 && lane == 0) {
         if (pending_dyk >= 0) mbar_arrive(&dyk_full[pending_dyk]);
-        mbar_arrive(&im_full[bi]);
+        mbar_arrive(BS ? &im_full[bi] : &im4_full[bi]);
         CONV_TRACE(gb, it, 3);
       }
       pending_dyk = -1;
-      if (BS && gb == 0 && d.ci < 2) {
-        // ---- MN-major copy of this tile's dY2 rows for the dWs UMMA, double buffered like the K-major tile it is copied
-        //      from (a single buffer drained the whole pipeline once per tile: its last reader is the LAST UMMA of the
-        //      previous tile): the last dWs UMMA of tile tl-2 must be done.  ALWAYS group 0, at its first iteration inside
-        //      the tile (ci 0, or 1 when the tile starts on an odd iteration): parity waits are only sound when one agent
-        //      walks the phases in order (tools/conv_tc_protocol_sim.py) ----
-        const int tbm = d.tl & 1;
-        mbar_wait(&dym_empty[tbm], ((uint32_t)(d.tl >> 1) & 1u) ^ 1u);
-        if (rq == 0 && lane == 0) CONV_TRACE(gb, it, 4);
-        uint8_t* dm = sm + O1_DYM + (uint32_t)tbm * SLAB;
-        {
-          // this thread's row of the K-major tile staged one tile earlier (zeros for rows past the batch), re-laid MN-major
-          mbar_wait(&dyk_full[tbm], (uint32_t)(d.tl >> 1) & 1u);      // acquire: the other group may have staged this tile
-          const uint8_t* dk = sm + OB_DYK + (uint32_t)tbm * KB_A;
-          float4 v[10];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(dk + sw128_off(r, j));
-          v[8] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm));
-          v[9] = *reinterpret_cast<const float4*>(sm + OB_TAIL + sw128_off(r, 2 * tbm + 1));
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) mn_store8(dm, 8 * j8, r, v[2 * j8], v[2 * j8 + 1]);   // mn = j, 8 per 32-byte chunk
-          mn_store8(sm + O1_TAILS + (uint32_t)tbm * SLAB, 0, r, v[8], v[9]);                   // j 32..39: chunk 0 of T[tbm]
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + gb, 128);
-        if (rq == 0 && lane == 0) { mbar_arrive(&dym_full[tbm]); CONV_TRACE(gb, it, 5); }
-      }
     }
   } else if (warp < SCAT_WARP0) {
     // =============================== epilogue: 16 warps = 4 lane quarters x 4 column quarters ===============================
@@ -960,8 +957,6 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     const bool swp = ((r >> 2) & 1) != 0;                            // see mn_store8
     const uint32_t o_mn_lo = o_mn8 + (swp ? 16u : 0u), o_mn_hi = o_mn8 + (swp ? 0u : 16u);
     const uint32_t o_tail = BS ? mn_off(8 + 2 * cq, r) : mn_off(32 + 2 * cq, r);
-    const uint32_t o_k0 = sw128_off(r, 2 * cq), o_k1 = sw128_off(r, 2 * cq + 1);
-    const uint32_t o_kt = sw128_off(r, 4 + (cq >> 1)) + (uint32_t)(cq & 1) * 8u;
     for (int it = 0; it < total_it; ++it) {
       const int bi = it & 1;
       const uint32_t n = (uint32_t)(it >> 1);
@@ -1008,11 +1003,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         if constexpr (BS) {    // filters 32..39 -> mn 8..15 (chunk 1) of the shared tail slab T[bi]
           *reinterpret_cast<float2*>(sm + O1_TAILS + (uint32_t)bi * SLAB + o_tail) = make_float2(z[8], z[9]);
         } else {
-          *reinterpret_cast<float2*>(mt + o_tail) = make_float2(z[8], z[9]);
-          uint8_t* kt = sm + O2_DYK2;                                    // K-major: row r, columns k (tail -> k-step 2 of OB_TAIL)
-          *reinterpret_cast<float4*>(kt + o_k0) = v0;
-          *reinterpret_cast<float4*>(kt + o_k1) = v1;
-          *reinterpret_cast<float2*>(sm + OB_TAIL + o_kt) = make_float2(z[8], z[9]);
+          *reinterpret_cast<float2*>(mt + o_tail) = make_float2(z[8], z[9]);      // the G UMMA reads this tile K-major
         }
       }
       fence_proxy_async_smem();
@@ -1168,9 +1159,16 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     // =============================== control A: weight TMA (once), conv + dA1 UMMAs ===============================
     constexpr uint32_t idesc48 = umma_idesc_tf32(128, N48, 0, 0), idesc_conv = umma_idesc_tf32(128, (int)Y_COLS, 0, 0);
     const uint32_t s0 = smem_u32(sm);
-    const uint64_t d_bc = desc_k(s0 + O_BC), d_tail = desc_k(s0 + OB_TAIL), d_wst = desc_k(s0 + OB_WST), d_wstt = desc_k(s0 + OB_WSTT);
-    uint64_t d_im[2], d_dyk[2];
-    for (int b = 0; b < 2; ++b) { d_im[b] = desc_k(s0 + OB_IMK + (uint32_t)b * KB_A); d_dyk[b] = desc_k(s0 + OB_DYK + (uint32_t)b * KB_A); }
+    const uint64_t d_bc = desc_k(s0 + O_BC), d_wst = desc_k(s0 + OB_WST), d_wstt = desc_k(s0 + OB_WSTT);
+    uint64_t d_im[4], d_dyk[2];
+    uint64_t d_dyt[2];                                   // the 8-column tail k-step of dY2 tile buffer b
+    for (int b = 0; b < 2; ++b) {
+      d_dyk[b] = BS ? desc_k_of_mn(s0 + O1_DYM + (uint32_t)b * SLAB) : desc_k(s0 + OB_DYK + (uint32_t)b * KB_A);
+      d_dyt[b] = BS ? desc_k_of_mn(s0 + O1_TAILS + (uint32_t)b * SLAB) : desc_adv(desc_k(s0 + OB_TAIL), (uint32_t)b * 32u);
+    }
+    for (int b = 0; b < 4; ++b)
+      d_im[b] = BS ? desc_k(s0 + OB_IMK + (uint32_t)(b & 1) * KB_A)
+                   : desc_k_of_mn(s0 + (b < 2 ? O2_IMM + (uint32_t)b * SLAB : OB_IMK + (uint32_t)(b - 2) * SLAB));
     if (total_it > 0) {
       mbar_arrive_expect_tx(wst_full, GC * KB_48 + KB_48);
       tma_load_2d(&tmWst, wst_full, sm + OB_WST, 0, g * GC * N48);           // [4 channels x 48 rows][32]
@@ -1179,9 +1177,10 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bi = it & 1, tb = d.tl & 1;
+      const int ib = BS ? bi : (it & 3);                 // im2col buffer
       const uint32_t n = (uint32_t)(it >> 1);
       CONV_TRACE(4, it, 0);
-      mbar_wait(&im_full[bi], n & 1u);
+      mbar_wait(BS ? &im_full[ib] : &im4_full[ib], BS ? (n & 1u) : ((uint32_t)(it >> 2) & 1u));
       CONV_TRACE(4, it, 1);
       mbar_wait(&c_empty[bi], (n & 1u) ^ 1u);
       CONV_TRACE(4, it, 2);
@@ -1189,8 +1188,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       // conv UMMA (plain TF32 in the backward), both affine maps folded in: Y[bi] = [im2col | 1 | 1] . [z rows | lin rows]^T
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        tc_mma_tf32(tmem_base + (uint32_t)bi * Y_COLS, desc_adv(d_im[bi], kk * 32), desc_adv(d_bc, kk * 32), idesc_conv, kk > 0 ? 1u : 0u);
-      tc_commit(&im_empty[bi]);                          // B2: control B adds the second arrival (MN-major copy, dwt UMMA)
+        tc_mma_tf32(tmem_base + (uint32_t)bi * Y_COLS, desc_adv(d_im[ib], kk * 32), desc_adv(d_bc, kk * 32), idesc_conv, kk > 0 ? 1u : 0u);
+      tc_commit(BS ? &im_empty[ib] : &im4_empty[ib]);    // B2: control B adds the second arrival (dwt UMMA on the same tile)
       if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);
       if (it == 0) mbar_wait(wst_full, 0);
       tc_fence_after();
@@ -1199,7 +1198,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
         tc_mma_tf32(tmem_base + T_DA + (uint32_t)(bi * 48), desc_adv(d_dyk[tb], kk * 32), desc_adv(d_w, kk * 32), idesc48, kk > 0 ? 1u : 0u);
-      tc_mma_tf32(tmem_base + T_DA + (uint32_t)(bi * 48), desc_adv(d_tail, (uint32_t)tb * 32u), desc_adv(d_wstt, (uint32_t)d.ci * 32u), idesc48, 1u);
+      tc_mma_tf32(tmem_base + T_DA + (uint32_t)(bi * 48), d_dyt[tb], desc_adv(d_wstt, (uint32_t)d.ci * 32u), idesc48, 1u);
       tc_commit(&c_full[bi]);
       CONV_TRACE(4, it, 3);
       if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);     // nothing reads the K-major dY2 tile after its last dA1 UMMA
@@ -1216,16 +1215,19 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     // B1 operands: first slab + shared tail slab T[x] (x = the operand's own buffer index)
     const uint64_t d_dym1[2] = {desc_mn_split(s0 + O1_DYM, O1_TAILS - O1_DYM), desc_mn_split(s0 + O1_DYM + SLAB, O1_TAILS - O1_DYM)};
     const uint64_t d_a1m0 = desc_mn_split(s0 + O1_A1M, O1_TAILS - O1_A1M), d_a1m1 = desc_mn_split(s0 + O1_A1M + SLAB, O1_TAILS - O1_A1M);
-    const uint64_t d_dyk2 = desc_k(s0 + O2_DYK2), d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + OB_TAIL + 3u * 32u);
-    const uint64_t d_tail2 = desc_k(s0 + OB_TAIL + 2u * 32u), d_dym2 = desc_mn(s0 + O2_DYM);
-    const uint64_t d_imm0 = desc_mn(s0 + O2_IMM), d_imm1 = desc_mn(s0 + O2_IMM + SLAB);
+    // the dy tile (MN-major, written once by the epilogue) read K-major by the G UMMA: columns 0..31 = first slab,
+    // 32..39 = k-step 0 of the second slab
+    const uint64_t d_dyk2 = desc_k_of_mn(s0 + O2_DYM), d_tail2 = desc_k_of_mn(s0 + O2_DYM + SLAB);
+    const uint64_t d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + OB_TAIL + 3u * 32u), d_dym2 = desc_mn(s0 + O2_DYM);
+    uint64_t d_imm[4];
+    for (int b = 0; b < 4; ++b) d_imm[b] = desc_mn(s0 + (b < 2 ? O2_IMM + (uint32_t)b * SLAB : OB_IMK + (uint32_t)(b - 2) * SLAB));
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bj = it & 1;
       CONV_TRACE(5, it, 0);
       if (BS) {
         const int tb = d.tl & 1;
-        if (d.ci == 0) mbar_wait(&dym_full[tb], (uint32_t)(d.tl >> 1) & 1u);
+        if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);     // the tile control A reads K-major
         CONV_TRACE(5, it, 1);
         mbar_wait(&op_full[bj], (uint32_t)(it >> 1) & 1u);
         CONV_TRACE(5, it, 2);
@@ -1239,7 +1241,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
           tc_mma_tf32(dcol, desc_adv(d_dym1[tb], kk * 1024), desc_adv(db, kk * 1024), idesc48_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[bj]);
         CONV_TRACE(5, it, 3);
-        if (d.ci == gc - 1) tc_commit(&dym_empty[tb]);
+        if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);   // second arrival (control A: last dA1 UMMA of the tile)
       } else {
         mbar_wait(&op_full[0], (uint32_t)it & 1u);
         CONV_TRACE(5, it, 1);
@@ -1254,13 +1256,13 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         tc_mma_tf32(gcol, d_tail2, d_wttt, idesc32, 1u);
         tc_commit(&gg_full[bj]);
         // dwt[k, t] += sum_rows dy[row, k] * im2col[row, t]  (column 25 of the im2col operand is the ones column)
-        const uint64_t dbm = bj ? d_imm1 : d_imm0;
+        const uint64_t dbm = d_imm[it & 3];
         const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk)
           tc_mma_tf32(tmem_base + T_DWT, desc_adv(d_dym2, kk * 1024), desc_adv(dbm, kk * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[0]);
-        tc_commit(&im_empty[bj]);
+        tc_commit(&im4_empty[it & 3]);
         CONV_TRACE(5, it, 3);
       }
     }

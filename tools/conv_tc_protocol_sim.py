@@ -27,10 +27,12 @@ def run(mode, gc, n_tiles, seed, verbose=False):
     BS = mode == "B1"
     total = n_tiles * gc
     B = {}
-    for nm, cnt in (("im_full", 1), ("im_empty", 1 if BS else 2), ("dyk_full", 1), ("dyk_empty", 1), ("c_full", 1),
+    for nm, cnt in (("im_full", 1), ("im_empty", 1), ("dyk_full", 1), ("dyk_empty", 2 if BS else 1), ("c_full", 1),
                     ("c_empty", 16), ("op_full", 16), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4),
                     ("dym_full", 1), ("dym_empty", 1)):
         B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
+    B["im4_full"] = [Bar(f"im4_full[{i}]", 1) for i in range(4)]
+    B["im4_empty"] = [Bar(f"im4_empty[{i}]", 2) for i in range(4)]
     for nm in ("final_a", "final_b"):
         B[nm] = Bar(nm, 1)
     delayed = []            # (time, barrier): tcgen05.commit arrivals
@@ -51,20 +53,17 @@ def run(mode, gc, n_tiles, seed, verbose=False):
             pending = 0
         for it in range(gb, total, 2):
             tl, ci = dec(it)
-            bi, n = gb, it >> 1
+            bi, n = (gb, it >> 1) if BS else (it & 3, it >> 2)
+            imf, ime = ("im_full", "im_empty") if BS else ("im4_full", "im4_empty")
             if ci == gc - 1 and tl + 1 < n_tiles:
                 tb = (tl + 1) & 1
                 yield ("wait", B["dyk_empty"][tb], (((tl + 1) >> 1) & 1) ^ 1)
                 pending = tb
-            yield ("wait", B["im_empty"][bi], (n & 1) ^ 1)
+            yield ("wait", B[ime][bi], (n & 1) ^ 1)
             if pending >= 0:
                 yield ("arrive", B["dyk_full"][pending])
-            yield ("arrive", B["im_full"][bi])
+            yield ("arrive", B[imf][bi])
             pending = -1
-            if BS and gb == 0 and ci < 2:
-                yield ("wait", B["dym_empty"][tl & 1], ((tl >> 1) & 1) ^ 1)
-                yield ("wait", B["dyk_full"][tl & 1], (tl >> 1) & 1)
-                yield ("arrive", B["dym_full"][tl & 1])
 
     def epilogue(ge, w):
         for it in range(total):
@@ -90,9 +89,12 @@ def run(mode, gc, n_tiles, seed, verbose=False):
         for it in range(total):
             tl, ci = dec(it)
             bi, tb, n = it & 1, tl & 1, it >> 1
-            yield ("wait", B["im_full"][bi], n & 1)
+            if BS:
+                yield ("wait", B["im_full"][bi], n & 1)
+            else:
+                yield ("wait", B["im4_full"][it & 3], (it >> 2) & 1)
             yield ("wait", B["c_empty"][bi], (n & 1) ^ 1)
-            yield ("commit", B["im_empty"][bi])
+            yield ("commit", B["im_empty"][bi] if BS else B["im4_empty"][it & 3])
             if ci == 0:
                 yield ("wait", B["dyk_full"][tb], (tl >> 1) & 1)
             yield ("commit", B["c_full"][bi])
@@ -106,17 +108,17 @@ def run(mode, gc, n_tiles, seed, verbose=False):
             bj = it & 1
             if BS:
                 if ci == 0:
-                    yield ("wait", B["dym_full"][tl & 1], (tl >> 1) & 1)
+                    yield ("wait", B["dyk_full"][tl & 1], (tl >> 1) & 1)
                 yield ("wait", B["op_full"][bj], (it >> 1) & 1)
                 yield ("commit", B["op_empty"][bj])
                 if ci == gc - 1:
-                    yield ("commit", B["dym_empty"][tl & 1])
+                    yield ("commit", B["dyk_empty"][tl & 1])
             else:
                 yield ("wait", B["op_full"][0], it & 1)
                 yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
                 yield ("commit", B["gg_full"][bj])
                 yield ("commit", B["op_empty"][0])
-                yield ("commit", B["im_empty"][bj])
+                yield ("commit", B["im4_empty"][it & 3])
         yield ("commit", B["final_b"])
 
     roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a(), "ctrlB": ctrl_b()}
