@@ -361,3 +361,49 @@ def test_normalize_option_matches_l2_normalised_reference(lib):
     twins[1].backprop(d_raw)
     for k in ("proj_eeg.2.weight", "proj_eeg.0.weight", "enc_eeg.0.tsconv.4.weight", "encoder.enc_embedding.value_embedding.weight"):
         assert rel_l2(twins[0].grad_view(k), twins[1].grad_view(k)) < 5e-3, k
+
+
+@pytest.mark.gpu
+def test_umma_reads_one_tile_in_both_majors(lib):
+    """csrc/conv_tc.cu backward kernels keep ONE copy of dY2 / im2col / dy in the MN-major SWIZZLE_128B_BASE32B layout and
+    read it K-major for the second product (descriptor LBO 4096, SBO 512, 32-byte k-steps): exact on random integers"""
+    import ctypes
+    import numpy as np
+    _lib = lib
+    L = _lib.lib()
+    L.eegb200_debug_umma_generic.argtypes = [ctypes.c_void_p] * 5
+    rng = np.random.default_rng(3)
+    N = 48
+    X = rng.integers(-8, 9, size=(128, 32)).astype(np.float32)
+    W = rng.integers(-4, 5, size=(N, 32)).astype(np.float32)
+    a_img, b_img = np.zeros(8192, np.float32), np.zeros(8192, np.float32)
+    for r in range(128):
+        for c in range(32):
+            a_img[(r * 128 + (((c >> 3) ^ (r & 3)) << 5) + (c & 7) * 4) // 4] = X[r, c]        # MN-major slab image
+    for r in range(N):
+        for c in range(32):
+            b_img[((r >> 3) * 1024 + (r & 7) * 128 + (((c >> 2) ^ (r & 7)) << 4) + (c & 3) * 4) // 4] = W[r, c]
+    a, b = torch.from_numpy(a_img).cuda(), torch.from_numpy(b_img).cuda()
+    cfg = torch.tensor([1, 4096, 512, 32, 0, 2, 16, 1024, 32, 0, N, 4], dtype=torch.int32)
+    out = torch.zeros(128 * N, device="cuda")
+    _lib.check(L.eegb200_debug_umma_generic(_lib.ptr(a), _lib.ptr(b), cfg.data_ptr(), _lib.ptr(out), _lib.stream_ptr()), "probe")
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(128, N), X @ W.T)
+
+
+@pytest.mark.gpu
+def test_peer_sum_single_rank_and_sequence(lib):
+    """eegb200_peer_sum_f64 (csrc/peer_sum.cu) with world = 1: the vector passes through its own slot unchanged, the
+    device-side sequence number advances, both buffer sets get used, no error flag.  (W > 1: tests/dist_check.py.)"""
+    import ctypes
+    _lib = lib
+    buf = torch.zeros(_lib.peer_sum_buffer_bytes(), dtype=torch.uint8, device="cuda")
+    seq = torch.zeros(1, dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ptrs = (ctypes.c_void_p * 1)(buf.data_ptr())
+    for i in range(5):
+        v = torch.arange(80, dtype=torch.float64, device="cuda") * (i + 1) + 0.25
+        want = v.clone()
+        _lib.peer_sum_f64(v, ptrs, 0, 1, seq, err)
+        torch.cuda.synchronize()
+        assert torch.equal(v, want) and int(seq.item()) == i + 1 and int(err.item()) == 0

@@ -19,8 +19,12 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_
 cut -c1-400 $OUT/${TAG}_bench_ref.json
 echo "== ncu launch list" ; date +%T
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python tools/ncu_step.py 3 > $OUT/${TAG}_ncu_list.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu > $OUT/${TAG}_ncu_list.log 2>&1
 wc -l $OUT/${TAG}_launches.csv
+echo "== ncu full capture of the fused conv kernels" ; date +%T
+timeout 400 ncu --set full --clock-control none -k regex:conv_tc -c 8 -f -o $OUT/${TAG}_conv \
+    python tools/ncu_step.py 2 > $OUT/${TAG}_ncu_conv.log 2>&1
+ls -la $OUT/${TAG}_conv.ncu-rep
 echo "== timeline" ; date +%T
 timeout 300 python tools/trace_step.py $OUT/${TAG}_trace.json 2>&1 | tail -1
 date +%T
