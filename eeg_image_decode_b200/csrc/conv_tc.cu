@@ -16,16 +16,23 @@
 //   B2 conv_tc_bwd_apply  same recomputation -> dy = A*dz + B*y + C (folded BatchNorm backward) -> G = dy . wt (UMMA)
 //                         scattered into the pooled positions, prefix-summed into d x3; dwt += dy^T . im2col (UMMA)
 //
-// Roles inside a CTA (one CTA per SM).  Every per-iteration resource is double buffered and the work of iteration `it`
-// belongs to group it & 1, so two iterations are always in flight:
-//   builders  2 groups x 4 warps   token rows (prefetched two iterations ahead) -> pooled sums -> im2col operand in
-//                                  swizzled shared memory (+ the dY2 tile in the backward kernels)
-//   epilogue  2 groups x 8 warps   thread = TMEM lane = tile row, two column halves; all the per-element math
-//   scatter   4 warps (B2 only)    G -> pooled positions -> prefix sums -> d x3 rows
+// Roles inside a CTA (one CTA per SM); iterations = (tile, channel), two or more always in flight:
+//   builders  2 groups x 4 warps   group it & 1: token rows (prefetched two iterations ahead) -> pooled sums (register
+//                                  prefix scan) -> im2col operand in swizzled shared memory (+ the dY2 tile, cp.async)
+//   epilogue  16 warps             4 TMEM lane quarters x 4 column quarters (10 filters per thread): all per-element math
+//   scatter   4 warps (B2 only)    G -> pooled positions (warp shuffles + halo) -> prefix sums -> d x3 rows
 //   control   2 threads            A: first-stage UMMAs (conv, dA1); B: TMA + second-stage UMMAs (spatial / dWs / G, dwt)
 //
 // F1 / F2 work items are (tile, 21 channels) spread over all SMs; B1 / B2 CTAs own a group of 4 channels and stride
 // over the tiles, so that the dWs / dwt accumulators stay in TMEM for the whole kernel.
+//
+// Three tricks carry most of the speed:
+//   * the BatchNorm affine maps are folded into the conv UMMA's B operand (scaled rows; shifts as TF32 hi + lo pairs
+//     against two ones-columns of the im2col tile), so the accumulator is z (and yhat / Bc*y + Cc) directly and rows
+//     past the batch are exact zeros -- no per-column constants, FMAs or masks in the epilogues;
+//   * a tile that two UMMAs contract over different axes (dY2, im2col, dy) exists ONCE, as an MN-major slab that the
+//     other product reads K-major with the same swizzle (desc_k_of_mn);
+//   * MN-major operands with 40 useful columns share their second slab (one 32-byte chunk per row each).
 #include "kernels.h"
 #include <stdlib.h>
 #include <string.h>
