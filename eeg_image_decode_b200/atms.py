@@ -387,6 +387,7 @@ class ATMS(nn.Module):
             for bn in (self.enc_eeg[0].tsconv[2], self.enc_eeg[0].tsconv[5]):
                 bn.num_batches_tracked.add_(1)
         self._last = (io, x, subject_ids, out, perm, getattr(self, "_grp_arrs", None))
+        self._fwd_gen = getattr(self, "_fwd_gen", 0) + 1      # which forward owns the saved activations (autograd bridge)
         self._last_subjects = sorted({g[1] for g in groups}) if groups else None
         if perm is not None:          # hand the embeddings back in the caller's trial order
             res = user_out if user_out is not None else torch.empty_like(out)
@@ -436,6 +437,7 @@ class _ATMSFunction(torch.autograd.Function):
     def forward(ctx, model, x, subject_ids, *params):
         out = model.encode(x, subject_ids, train=True)
         ctx.model = model
+        ctx.gen = model._fwd_gen
         ctx.use_shared = bool((subject_ids >= N_SUBJECT_ROWS).any().item()) or bool((subject_ids < 0).any().item())
         ctx.subjects = model._last_subjects
         return out
@@ -443,6 +445,10 @@ class _ATMSFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         model = ctx.model
+        if ctx.gen != model._fwd_gen:
+            # the saved activations live in ONE workspace per batch size: a later forward (train or eval) has replaced them
+            raise RuntimeError("eeg_image_decode_b200: backward() through an ATMS forward whose activations were "
+                               "overwritten by a later forward of the same model; call backward() before the next forward")
         model.flat_grads.zero_()
         model.backprop(d_out.contiguous())
         tab, sh = _lib.P_NAMES[_lib.P_SUBJ_TABLE], _lib.P_NAMES[_lib.P_SUBJ_SHARED]

@@ -240,7 +240,10 @@ __global__ void infonce_grad_kernel(InfoNceArgs a, float* __restrict__ L, const 
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[q];
-    atomicAdd(dscale, s / __ldg(scale_dev));
+    // d loss / d scale = sum(G .* L) / scale (L = scale * <E,T>); at scale == 0 every logit is 0 and the quotient is 0/0:
+    // report 0 there instead of NaN (the raw dot products are not kept)
+    const float sc = __ldg(scale_dev);
+    atomicAdd(dscale, sc != 0.f ? s / sc : 0.f);
   }
 }
 // the same on a 2-D grid: blockIdx.x = 1024-column slab (float4 per thread), blockIdx.y strides over the rows -- no
@@ -276,7 +279,10 @@ __global__ void infonce_grad_vec_kernel(InfoNceArgs a, float* __restrict__ L, co
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) s += red[q];
-    atomicAdd(dscale, s / __ldg(scale_dev));
+    // d loss / d scale = sum(G .* L) / scale (L = scale * <E,T>); at scale == 0 every logit is 0 and the quotient is 0/0:
+    // report 0 there instead of NaN (the raw dot products are not kept)
+    const float sc = __ldg(scale_dev);
+    atomicAdd(dscale, sc != 0.f ? s / sc : 0.f);
   }
 }
 int infonce_grad(const InfoNceArgs& a, float* logits_inout, const float* row_lse, const float* col_lse, float w_img,

@@ -54,6 +54,11 @@ class _InfoNCE:
     def run(self, eeg, tgt_img, tgt_txt, logit_scale, w_img, w_txt, row_offset, need_grad, grad_out=1.0, group=None,
             world_size=1):
         """targets are the GLOBAL (already gathered) [N,D] matrices.  Returns (loss[3] device, d_eeg, d_scale)."""
+        for name, t in (("eeg", eeg), ("tgt_img", tgt_img), ("tgt_txt", tgt_txt)):
+            # raw device pointers cross the C ABI: anything but a dense fp32 matrix would be read as garbage
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.dim() != 2):
+                raise RuntimeError(f"InfoNCE: {name} must be a contiguous 2-D float32 CUDA tensor, got {t.dtype} "
+                                   f"{tuple(t.shape)} strides {t.stride()}")
         B, D = eeg.shape
         N = tgt_img.shape[0]
         nt = 2 if tgt_txt is not None else 1

@@ -430,7 +430,9 @@ class GraphedTrainStep:
         B = eeg.shape[0]
         # data-parallel steps are captured too (NCCL collectives are graph-capturable); EEGB200_CUDA_GRAPH_DP=0 opts out
         ok = self.enabled and eng.fused and (eng.world == 1 or self.dp_ok)
-        if not ok or (self.graph is None and self.calls < 2) or (self.B is not None and B != self.B):
+        if self.calls == 0:
+            self._nominal_B = B             # the loader's batch size; a ragged batch must not become the captured shape
+        if not ok or (self.graph is None and (self.calls < 2 or B != self._nominal_B)) or (self.B is not None and B != self.B):
             self.calls += 1
             return self._body(eeg, sid, img, txt, labels, None)
         if self.graph is None:
@@ -565,7 +567,9 @@ def _BN_SCALE_SHIFT(world: int) -> int:
 # ------------------------------------------------------------------------------------------------
 def train_model(sub, eeg_model, dataloader, optimizer, device, text_features_all, img_features_all, config, *,
                 step_callback=None):
-    """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254.
+    """One epoch.  Returns (average_loss, accuracy, features[n_seen,1024]) like ATMS_retrieval.py:199-254.  Under
+    torch.distributed every rank feeds its shard (equal batch sizes on all ranks): loss and accuracy are the global-batch
+    values on every rank, the features are the rank's own rows.
     ``step_callback(step_index, loss[3] on the HOST)`` (optional, keyword only) receives every step's loss (mix, image,
     text share), read back from the device like the reference does (:238) but delivered one step late so that the
     read-back does not stall the next launch.
@@ -666,7 +670,12 @@ def _train_epoch(sub, eeg_model, dataloader, optimizer, device, text_features_al
     if n_batches == 0:
         raise RuntimeError("train_model: empty dataloader")
     if eng.world > 1:
+        # loss shares sum to the global-batch loss; accuracy is reported over the global batch too (the features returned
+        # below stay this rank's rows)
+        counts = torch.stack([correct[0].to(torch.float64), torch.tensor(float(total), device=device, dtype=torch.float64)])
         torch.distributed.all_reduce(loss_acc)
+        torch.distributed.all_reduce(counts)
+        correct, total = counts[0:1], int(counts[1].item())
         eng.check_collectives()
     publish_optimizer_state(eeg_model, optimizer if eng.fused else None)
     average_loss = float(loss_acc[0].item()) / n_batches

@@ -294,3 +294,20 @@ def test_reconstruction_loops_and_feature_export(lib, tmp_path):
     want = O.reconstruction_loss(ft[:5], timg_all[tlabels][:5], m.logit_scale.detach().cpu(), 0.9)
     want2 = O.reconstruction_loss(ft[5:], timg_all[tlabels][5:], m.logit_scale.detach().cpu(), 0.9)
     assert abs(l2 - 0.5 * (want.item() + want2.item())) < 3e-3 * abs(l2)
+
+
+@pytest.mark.gpu
+def test_autograd_bridge_refuses_stale_activations():
+    """the saved activations live in one workspace per batch size: backward() through a forward that a later forward has
+    overwritten must raise instead of silently differentiating the wrong batch"""
+    from eeg_image_decode_b200.atms import ATMS
+    torch.manual_seed(0)
+    m = ATMS().cuda().train()
+    x = torch.randn(4, 63, 250, device="cuda")
+    sid = torch.full((4,), 8, device="cuda")
+    out1 = m(x, sid)
+    out2 = m(x * 0.5, sid)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        out1.sum().backward()
+    out2.sum().backward()                      # the latest forward still works
+    assert m.enc_eeg[0].projection[0].weight.grad is not None

@@ -235,3 +235,16 @@ def test_optimizer_state_is_imported_and_tied_to_the_optimizer_object():
     # a different optimizer object does not inherit them
     adopt_optimizer(m, torch.optim.AdamW(m.parameters(), lr=3e-4))
     assert m._adam_steps["main"] == 0 and float(m._adam_m.abs().sum()) == 0.0
+
+
+def test_infonce_rejects_strided_or_non_fp32_inputs():
+    """raw pointers cross the C ABI: the loss front end refuses anything but dense fp32 matrices (no silent garbage)"""
+    import pytest
+    import torch
+    from eeg_image_decode_b200.loss import _InfoNCE
+    e = torch.zeros(4, 8)
+    s = torch.tensor(1.0)
+    with pytest.raises(RuntimeError, match="contiguous 2-D float32"):
+        _InfoNCE().run(e, torch.zeros(8, 4).t(), None, s, 1.0, 0.0, 0, False)
+    with pytest.raises(RuntimeError, match="contiguous 2-D float32"):
+        _InfoNCE().run(e.half(), torch.zeros(4, 8), None, s, 1.0, 0.0, 0, False)
