@@ -608,8 +608,14 @@ __global__ void pack_ws_tc_kernel(const float* __restrict__ ws, float* __restric
 // backward
 // =================================================================================================================
 enum { MODE_BSTATS = 0, MODE_BAPPLY = 1 };
-constexpr int B1_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 2) * 32;         // 832
-constexpr int B2_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 4 + 2) * 32;     // 960: + 4 scatter warps
+// One thread issues a tcgen05.mma every ~80-100 cycles however small it is, but a SECOND issuing thread runs at the same
+// rate beside it (tools/gpu_mma_cost.py: 2 issuers = twice the UMMAs per cycle): the per-iteration UMMAs are spread over
+// several single-thread "control" warps so that no thread issues more than ~9 of them.
+//   B1: control A (conv 4 + dA1 5), control B0 / B1 (the 16 dWs UMMAs of the even / odd iterations)
+//   B2: control A (conv 4 + dA1 5), control B0 (G 5), control B1 / B2 (dwt: k-steps 0..7 / 8..15, two accumulators)
+constexpr int B1_CTRL2 = 2, B2_CTRL2 = 3;
+constexpr int B1_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 1 + B1_CTRL2) * 32;         // 864
+constexpr int B2_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 4 + 1 + B2_CTRL2) * 32;     // 1024: + 4 scatter warps
 constexpr int SCAT_WARP0 = N_BUILD_WARPS + N_EPI_WARPS;
 constexpr uint32_t FWD_PACK_FLOATS = N_CH * N48 * 64;        // pack_ws_tc_kernel output
 constexpr uint32_t WST_MAIN_FLOATS = N_GROUPS * GC * N48 * 32;   // [c (64 slots)][48 rows k][32 floats j 0..31]
@@ -649,7 +655,7 @@ static_assert(O1_DYM % 1024 == 0 && O2_DYM % 1024 == 0 && O2_WTT % 1024 == 0, "s
 // barriers, tmem slot
 constexpr uint32_t M_PS = 0;
 constexpr uint32_t M_DPS = M_PS + 2 * POOL_BYTES;
-constexpr int NB_BARS = 8 * 2 + 1 + 2 * 2 + 2 * 2 + 2 + 8;
+constexpr int NB_BARS = 8 * 2 + 1 + 2 * 2 + 2 * 2 + 2 + 8 + 2;
 template <int MODE> struct BwdMisc {
   static constexpr uint32_t TAB = M_DPS + (MODE == MODE_BAPPLY ? SCAN_BYTES : 0u);
   static constexpr uint32_t RED = TAB + 5 * 48 * 4;
@@ -699,13 +705,13 @@ __global__ void __launch_bounds__(MODE == MODE_BSTATS ? B1_THREADS : B2_THREADS,
 conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_constant__ CUtensorMap tmWstt, const ConvBwdParams p) {
   constexpr bool BS = MODE == MODE_BSTATS;
   constexpr int NTHREADS = BS ? B1_THREADS : B2_THREADS;
-  constexpr int CTRL_A = BS ? SCAT_WARP0 : SCAT_WARP0 + 4, CTRL_B = CTRL_A + 1;
+  constexpr int CTRL_A = BS ? SCAT_WARP0 : SCAT_WARP0 + 4, CTRL_B = CTRL_A + 1, N_CTRL2 = BS ? B1_CTRL2 : B2_CTRL2;
   constexpr uint32_t O_MISC = BS ? O1_MISC : O2_MISC;
   constexpr uint32_t O_BC = BS ? O1_BC : O2_BC;
   // TMEM columns.  Y[2] = the folded conv product (B1: z | yhat = 96 columns, B2: z | lin_hi | lin_lo = 144), DA[2] = dA1
   // (48), then B1: dWs[ci] (48 each);  B2: G[2] (32 each), dwt (32)
-  constexpr uint32_t Y_COLS = BS ? 96u : 144u, T_DA = 2 * Y_COLS, T_ACC = T_DA + 96u, T_DWT = T_ACC + 64u;
-  static_assert(BS ? T_ACC + 4 * 48 <= 512 : T_DWT + 32 <= 512, "TMEM columns");
+  constexpr uint32_t Y_COLS = BS ? 96u : 144u, T_DA = 2 * Y_COLS, T_ACC = T_DA + 96u, T_DWT = T_ACC + 64u;   // B2: dwt x 2 halves
+  static_assert(BS ? T_ACC + 4 * 48 <= 512 : T_DWT + 2 * 32 <= 512, "TMEM columns");
   using MM = BwdMisc<MODE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -734,7 +740,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
   // is the LAST stage of the pipeline) in a ring of 4: the tile is held for the whole pipeline latency, two buffers
   // throttled the kernel to latency / 2 per iteration
   uint64_t* im4_full = bars + 27;        // [4] builders -> control A
-  uint64_t* im4_empty = bars + 31;       // [4] conv UMMAs (control A) + dwt UMMAs (control B) done -> builders
+  uint64_t* im4_empty = bars + 31;       // [4] conv UMMAs (control A) + both halves of the dwt UMMAs done -> builders
+  uint64_t* final_c = bars + 35;         // [2] everything issued by the second / third second-stage control thread
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + MM::TMEM);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -749,11 +756,11 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       mbar_init(&im_full[i], 1);
       mbar_init(&im_empty[i], BS ? 1 : 2);
       mbar_init(&dyk_full[i], 1);
-      mbar_init(&dyk_empty[i], BS ? 2 : 1);
+      mbar_init(&dyk_empty[i], BS ? 3 : 1);          // B1: control A + the two dWs issuers
       mbar_init(&c_full[i], 1);
       mbar_init(&c_empty[i], N_EPI_WARPS);
       mbar_init(&op_full[i], N_EPI_WARPS);
-      mbar_init(&op_empty[i], 1);
+      mbar_init(&op_empty[i], BS ? 1 : 3);           // B2: the dy tile is read by the G and both dwt issuers
       mbar_init(&gg_full[i], 1);
       mbar_init(&gg_empty[i], 4);
       mbar_init(&dym_full[i], 1);
@@ -761,11 +768,13 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&im4_full[i], 1);
-      mbar_init(&im4_empty[i], 2);
+      mbar_init(&im4_empty[i], 3);
     }
     mbar_init(wst_full, 1);
     mbar_init(final_a, 1);
     mbar_init(final_b, 1);
+    mbar_init(&final_c[0], 1);
+    mbar_init(&final_c[1], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmWst);
     tma_prefetch_desc(&tmWstt);
@@ -1021,6 +1030,8 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     // ---- after the loop: the accumulators that lived in TMEM for the whole kernel ----
     mbar_wait(final_a, 0);
     mbar_wait(final_b, 0);
+    mbar_wait(&final_c[0], 0);
+    mbar_wait(&final_c[1], 0);
     tc_fence_after();
     if constexpr (BS) {
       const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
@@ -1048,9 +1059,12 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     } else {
       const int row64 = 16 * q + lane;                                 // row of an M = 64 accumulator held by this TMEM lane
       if (total_it > 0 && q < 3) {                                     // accumulator row = filter k, column = tap t (25: ones column)
-        float w[8];
+        float w[8], w2[8];
         tmem_ld8_nw(tmem_base + lane_addr + T_DWT + (uint32_t)(8 * cq), w);
+        tmem_ld8_nw(tmem_base + lane_addr + T_DWT + 32u + (uint32_t)(8 * cq), w2);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] += w2[i];
         if (lane < 16 && row64 < N_FILT) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1211,8 +1225,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);     // nothing reads the K-major dY2 tile after its last dA1 UMMA
     }
     tc_commit(final_a);
-  } else if (warp == CTRL_B && lane == 0) {
-    // =============================== control B: second-stage UMMAs ===============================
+  } else if (warp >= CTRL_B && warp < CTRL_B + N_CTRL2 && lane == 0) {
+    // =============================== control B0 .. : second-stage UMMAs ===============================
+    const int cb = warp - CTRL_B;
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32, 0, 0);
     // the weight-gradient UMMAs have only 40 useful output rows: M = 64 halves the A-operand traffic (2 slabs instead of 4).
     // An M = 64 accumulator keeps row i in TMEM lane 32*(i/16) + i%16 (tools/gpu_m64_probe.py)
@@ -1228,16 +1243,22 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     const uint64_t d_wtt = desc_k(s0 + O2_WTT), d_wttt = desc_k(s0 + OB_TAIL + 3u * 32u), d_dym2 = desc_mn(s0 + O2_DYM);
     uint64_t d_imm[4];
     for (int b = 0; b < 4; ++b) d_imm[b] = desc_mn(s0 + (b < 2 ? O2_IMM + (uint32_t)b * SLAB : OB_IMK + (uint32_t)(b - 2) * SLAB));
+    // B1: issuer cb takes the iterations with it & 1 == cb: its own a1 buffer and op_full / op_empty pair, and (4 channels
+    // per tile) always the same two dWs accumulators, so every accumulator is fed by ONE thread, in order.  The 3-channel
+    // group would alternate accumulators between the two threads: there issuer 0 does everything.
+    const bool solo = BS && gc != GC;
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bj = it & 1;
-      CONV_TRACE(5, it, 0);
       if (BS) {
+        if (solo ? cb != 0 : bj != cb) continue;
         const int tb = d.tl & 1;
-        if (d.ci == 0) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);     // the tile control A reads K-major
-        CONV_TRACE(5, it, 1);
+        if (cb == 0) CONV_TRACE(5, it, 0);
+        // first iteration of this thread inside the tile: the dY2 tile (shared with control A) has landed
+        if (d.ci == (solo ? 0 : cb)) mbar_wait(&dyk_full[tb], (uint32_t)(d.tl >> 1) & 1u);
+        if (cb == 0) CONV_TRACE(5, it, 1);
         mbar_wait(&op_full[bj], (uint32_t)(it >> 1) & 1u);
-        CONV_TRACE(5, it, 2);
+        if (cb == 0) CONV_TRACE(5, it, 2);
         tc_fence_after();
         // dWs_c[j, k] += sum_rows dY2[row, j] * a1[row, k]: both operands MN-major, K = the 128 tile rows
         const uint64_t db = bj ? d_a1m1 : d_a1m0;
@@ -1247,33 +1268,48 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
         for (int kk = 0; kk < 16; ++kk)
           tc_mma_tf32(dcol, desc_adv(d_dym1[tb], kk * 1024), desc_adv(db, kk * 1024), idesc48_mn, kk > 0 ? 1u : acc0);
         tc_commit(&op_empty[bj]);
-        CONV_TRACE(5, it, 3);
-        if (d.ci == gc - 1) tc_commit(&dyk_empty[tb]);   // second arrival (control A: last dA1 UMMA of the tile)
+        if (cb == 0) CONV_TRACE(5, it, 3);
+        // last iteration of this thread inside the tile: its dWs UMMAs no longer read the dY2 tile (arrivals: control A,
+        // issuer 0, issuer 1 -- in the solo case issuer 0 also stands in for the idle one)
+        if (d.ci == (solo ? gc - 1 : 2 + cb)) {
+          tc_commit(&dyk_empty[tb]);
+          if (solo) tc_commit(&dyk_empty[tb]);
+        }
       } else {
+        if (cb == 0) CONV_TRACE(5, it, 0);
         mbar_wait(&op_full[0], (uint32_t)it & 1u);
-        CONV_TRACE(5, it, 1);
-        mbar_wait(&gg_empty[bj], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        CONV_TRACE(5, it, 2);
-        tc_fence_after();
-        // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
-        const uint32_t gcol = tmem_base + T_ACC + (uint32_t)(bj * 32);
+        if (cb == 0) CONV_TRACE(5, it, 1);
+        if (cb == 0) {
+          mbar_wait(&gg_empty[bj], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          CONV_TRACE(5, it, 2);
+          tc_fence_after();
+          // G[(s,p), t] = sum_k dy[(s,p), k] * wt[k, t]
+          const uint32_t gcol = tmem_base + T_ACC + (uint32_t)(bj * 32);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          tc_mma_tf32(gcol, desc_adv(d_dyk2, kk * 32), desc_adv(d_wtt, kk * 32), idesc32, kk > 0 ? 1u : 0u);
-        tc_mma_tf32(gcol, d_tail2, d_wttt, idesc32, 1u);
-        tc_commit(&gg_full[bj]);
-        // dwt[k, t] += sum_rows dy[row, k] * im2col[row, t]  (column 25 of the im2col operand is the ones column)
-        const uint64_t dbm = d_imm[it & 3];
-        const uint32_t acc0 = it > 0 ? 1u : 0u;
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma_tf32(gcol, desc_adv(d_dyk2, kk * 32), desc_adv(d_wtt, kk * 32), idesc32, kk > 0 ? 1u : 0u);
+          tc_mma_tf32(gcol, d_tail2, d_wttt, idesc32, 1u);
+          tc_commit(&gg_full[bj]);
+          tc_commit(&op_empty[0]);
+          CONV_TRACE(5, it, 3);
+        } else {
+          tc_fence_after();
+          // dwt[k, t] += sum_rows dy[row, k] * im2col[row, t]  (column 25 of the im2col operand is the ones column):
+          // issuer 1 takes the tile rows 0..63, issuer 2 the rows 64..127, each into its own accumulator
+          const uint64_t dbm = d_imm[it & 3];
+          const uint32_t acc0 = it > 0 ? 1u : 0u;
+          const uint32_t dcol = tmem_base + T_DWT + (uint32_t)(cb - 1) * 32u;
+          const int k0 = (cb - 1) * 8;
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          tc_mma_tf32(tmem_base + T_DWT, desc_adv(d_dym2, kk * 1024), desc_adv(dbm, kk * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
-        tc_commit(&op_empty[0]);
-        tc_commit(&im4_empty[it & 3]);
-        CONV_TRACE(5, it, 3);
+          for (int kk = 0; kk < 8; ++kk)
+            tc_mma_tf32(dcol, desc_adv(d_dym2, (k0 + kk) * 1024), desc_adv(dbm, (k0 + kk) * 1024), idesc32_mn, kk > 0 ? 1u : acc0);
+          tc_commit(&op_empty[0]);
+          tc_commit(&im4_empty[it & 3]);
+        }
       }
     }
-    tc_commit(final_b);
+    tc_commit(cb == 0 ? final_b : &final_c[cb - 1]);
+    if (BS && cb == 0) tc_commit(&final_c[1]);          // B1 has two second-stage issuers: nobody else raises final_c[1]
   }
 
   tc_fence_before();

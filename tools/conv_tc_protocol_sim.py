@@ -27,13 +27,13 @@ def run(mode, gc, n_tiles, seed, verbose=False):
     BS = mode == "B1"
     total = n_tiles * gc
     B = {}
-    for nm, cnt in (("im_full", 1), ("im_empty", 1), ("dyk_full", 1), ("dyk_empty", 2 if BS else 1), ("c_full", 1),
-                    ("c_empty", 16), ("op_full", 16), ("op_empty", 1), ("gg_full", 1), ("gg_empty", 4),
+    for nm, cnt in (("im_full", 1), ("im_empty", 1), ("dyk_full", 1), ("dyk_empty", 3 if BS else 1), ("c_full", 1),
+                    ("c_empty", 16), ("op_full", 16), ("op_empty", 1 if BS else 3), ("gg_full", 1), ("gg_empty", 4),
                     ("dym_full", 1), ("dym_empty", 1)):
         B[nm] = [Bar(f"{nm}[{i}]", cnt) for i in range(2)]
     B["im4_full"] = [Bar(f"im4_full[{i}]", 1) for i in range(4)]
-    B["im4_empty"] = [Bar(f"im4_empty[{i}]", 2) for i in range(4)]
-    for nm in ("final_a", "final_b"):
+    B["im4_empty"] = [Bar(f"im4_empty[{i}]", 3) for i in range(4)]
+    for nm in ("final_a", "final_b", "final_c0", "final_c1"):
         B[nm] = Bar(nm, 1)
     delayed = []            # (time, barrier): tcgen05.commit arrivals
     now = [0]
@@ -78,6 +78,8 @@ def run(mode, gc, n_tiles, seed, verbose=False):
                 yield ("arrive", B["op_full"][0])
         yield ("wait", B["final_a"], 0)
         yield ("wait", B["final_b"], 0)
+        yield ("wait", B["final_c0"], 0)
+        yield ("wait", B["final_c1"], 0)
 
     def scatter(w):
         for it in range(total):
@@ -102,26 +104,40 @@ def run(mode, gc, n_tiles, seed, verbose=False):
                 yield ("commit", B["dyk_empty"][tb])
         yield ("commit", B["final_a"])
 
-    def ctrl_b():
+    def ctrl_b(cb):
+        # second-stage issuers.  B1: cb 0 / 1 = dWs of the even / odd iterations (the 3-channel group: cb 0 alone);
+        # B2: cb 0 = G, cb 1 / 2 = the two halves of the dwt chain
+        solo = BS and gc != 4
         for it in range(total):
             tl, ci = dec(it)
             bj = it & 1
             if BS:
-                if ci == 0:
+                if (cb != 0) if solo else (bj != cb):
+                    continue
+                if ci == (0 if solo else cb):
                     yield ("wait", B["dyk_full"][tl & 1], (tl >> 1) & 1)
                 yield ("wait", B["op_full"][bj], (it >> 1) & 1)
                 yield ("commit", B["op_empty"][bj])
-                if ci == gc - 1:
+                if ci == (gc - 1 if solo else 2 + cb):
                     yield ("commit", B["dyk_empty"][tl & 1])
+                    if solo:
+                        yield ("commit", B["dyk_empty"][tl & 1])
             else:
                 yield ("wait", B["op_full"][0], it & 1)
-                yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
-                yield ("commit", B["gg_full"][bj])
-                yield ("commit", B["op_empty"][0])
-                yield ("commit", B["im4_empty"][it & 3])
-        yield ("commit", B["final_b"])
+                if cb == 0:
+                    yield ("wait", B["gg_empty"][bj], ((it >> 1) & 1) ^ 1)
+                    yield ("commit", B["gg_full"][bj])
+                    yield ("commit", B["op_empty"][0])
+                else:
+                    yield ("commit", B["op_empty"][0])
+                    yield ("commit", B["im4_empty"][it & 3])
+        yield ("commit", B["final_b"] if cb == 0 else B["final_c0" if cb == 1 else "final_c1"])
+        if BS and cb == 0:
+            yield ("commit", B["final_c1"])
 
-    roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a(), "ctrlB": ctrl_b()}
+    roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a()}
+    for cb in range(2 if BS else 3):
+        roles[f"ctrlB{cb}"] = ctrl_b(cb)
     for ge in range(2):
         for w in range(8):
             roles[f"epi{ge}.{w}"] = epilogue(ge, w)
