@@ -611,9 +611,12 @@ enum { MODE_BSTATS = 0, MODE_BAPPLY = 1 };
 // One thread issues a tcgen05.mma every ~80-100 cycles however small it is, but a SECOND issuing thread runs at the same
 // rate beside it (tools/gpu_mma_cost.py: 2 issuers = twice the UMMAs per cycle): the per-iteration UMMAs are spread over
 // several single-thread "control" warps so that no thread issues more than ~9 of them.
-//   B1: control A (conv 4 + dA1 5), control B0 / B1 (the 16 dWs UMMAs of the even / odd iterations)
-//   B2: control A (conv 4 + dA1 5), control B0 (G 5), control B1 / B2 (dwt: k-steps 0..7 / 8..15, two accumulators)
-constexpr int B1_CTRL2 = 2, B2_CTRL2 = 3;
+//   B2: control A (conv 4 + dA1 5), control B0 (G 5), control B1 / B2 (dwt: k-steps 0..7 / 8..15, two accumulators):
+//       295 -> 248 us.
+//   B1: control A (conv 4 + dA1 5), control B0 (dWs 16).  Splitting the dWs UMMAs over two issuers (even / odd
+//       iterations, B1_CTRL2 = 2: implemented, measured) made B1 SLOWER (206 -> 214 us): it is bound by SIMT issue slots
+//       and another polling warp costs more than the shorter UMMA chain gains.
+constexpr int B1_CTRL2 = 1, B2_CTRL2 = 3;
 constexpr int B1_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 1 + B1_CTRL2) * 32;         // 864
 constexpr int B2_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 4 + 1 + B2_CTRL2) * 32;     // 1024: + 4 scatter warps
 constexpr int SCAT_WARP0 = N_BUILD_WARPS + N_EPI_WARPS;
@@ -1246,7 +1249,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     // B1: issuer cb takes the iterations with it & 1 == cb: its own a1 buffer and op_full / op_empty pair, and (4 channels
     // per tile) always the same two dWs accumulators, so every accumulator is fed by ONE thread, in order.  The 3-channel
     // group would alternate accumulators between the two threads: there issuer 0 does everything.
-    const bool solo = BS && gc != GC;
+    const bool solo = BS && (gc != GC || N_CTRL2 == 1);
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bj = it & 1;
@@ -1309,7 +1312,9 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
       }
     }
     tc_commit(cb == 0 ? final_b : &final_c[cb - 1]);
-    if (BS && cb == 0) tc_commit(&final_c[1]);          // B1 has two second-stage issuers: nobody else raises final_c[1]
+    if (cb == 0) {                                       // issuer 0 also raises the barriers of the issuers this mode lacks
+      for (int i = N_CTRL2; i < 3; ++i) tc_commit(&final_c[i - 1]);
+    }
   }
 
   tc_fence_before();

@@ -440,6 +440,16 @@ class GraphedTrainStep:
             m._ws_pinned.add(B)          # the graph bakes in pointers into this workspace: it must outlive other batch sizes
             self._ws_keep = m.workspace(B)
             self.s = [t.clone() for t in (eeg, sid, img, txt, labels)]
+            # single GPU, retrieval loss: the static target buffers ARE the logits GEMM's operand inside the loss workspace
+            # and the per-step copy-in rounds to TF32 on the way (one kernel instead of a memcpy + the loss's own
+            # round-and-copy pass per target)
+            self._tgt_in_place = (eng.world == 1 and eng.variant == "retrieval" and img.dtype == torch.float32
+                                  and txt.dtype == torch.float32 and img.dim() == 2 and img.shape == txt.shape)
+            if self._tgt_in_place:
+                slots = eng.nce.target_slots(B, B, img.shape[1], 2, img.device)
+                for i, t in ((2, img), (3, txt)):
+                    _lib.tf32_round(t.contiguous(), slots[i - 2])
+                    self.s[i] = slots[i - 2]
             self.dev_steps = {k: torch.tensor([v], dtype=torch.int64, device=eeg.device) for k, v in m._adam_steps.items()}
             self._dev_host = dict(m._adam_steps)     # what the device counters hold, mirrored on the host
             torch.cuda.synchronize()
@@ -451,8 +461,11 @@ class GraphedTrainStep:
             self.launches_per_replay = _lib.launch_count() - n0
             self.graph = g
         else:
-            for dst, src in zip(self.s, (eeg, sid, img, txt, labels)):
-                dst.copy_(src, non_blocking=True)
+            for i, (dst, src) in enumerate(zip(self.s, (eeg, sid, img, txt, labels))):
+                if self._tgt_in_place and i in (2, 3):
+                    _lib.tf32_round(src.contiguous(), dst)
+                else:
+                    dst.copy_(src, non_blocking=True)
         # steps taken outside this graph (a ragged last batch run eagerly, another captured step on the same model) moved
         # the host-side AdamW step numbers: bring the device counters back in line before replaying
         for name, v in m._adam_steps.items():

@@ -22,6 +22,9 @@ class Bar:
         return (self.phase & 1) != parity
 
 
+N_B1_ISSUERS = 1        # B1_CTRL2 in csrc/conv_tc.cu (2 = dWs UMMAs of even / odd iterations on two threads)
+
+
 def run(mode, gc, n_tiles, seed, verbose=False):
     rnd = random.Random(seed)
     BS = mode == "B1"
@@ -107,7 +110,7 @@ def run(mode, gc, n_tiles, seed, verbose=False):
     def ctrl_b(cb):
         # second-stage issuers.  B1: cb 0 / 1 = dWs of the even / odd iterations (the 3-channel group: cb 0 alone);
         # B2: cb 0 = G, cb 1 / 2 = the two halves of the dwt chain
-        solo = BS and gc != 4
+        solo = BS and (gc != 4 or N_B1_ISSUERS == 1)
         for it in range(total):
             tl, ci = dec(it)
             bj = it & 1
@@ -132,11 +135,12 @@ def run(mode, gc, n_tiles, seed, verbose=False):
                     yield ("commit", B["op_empty"][0])
                     yield ("commit", B["im4_empty"][it & 3])
         yield ("commit", B["final_b"] if cb == 0 else B["final_c0" if cb == 1 else "final_c1"])
-        if BS and cb == 0:
-            yield ("commit", B["final_c1"])
+        if cb == 0:
+            for i in range(N_B1_ISSUERS if BS else 3, 3):
+                yield ("commit", B["final_c0" if i == 1 else "final_c1"])
 
     roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a()}
-    for cb in range(2 if BS else 3):
+    for cb in range(N_B1_ISSUERS if BS else 3):
         roles[f"ctrlB{cb}"] = ctrl_b(cb)
     for ge in range(2):
         for w in range(8):
