@@ -613,10 +613,9 @@ enum { MODE_BSTATS = 0, MODE_BAPPLY = 1 };
 // several single-thread "control" warps so that no thread issues more than ~9 of them.
 //   B2: control A (conv 4 + dA1 5), control B0 (G 5), control B1 / B2 (dwt: k-steps 0..7 / 8..15, two accumulators):
 //       295 -> 248 us.
-//   B1: control A (conv 4 + dA1 5), control B0 (dWs 16).  Splitting the dWs UMMAs over two issuers (even / odd
-//       iterations, B1_CTRL2 = 2: implemented, measured) made B1 SLOWER (206 -> 214 us): it is bound by SIMT issue slots
-//       and another polling warp costs more than the shorter UMMA chain gains.
-constexpr int B1_CTRL2 = 1, B2_CTRL2 = 3;
+//   B1: control A (conv 4 + dA1 5), control B0 / B1 (the 16 dWs UMMAs of the even / odd iterations); EEGB200_B1_ISSUERS=1
+//       leaves them all to B0 (B1 is bound by SIMT issue slots, the second issuer is worth little there)
+constexpr int B1_CTRL2 = 2, B2_CTRL2 = 3;
 constexpr int B1_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 1 + B1_CTRL2) * 32;         // 864
 constexpr int B2_THREADS = (N_BUILD_WARPS + N_EPI_WARPS + 4 + 1 + B2_CTRL2) * 32;     // 1024: + 4 scatter warps
 constexpr int SCAT_WARP0 = N_BUILD_WARPS + N_EPI_WARPS;
@@ -689,6 +688,7 @@ struct ConvBwdParams {
   float gscale;             // 1 / world size for the parameters whose gradient every rank computes in full
   int B;
   int n_tiles;
+  int b1_issuers;           // B1: 1 = control B0 issues every dWs UMMA, 2 = even / odd iterations on B0 / B1
   long long* trace;         // nullptr unless tracing
 };
 
@@ -1249,7 +1249,7 @@ conv_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWst, const __grid_const
     // B1: issuer cb takes the iterations with it & 1 == cb: its own a1 buffer and op_full / op_empty pair, and (4 channels
     // per tile) always the same two dWs accumulators, so every accumulator is fed by ONE thread, in order.  The 3-channel
     // group would alternate accumulators between the two threads: there issuer 0 does everything.
-    const bool solo = BS && (gc != GC || N_CTRL2 == 1);
+    const bool solo = BS && (gc != GC || p.b1_issuers == 1);
     for (int it = 0; it < total_it; ++it) {
       const BwdIt d = bwd_decode(it, gc, g, slot, n_slots, p.B);
       const int bj = it & 1;
@@ -1434,6 +1434,12 @@ int conv_tc_apply(const float* x3, const float* wt, const float* bt, const float
 static int bwd_launch(int mode, const ConvBwdParams& p_in, float* wst_packed, const float* ws_to_pack, cudaStream_t s) {
   ConvBwdParams p = p_in;
   p.trace = trace_buffer(s);
+  static int issuers = -1;
+  if (issuers < 0) {
+    const char* e = getenv("EEGB200_B1_ISSUERS");
+    issuers = (e && e[0] == '1') ? 1 : 2;
+  }
+  p.b1_issuers = issuers;
   if (ws_to_pack != nullptr) {
     pack_wst_tc_kernel<<<cdiv((int)(WST_MAIN_FLOATS + WST_TAIL_FLOATS), 256), 256, 0, s>>>(ws_to_pack, wst_packed);
     EEG_CUDA_OK(cudaGetLastError());

@@ -22,7 +22,7 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-N_B1_ISSUERS = 1        # B1_CTRL2 in csrc/conv_tc.cu (2 = dWs UMMAs of even / odd iterations on two threads)
+N_B1_ISSUERS = 2        # EEGB200_B1_ISSUERS (csrc/conv_tc.cu): 2 = dWs UMMAs of even / odd iterations on two threads
 
 
 def run(mode, gc, n_tiles, seed, verbose=False):
@@ -136,11 +136,11 @@ def run(mode, gc, n_tiles, seed, verbose=False):
                     yield ("commit", B["im4_empty"][it & 3])
         yield ("commit", B["final_b"] if cb == 0 else B["final_c0" if cb == 1 else "final_c1"])
         if cb == 0:
-            for i in range(N_B1_ISSUERS if BS else 3, 3):
+            for i in range(2 if BS else 3, 3):
                 yield ("commit", B["final_c0" if i == 1 else "final_c1"])
 
     roles = {"builder0": builder(0), "builder1": builder(1), "ctrlA": ctrl_a()}
-    for cb in range(N_B1_ISSUERS if BS else 3):
+    for cb in range(2 if BS else 3):
         roles[f"ctrlB{cb}"] = ctrl_b(cb)
     for ge in range(2):
         for w in range(8):
