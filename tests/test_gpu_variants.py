@@ -311,3 +311,39 @@ def test_autograd_bridge_refuses_stale_activations():
         out1.sum().backward()
     out2.sum().backward()                      # the latest forward still works
     assert m.enc_eeg[0].projection[0].weight.grad is not None
+
+
+@pytest.mark.gpu
+def test_graphed_step_captures_the_loader_batch_size_not_a_ragged_one():
+    """a ragged batch arriving when the capture would happen (third call) must run eagerly and leave the capture to the
+    next full batch; targets of the captured step live in the loss workspace (rounded in place) and still give the same
+    loss as the eager step"""
+    from eeg_image_decode_b200.atms import ATMS
+    from eeg_image_decode_b200.train import GraphedTrainStep, StepEngine
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(5)
+    gal = torch.nn.functional.normalize(torch.randn(50, 1024, generator=g), dim=-1).cuda()
+
+    def batch(B):
+        x = torch.randn(B, 63, 250, generator=g).cuda()
+        img = torch.nn.functional.normalize(torch.randn(B, 1024, generator=g), dim=-1).cuda()
+        txt = torch.nn.functional.normalize(torch.randn(B, 1024, generator=g), dim=-1).cuda()
+        return x, torch.full((B,), 8, device="cuda"), img, txt, torch.randint(0, 50, (B,), generator=g).cuda()
+
+    losses = {}
+    for graphed in (False, True):
+        m = ATMS()
+        m.load_state_dict(recipe.make_state_dict())
+        m = m.cuda().train()
+        m.dropout_p = [0.0] * 8
+        gs = GraphedTrainStep(StepEngine(m, torch.optim.AdamW(m.parameters(), lr=3e-4)), gal, use_shared=False, enabled=graphed)
+        g.manual_seed(5)
+        out = []
+        for B in (8, 8, 5, 8, 8, 5, 8):
+            loss, feats, _ = gs(*batch(B))
+            out.append(loss[0].item())
+        if graphed:
+            assert gs.graph is not None and gs.B == 8 and gs.replays >= 2
+        losses[graphed] = out
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) < 2e-3 * abs(a), (losses[False], losses[True])
