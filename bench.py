@@ -422,7 +422,7 @@ def bench_ours(args):
         run()
         t0 = time.perf_counter()
         n = 0
-        while n < 2 or (time.perf_counter() - t0 < 8.0 and n < 8):
+        while n < 2 or (time.perf_counter() - t0 < 15.0 and n < 8):        # ~10-20 s of CPU work at batch 1024
             run()
             n += 1
         dtc = time.perf_counter() - t0
@@ -508,8 +508,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=None, help="batch of the CPU legs (default: 1024 for --impl reference, "
-                    "128 for the cpu_baseline sample of our arm)")
+    ap.add_argument("--cpu-batch", type=int, default=None, help="batch of the CPU legs (default: the bench batch, 1024)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -522,7 +521,7 @@ def main():
         bench_reference(args)
     else:
         if args.cpu_batch is None:
-            args.cpu_batch = 128
+            args.cpu_batch = B_LOCAL        # the cpu_baseline sample runs the same batch-1024 step, a few of them
         bench_ours(args)
 
 
