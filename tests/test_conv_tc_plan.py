@@ -21,12 +21,15 @@ def test_conv_tc_kernel_protocol_has_no_deadlock_or_hazard():
     """mbarrier / commit / TMA protocol of the four csrc/conv_tc.cu kernels replayed with randomised timing
     (tools/conv_tc_protocol_sim.py): every role issues the same wait / arrive / commit sequence as the CUDA code"""
     import conv_tc_protocol_sim as S
-    for mode in ("B1", "B2"):
-        for gc in (4, 3):
-            for n_tiles in (1, 2, 3, 7):
-                for seed in range(8):
-                    ok, stuck = S.run(mode, gc, n_tiles, seed)
-                    assert ok, (mode, gc, n_tiles, seed, stuck)
+    for issuers in (2, 1):                 # EEGB200_B1_ISSUERS: dWs UMMAs on two issuer threads (default) or one
+        S.N_B1_ISSUERS = issuers
+        for mode in ("B1", "B2"):
+            for gc in (4, 3):
+                for n_tiles in (1, 2, 3, 7):
+                    for seed in range(6):
+                        ok, stuck = S.run(mode, gc, n_tiles, seed)
+                        assert ok, (issuers, mode, gc, n_tiles, seed, stuck)
+    S.N_B1_ISSUERS = 2
     for n_items in (1, 3):
         for seed in range(8):
             ok, stuck = S.run_fwd(n_items, seed)
